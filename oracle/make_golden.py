@@ -1,0 +1,418 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference.
+
+Run in the authoring container only (``/root/reference`` does not exist on
+the GPU box):
+
+    python -m oracle.make_golden            # from the repo root
+
+For every fixture the script (1) builds seeded inputs from
+``canonicalsg2im_b200.synth`` (pure integer hashing, reproducible anywhere),
+(2) runs the reference's own code on them, (3) asserts that the oracle
+restatement under ``oracle/`` reproduces the reference, and (4) stores inputs
+that are not regenerable plus the reference outputs.  TEST INFRASTRUCTURE ONLY.
+"""
+import argparse
+import os
+import pickle
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+REF = os.environ.get("CSG_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    """sg2im/utils.py:2 imports ``torch.tensor.Tensor`` which no longer exists."""
+    shim = types.ModuleType("torch.tensor")
+    shim.Tensor = torch.Tensor
+    sys.modules.setdefault("torch.tensor", shim)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import scripts.graphs_utils as gu
+    import sg2im.data.base_dataset as bd
+    import sg2im.graph as rgraph
+    import sg2im.model as rmodel
+    import sg2im.layout as rlayout
+    import sg2im.bilinear as rbil
+    return gu, bd, rgraph, rmodel, rlayout, rbil
+
+
+sys.path.insert(0, ROOT)
+from canonicalsg2im_b200 import synth  # noqa: E402
+from oracle import canon as ocanon, graph as ograph, layout as olayout  # noqa: E402
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+# ----------------------------------------------------------------------------
+def gen_canon(gu, bd):
+    out = {}
+    # --- reference KAT (graphs_utils.py:159-174) ---
+    kat = [[0, 1, 1], [0, 1, 2], [0, 1, 3], [1, 1, 2], [3, 1, 1], [3, 1, 2]]
+    adj = np.array(gu.triplets_to_adj_matrix(kat))
+    mini = np.array(gu.triplets_to_minimal(kat)).astype(np.int64)
+    cur, trans = gu.get_current_and_transitive_triplets(mini)
+    cyc_cur, cyc_trans = gu.get_current_and_transitive_triplets(np.array([[0, 1, 1], [1, 1, 0]]))
+    out.update(kat_triplets=np.array(kat), kat_adj=adj, kat_minimal=mini,
+               kat_transitive=np.array(trans).astype(np.int64),
+               cyc_transitive=np.array(cyc_trans).astype(np.int64))
+    assert (mini == np.array([[0, 1, 3], [1, 1, 2], [3, 1, 1]])).all()          # graphs_utils.py:166-168
+    assert (ocanon.triplets_to_adj(kat) == adj.astype(bool)).all()
+    assert (ocanon.triplets_to_minimal(kat) == mini).all()
+    assert (ocanon.current_and_transitive(mini)[1] == out["kat_transitive"]).all()
+    assert (ocanon.current_and_transitive([[0, 1, 1], [1, 1, 0]])[1] == out["cyc_transitive"]).all()
+
+    # --- random adjacency: closure / hsu / minimal (incl. cyclic graphs) ---
+    for i, (n, dens) in enumerate([(5, 0.3), (12, 0.15), (33, 0.08), (64, 0.05), (20, 0.5)]):
+        a = (synth.det_uniform(n * n, 900 + i).reshape(n, n) < dens).astype(np.uint8)
+        ref_path = np.array(gu.path(a.tolist()), dtype=bool)
+        m = [list(r) for r in ref_path.astype(np.uint8)]
+        gu.hsu(m)
+        ref_min = np.array(m, dtype=bool)
+        assert (ocanon.closure(a) == ref_path).all()
+        assert (ocanon.hsu_reduce(ocanon.closure(a)) == ref_min).all()
+        out["adj%d" % i], out["adj%d_path" % i], out["adj%d_min" % i] = a, ref_path, ref_min
+    out["num_adj"] = np.array(5)
+
+    # --- add_location_triplets + add_dummy_triplets + add_learnt_triplets ---
+    cases = []
+    specs = [  # (vocab, n_min, n_max, include_dummies, box_mode, converse, transitive)
+        (synth.Vocab(0), 3, 8, True, "coco", 1, 1),
+        (synth.Vocab(0), 3, 8, True, "coco", 0, 0),
+        (synth.Vocab(0), 6, 12, False, "coco", 1, 0),
+        (synth.Vocab(0), 6, 12, True, "clevr", 0, 1),
+        (synth.Vocab(42), 3, 30, True, "coco", 1, 1),
+        (synth.Vocab(42), 20, 30, True, "coco", 1, 1),
+        (synth.Vocab(0, num_attributes=4), 32, 40, True, "clevr", 1, 1),
+    ]
+    for ci, (vocab, n0, n1, dummies, mode, conv, trans) in enumerate(specs):
+        g = synth.make_graph(4000 + ci, n0, n1, vocab, include_dummies=dummies, box_mode=mode)
+        ds = bd.BaseDataset()
+        ds.vocab = {"pred_name_to_idx": dict(vocab.pred_ids), "pred_idx_to_name": list(vocab.pred_names),
+                    "object_name_to_idx": {"__image__": vocab.image_obj_id},
+                    "attributes": {"objects": {"__image__": vocab.image_obj_id}}}
+        ds.include_dummies = dummies
+        ds.learned_converse, ds.learned_transitivity = bool(conv), bool(trans)
+        W = synth.make_conv_weights(vocab, seed=ci)
+        ds.converse_candidates_weights = W
+        # reference spatial + dummy triples
+        n_real = len(g.centers)
+        cen = np.concatenate([g.centers, np.zeros((len(g.boxes) - n_real, 2), np.float32)])
+        ref_trip = []
+        ds.add_location_triplets(t(g.boxes), t(cen), t(g.objs[:, 0]), ref_trip)
+        n_loc = len(ref_trip)
+        ds.add_dummy_triplets(t(g.objs[:, 0]), ref_trip)
+        ref_base = np.array([np.asarray(x) for x in ref_trip]).astype(np.int64)
+        # oracle + synth agree with the reference
+        o_loc = ocanon.add_location_triplets(g.boxes, cen, g.objs[:, 0], vocab.image_obj_id, vocab.pred_ids)
+        assert (np.array(o_loc).reshape(-1, 3) == ref_base[:n_loc]).all(), "oracle add_location_triplets"
+        spatial = g.triplets[np.isin(g.triplets[:, 1], [vocab.pred_ids[a] for a in synth.AUGMENTED_RELATIONS])]
+        assert (spatial == ref_base[:n_loc]).all(), "synth.location_triplets"
+        o_dummy = ocanon.add_dummy_triplets(g.objs[:, 0], vocab.image_obj_id, vocab.in_image_id, dummies)
+        assert (np.array(o_dummy).reshape(-1, 3) == ref_base[n_loc:]).all()
+        base = g.triplets  # includes the VG-like dataset predicates when present
+        seed = 77 + ci
+        np.random.seed(seed)
+        r_trip, r_counts, r_type = ds.add_learnt_triplets([list(x) for x in base], len(g.objs))
+        uniforms = np.random.RandomState(seed).random_sample(len(base) * 2 + 8)
+        o_trip, o_counts, o_type, used = ocanon.add_learnt_triplets(
+            base, vocab.num_preds, vocab.meta_ids, W, bool(conv), bool(trans), uniforms)
+        assert (o_trip == np.asarray(r_trip).astype(np.int64)).all(), "oracle add_learnt_triplets (edges)"
+        assert (o_counts == r_counts).all() and (o_type == np.asarray(r_type)).all()
+        out["c%d_spec" % ci] = np.array([vocab.num_base_preds, vocab.num_attributes, n0, n1, int(dummies),
+                                        int(mode == "clevr"), conv, trans, 4000 + ci, ci, used])
+        out["c%d_uniforms" % ci] = uniforms[:max(used, 1)]
+        out["c%d_base" % ci] = ref_base
+        out["c%d_triplets" % ci] = np.asarray(r_trip).astype(np.int64)
+        out["c%d_counts" % ci] = r_counts
+        out["c%d_type" % ci] = np.asarray(r_type).astype(np.int64)
+        cases.append(ci)
+        print("canon case %d: O=%d base=%d -> T'=%d (type1=%d) draws=%d" % (
+            ci, len(g.objs), len(base), len(r_trip), int(np.sum(np.asarray(r_type) == 1)), used))
+    out["num_cases"] = np.array(len(cases))
+
+    # --- shipped CLEVR graphs (sg2im/data/scene_graphs.pkl), all-pairs relations, closure on ---
+    with open(os.path.join(REF, "sg2im", "data", "scene_graphs.pkl"), "rb") as f:
+        sgs = pickle.load(f)
+    vocab = synth.Vocab(0)
+    for gi in range(2):
+        sg = sgs[gi]
+        ds = bd.BaseDataset()
+        ds.vocab = {"pred_name_to_idx": dict(vocab.pred_ids), "pred_idx_to_name": list(vocab.pred_names)}
+        ds.learned_converse, ds.learned_transitivity = True, True
+        W = synth.make_conv_weights(vocab, seed=50 + gi)
+        ds.converse_candidates_weights = W
+        base = np.array(sg["relationships"]).astype(np.int64)
+        np.random.seed(5 + gi)
+        r_trip, r_counts, r_type = ds.add_learnt_triplets([list(x) for x in base], len(sg["objects"]))
+        uniforms = np.random.RandomState(5 + gi).random_sample(len(base) + 8)
+        o_trip, o_counts, o_type, used = ocanon.add_learnt_triplets(
+            base, vocab.num_preds, vocab.meta_ids, W, True, True, uniforms)
+        assert (o_trip == np.asarray(r_trip)).all() and (o_counts == r_counts).all()
+        out["pkl%d_base" % gi] = base
+        out["pkl%d_uniforms" % gi] = uniforms[:used]
+        out["pkl%d_seed" % gi] = np.array(50 + gi)
+        out["pkl%d_triplets" % gi] = np.asarray(r_trip).astype(np.int64)
+        out["pkl%d_counts" % gi] = r_counts
+        out["pkl%d_type" % gi] = np.asarray(r_type).astype(np.int64)
+        print("pkl graph %d: O=%d base=%d -> T'=%d" % (gi, len(sg["objects"]), len(base), len(r_trip)))
+    np.savez_compressed(os.path.join(OUT, "canon.npz"), **out)
+
+
+# ----------------------------------------------------------------------------
+def layer_inputs(seed=0, B=3, O=7, T=24, D=128, P=8):
+    """Hand-shaped padded batch for one GraphTripleConv layer: padded rows, all four
+    edge types, a self loop, a duplicate triple and an object no triple touches."""
+    obj = synth.det_tensor((B, O, D), seed + 1, 1.0)
+    pred = synth.det_tensor((B, T, D), seed + 2, 1.0)
+    s = synth.det_int(B * T, seed + 3, 0, O - 2).reshape(B, T)      # object O-1 never used -> count 0
+    o = synth.det_int(B * T, seed + 4, 0, O - 2).reshape(B, T)
+    p = synth.det_int(B * T, seed + 5, 1, P - 1).reshape(B, T)
+    ty = (synth.det_uniform(B * T, seed + 6).reshape(B, T) * 4).astype(np.int64)   # 0..3
+    ty[:, :6] = 0
+    s[0, 1], o[0, 1] = 2, 2                      # self loop
+    s[0, 3], o[0, 3], p[0, 3], ty[0, 3] = s[0, 2], o[0, 2], p[0, 2], ty[0, 2]    # duplicate
+    n_real = [T, T - 5, T - 11]
+    for b in range(B):                            # collate padding: [0, __padding__, 0], type 0
+        s[b, n_real[b]:], o[b, n_real[b]:], p[b, n_real[b]:], ty[b, n_real[b]:] = 0, 0, 0, 0
+    return obj, pred, s, o, p, ty
+
+
+def layer_state(seed, D=128, H=512, P=8):
+    st = {}
+    k = seed * 17
+
+    def lin(name, of, inf):
+        nonlocal k
+        k += 2
+        st[name + ".weight"] = synth.det_tensor((of, inf), k, float(np.sqrt(6.0 / inf)))
+        st[name + ".bias"] = synth.det_tensor((of,), k + 1, float(1.0 / np.sqrt(inf)))
+    lin("net1.0", H, 3 * D)
+    lin("net1.2", 2 * H + D, H)
+    lin("net2.0", H, H)
+    lin("net2.2", D, H)
+    st["predicates_transitive_weights"] = synth.det_tensor((P,), k + 9, 1.0)
+    return st
+
+
+GRAD_STRIDE = 97   # weight gradients are stored subsampled (flat[::GRAD_STRIDE]) to keep fixtures small
+
+
+def gen_gconv(rgraph):
+    D, H, P = 128, 512, 8
+    obj, pred, s, o, p, ty = layer_inputs()
+    st = layer_state(3)
+    w_trans = torch.nn.Parameter(t(st["predicates_transitive_weights"]).clone())
+    layer = rgraph.GraphTripleConv(D, D, D, D, H, 1, predicates_transitive_weights=w_trans)
+    sd = {k: t(v) for k, v in st.items() if k != "predicates_transitive_weights"}
+    layer.load_state_dict(sd, strict=False)
+    obj_t = t(obj).clone().requires_grad_(True)
+    pred_t = t(pred).clone().requires_grad_(True)
+    edges = torch.stack([t(s), t(o)], dim=-1)
+    ind = t(p) != 0
+    new_obj, new_p = layer(obj_t, pred_t, edges, ind, t(ty), t(p))
+    g_obj = t(synth.det_tensor(tuple(new_obj.shape), 41, 1.0))
+    g_p = t(synth.det_tensor(tuple(new_p.shape), 42, 1.0))
+    loss = (new_obj * g_obj).sum() + (new_p * g_p).sum()
+    loss.backward()
+    out = dict(new_obj=new_obj.detach().numpy(), new_p=new_p.detach().numpy(),
+               d_obj=obj_t.grad.numpy(), d_pred=pred_t.grad.numpy(), d_w_trans=w_trans.grad.numpy())
+    for name, prm in layer.named_parameters():
+        if name == "predicates_transitive_weights":
+            continue
+        gflat = prm.grad.numpy().reshape(-1)
+        out["dsub_" + name] = gflat[::GRAD_STRIDE].copy()
+        out["dnorm_" + name] = np.array(np.linalg.norm(gflat.astype(np.float64)))
+    # oracle restatement reproduces the reference (same ops, same order -> tight tolerance)
+    st_t = {k: t(v).clone().requires_grad_(True) for k, v in st.items()}
+    oo = t(obj).clone().requires_grad_(True)
+    pp = t(pred).clone().requires_grad_(True)
+    o_obj, o_p = ograph.graph_triple_conv(st_t, "", oo, pp, edges, ind, t(ty), t(p),
+                                          st_t["predicates_transitive_weights"], H, D)
+    ((o_obj * g_obj).sum() + (o_p * g_p).sum()).backward()
+    assert torch.allclose(o_obj, new_obj, rtol=1e-6, atol=1e-6), "oracle GraphTripleConv fwd"
+    assert torch.allclose(o_p, new_p, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(oo.grad, obj_t.grad, rtol=1e-5, atol=1e-6), "oracle GraphTripleConv bwd"
+    assert torch.allclose(st_t["predicates_transitive_weights"].grad, w_trans.grad, rtol=1e-5, atol=1e-6)
+    np.savez_compressed(os.path.join(OUT, "gconv_layer.npz"), **out)
+    print("gconv layer: new_obj", tuple(new_obj.shape), "new_p", tuple(new_p.shape))
+
+
+def model_batch(vocab, graphs, W_conv, seed, conv=True, trans=True):
+    """Canonicalise each synthetic graph with the oracle, then pad like the reference collate
+    (packed_coco.py:385-478)."""
+    per = []
+    for gi, g in enumerate(graphs):
+        uni = synth.det_uniform(len(g.triplets) * 2 + 8, seed * 1000 + gi)
+        trip, _, ty, _ = ocanon.add_learnt_triplets(g.triplets, vocab.num_preds, vocab.meta_ids, W_conv,
+                                                    conv, trans, uni)
+        per.append((g, trip, ty))
+    Omax = max(len(g.objs) for g, _, _ in per)
+    Tmax = max(len(tr) for _, tr, _ in per)
+    B, A = len(per), vocab.num_attributes
+    objs = np.zeros((B, Omax, A), np.int64)
+    boxes = -np.ones((B, Omax, 4), np.float32)
+    trips = np.zeros((B, Tmax, 3), np.int64)
+    trips[:, :, 1] = vocab.padding_id
+    types = np.zeros((B, Tmax), np.int64)
+    for b, (g, tr, ty) in enumerate(per):
+        objs[b, :len(g.objs)] = g.objs
+        boxes[b, :len(g.boxes)] = g.boxes
+        trips[b, :len(tr)] = tr
+        types[b, :len(ty)] = ty
+    return objs, boxes, trips, types
+
+
+def gen_model(rmodel):
+    vocab = synth.Vocab(0)
+    graphs = synth.make_graphs(4, 11, 3, 8, vocab, include_dummies=True)
+    W = synth.make_conv_weights(vocab, 1)
+    objs, boxes, trips, types = model_batch(vocab, graphs, W, seed=3)
+    st = synth.make_state(vocab, seed=2)
+    opt = argparse.Namespace(
+        vocab={"attributes": {"objects": {str(i): i for i in range(vocab.num_obj_classes)}},
+               "pred_idx_to_name": vocab.pred_names, "pred_name_to_idx": vocab.pred_ids},
+        image_size=(64, 64), layout_noise_dim=0, mask_noise_dim=0, embedding_dim=128, gconv_dim=128,
+        gconv_hidden_dim=512, gconv_pooling="avg", gconv_num_layers=5, mlp_normalization="none",
+        mask_size=0, learned_init="uniform")
+    model = rmodel.Sg2LayoutModel(opt)
+    missing = model.load_state_dict({k: t(v) for k, v in st.items()}, strict=False)
+    # every GraphTripleConv registers the shared transitive weights a second time (graph.py:42)
+    assert all("predicates_transitive_weights" in k for k in missing.missing_keys), missing
+    obj_vecs, boxes_pred, masks_pred = model(t(objs), t(trips), t(types))
+    assert masks_pred is None
+    real = t((boxes >= 0).all(-1))
+    loss = boxes_pred.pow(2).sum() + (obj_vecs * t(synth.det_tensor(tuple(obj_vecs.shape), 5, 1.0))).sum()
+    loss.backward()
+    out = dict(objs=objs, boxes=boxes, triplets=trips, types=types,
+               obj_vecs=obj_vecs.detach().numpy(), boxes_pred=boxes_pred.detach().numpy(),
+               loss=np.array(loss.item()))
+    for name, prm in model.named_parameters():
+        if "predicates_transitive_weights" in name or prm.grad is None:
+            continue
+        gflat = prm.grad.numpy().reshape(-1)
+        if gflat.size <= 4096:
+            out["d_" + name] = prm.grad.numpy().copy()
+        else:
+            out["dsub_" + name] = gflat[::GRAD_STRIDE].copy()
+        out["dnorm_" + name] = np.array(np.linalg.norm(gflat.astype(np.float64)))
+    assert model.converse_candidates_weights.grad is None
+    # oracle check
+    st_t = {k: t(v).clone().requires_grad_(True) for k, v in st.items()}
+    o_vecs, o_boxes = ograph.sg2layout_forward(st_t, t(objs), t(trips), t(types), vocab.padding_id)
+    assert torch.allclose(o_vecs, obj_vecs, rtol=1e-5, atol=1e-6), "oracle Sg2LayoutModel"
+    assert torch.allclose(o_boxes, boxes_pred, rtol=1e-5, atol=1e-6)
+    np.savez_compressed(os.path.join(OUT, "sg2layout_model.npz"), **out)
+    print("model: B=%d O=%d T=%d loss=%.6f" % (objs.shape[0], objs.shape[1], trips.shape[1], loss.item()))
+    _ = real
+
+
+def gen_layout(rlayout, rbil):
+    import torch.nn.functional as F
+    out = {}
+    demo_vecs = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 0, 0], [0, 1, 0], [0, 0, 1]], np.float32)
+    demo_boxes = np.array([[0.25, 0.125, 0.5, 0.875], [0, 0, 1, 0.25], [0.6125, 0, 0.875, 1],
+                           [0, 0.8, 1, 1.0], [0.25, 0.125, 0.5, 0.875], [0.6125, 0, 0.875, 1]], np.float32)
+    plus = np.array([[0, 0, 1, 0, 0], [0, 1, 1, 1, 0], [1, 1, 1, 1, 1], [0, 1, 1, 1, 0], [0, 0, 1, 0, 0]], np.float32)
+    ring = np.array([[0, 0, 1, 0, 0], [0, 1, 0, 1, 0], [1, 0, 0, 0, 1], [0, 1, 0, 1, 0], [0, 0, 1, 0, 0]], np.float32)
+    demo_masks = np.stack([plus, ring, plus, plus, plus, plus])              # layout.py:215-258
+    out.update(demo_vecs=demo_vecs, demo_boxes=demo_boxes, demo_masks=demo_masks)
+
+    def run(tag, vecs, boxes, masks, H, W, test_mode=False, float_masks=False, legacy=False):
+        v = t(vecs).clone().requires_grad_(True)
+        b = t(boxes).clone().requires_grad_(True)
+        m = None
+        orig = F.grid_sample
+        if legacy:   # torch<=1.2 semantics the checkpoints were trained under
+            F.grid_sample = lambda *a, **k: orig(*a, **{**k, "align_corners": True})
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                if masks is None:
+                    y = rlayout.boxes_to_layout(v, b, H, W)
+                    oy = olayout.boxes_to_layout(t(vecs), t(boxes), H, W, align_corners=legacy)
+                else:
+                    m = t(masks).clone()
+                    if float_masks:
+                        m.requires_grad_(True)
+                    y = rlayout.masks_to_layout(v, b, m, H, W, test_mode=test_mode)
+                    oy = olayout.masks_to_layout(t(vecs), t(boxes), t(masks), H, W, test_mode=test_mode,
+                                                 align_corners=legacy)
+        finally:
+            F.grid_sample = orig
+        assert torch.equal(oy, y.detach()), "oracle layout %s" % tag
+        out[tag + "_out"] = y.detach().numpy()
+        if not test_mode:
+            g = t(synth.det_tensor(tuple(y.shape), 77, 1.0))
+            (y * g).sum().backward()
+            out[tag + "_dvecs"] = v.grad.numpy()
+            out[tag + "_dboxes"] = b.grad.numpy()
+            if float_masks:
+                out[tag + "_dmasks"] = m.grad.numpy()
+
+    run("demo_boxes64", demo_vecs, demo_boxes, None, 64, 64)
+    run("demo_masks64", demo_vecs, demo_boxes, demo_masks, 64, 64, float_masks=True)
+    run("demo_masks64_test", demo_vecs, demo_boxes, demo_masks, 64, 64, test_mode=True)
+    run("demo_boxes64_legacy", demo_vecs, demo_boxes, None, 64, 64, legacy=True)
+    run("demo_masks64_legacy", demo_vecs, demo_boxes, demo_masks, 64, 64, legacy=True, float_masks=True)
+    # random objects: D=16, rectangular canvas, boxes partly outside the canvas, int64 masks
+    vocab = synth.Vocab(0)
+    g = synth.make_graph(123, 7, 7, vocab, include_dummies=False, mask_size=16)
+    vecs = synth.det_tensor((7, 16), 9, 1.0)
+    boxes = g.boxes.copy()
+    boxes[0] = [-0.2, 0.1, 0.5, 0.4]
+    boxes[1] = [0.7, 0.8, 0.6, 0.5]
+    boxes[2] = [1.5, 1.5, 0.2, 0.2]          # entirely outside: contributes zeros
+    boxes[3] = [0.3, 0.3, 0.02, 0.015]       # sub-pixel box
+    out.update(rnd_vecs=vecs, rnd_boxes=boxes, rnd_masks=g.masks)
+    run("rnd_boxes", vecs, boxes, None, 32, 48)
+    run("rnd_masks", vecs, boxes, g.masks, 32, 48)
+    run("rnd_masks_f", vecs, boxes, synth.det_uniform(7 * 16 * 16, 5).reshape(7, 16, 16).astype(np.float32),
+        40, 40, float_masks=True)
+    out["rnd_masks_f_in"] = synth.det_uniform(7 * 16 * 16, 5).reshape(7, 16, 16).astype(np.float32)
+    run("rnd_masks_test", vecs, boxes, g.masks, 32, 48, test_mode=True)
+    # single object / avg pooling value
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import io
+        import contextlib
+        with contextlib.redirect_stdout(io.StringIO()):
+            out["rnd_boxes_avg_out"] = rlayout.boxes_to_layout(t(vecs), t(boxes), 32, 48, pooling="avg").numpy()
+
+    # crop_bbox (bilinear.py:65-94)
+    imgs = synth.det_tensor((3, 3, 24, 20), 31, 1.0)
+    bb = np.array([[0.1, 0.2, 0.5, 0.6], [0.0, 0.0, 1.0, 1.0], [0.6, 0.5, 0.7, 0.8]], np.float32)
+    im = t(imgs).clone().requires_grad_(True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        crops = rbil.crop_bbox(im, t(bb), 8, 12)
+    gc = t(synth.det_tensor(tuple(crops.shape), 32, 1.0))
+    (crops * gc).sum().backward()
+    assert torch.equal(olayout.crop_bbox(t(imgs), t(bb), 8, 12), crops.detach())
+    out.update(crop_imgs=imgs, crop_boxes=bb, crop_out=crops.detach().numpy(), crop_dimgs=im.grad.numpy())
+    np.savez_compressed(os.path.join(OUT, "layout.npz"), **out)
+    print("layout fixtures:", len(out), "arrays")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    gu, bd, rgraph, rmodel, rlayout, rbil = import_reference()
+    gen_canon(gu, bd)
+    gen_gconv(rgraph)
+    gen_model(rmodel)
+    gen_layout(rlayout, rbil)
+    for f in sorted(os.listdir(OUT)):
+        print("%-28s %8.1f KB" % (f, os.path.getsize(os.path.join(OUT, f)) / 1024))
+
+
+if __name__ == "__main__":
+    main()
