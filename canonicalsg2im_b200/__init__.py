@@ -1,0 +1,30 @@
+"""canonicalsg2im_b200 -- B200 (sm_100a) kernels for the scene-graph -> layout hot path of
+roeiherz/CanonicalSg2Im, behind the reference's own Python operator surface.
+
+    from canonicalsg2im_b200 import GraphTripleConv, GraphTripleConvNet, Sg2LayoutModel
+    from canonicalsg2im_b200 import boxes_to_layout, masks_to_layout, layout_batched
+    from canonicalsg2im_b200 import add_learnt_triplets, add_learnt_triplets_batched
+
+Everything computes in ``libcsg2im.so`` (hand-written CUDA, C ABI in ``include/csg2im.h``); importing
+the operators without the built library, or calling them on CPU tensors, raises.
+"""
+from . import synth  # noqa: F401  (host-side synthetic inputs; no kernels)
+
+__all__ = ["synth", "GraphTripleConv", "GraphTripleConvNet", "TripleBatch", "Sg2LayoutModel", "get_conv_converse",
+           "boxes_to_layout", "masks_to_layout", "layout_batched", "add_learnt_triplets",
+           "add_learnt_triplets_batched", "converse_tables", "closure"]
+
+_LAZY = {
+    "GraphTripleConv": "graph", "GraphTripleConvNet": "graph", "TripleBatch": "graph",
+    "Sg2LayoutModel": "model", "get_conv_converse": "model",
+    "boxes_to_layout": "layout", "masks_to_layout": "layout", "layout_batched": "layout",
+    "add_learnt_triplets": "canonicalize", "add_learnt_triplets_batched": "canonicalize",
+    "converse_tables": "canonicalize", "closure": "canonicalize",
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+        return getattr(importlib.import_module("." + _LAZY[name], __name__), name)
+    raise AttributeError(name)

@@ -1,0 +1,138 @@
+"""WSGC canonicalization on the GPU: batched drop-in for ``BaseDataset.add_learnt_triplets``
+(reference ``sg2im/data/base_dataset.py:89-139`` with ``scripts/graphs_utils.py:15-155``).
+
+The reference canonicalises one graph at a time on the CPU inside ``Dataset.__getitem__``; here a
+whole batch of graphs is completed by two launches of an integer bitset kernel (csrc/canon.cu).
+Results are bit-exact given the converse draws: pass the doubles that ``np.random.choice`` would
+have consumed (one per unique non-meta triple, in the reference's visiting order) as ``uniforms``.
+
+Host-side pieces (tiny, weight-dependent only): the per-relation softmax CDF table
+(``graphs_utils.py:132-139``), built in float64 with numpy exactly as the reference does.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .ops import lib, ptr, need_cuda, _stream
+
+ORIGINAL_EDGE, TRANSITIVE_EDGE = 0, 1          # base_dataset.py:7-8
+
+
+def converse_tables(conv_weights, num_rel, meta_ids):
+    """CDF / value tables of the converse sampler.
+
+    For every non-meta relation ``rel`` the candidates are the other non-meta relations (ascending)
+    plus the "no edge" outcome ``num_rel`` with logit 0 (``graphs_utils.py:132-137``); probabilities
+    are a float64 softmax and ``np.random.choice`` searches their normalised cumulative sum.
+    Returns (cdf [P, ncand] float64, vals [P, ncand] int32)."""
+    W = np.asarray(conv_weights.detach().cpu() if torch.is_tensor(conv_weights) else conv_weights, dtype=np.float64)
+    non_meta = [r for r in range(num_rel) if r not in tuple(meta_ids)]
+    ncand = len(non_meta)          # (len(non_meta) - 1) candidates + "no edge"
+    cdf = np.ones((num_rel, max(ncand, 1)), dtype=np.float64)
+    vals = np.full((num_rel, max(ncand, 1)), num_rel, dtype=np.int32)
+    for rel in non_meta:
+        cands = [c for c in non_meta if c != rel]
+        logits = np.array([W[rel, c] for c in cands] + [0.0], dtype=np.float64)
+        e = np.exp(logits - logits.max())
+        p = e / e.sum()
+        c = p.cumsum()
+        c /= c[-1]
+        cdf[rel, :len(c)] = c
+        vals[rel, :len(cands)] = cands
+    return cdf, vals
+
+
+class CanonResult:
+    def __init__(self, triplets, triplet_type, tri_off, conv_counts):
+        self.triplets = triplets            # [NT', 3] int64, graph-local object ids
+        self.triplet_type = triplet_type    # [NT'] int64 (0 original, 1 transitive)
+        self.tri_off = tri_off              # [B+1] int32
+        self.conv_counts = conv_counts      # [B, P, P+1] int32
+
+    def split(self):
+        """Per-graph (triplets, conv_counts, triplet_type) like the reference returns them."""
+        off = self.tri_off.cpu().tolist()
+        return [(self.triplets[off[b]:off[b + 1]], self.conv_counts[b], self.triplet_type[off[b]:off[b + 1]])
+                for b in range(len(off) - 1)]
+
+
+def add_learnt_triplets_batched(triplets, tri_off, obj_off, num_rel, meta_ids, conv_weights=None,
+                                learned_converse=False, learned_transitivity=False, uniforms=None,
+                                max_objs_per_graph=None, tables=None):
+    """Canonicalise B graphs at once.
+
+    triplets [NTin, 3] int64 (graph-local ids, any order, duplicates allowed), tri_off / obj_off [B+1]
+    int32 (CUDA), ``uniforms`` [>= NTin] float64 (CUDA): the k-th converse draw of graph g is
+    ``uniforms[tri_off[g] + k]``.  Returns a :class:`CanonResult` (device tensors)."""
+    need_cuda(triplets, tri_off, obj_off, uniforms)
+    dev = triplets.device
+    L = lib()
+    B = tri_off.numel() - 1
+    tr = triplets.contiguous().to(torch.int64)
+    tri_off = tri_off.to(torch.int32).contiguous()
+    obj_off = obj_off.to(torch.int32).contiguous()
+    meta = list(meta_ids) + [-1, -1]
+    if max_objs_per_graph is None:
+        max_objs_per_graph = int((obj_off[1:] - obj_off[:-1]).max().item()) if B else 1
+    cdf_t = vals_t = None
+    ncand = 0
+    if learned_converse:
+        if tables is None:
+            tables = converse_tables(conv_weights, num_rel, meta_ids)
+        cdf, vals = tables
+        cdf_t = cdf if torch.is_tensor(cdf) else torch.from_numpy(cdf)
+        vals_t = vals if torch.is_tensor(vals) else torch.from_numpy(vals)
+        cdf_t, vals_t = cdf_t.to(dev).contiguous(), vals_t.to(dev).contiguous()
+        ncand = cdf_t.shape[1]
+        if uniforms is None or uniforms.numel() < tr.shape[0]:
+            raise ValueError("learned_converse needs one float64 draw per input triple")
+        uniforms = uniforms.to(torch.float64).contiguous()
+    cnt = torch.empty((2, max(B, 1)), dtype=torch.int32, device=dev)
+    conv_counts = torch.empty((max(B, 1), num_rel, num_rel + 1), dtype=torch.int32, device=dev)
+    args = (ptr(tr), ptr(tri_off), ptr(obj_off), B, ptr(uniforms) if learned_converse else 0, ptr(cdf_t), ptr(vals_t),
+            ncand, num_rel, meta[0], meta[1], int(learned_converse), int(learned_transitivity), int(max_objs_per_graph))
+    _lib.check(L.csg_canon_count(*args, ptr(cnt[0]), ptr(cnt[1]), ptr(conv_counts), _stream()), "csg_canon_count")
+    if B and int(cnt[0, :B].min().item()) < 0:
+        raise _lib.CsgError("canonicalize: a graph has more objects than max_objs_per_graph=%d" % max_objs_per_graph)
+    out_off = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+    if B:
+        out_off[1:] = torch.cumsum((cnt[0, :B] + cnt[1, :B]).to(torch.int64), 0).to(torch.int32)
+    total = int(out_off[-1].item())            # sizes the output allocation (one host sync per batch)
+    out_t = torch.empty((max(total, 1), 3), dtype=torch.int64, device=dev)
+    out_ty = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+    _lib.check(L.csg_canon_emit(*args, ptr(out_off), ptr(out_t), ptr(out_ty), _stream()), "csg_canon_emit")
+    return CanonResult(out_t[:total], out_ty[:total], out_off, conv_counts[:B])
+
+
+def add_learnt_triplets(triplets, O, num_rel, meta_ids, conv_weights=None, learned_converse=False,
+                        learned_transitivity=False, uniforms=None, device="cuda"):
+    """Single-graph form mirroring ``BaseDataset.add_learnt_triplets(triplets, O)`` (base_dataset.py:89):
+    returns (triplets' [T',3] int64 ndarray, conv_counts [P,P+1] float64 ndarray, triplet_type list)."""
+    t = torch.as_tensor(np.asarray(triplets, dtype=np.int64).reshape(-1, 3), device=device)
+    n = t.shape[0]
+    tri_off = torch.tensor([0, n], dtype=torch.int32, device=device)
+    obj_off = torch.tensor([0, int(O)], dtype=torch.int32, device=device)
+    u = None
+    if learned_converse:
+        u = torch.zeros(max(n, 1), dtype=torch.float64, device=device)
+        src = torch.as_tensor(np.asarray(uniforms, dtype=np.float64), device=device)
+        k = min(n, src.numel())
+        u[:k] = src[:k]
+    res = add_learnt_triplets_batched(t, tri_off, obj_off, num_rel, meta_ids, conv_weights, learned_converse,
+                                      learned_transitivity, u, max_objs_per_graph=int(O))
+    return (res.triplets.cpu().numpy(), res.conv_counts[0].cpu().numpy().astype(np.float64),
+            res.triplet_type.cpu().tolist())
+
+
+def closure(adj, reduce=False):
+    """``path`` (graphs_utils.py:15-27) or, with ``reduce``, ``get_minimal_graph`` (:41-44) of a batch
+    of adjacency matrices [G, n, n] (uint8/bool CUDA tensor)."""
+    need_cuda(adj)
+    a = adj.to(torch.uint8).contiguous()
+    squeeze = a.dim() == 2
+    if squeeze:
+        a = a[None]
+    out = torch.empty_like(a)
+    _lib.check(lib().csg_canon_closure(ptr(a), a.shape[0], a.shape[1], int(reduce), ptr(out), _stream()),
+               "csg_canon_closure")
+    return out[0] if squeeze else out

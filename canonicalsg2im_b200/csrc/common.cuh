@@ -1,0 +1,55 @@
+// Shared helpers for the csg2im sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifndef CSG_API
+#define CSG_API extern "C" __attribute__((visibility("default")))
+#endif
+
+// Thread-local error text returned by csg_last_error(); no exception crosses the C ABI.
+void csg_set_error(const char* fmt, ...);
+
+#define CSG_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      csg_set_error(__VA_ARGS__);         \
+      return 1;                           \
+    }                                     \
+  } while (0)
+
+// Launch errors are checked immediately (no deferred sync), SURVEY.md §8(b).
+#define CSG_CHECK_LAUNCH(name)                                                      \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      csg_set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e__));   \
+      return 2;                                                                     \
+    }                                                                               \
+  } while (0)
+
+#define CSG_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      csg_set_error("%s failed: %s", #call, cudaGetErrorString(e__));               \
+      return 2;                                                                     \
+    }                                                                               \
+  } while (0)
+
+static inline int csg_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int csg_num_sms();   // SM count of the current device (cached per device)
+
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// streaming (evict-first) 128-bit store: canvas tiles are written once and not re-read by the writer
+__device__ __forceinline__ void st_f4_stream(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ float4 ld_f4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

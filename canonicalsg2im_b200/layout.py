@@ -1,0 +1,144 @@
+"""Layout compositor: drop-in for ``sg2im/layout.py`` of the reference.
+
+``boxes_to_layout`` / ``masks_to_layout`` keep the reference's signatures
+(``sg2im/layout.py:12,48``: one image per call, boxes ``[x0, y0, w, h]``) and
+add ``align_corners`` (the reference relies on the torch default, which flipped
+from True to False in torch 1.3).  ``layout_batched`` is the
+ragged form (flat objects + ``obj_offsets``), one launch for all images, whose
+result equals ``torch.cat`` of the per-image reference calls
+(``spade/models/networks/generator.py:81-96``).
+
+All arithmetic runs in ``csg_layout_*`` (csrc/layout.cu); a missing library or
+CPU tensors raise.
+"""
+import torch
+
+from . import _lib
+from .ops import lib, ptr, need_cuda, f32c, workspace, _stream
+
+_LIN = {}
+
+
+def _linspace(steps, device):
+    """fp32 ``torch.linspace(0, 1, steps)`` built on the CPU and moved, exactly like
+    ``sg2im/layout.py:98-99`` (``torch.linspace(...).to(boxes)``)."""
+    key = (int(steps), str(device))
+    t = _LIN.get(key)
+    if t is None:
+        t = torch.linspace(0, 1, steps=int(steps)).to(device)
+        _LIN[key] = t
+    return t
+
+
+def _offsets(obj_offsets, device):
+    if obj_offsets.dtype != torch.int32:
+        obj_offsets = obj_offsets.to(torch.int32)
+    return obj_offsets.to(device).contiguous()
+
+
+class _LayoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vecs, boxes, masks, obj_off, H, W, align_corners, max_objs):
+        need_cuda(vecs, boxes, masks, obj_off)
+        vecs_c, boxes_c = f32c(vecs), f32c(boxes)
+        masks_c = f32c(masks) if masks is not None else None
+        NO, D = vecs_c.shape
+        N = obj_off.numel() - 1
+        M = masks_c.shape[1] if masks_c is not None else 0
+        lin_x, lin_y = _linspace(W, vecs.device), _linspace(H, vecs.device)
+        out = torch.empty((N, D, H, W), dtype=torch.float32, device=vecs.device)
+        rc = lib().csg_layout_fwd(ptr(vecs_c), ptr(boxes_c), ptr(masks_c), ptr(obj_off), ptr(lin_x), ptr(lin_y),
+                                  ptr(out), N, D, H, W, M, int(align_corners), int(max_objs), _stream())
+        _lib.check(rc, "csg_layout_fwd")
+        ctx.save_for_backward(vecs_c, boxes_c, masks_c, obj_off)
+        ctx.dims = (N, NO, D, H, W, M, int(align_corners), int(max_objs))
+        ctx.masks_float = masks is not None and masks.is_floating_point()
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        vecs, boxes, masks, obj_off = ctx.saved_tensors
+        N, NO, D, H, W, M, align, max_objs = ctx.dims
+        dout = f32c(dout)
+        dvecs = dboxes = dmasks = None
+        L = lib()
+        lin_x, lin_y = _linspace(W, dout.device), _linspace(H, dout.device)
+        if ctx.needs_input_grad[0]:
+            dvecs = torch.empty((NO, D), dtype=torch.float32, device=dout.device)
+            ws = workspace(L.csg_layout_bwd_vecs_workspace(NO, D, H, W), dout.device)
+            rc = L.csg_layout_bwd_vecs(ptr(dout), ptr(boxes), ptr(masks), ptr(obj_off), ptr(lin_x), ptr(lin_y),
+                                       ptr(dvecs), N, NO, D, H, W, M, align, max_objs, ptr(ws), ws.numel(), _stream())
+            _lib.check(rc, "csg_layout_bwd_vecs")
+        need_geom = ctx.needs_input_grad[1] or (ctx.needs_input_grad[2] and ctx.masks_float)
+        if need_geom:
+            if not hasattr(L, "csg_layout_bwd_geom"):
+                raise NotImplementedError("gradients wrt boxes / masks need csg_layout_bwd_geom")
+            dboxes = torch.zeros((NO, 4), dtype=torch.float32, device=dout.device)
+            want_dm = ctx.needs_input_grad[2] and ctx.masks_float
+            dmasks = torch.zeros_like(masks) if want_dm else None
+            ws = workspace(L.csg_layout_bwd_geom_workspace(NO, D, H, W, M), dout.device)
+            rc = L.csg_layout_bwd_geom(ptr(dout), ptr(vecs), ptr(boxes), ptr(masks), ptr(obj_off), ptr(lin_x),
+                                       ptr(lin_y), ptr(dboxes), ptr(dmasks), N, NO, D, H, W, M, align,
+                                       ptr(ws), ws.numel(), _stream())
+            _lib.check(rc, "csg_layout_bwd_geom")
+            if not ctx.needs_input_grad[1]:
+                dboxes = None
+        return dvecs, dboxes, dmasks, None, None, None, None, None
+
+
+def layout_batched(vecs, boxes, obj_offsets, H, W=None, masks=None, pooling="sum", test_mode=False,
+                   align_corners=False, max_objs_per_image=0):
+    """Ragged compositor: ``vecs [NO, D]``, ``boxes [NO, 4]`` (xywh), optional ``masks [NO, M, M]``,
+    ``obj_offsets [N+1]`` (objects of image n are ``obj_offsets[n]:obj_offsets[n+1]``)
+    -> ``[N, D, H, W]``.  ``max_objs_per_image`` is a sizing hint (0 = unknown)."""
+    if pooling not in ("sum", "avg"):
+        raise ValueError('Invalid pooling "%s"' % pooling)
+    W = H if W is None else W
+    need_cuda(vecs, boxes, masks)
+    off = _offsets(obj_offsets, vecs.device)
+    if masks is not None:
+        O, M = masks.shape[0], masks.shape[1]
+        assert tuple(masks.shape) == (vecs.shape[0], M, M)            # layout.py:63
+    if test_mode:
+        if masks is None:
+            raise ValueError("test_mode needs masks")
+        return _occlude(vecs, boxes, masks, off, H, W, align_corners)
+    out = _LayoutFn.apply(vecs, boxes, masks, off, int(H), int(W), bool(align_corners), int(max_objs_per_image))
+    if pooling == "avg":                                              # layout.py:176-184
+        cnt = (off[1:] - off[:-1]).clamp(min=1).to(out.dtype)
+        out = out / cnt.view(-1, 1, 1, 1)
+    return out
+
+
+def _occlude(vecs, boxes, masks, off, H, W, align_corners):
+    L = lib()
+    vecs_c, boxes_c, masks_c = f32c(vecs), f32c(boxes), f32c(masks)
+    NO, D = vecs_c.shape
+    N, M = off.numel() - 1, masks_c.shape[1]
+    out = torch.empty((N, D, H, W), dtype=torch.float32, device=vecs.device)
+    ws = workspace(L.csg_layout_occlude_workspace(NO), vecs.device)
+    lin_x, lin_y = _linspace(W, vecs.device), _linspace(H, vecs.device)
+    rc = L.csg_layout_occlude_fwd(ptr(vecs_c), ptr(boxes_c), ptr(masks_c), ptr(off), ptr(lin_x), ptr(lin_y), ptr(out),
+                                  N, NO, D, H, W, M, int(align_corners), ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "csg_layout_occlude_fwd")
+    return out
+
+
+def _single_offsets(O, device):
+    return torch.tensor([0, O], dtype=torch.int32, device=device)
+
+
+def boxes_to_layout(vecs, boxes, H, W=None, pooling="sum", align_corners=False):
+    """``sg2im/layout.py:12-45``: vecs [O, D], boxes [O, 4] xywh -> [1, D, H, W]."""
+    O = vecs.size(0)
+    return layout_batched(vecs, boxes, _single_offsets(O, vecs.device), H, W, None, pooling,
+                          align_corners=align_corners, max_objs_per_image=O)
+
+
+def masks_to_layout(vecs, boxes, masks, H, W=None, pooling="sum", test_mode=False, align_corners=False):
+    """``sg2im/layout.py:48-77``: + masks [O, M, M] (int 0/1 or float)."""
+    O = vecs.size(0)
+    if pooling != "sum":                                              # layout.py:150-151
+        raise ValueError('Invalid pooling "%s"' % pooling)
+    return layout_batched(vecs, boxes, _single_offsets(O, vecs.device), H, W, masks, pooling, test_mode=test_mode,
+                          align_corners=align_corners, max_objs_per_image=O)

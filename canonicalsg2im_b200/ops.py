@@ -1,0 +1,97 @@
+"""Thin call layer over the C ABI: torch tensors in, raw device pointers out.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; all
+arithmetic of the hot path happens in ``libcsg2im.so``.  Every helper insists
+on CUDA tensors -- there is no CPU path.
+"""
+import torch
+
+from . import _lib
+
+A_ROW, A_COL, A_GATHER = 0, 1, 2
+B_NK, B_KN, B_GATHER = 0, 1, 2
+
+
+def lib():
+    return _lib.load()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("csg2im kernels need CUDA tensors (got a %s tensor); there is no CPU fallback"
+                               % t.device.type)
+
+
+def f32c(t):
+    """contiguous fp32 view/copy"""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------------------- GEMM family (fp32)
+class Gather:
+    """Sources of the fused triple-input gather [obj[s] | pred | obj[o]] (graph.py:63-66)."""
+
+    def __init__(self, obj, pred, s_idx, o_idx):
+        assert obj.is_contiguous() and pred.stride(-1) == 1
+        self.obj, self.pred, self.s_idx, self.o_idx = obj, pred, s_idx, o_idx
+        self.din, self.dp, self.ldp = obj.shape[1], pred.shape[1], pred.stride(0)
+
+    @property
+    def width(self):
+        return 2 * self.din + self.dp
+
+
+def gemm_f32(amode, bmode, M, N, K, A, B, out=None, bias=None, relu=False, rowscale=None, mask_aux=None,
+             gather=None, lda=None, ldb=None):
+    dev = (A if A is not None else B).device
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    need_cuda(A, B, out, bias, rowscale, mask_aux)
+    L = lib()
+    ws = None
+    nws = L.csg_gemm_f32_workspace(M, N, K, amode) if (amode == A_COL and K > 4096) else 0
+    if nws:
+        ws = workspace(nws, dev)
+    g = gather
+    rc = L.csg_gemm_f32(
+        amode, bmode, M, N, K,
+        ptr(A), (lda if lda is not None else (A.stride(0) if A is not None else 0)),
+        ptr(B), (ldb if ldb is not None else (B.stride(0) if B is not None else 0)),
+        ptr(out), out.stride(0),
+        ptr(bias), int(relu), ptr(rowscale), ptr(mask_aux), (mask_aux.stride(0) if mask_aux is not None else 0),
+        ptr(g.obj) if g else 0, ptr(g.pred) if g else 0, ptr(g.s_idx) if g else 0, ptr(g.o_idx) if g else 0,
+        g.din if g else 0, g.dp if g else 0, g.ldp if g else 0,
+        ptr(ws), (ws.numel() if ws is not None else 0), _stream())
+    _lib.check(rc, "csg_gemm_f32")
+    return out
+
+
+def colsum_f32(X):
+    M, N = X.shape
+    out = torch.empty(N, dtype=torch.float32, device=X.device)
+    L = lib()
+    ws = workspace(L.csg_colsum_f32_workspace(M, N), X.device)
+    _lib.check(L.csg_colsum_f32(ptr(X), M, N, X.stride(0), ptr(out), ptr(ws), ws.numel(), _stream()), "csg_colsum_f32")
+    return out
+
+
+def relu_mask_f32(dy, y):
+    dy, y = f32c(dy), f32c(y)
+    out = torch.empty_like(dy)
+    _lib.check(lib().csg_relu_mask_f32(ptr(dy), ptr(y), ptr(out), dy.numel(), _stream()), "csg_relu_mask_f32")
+    return out

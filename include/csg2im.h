@@ -1,0 +1,125 @@
+/* csg2im.h -- C ABI of libcsg2im.so: B200 (sm_100a) kernels for the scene-graph -> layout hot
+ * path of roeiherz/CanonicalSg2Im.
+ *
+ * The reference has no FFI of its own: the path is plain Python/PyTorch
+ * (sg2im/graph.py, sg2im/layout.py, sg2im/bilinear.py, sg2im/data/base_dataset.py,
+ * scripts/graphs_utils.py).  These entry points are what a ctypes binding on the reference side
+ * would call; canonicalsg2im_b200/_lib.py is exactly such a binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated otherwise; the caller owns all inputs,
+ *    outputs and workspaces, the library never allocates or frees device memory and keeps no
+ *    state between calls (re-entrant; honours the current device and the stream passed in);
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *  - all functions return 0 on success; on failure a non-zero code, and csg_last_error()
+ *    returns a thread-local message.  No exception crosses the ABI.  Kernel launch errors are
+ *    reported by the call that launched (cudaGetLastError), never deferred;
+ *  - batches are FLAT: objects [NO, .] and triples [NT, .] with per-graph ranges obj_off[B+1] /
+ *    tri_off[B+1].  The reference's padded [B, O, .] / [B, T, .] tensors are the special case
+ *    obj_off[b] = b*O, tri_off[b] = b*T;
+ *  - boxes are [x0, y0, w, h] (sg2im/layout.py:95-96).
+ */
+#ifndef CSG2IM_H_
+#define CSG2IM_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* csg_stream_t;
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* csg_last_error(void);
+void csg_clear_error(void);
+int csg_version(void);
+int csg_device_sms(void);
+
+/* ---- layout compositor: sg2im/layout.py:12-45 (boxes_to_layout), :48-77 (masks_to_layout),
+ *      :80-112 (_boxes_to_grid), :156-188 (_pool_samples), batched over images as the caller
+ *      loop spade/models/networks/generator.py:81-96 does ------------------------------------ */
+/* out[n, d, y, x] = sum_{o in image n} vecs[o, d] * S_o(y, x);  masks == NULL selects boxes_to_layout.
+ * lin_x[W], lin_y[H] = torch.linspace(0, 1, steps) in fp32 (layout.py:98-99).  out is fully written. */
+int csg_layout_fwd(const float* vecs, const float* boxes, const float* masks, const int* obj_off,
+                   const float* lin_x, const float* lin_y, float* out, int N, int D, int H, int W,
+                   int M, int align_corners, int max_objs_per_image, csg_stream_t stream);
+size_t csg_layout_bwd_vecs_workspace(int NO, int D, int H, int W);
+/* dvecs[o, d] = sum_{y, x} dout[n(o), d, y, x] * S_o(y, x)  (autograd of the above wrt vecs) */
+int csg_layout_bwd_vecs(const float* dout, const float* boxes, const float* masks, const int* obj_off,
+                        const float* lin_x, const float* lin_y, float* dvecs, int N, int NO, int D,
+                        int H, int W, int M, int align_corners, int max_objs_per_image,
+                        void* workspace, size_t workspace_bytes, csg_stream_t stream);
+
+/* ---- triple graph convolution: sg2im/graph.py:44-113 ---------------------------------------- */
+int csg_offsets_uniform(int* off, int B, int stride, csg_stream_t stream);
+/* model.py:104-107 + graph.py:60-61: split int64 triplets, globalise indices, valid = (p != padding) */
+int csg_triple_prep(const long long* triplets, const long long* triplet_type, const int* tri_off,
+                    const int* obj_off, int B, int NT, int T_pad, int O_pad, int padding_id,
+                    int* s_idx, int* o_idx, int* pred, int* type32, int* valid, csg_stream_t stream);
+/* same, from GraphTripleConv.forward's argument layout (graph.py:44): edges [NT,2], predicate ids,
+ * pred_indicators (uint8/bool, may be NULL = all valid) */
+int csg_triple_prep_edges(const long long* edges, const long long* pred_ids, const unsigned char* indicators,
+                          const long long* triplet_type, const int* tri_off, const int* obj_off, int B,
+                          int NT, int T_pad, int O_pad, int* s_idx, int* o_idx, int* pred, int* type32,
+                          int* valid, csg_stream_t stream);
+/* stable CSR orderings by subject and by object (replace scatter_add, graph.py:98-103) */
+size_t csg_csr_workspace(int NO);
+int csg_csr_build(const int* keys_s, const int* keys_o, const int* tri_off, int B, int NT, int NO,
+                  int* rowptr_s, int* perm_s, int* rowptr_o, int* perm_o,
+                  void* workspace, size_t workspace_bytes, csg_stream_t stream);
+/* graph.py:69-74 */
+int csg_triple_conf(const int* type32, const int* pred, const float* w_trans, int NT, float* conf,
+                    csg_stream_t stream);
+/* graph.py:85-107 (avg = 1) or a plain segmented sum (avg = 0, backward of the gathers graph.py:63-64) */
+int csg_segpool_f32(const float* X, int ldx, int col_s, int col_o, int W,
+                    const int* rowptr_s, const int* perm_s, const int* rowptr_o, const int* perm_o,
+                    const int* valid, const float* conf, int NO, float* out, int ldo, float* cnt_out,
+                    int avg, csg_stream_t stream);
+int csg_pool_bwd_obj(const float* dpooled, const float* pooled, const float* cnt, int NO, int W,
+                     float* dS, float* dcnt, csg_stream_t stream);
+int csg_triple_bwd_assemble(const float* out, const float* dS, const float* d_newp, const float* dcnt,
+                            const int* s_idx, const int* o_idx, const int* valid, const int* type32,
+                            const float* conf, int NT, int H, int Dp, float* g, float* dconf,
+                            csg_stream_t stream);
+size_t csg_conf_bwd_workspace(int P);
+int csg_conf_bwd(const float* dconf, const int* type32, const int* pred, const float* w_trans, int NT, int P,
+                 float* dw, void* workspace, size_t workspace_bytes, csg_stream_t stream);
+
+/* ---- MLPs (net1 / net2 / box_net: graph.py:33-41,67,110; model.py:58-60,115; layers.py:6-25) --- */
+/* fp32 SIMT GEMM with fused gather / bias / ReLU / confidence / ReLU-mask epilogues.
+ * amode: 0 A[m,k]  1 A[k,m]  2 gathered triple rows;  bmode: 0 B[n,k]  1 B[k,n]  2 gathered rows. */
+size_t csg_gemm_f32_workspace(int M, int N, int K, int amode);
+int csg_gemm_f32(int amode, int bmode, int M, int N, int K,
+                 const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                 const float* bias, int relu, const float* rowscale,
+                 const float* mask_aux, int ld_aux,
+                 const float* g_obj, const float* g_pred, const int* g_sidx, const int* g_oidx,
+                 int g_din, int g_dp, int g_ldp,
+                 void* workspace, size_t workspace_bytes, csg_stream_t stream);
+int csg_relu_mask_f32(const float* dy, const float* y, float* out, long long n, csg_stream_t stream);
+size_t csg_colsum_f32_workspace(int M, int N);
+int csg_colsum_f32(const float* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
+                   csg_stream_t stream);
+
+/* ---- canonicalization: sg2im/data/base_dataset.py:89-139, scripts/graphs_utils.py:15-155 ------ */
+/* pass 1: per-graph output sizes (cnt0 = type-0 edges, cnt1 = transitive edges; cnt0 = -1 flags a
+ * graph with more than max_objs_per_graph objects) and conv_counts [B, P, P+1] */
+int csg_canon_count(const long long* triplets, const int* tri_off, const int* obj_off, int B,
+                    const double* uniforms, const double* cdf, const int* vals, int ncand,
+                    int P, int meta0, int meta1, int learned_converse, int learned_transitivity,
+                    int max_objs_per_graph, int* cnt0, int* cnt1, int* conv_counts, csg_stream_t stream);
+/* pass 2: emit [s, p, o] int64 rows + edge types at out_off[g] (exclusive scan of cnt0 + cnt1) */
+int csg_canon_emit(const long long* triplets, const int* tri_off, const int* obj_off, int B,
+                   const double* uniforms, const double* cdf, const int* vals, int ncand,
+                   int P, int meta0, int meta1, int learned_converse, int learned_transitivity,
+                   int max_objs_per_graph, const int* out_off, long long* out_triplets, long long* out_type,
+                   csg_stream_t stream);
+/* graphs_utils.py:15-27 (reduce = 0) / :41-44 (reduce = 1) on G adjacency matrices [G, n, n] uint8 */
+int csg_canon_closure(const unsigned char* adj, int G, int n, int reduce, unsigned char* out,
+                      csg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSG2IM_H_ */

@@ -1,0 +1,156 @@
+"""CUDA GraphTripleConv / Sg2LayoutModel (fp32 engine) vs golden outputs of the reference.
+Tolerance 1e-5 relative to the tensor scale (north_star, fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from canonicalsg2im_b200 import synth
+from tests import golden_inputs as gi
+from tests.util import t, assert_close, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _layer(precision="fp32"):
+    from canonicalsg2im_b200.graph import GraphTripleConv
+    st = gi.layer_state()
+    w = torch.nn.Parameter(t(st["predicates_transitive_weights"]))
+    layer = GraphTripleConv(128, 128, 128, 128, 512, 1, predicates_transitive_weights=w, precision=precision).cuda()
+    layer.load_state_dict({k: t(v) for k, v in st.items()}, strict=True)
+    return layer
+
+
+def test_csr_is_stable_sort():
+    from canonicalsg2im_b200.graph import TripleBatch
+    vocab = synth.Vocab(0)
+    B, O, T = 7, 9, 50
+    s = synth.det_int(B * T, 1, 0, O - 1).reshape(B, T)
+    o = synth.det_int(B * T, 2, 0, O - 1).reshape(B, T)
+    edges = t(np.stack([s, o], -1))
+    p = t(synth.det_int(B * T, 3, 0, 7).reshape(B, T))
+    batch = TripleBatch.from_padded_edges(edges, p != 0, torch.zeros_like(p), p, O)
+    gs = (torch.arange(B, device="cuda")[:, None] * O + t(s)).reshape(-1)
+    go = (torch.arange(B, device="cuda")[:, None] * O + t(o)).reshape(-1)
+    assert (batch.s_idx.long() == gs).all() and (batch.o_idx.long() == go).all()
+    assert (batch.valid.bool() == (p != 0).reshape(-1)).all()
+    for keys, rowptr, perm in [(gs, batch.rowptr_s, batch.perm_s), (go, batch.rowptr_o, batch.perm_o)]:
+        order = torch.sort(keys, stable=True).indices                   # bit-exact oracle
+        assert (perm[:B * T].long() == order).all()
+        cnt = torch.bincount(keys, minlength=B * O)
+        assert (rowptr.long() == torch.cat([torch.zeros(1, device="cuda", dtype=torch.long), cnt.cumsum(0)])).all()
+    _ = vocab
+
+
+def test_gemm_f32_modes():
+    from canonicalsg2im_b200 import ops
+    gen = torch.Generator("cuda").manual_seed(0)
+    M, N, K = 300, 200, 5000
+    A = torch.randn(M, K, device="cuda", generator=gen)
+    Wt = torch.randn(N, K, device="cuda", generator=gen)
+    bias = torch.randn(N, device="cuda", generator=gen)
+    ref = torch.relu(A.double() @ Wt.double().T + bias.double())
+    assert_close(ops.gemm_f32(ops.A_ROW, ops.B_NK, M, N, K, A, Wt, bias=bias, relu=True), ref, 1e-5, "NT")
+    Bk = torch.randn(K, N, device="cuda", generator=gen)
+    assert_close(ops.gemm_f32(ops.A_ROW, ops.B_KN, M, N, K, A, Bk), A.double() @ Bk.double(), 1e-5, "NN")
+    At = torch.randn(K, M, device="cuda", generator=gen)     # split-K path (K > 4096)
+    assert_close(ops.gemm_f32(ops.A_COL, ops.B_KN, M, N, K, At, Bk), At.double().T @ Bk.double(), 1e-5, "TN")
+    assert_close(ops.colsum_f32(A), A.double().sum(0), 1e-5, "colsum")
+
+
+def test_layer_golden_fwd_bwd(golden):
+    g = golden("gconv_layer")
+    obj, pred, s, o, p, ty = gi.layer_inputs()
+    layer = _layer()
+    oo, pp = t(obj).requires_grad_(True), t(pred).requires_grad_(True)
+    edges = t(np.stack([s, o], -1))
+    new_obj, new_p = layer(oo, pp, edges, t(p) != 0, t(ty), t(p))
+    assert new_obj.shape == (3, 7, 128) and new_p.shape == (3, 24, 128)
+    assert_close(new_obj, g["new_obj"], TOL, "new_obj")
+    assert_close(new_p, g["new_p"], TOL, "new_p")
+    assert (new_p[t(ty) >= 2] == 0).all()
+    go, gp = gi.layer_out_grads(new_obj.shape, new_p.shape)
+    ((new_obj * t(go)).sum() + (new_p * t(gp)).sum()).backward()
+    assert_close(oo.grad, g["d_obj"], TOL, "d_obj")
+    assert_close(pp.grad, g["d_pred"], TOL, "d_pred")
+    assert_close(layer.predicates_transitive_weights.grad, g["d_w_trans"], TOL, "d_w_trans")
+    for name, prm in layer.named_parameters():
+        if name == "predicates_transitive_weights":
+            continue
+        assert_close(prm.grad.reshape(-1)[::gi.GRAD_STRIDE], g["dsub_" + name], TOL, "d " + name)
+        assert abs(prm.grad.double().norm().item() - float(g["dnorm_" + name])) <= 1e-5 * float(g["dnorm_" + name])
+
+
+def _model(precision="fp32"):
+    import argparse
+    from canonicalsg2im_b200.model import Sg2LayoutModel
+    vocab = synth.Vocab(0)
+    opt = argparse.Namespace(
+        vocab={"attributes": {"objects": {str(i): i for i in range(vocab.num_obj_classes)}},
+               "pred_idx_to_name": vocab.pred_names, "pred_name_to_idx": vocab.pred_ids},
+        embedding_dim=128, gconv_dim=128, gconv_hidden_dim=512, gconv_pooling="avg", gconv_num_layers=5,
+        mlp_normalization="none", mask_size=0, learned_init="uniform")
+    model = Sg2LayoutModel(opt, precision=precision).cuda()
+    st = {k: t(v) for k, v in gi.model_state().items()}
+    for i in range(5):
+        st["gconvs.%d.predicates_transitive_weights" % i] = st["trans_candidates_weights"]
+    model.load_state_dict(st, strict=True)                      # reference state-dict keys
+    return model
+
+
+def test_model_golden_fwd_bwd(golden):
+    g = golden("sg2layout_model")
+    model = _model()
+    obj_vecs, boxes, masks = model(t(g["objs"]), t(g["triplets"]), t(g["types"]))
+    assert masks is None
+    assert_close(obj_vecs, g["obj_vecs"], TOL, "obj_vecs")
+    assert_close(boxes, g["boxes_pred"], TOL, "boxes_pred")
+    loss = boxes.pow(2).sum() + (obj_vecs * t(gi.model_obj_grad(obj_vecs.shape))).sum()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    assert model.converse_candidates_weights.grad is None
+    checked = 0
+    for name, prm in model.named_parameters():
+        if "d_" + name in g.files:
+            assert_close(prm.grad, g["d_" + name], 2e-5, "d " + name); checked += 1
+        elif "dsub_" + name in g.files:
+            assert_close(prm.grad.reshape(-1)[::gi.GRAD_STRIDE], g["dsub_" + name], 2e-5, "d " + name); checked += 1
+    assert checked >= 40
+
+
+def test_ragged_equals_padded(golden):
+    """Flat (ragged) execution computes the real rows of the padded batch."""
+    g = golden("sg2layout_model")
+    model = _model()
+    objs, trips, types = g["objs"], g["triplets"], g["types"]
+    B, O, T = objs.shape[0], objs.shape[1], trips.shape[1]
+    n_obj = [int((g["boxes"][b] >= 0).all(-1).sum()) + 1 for b in range(B)]      # + __image__ dummy
+    n_tri = [int((trips[b, :, 1] != 0).sum()) for b in range(B)]
+    fo = np.concatenate([objs[b, :n_obj[b]] for b in range(B)])
+    ft = np.concatenate([trips[b, :n_tri[b]] for b in range(B)])
+    fy = np.concatenate([types[b, :n_tri[b]] for b in range(B)])
+    tri_off = t(np.concatenate([[0], np.cumsum(n_tri)]).astype(np.int32))
+    obj_off = t(np.concatenate([[0], np.cumsum(n_obj)]).astype(np.int32))
+    vecs_r, boxes_r = model.forward_ragged(t(fo), t(ft), t(fy), tri_off, obj_off)
+    vecs_p, boxes_p, _ = model(t(objs), t(trips), t(types))
+    sel = torch.cat([vecs_p[b, :n_obj[b]] for b in range(B)])
+    assert_close(vecs_r, sel, 1e-6, "ragged vs padded")
+    assert_close(boxes_r, torch.cat([boxes_p[b, :n_obj[b]] for b in range(B)]), 1e-6, "ragged boxes")
+    # padded object rows are the constant net2(0) row
+    pad_rows = torch.cat([vecs_p[b, n_obj[b]:] for b in range(B) if n_obj[b] < O])
+    assert rel_err(pad_rows, pad_rows[0:1].expand_as(pad_rows)) == 0.0
+
+
+def test_layer_determinism():
+    obj, pred, s, o, p, ty = gi.layer_inputs()
+    layer = _layer()
+    edges = t(np.stack([s, o], -1))
+    outs = []
+    for _ in range(2):
+        oo = t(obj).requires_grad_(True)
+        a, b = layer(oo, t(pred), edges, t(p) != 0, t(ty), t(p))
+        (a.sum() + b.sum()).backward()
+        outs.append((a.detach().clone(), oo.grad.clone(), layer.net1[0].weight.grad.clone()))
+        layer.zero_grad()
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)

@@ -1,0 +1,146 @@
+"""CUDA layout compositor (csrc/layout.cu through the C ABI) vs the reference's golden outputs and the
+oracle.  Tolerance: 1e-5 relative to the tensor scale in fp32 (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from canonicalsg2im_b200 import synth
+from tests import golden_inputs as gi
+from tests.util import t, assert_close
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def L():
+    from canonicalsg2im_b200 import layout
+    return layout
+
+
+def test_golden_demo(golden, L):
+    g = golden("layout")
+    v, b, m = t(g["demo_vecs"]), t(g["demo_boxes"]), t(g["demo_masks"])
+    # D=3 is padded to 4 channels for the kernel (vector width); the extra channel is dropped
+    v4 = torch.cat([v, torch.zeros(6, 1, device="cuda")], 1)
+    assert_close(L.boxes_to_layout(v4, b, 64)[:, :3], g["demo_boxes64_out"], TOL, "boxes64")
+    assert_close(L.masks_to_layout(v4, b, m, 64)[:, :3], g["demo_masks64_out"], TOL, "masks64")
+    assert_close(L.boxes_to_layout(v4, b, 64, align_corners=True)[:, :3], g["demo_boxes64_legacy_out"], TOL, "legacy")
+    assert_close(L.masks_to_layout(v4, b, m, 64, align_corners=True)[:, :3], g["demo_masks64_legacy_out"], TOL, "legacy m")
+
+
+def test_golden_random_fwd_bwd(golden, L):
+    g = golden("layout")
+    for tag, masks in [("rnd_boxes", None), ("rnd_masks", g["rnd_masks"])]:
+        v = t(g["rnd_vecs"]).requires_grad_(True)
+        b = t(g["rnd_boxes"])
+        if masks is None:
+            y = L.boxes_to_layout(v, b, 32, 48)
+        else:
+            y = L.masks_to_layout(v, b, t(masks), 32, 48)
+        assert y.shape == (1, 16, 32, 48)
+        assert_close(y, g[tag + "_out"], TOL, tag)
+        (y * t(gi.layout_out_grad(y.shape))).sum().backward()
+        assert_close(v.grad, g[tag + "_dvecs"], TOL, tag + " dvecs")
+    y = L.boxes_to_layout(t(g["rnd_vecs"]), t(g["rnd_boxes"]), 32, 48, pooling="avg")
+    assert_close(y, g["rnd_boxes_avg_out"], TOL, "avg")
+    # float masks
+    v = t(g["rnd_vecs"]).requires_grad_(True)
+    y = L.masks_to_layout(v, t(g["rnd_boxes"]), t(g["rnd_masks_f_in"]), 40, 40)
+    assert_close(y, g["rnd_masks_f_out"], TOL, "float masks")
+    (y * t(gi.layout_out_grad(y.shape))).sum().backward()
+    assert_close(v.grad, g["rnd_masks_f_dvecs"], TOL, "float masks dvecs")
+
+
+def _rand_objs(seed, n_img, n_min, n_max, D, M):
+    vocab = synth.Vocab(0)
+    vecs, boxes, masks, off = [], [], [], [0]
+    for i in range(n_img):
+        g = synth.make_graph(seed * 100 + i, n_min, n_max, vocab, include_dummies=False, mask_size=M)
+        n = len(g.boxes)
+        vecs.append(synth.det_tensor((n, D), seed * 1000 + i, 1.0))
+        boxes.append(g.boxes)
+        masks.append(g.masks)
+        off.append(off[-1] + n)
+    return np.concatenate(vecs), np.concatenate(boxes), np.concatenate(masks), np.array(off, np.int32)
+
+
+@pytest.mark.parametrize("H,W,D,M,use_masks", [(64, 64, 128, 16, False), (64, 64, 128, 16, True),
+                                               (40, 52, 8, 5, True), (17, 30, 4, 3, False),
+                                               (128, 256, 32, 16, True)])
+def test_batched_equals_per_image_oracle(L, H, W, D, M, use_masks):
+    """Ragged launch == torch.cat of per-image reference calls (generator.py:81-96), fwd + dvecs."""
+    from oracle import layout as olayout
+    vecs, boxes, masks, off = _rand_objs(3, 5, 1, 9, D, M)
+    v = t(vecs).requires_grad_(True)
+    y = L.layout_batched(v, t(boxes), t(off), H, W, masks=t(masks) if use_masks else None, max_objs_per_image=9)
+    gy = synth.det_tensor(tuple(y.shape), 91, 1.0)
+    (y * t(gy)).sum().backward()
+    vc = torch.from_numpy(vecs).requires_grad_(True)
+    outs = olayout.batched_layout([vc[off[i]:off[i + 1]] for i in range(5)],
+                                  [torch.from_numpy(boxes[off[i]:off[i + 1]]) for i in range(5)],
+                                  [torch.from_numpy(masks[off[i]:off[i + 1]]) for i in range(5)] if use_masks else None,
+                                  H, W)
+    (outs * torch.from_numpy(gy)).sum().backward()
+    assert_close(y, outs, TOL, "batched fwd")
+    assert_close(v.grad, vc.grad, TOL, "batched dvecs")
+
+
+def test_many_objects_chunking(L):
+    """More objects per tile than the shared-memory list holds -> multi-pass accumulation."""
+    from oracle import layout as olayout
+    n = 70
+    boxes = np.stack([synth.det_uniform(n, 1) * 0.3, synth.det_uniform(n, 2) * 0.3,
+                      0.5 + 0.2 * synth.det_uniform(n, 3), 0.5 + 0.2 * synth.det_uniform(n, 4)], 1).astype(np.float32)
+    vecs = synth.det_tensor((n, 8), 5, 1.0)
+    v = t(vecs).requires_grad_(True)
+    y = L.boxes_to_layout(v, t(boxes), 32, 64)
+    vc = torch.from_numpy(vecs).requires_grad_(True)
+    ref = olayout.boxes_to_layout(vc, torch.from_numpy(boxes), 32, 64)
+    assert_close(y, ref, TOL, "70 objects fwd")
+    gy = synth.det_tensor(tuple(y.shape), 6, 1.0)
+    (y * t(gy)).sum().backward()
+    (ref * torch.from_numpy(gy)).sum().backward()
+    assert_close(v.grad, vc.grad, TOL, "70 objects dvecs")
+
+
+def test_edge_cases(L):
+    # zero objects: the reference raises (layout.py:128); defined here as an all-zero canvas
+    y = L.layout_batched(torch.zeros(0, 8, device="cuda"), torch.zeros(0, 4, device="cuda"),
+                         torch.tensor([0, 0, 0], dtype=torch.int32, device="cuda"), 16, 16)
+    assert y.shape == (2, 8, 16, 16) and (y == 0).all()
+    # degenerate box poisons the whole canvas with NaN, like grid_sample does
+    v = torch.ones(2, 4, device="cuda")
+    b = torch.tensor([[0.1, 0.1, 0.5, 0.5], [0.2, 0.2, 0.0, 0.3]], device="cuda")
+    y = L.boxes_to_layout(v, b, 16)
+    assert torch.isnan(y).all()
+    # padded (-1) boxes and boxes outside the canvas contribute exact zeros
+    b = torch.tensor([[-1., -1., -1., -1.], [1.5, 1.5, 0.2, 0.2]], device="cuda")
+    assert (L.boxes_to_layout(v, b, 16) == 0).all()
+    with pytest.raises(ValueError):
+        L.boxes_to_layout(v, b, 16, pooling="max")
+
+
+def test_full_size_properties(L):
+    """cfg3 size (B=16, 256x256, D=128, M=16): linearity in vecs and additivity over objects — the
+    size-independent properties of the compositor; no oracle needed at 512 MiB."""
+    vecs, boxes, masks, off = _rand_objs(11, 16, 3, 8, 128, 16)
+    v, b, m, o = t(vecs), t(boxes), t(masks), t(off)
+    y1 = L.layout_batched(v, b, o, 256, 256, masks=m, max_objs_per_image=8)
+    assert y1.shape == (16, 128, 256, 256)
+    y2 = L.layout_batched(2.5 * v, b, o, 256, 256, masks=m, max_objs_per_image=8)
+    assert_close(y2, 2.5 * y1, 1e-6, "linearity")
+    del y2
+    # additivity: splitting every image's objects into two calls and summing gives the same canvas
+    keep = torch.arange(v.shape[0], device="cuda") % 2 == 0
+    ya = L.layout_batched(torch.where(keep[:, None], v, torch.zeros_like(v)), b, o, 256, 256, masks=m)
+    ya += L.layout_batched(torch.where(keep[:, None], torch.zeros_like(v), v), b, o, 256, 256, masks=m)
+    assert_close(ya, y1, 1e-6, "additivity")
+    # adjoint identity <y, G> == <v, dvecs(G)> ties the backward kernel to the forward one
+    vg = v.clone().requires_grad_(True)
+    y = L.layout_batched(vg, b, o, 256, 256, masks=m, max_objs_per_image=8)
+    G = torch.randn(y.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(0))
+    lhs = (y.double() * G.double()).sum()
+    y.backward(G)
+    rhs = (vg.detach().double() * vg.grad.double()).sum()
+    assert abs(lhs.item() - rhs.item()) <= 1e-5 * abs(lhs.item())
