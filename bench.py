@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- scene graphs/sec of the SG -> layout training step (GCN + layout, fwd + bwd).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...     # CPU restatement of the reference (oracle port)
+
+Workload (BASELINE.json configs[1], "cfg2"): 128 scene graphs per GPU, 3-30 objects each (+ the
+__image__ dummy), VG-like vocabulary (50 predicates), WSGC canonicalization with learned converse +
+transitive edges, 5-layer GraphTripleConv stack (embed 128 / hidden 512) + box_net, boxes_to_layout
+64x64x128 canvas on the GT boxes, backward through both, Adam.  Synthetic graphs, random-init weights.
+One JSON line on rank 0; see the prompt's bench contract for the keys.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+from canonicalsg2im_b200 import synth   # noqa: E402
+
+METRIC = "scene_graphs_per_sec_gcn_layout_fwd_bwd"
+UNIT = "graphs/s"
+WORKLOAD = ("cfg2: packed_vg-like SG->layout training step with WSGC canonicalization, batch 128/GPU, 3-30 objects, "
+            "P=50, 5x GraphTripleConv(128/512) + box_net + boxes_to_layout 64x64x128, fwd+bwd+Adam")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("CSG_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=128, help="graphs per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="graphs in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_graphs(batch, seed):
+    vocab = synth.Vocab(42)
+    return vocab, synth.make_graphs(batch, 1000 + seed, 3, 30, vocab, include_dummies=True)
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_runner(vocab, sample, threads):
+    from oracle.step import CpuStep
+    torch.set_num_threads(threads)
+    _, graphs = workload_graphs(sample, 0)
+    W = synth.make_conv_weights(vocab, 0)
+    step = CpuStep(vocab, synth.make_state(vocab, seed=0), W)
+    uni = synth.det_uniform(sum(len(g.triplets) for g in graphs), 13)
+    return step, graphs, uni
+
+
+def run_cpu_baseline(sample, threads, budget_s=25.0):
+    vocab = synth.Vocab(42)
+    step, graphs, uni = cpu_step_runner(vocab, sample, threads)
+    step.step(graphs, uni)                       # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        step.step(graphs, uni)
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 5:
+            break
+    dt = (time.perf_counter() - t0) / n
+    return {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d graphs of the cfg2 workload per step, %d timed steps, oracle/step.py (torch-CPU + numpy)"
+                      % (sample, n)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vocab = synth.Vocab(42)
+    sample = max(1, args.cpu_sample // 2)         # bounded so that K steps end within a few minutes
+    step, graphs, uni = cpu_step_runner(vocab, sample, threads)
+    step.step(graphs, uni)                       # one bounded warm-up step (each CPU step costs seconds)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step.step(graphs, uni)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_graphs_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d graphs of the cfg2 workload per step (oracle/step.py, torch-CPU + numpy)" % sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from canonicalsg2im_b200 import _lib, ops
+    from canonicalsg2im_b200.pipeline import SgToLayoutStep, HostBatch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device for --impl ours (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.load()
+    pk = peaks()
+
+    vocab, graphs = workload_graphs(args.batch, rank)
+    hb = HostBatch(graphs, seed=rank)
+    step = SgToLayoutStep(vocab, dev, precision=args.precision, distributed=world > 1, seed=0)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    G = torch.randn((args.batch, 128, 64, 64), device=dev, generator=gen) * 1e-3
+    d = hb.to_device(dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_tri = 0
+    for _ in range(max(args.warmup, 3)):
+        _, n_tri = step.step(d, G)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM
+    timer = ops.KernelTimer()
+    ops.TIMERS["gemm"] = timer
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.csg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss, n_tri = step.step(d, G)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = L.csg_launch_count() - launches0
+    ops.TIMERS.clear()
+    sec = e0.elapsed_time(e1) * 1e-3
+    gemm_flops, gemm_sec, gemm_n = timer.summary()
+    tsec = torch.tensor([sec], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+    sec = float(tsec.item())
+    value = world * args.batch * args.steps / sec
+
+    # ---- timed region 2: end to end through the public API with HOST buffers (H2D + D2H every step)
+    for _ in range(2):
+        dd = hb.to_device(dev)
+        l, _ = step.step(dd, G)
+        float(l.item())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dd = hb.to_device(dev)
+        l, _ = step.step(dd, G)
+        lv = float(l.item())
+    torch.cuda.synchronize()
+    e2e_sec = time.perf_counter() - t0
+    tsec = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+    e2e_sec = float(tsec.item())
+    e2e = {"value": world * args.batch * args.steps / e2e_sec, "unit": UNIT,
+           "h2d_bytes_per_step": int(hb.nbytes), "d2h_bytes_per_step": 4 + 4,   # loss scalar + canon size sync
+           "ms_per_step": 1e3 * e2e_sec / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_obj = int(hb.obj_off[-1])
+    peak_tf = pk["tf_sustained"]
+    ach_tf = gemm_flops / gemm_sec / 1e12 if gemm_sec > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.precision)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "graphs_per_gpu": args.batch, "objects": n_obj, "triples_after_canon": n_tri,
+                   "precision": args.precision, "parallelism": "graph-sharded dp%d" % world,
+                   "l2": "per-step working set (net1 activations %.0f MB + 268 MB canvas + 268 MB canvas grad) exceeds the 126 MB L2"
+                         % (n_tri * (1152 + 512) * (4 if args.precision == "fp32" else 2) / 1e6)},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "net1/net2 GEMMs (%s)" % ("gemm_f32_kernel" if args.precision == "fp32" else "gemm_tc_kernel"),
+                     "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": ach_tf / peak_tf, "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
+                     "launches_timed": gemm_n, "share_of_step": gemm_sec / sec if sec > 0 else None},
+        "loss": lv,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            line["cpu_baseline"] = run_cpu_baseline(args.cpu_sample, os.cpu_count() or 1)
+        except Exception as ex:   # the baseline is a reported number, never a reason to lose the GPU line
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "failed: %r" % (ex,)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

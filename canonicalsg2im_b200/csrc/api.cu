@@ -24,6 +24,11 @@ int csg_num_sms() {
   return cached;
 }
 
+static unsigned long long g_launches = 0;
+void csg_count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+// number of kernel-launch sites passed since load (a launch site may issue 1-2 kernels); bench.py reports it
+CSG_API long long csg_launch_count(void) { return (long long)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 CSG_API const char* csg_last_error(void) { return g_err; }
 CSG_API void csg_clear_error(void) { g_err[0] = 0; }
 CSG_API int csg_version(void) { return 100; }   // 0.1.0

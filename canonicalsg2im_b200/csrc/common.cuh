@@ -20,8 +20,10 @@ void csg_set_error(const char* fmt, ...);
   } while (0)
 
 // Launch errors are checked immediately (no deferred sync), SURVEY.md §8(b).
+void csg_count_launch();
 #define CSG_CHECK_LAUNCH(name)                                                      \
   do {                                                                              \
+    csg_count_launch();                                                             \
     cudaError_t e__ = cudaGetLastError();                                           \
     if (e__ != cudaSuccess) {                                                       \
       csg_set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e__));   \

@@ -113,7 +113,12 @@ __device__ void build_list(const LayoutParams& p, const Smem& s, int oend, int x
       bool keep = false;
       if (o < oend) {
         float4 b = ld_f4(p.boxes + 4 * (size_t)o);
-        keep = axis_may_touch(b.x, b.z, xlo, xhi, S, p.align) && axis_may_touch(b.y, b.w, ylo, yhi, S, p.align);
+        // zero / NaN extents and non-finite origins give NaN weights that poison every pixel of the image
+        // (0 * NaN in grid_sample), whatever the other axis says: never cull those
+        const bool poison = !(b.z > 0.f || b.z < 0.f) || !(b.w > 0.f || b.w < 0.f) ||
+                            !(fabsf(b.x) < INFINITY) || !(fabsf(b.y) < INFINITY);
+        keep = poison ||
+               (axis_may_touch(b.x, b.z, xlo, xhi, S, p.align) && axis_may_touch(b.y, b.w, ylo, yhi, S, p.align));
       }
       unsigned bal = __ballot_sync(0xffffffffu, keep);
       int pos = count + __popc(bal & ((1u << lane) - 1u));

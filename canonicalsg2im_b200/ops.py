@@ -38,6 +38,35 @@ def f32c(t):
     return t.contiguous()
 
 
+class KernelTimer:
+    """CUDA-event timing of one kernel class on the launching stream (bench.py's roofline leg)."""
+
+    def __init__(self):
+        self.records = []      # (work, start_event, end_event)
+        self._pool = []
+
+    def events(self):
+        if self._pool:
+            return self._pool.pop()
+        return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def add(self, work, e0, e1):
+        self.records.append((work, e0, e1))
+
+    def summary(self):
+        """(total work, total seconds, launches); call after a synchronize."""
+        work = sum(r[0] for r in self.records)
+        sec = sum(r[1].elapsed_time(r[2]) for r in self.records) * 1e-3
+        n = len(self.records)
+        for r in self.records:
+            self._pool.append((r[1], r[2]))
+        self.records = []
+        return work, sec, n
+
+
+TIMERS = {}     # kernel class name -> KernelTimer (set by bench.py; empty = no timing overhead)
+
+
 def workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -68,6 +97,10 @@ def gemm_f32(amode, bmode, M, N, K, A, B, out=None, bias=None, relu=False, rowsc
     if nws:
         ws = workspace(nws, dev)
     g = gather
+    timer = TIMERS.get("gemm")
+    if timer is not None:
+        e0, e1 = timer.events()
+        e0.record()
     rc = L.csg_gemm_f32(
         amode, bmode, M, N, K,
         ptr(A), (lda if lda is not None else (A.stride(0) if A is not None else 0)),
@@ -78,6 +111,9 @@ def gemm_f32(amode, bmode, M, N, K, A, B, out=None, bias=None, relu=False, rowsc
         g.din if g else 0, g.dp if g else 0, g.ldp if g else 0,
         ptr(ws), (ws.numel() if ws is not None else 0), _stream())
     _lib.check(rc, "csg_gemm_f32")
+    if timer is not None:
+        e1.record()
+        timer.add(2.0 * M * N * K, e0, e1)
     return out
 
 

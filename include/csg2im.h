@@ -35,6 +35,7 @@ const char* csg_last_error(void);
 void csg_clear_error(void);
 int csg_version(void);
 int csg_device_sms(void);
+long long csg_launch_count(void);   /* kernel-launch sites passed since the library was loaded */
 
 /* ---- layout compositor: sg2im/layout.py:12-45 (boxes_to_layout), :48-77 (masks_to_layout),
  *      :80-112 (_boxes_to_grid), :156-188 (_pool_samples), batched over images as the caller

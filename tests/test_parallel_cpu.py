@@ -1,0 +1,62 @@
+"""Host logic of the multi-GPU path on CPU: the graph-boundary sharder and the bucketed gradient
+all-reduce (gloo, world_size 2)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from canonicalsg2im_b200.parallel import shard_by_cost, BucketedGradAllReduce
+
+
+def test_shard_by_cost_balances_and_covers():
+    costs = [5, 1, 1, 1, 8, 2, 2, 4, 4, 4, 1, 7]
+    for world in (1, 2, 3, 4, 8):
+        ranges = shard_by_cost(costs, world)
+        assert len(ranges) == world and ranges[0][0] == 0 and ranges[-1][1] == len(costs)
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+        sums = [sum(costs[a:b]) for a, b in ranges]
+        assert max(sums) <= sum(costs) / world + max(costs)
+    assert shard_by_cost([], 2) == [(0, 0), (0, 0)]
+    assert shard_by_cost([3], 4)[0] == (0, 1)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    red = BucketedGradAllReduce([list(net[2].parameters()), list(net[0].parameters())])
+    x = torch.arange(24, dtype=torch.float32).view(4, 6) / 10 + rank        # each rank: its own shard
+    net(x).pow(2).sum().backward()
+    red.finish()
+    out[rank] = [p.grad.clone() for p in net.parameters()]
+    # second step: buffers are reusable after zero()
+    red.zero()
+    net(x).pow(2).sum().backward()
+    red.finish()
+    out[rank + world] = [p.grad.clone() for p in net.parameters()]
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_equals_mean_of_shard_grads():
+    world, port = 2, 29611
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    ref = None
+    for rank in range(world):
+        net.zero_grad()
+        x = torch.arange(24, dtype=torch.float32).view(4, 6) / 10 + rank
+        net(x).pow(2).sum().backward()
+        g = [p.grad.clone() for p in net.parameters()]
+        ref = g if ref is None else [a + b for a, b in zip(ref, g)]
+    ref = [r / world for r in ref]
+    for rank in range(world):
+        for a, b in zip(out[rank], ref):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
+        for a, b in zip(out[rank + world], ref):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
