@@ -131,3 +131,39 @@ def relu_mask_f32(dy, y):
     out = torch.empty_like(dy)
     _lib.check(lib().csg_relu_mask_f32(ptr(dy), ptr(y), ptr(out), dy.numel(), _stream()), "csg_relu_mask_f32")
     return out
+
+
+# ---------------------------------------------------------------------------- GEMM family (bf16 tensor cores)
+def gemm_bf16(M, N, K, A, B, mn_major=False, out=None, out_f32=False, bias=None, relu=False, rowscale=None,
+              mask_aux=None, gather=None, gather_mode=0):
+    """tcgen05 GEMM.  mn_major=False: C = epi(A[M,K] @ B[N,K]^T); mn_major=True: C = A[K,M]^T @ B[K,N] (fp32 out)."""
+    dev = (A if A is not None else B).device
+    if mn_major:
+        out_f32 = True
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=dev)
+    need_cuda(A, B, out, bias, rowscale, mask_aux)
+    for x in (A, B, mask_aux):
+        assert x is None or (x.dtype == torch.bfloat16 and x.stride(-1) == 1)
+    L = lib()
+    ws = None
+    if mn_major:
+        ws = workspace(L.csg_gemm_bf16_workspace(M, N, K, 1), dev)
+    g = gather
+    timer = TIMERS.get("gemm")
+    if timer is not None:
+        e0, e1 = timer.events()
+        e0.record()
+    rc = L.csg_gemm_bf16(
+        int(mn_major), int(gather_mode), M, N, K,
+        ptr(A), A.stride(0) if A is not None else 0, ptr(B), B.stride(0) if B is not None else 0,
+        ptr(out), out.stride(0), int(out_f32),
+        ptr(bias), int(relu), ptr(rowscale), ptr(mask_aux), (mask_aux.stride(0) if mask_aux is not None else 0),
+        ptr(g.obj) if g else 0, ptr(g.pred) if g else 0, ptr(g.s_idx) if g else 0, ptr(g.o_idx) if g else 0,
+        g.din if g else 0, g.dp if g else 0, g.ldp if g else 0,
+        ptr(ws), (ws.numel() if ws is not None else 0), _stream())
+    _lib.check(rc, "csg_gemm_bf16")
+    if timer is not None:
+        e1.record()
+        timer.add(2.0 * M * N * K, e0, e1)
+    return out

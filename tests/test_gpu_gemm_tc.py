@@ -1,0 +1,85 @@
+"""tcgen05 bf16 GEMM family (csrc/gemm_tc.cu) vs torch fp32 matmul on the same bf16-rounded operands.
+Tolerance: the inputs are identical bf16 values and accumulation is fp32, so only the summation order and
+the bf16 rounding of the output differ: 1e-2 relative (north_star's bf16 MLP budget), 2e-5 for fp32 outputs."""
+import pytest
+import torch
+
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator("cuda").manual_seed(seed)
+    return (torch.randn(shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 512, 384), (1000, 1152, 512), (77, 128, 512),
+                                   (4096, 384, 512), (513, 192, 1152), (256, 64, 128)])
+def test_kmajor_plain(M, N, K):
+    from canonicalsg2im_b200 import ops
+    A, B = _rand((M, K), 1), _rand((N, K), 2, 0.05)
+    ref = A.float() @ B.float().T
+    out = ops.gemm_bf16(M, N, K, A, B, out_f32=True)
+    assert_close(out, ref, 2e-5, "fp32 out")
+    out = ops.gemm_bf16(M, N, K, A, B)
+    assert out.dtype == torch.bfloat16
+    assert_close(out.float(), ref, 1e-2, "bf16 out")
+
+
+def test_kmajor_epilogues():
+    from canonicalsg2im_b200 import ops
+    M, N, K = 777, 512, 384
+    A, B = _rand((M, K), 3), _rand((N, K), 4, 0.05)
+    bias = torch.randn(N, device="cuda")
+    rs = torch.rand(M, device="cuda")
+    aux = _rand((M, N), 5)
+    z = A.float() @ B.float().T + bias
+    assert_close(ops.gemm_bf16(M, N, K, A, B, out_f32=True, bias=bias, relu=True), torch.relu(z), 2e-5, "bias+relu")
+    assert_close(ops.gemm_bf16(M, N, K, A, B, out_f32=True, bias=bias, relu=True, rowscale=rs),
+                 torch.relu(z) * rs[:, None], 2e-5, "rowscale")
+    assert_close(ops.gemm_bf16(M, N, K, A, B, out_f32=True, mask_aux=aux),
+                 (A.float() @ B.float().T) * (aux.float() > 0), 2e-5, "mask")
+    # strided A (a column slice), as when pred vecs alias the previous layer's output
+    big = _rand((M, K + 128), 6)
+    assert_close(ops.gemm_bf16(M, N, K, big[:, 64:64 + K], B, out_f32=True), big[:, 64:64 + K].float() @ B.float().T,
+                 2e-5, "strided A")
+
+
+def _gather(NO, NT, Din, Dp, seed):
+    from canonicalsg2im_b200 import ops
+    g = torch.Generator("cuda").manual_seed(seed)
+    obj, pred = _rand((NO, Din), seed + 1), _rand((NT, Dp), seed + 2)
+    s = torch.randint(0, NO, (NT,), device="cuda", generator=g, dtype=torch.int32)
+    o = torch.randint(0, NO, (NT,), device="cuda", generator=g, dtype=torch.int32)
+    X = torch.cat([obj[s.long()], pred, obj[o.long()]], 1)
+    return ops.Gather(obj, pred, s, o), X
+
+
+@pytest.mark.parametrize("NT", [1, 130, 5000])
+def test_gather_a(NT):
+    from canonicalsg2im_b200 import ops
+    g, X = _gather(97, NT, 128, 128, 10)
+    W = _rand((512, 384), 11, 0.05)
+    bias = torch.randn(512, device="cuda")
+    ref = torch.relu(X.float() @ W.float().T + bias)
+    out = ops.gemm_bf16(NT, 512, 384, None, W, out_f32=True, bias=bias, relu=True, gather=g, gather_mode=1)
+    assert_close(out, ref, 2e-5, "gather A")
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 512, 64), (1152, 512, 3000), (128, 512, 200), (512, 384, 10000)])
+def test_mnmajor(M, N, K):
+    from canonicalsg2im_b200 import ops
+    A, B = _rand((K, M), 20, 0.1), _rand((K, N), 21, 0.1)
+    ref = A.float().T @ B.float()
+    assert_close(ops.gemm_bf16(M, N, K, A, B, mn_major=True), ref, 2e-5, "MN-major")
+
+
+@pytest.mark.parametrize("NT", [64, 1000, 20000])
+def test_gather_b(NT):
+    from canonicalsg2im_b200 import ops
+    g, X = _gather(300, NT, 128, 128, 30)
+    dh = _rand((NT, 512), 31, 0.1)
+    ref = dh.float().T @ X.float()
+    out = ops.gemm_bf16(512, 384, NT, dh, None, mn_major=True, gather=g, gather_mode=2)
+    assert_close(out, ref, 2e-5, "gather B")
