@@ -1,0 +1,165 @@
+"""Tensor-core (bf16 operands, fp32 accumulation) engine of the triple graph convolution.
+
+Same dataflow as ``graph._TripleConvF32`` with every GEMM on tcgen05 (csrc/gemm_tc.cu):
+
+    forward   F1 (gather fused into A)  ->  F2 (+bias, ReLU, x confidence)  ->  CSR pooling  ->  net2
+    backward  dW-type GEMMs are MN-major split-K GEMMs over the triples (dW1 re-gathers its B operand),
+              dX-type GEMMs use per-call transposed bf16 copies of the weights so both operands are K-major
+
+Activations between layers stay bf16; weight gradients, pooling sums and confidences are fp32.
+Tolerance vs the fp32 reference: 1e-2 relative (north_star).
+"""
+import torch
+
+from . import _lib
+from . import ops
+from .ops import lib, ptr, f32c, workspace, _stream, Gather
+
+BF = torch.bfloat16
+
+
+def cast_bf16(w, transpose=False):
+    """fp32 [rows, cols] -> bf16 copy (optionally transposed) in one kernel."""
+    w = f32c(w)
+    rows, cols = w.shape
+    out = torch.empty((cols, rows) if transpose else (rows, cols), dtype=BF, device=w.device)
+    _lib.check(lib().csg_cast_bf16(ptr(w), rows, cols, w.stride(0), ptr(out), out.stride(0), int(transpose), _stream()),
+               "csg_cast_bf16")
+    return out
+
+
+def as_bf16_rows(x):
+    """bf16 2-D tensor with unit inner stride and 16-byte aligned rows (views are kept)."""
+    if x.dtype != BF:
+        if x.dtype == torch.float32 and x.is_contiguous():
+            return cast_bf16(x)
+        x = x.to(BF)
+    if x.stride(-1) != 1 or x.stride(0) % 8 != 0 or x.data_ptr() % 16 != 0:
+        x = x.contiguous()
+    return x
+
+
+def segpool_bf16(X, col_s, col_o, W, batch, conf=None, avg=True, want_f32=True, want_bf16=True):
+    dev = X.device
+    out32 = torch.empty((batch.NO, W), dtype=torch.float32, device=dev) if want_f32 else None
+    out16 = torch.empty((batch.NO, W), dtype=BF, device=dev) if want_bf16 else None
+    cnt = torch.empty(batch.NO, dtype=torch.float32, device=dev) if avg else None
+    rc = lib().csg_segpool_bf16(ptr(X), X.stride(0), col_s, col_o, W, ptr(batch.rowptr_s), ptr(batch.perm_s),
+                                ptr(batch.rowptr_o), ptr(batch.perm_o), ptr(batch.valid) if avg else 0,
+                                ptr(conf) if avg else 0, batch.NO, ptr(out32), ptr(out16), W, ptr(cnt), int(avg), _stream())
+    _lib.check(rc, "csg_segpool_bf16")
+    return out32, out16, cnt
+
+
+def colsum_bf16(X):
+    M, N = X.shape
+    out = torch.empty(N, dtype=torch.float32, device=X.device)
+    L = lib()
+    ws = workspace(L.csg_colsum_bf16_workspace(M, N), X.device)
+    _lib.check(L.csg_colsum_bf16(ptr(X), M, N, X.stride(0), ptr(out), ptr(ws), ws.numel(), _stream()), "csg_colsum_bf16")
+    return out
+
+
+def relu_mask_bf16(dy, y):
+    dy = f32c(dy)
+    out = torch.empty(y.shape, dtype=BF, device=y.device)
+    _lib.check(lib().csg_relu_mask_bf16(ptr(dy), ptr(y), ptr(out), y.numel(), _stream()), "csg_relu_mask_bf16")
+    return out
+
+
+class _TripleConvBF16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, batch, H, Dpo, obj, pred, w1, b1, w2, b2, w3, b3, w4, b4, w_trans):
+        from .graph import triple_confidence
+        NT, NO = batch.NT, batch.NO
+        ctx.in_dtypes = (obj.dtype, pred.dtype)
+        obj_b, pred_b = as_bf16_rows(obj), as_bf16_rows(pred)
+        w1b, w2b, w3b, w4b = cast_bf16(w1), cast_bf16(w2), cast_bf16(w3), cast_bf16(w4)
+        g = Gather(obj_b, pred_b, batch.s_idx, batch.o_idx)
+        conf = triple_confidence(batch, w_trans)
+        Wd = 2 * H + Dpo
+        hidden = ops.gemm_bf16(NT, H, g.width, None, w1b, bias=f32c(b1), relu=True, gather=g, gather_mode=1)
+        out = ops.gemm_bf16(NT, Wd, H, hidden, w2b, bias=f32c(b2), relu=True, rowscale=conf)
+        pooled32, pooled16, cnt = segpool_bf16(out, 0, H + Dpo, H, batch, conf, avg=True)
+        h2 = ops.gemm_bf16(NO, H, H, pooled16, w3b, bias=f32c(b3), relu=True)
+        new_obj = ops.gemm_bf16(NO, w4.shape[0], H, h2, w4b, bias=f32c(b4), relu=True)
+        new_p = out[:, H:H + Dpo]
+        ctx.batch, ctx.H, ctx.Dpo = batch, H, Dpo
+        ctx.save_for_backward(obj_b, pred_b, w1, w2, w3, w4, f32c(w_trans), conf, hidden, out, pooled32, pooled16, cnt,
+                              h2, new_obj)
+        ctx.set_materialize_grads(False)
+        return new_obj, new_p
+
+    @staticmethod
+    def backward(ctx, d_obj_out, d_newp):
+        batch, H, Dpo = ctx.batch, ctx.H, ctx.Dpo
+        (obj, pred, w1, w2, w3, w4, w_trans, conf, hidden, out, pooled32, pooled16, cnt, h2, new_obj) = ctx.saved_tensors
+        NT, NO = batch.NT, batch.NO
+        dev = obj.device
+        L = lib()
+        Dout = w4.shape[0]
+        Din, Dp = obj.shape[1], pred.shape[1]
+        Wd = 2 * H + Dpo
+        if d_obj_out is None:
+            d_obj_out = torch.zeros((NO, Dout), dtype=torch.float32, device=dev)
+        # transposed bf16 weights: dy @ W needs W^T stored [in, out] so that K (= out features) is contiguous
+        w4t, w3t, w2t, w1t = (cast_bf16(w, transpose=True) for w in (w4, w3, w2, w1))
+        # ---- net2 backward
+        g4 = relu_mask_bf16(d_obj_out, new_obj)
+        dw4 = ops.gemm_bf16(Dout, H, NO, g4, h2, mn_major=True)
+        db4 = colsum_bf16(g4)
+        dh2 = ops.gemm_bf16(NO, H, Dout, g4, w4t, mask_aux=h2)
+        dw3 = ops.gemm_bf16(H, H, NO, dh2, pooled16, mn_major=True)
+        db3 = colsum_bf16(dh2)
+        dpooled = ops.gemm_bf16(NO, H, H, dh2, w3t, out_f32=True)
+        # ---- pooling backward
+        dS = torch.empty_like(dpooled)
+        dcnt = torch.empty(NO, dtype=torch.float32, device=dev)
+        _lib.check(L.csg_pool_bwd_obj(ptr(dpooled), ptr(pooled32), ptr(cnt), NO, H, ptr(dS), ptr(dcnt), _stream()),
+                   "csg_pool_bwd_obj")
+        dnp = None
+        if d_newp is not None:
+            dnp = d_newp if (d_newp.dtype == BF and d_newp.stride(-1) == 1 and d_newp.stride(0) % 8 == 0
+                             and d_newp.data_ptr() % 16 == 0) else d_newp.to(BF).contiguous()
+        g = torch.empty((NT, Wd), dtype=BF, device=dev)
+        dconf = torch.empty(max(NT, 1), dtype=torch.float32, device=dev)
+        rc = L.csg_triple_bwd_assemble_bf16(ptr(out), ptr(dS), ptr(dnp), dnp.stride(0) if dnp is not None else 0,
+                                            ptr(dcnt), ptr(batch.s_idx), ptr(batch.o_idx), ptr(batch.valid),
+                                            ptr(batch.type32), ptr(conf), NT, H, Dpo, ptr(g), ptr(dconf), _stream())
+        _lib.check(rc, "csg_triple_bwd_assemble_bf16")
+        # ---- net1 backward
+        dw2 = ops.gemm_bf16(Wd, H, NT, g, hidden, mn_major=True)
+        db2 = colsum_bf16(g)
+        dhid = ops.gemm_bf16(NT, H, Wd, g, w2t, mask_aux=hidden)
+        gat = Gather(obj, pred, batch.s_idx, batch.o_idx)
+        dw1 = ops.gemm_bf16(H, gat.width, NT, dhid, None, mn_major=True, gather=gat, gather_mode=2)
+        db1 = colsum_bf16(dhid)
+        dX = ops.gemm_bf16(NT, gat.width, H, dhid, w1t)
+        # ---- gather backward
+        dobj32, _, _ = segpool_bf16(dX, 0, Din + Dp, Din, batch, avg=False, want_f32=True, want_bf16=False)
+        dobj = dobj32 if ctx.in_dtypes[0] == torch.float32 else dobj32.to(ctx.in_dtypes[0])
+        dpred = dX[:, Din:Din + Dp]
+        if ctx.in_dtypes[1] != BF:
+            dpred = dpred.to(ctx.in_dtypes[1])
+        # ---- confidence backward
+        P = w_trans.numel()
+        dwt = torch.empty(P, dtype=torch.float32, device=dev)
+        ws = workspace(L.csg_conf_bwd_workspace(P), dev)
+        rc = L.csg_conf_bwd(ptr(dconf), ptr(batch.type32), ptr(batch.pred), ptr(w_trans), NT, P, ptr(dwt),
+                            ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "csg_conf_bwd")
+        return None, None, None, dobj, dpred, dw1, db1, dw2, db2, dw3, db3, dw4, db4, dwt
+
+
+def triple_conv(batch, obj, pred, params, w_trans, hidden_dim, pred_out_dim):
+    din, dp = obj.shape[1], pred.shape[1]
+    if din % 64 or dp % 64 or hidden_dim % 64 or pred_out_dim % 64:
+        raise _lib.CsgError("precision='bf16' needs feature widths that are multiples of 64 "
+                            "(got Din=%d Dp=%d H=%d Dp_out=%d); use precision='fp32'" % (din, dp, hidden_dim, pred_out_dim))
+    return _TripleConvBF16.apply(batch, hidden_dim, pred_out_dim, obj, pred, *params, w_trans)
+
+
+def dense_mlp2(x, w0, b0, w1, b1, final_relu):
+    """box_net (model.py:58-60): M = #objects, output width 4 -- too small to matter; it runs on the fp32 engine."""
+    from .graph import _DenseMLP2F32
+    return _DenseMLP2F32.apply(x.float() if x.dtype != torch.float32 else x, w0, b0, w1, b1, final_relu)

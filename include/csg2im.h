@@ -115,6 +115,22 @@ int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
                   int g_din, int g_dp, int g_ldp,
                   void* workspace, size_t workspace_bytes, csg_stream_t stream);
 
+/* bf16-activation twins of the pooling / assembly kernels (fp32 accumulation) + weight cast */
+int csg_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, int transpose,
+                  csg_stream_t stream);
+int csg_segpool_bf16(const void* X, int ldx, int col_s, int col_o, int W,
+                     const int* rowptr_s, const int* perm_s, const int* rowptr_o, const int* perm_o,
+                     const int* valid, const float* conf, int NO, float* out_f32, void* out_bf16, int ldo,
+                     float* cnt_out, int avg, csg_stream_t stream);
+int csg_relu_mask_bf16(const float* dy, const void* y, void* out, long long n, csg_stream_t stream);
+size_t csg_colsum_bf16_workspace(int M, int N);
+int csg_colsum_bf16(const void* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
+                    csg_stream_t stream);
+int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const void* d_newp, int ld_newp,
+                                 const float* dcnt, const int* s_idx, const int* o_idx, const int* valid,
+                                 const int* type32, const float* conf, int NT, int H, int Dp, void* g,
+                                 float* dconf, csg_stream_t stream);
+
 /* ---- canonicalization: sg2im/data/base_dataset.py:89-139, scripts/graphs_utils.py:15-155 ------ */
 /* pass 1: per-graph output sizes (cnt0 = type-0 edges, cnt1 = transitive edges; cnt0 = -1 flags a
  * graph with more than max_objs_per_graph objects) and conv_counts [B, P, P+1] */

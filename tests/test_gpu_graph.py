@@ -154,3 +154,83 @@ def test_layer_determinism():
         layer.zero_grad()
     for x, y in zip(*outs):
         assert torch.equal(x, y)
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core engine (bf16 operands / fp32 accumulation): 1e-2 relative (north_star's bf16 MLP budget)
+# ------------------------------------------------------------------------------------------------
+TOL_BF16 = 1e-2
+
+
+def test_layer_bf16_vs_golden(golden):
+    """Forward of the tensor-core engine vs the reference's golden outputs (1e-2), and its backward vs a
+    plain-PyTorch model of the same bf16 arithmetic (tests/bf16_ref.py).  Gradients are NOT compared with
+    the fp32 golden values in max norm: a ReLU whose pre-activation is within bf16 noise of zero flips its
+    mask and moves single gradient entries by O(1) on a 21-object fixture, whatever the kernel quality."""
+    from tests.bf16_ref import layer_bf16_ref
+    g = golden("gconv_layer")
+    obj, pred, s, o, p, ty = gi.layer_inputs()
+    layer = _layer("bf16")
+    B, O, T = obj.shape[0], obj.shape[1], pred.shape[1]
+    oo, pp = t(obj).requires_grad_(True), t(pred).requires_grad_(True)
+    edges = t(np.stack([s, o], -1))
+    new_obj, new_p = layer(oo, pp, edges, t(p) != 0, t(ty), t(p))
+    assert_close(new_obj.float(), g["new_obj"], TOL_BF16, "new_obj")
+    assert_close(new_p.float(), g["new_p"], TOL_BF16, "new_p")
+    assert (new_p[t(ty) >= 2] == 0).all()
+    go, gp = gi.layer_out_grads(new_obj.shape, new_p.shape)
+    ((new_obj.float() * t(go)).sum() + (new_p.float() * t(gp)).sum()).backward()
+    assert oo.grad.dtype == torch.float32 and pp.grad.dtype == torch.float32
+    # bf16-arithmetic reference with identical masks
+    st = {k: t(v).clone().requires_grad_(True) for k, v in gi.layer_state().items()}
+    ro, rp = t(obj).reshape(B * O, -1).clone().requires_grad_(True), t(pred).reshape(B * T, -1).clone().requires_grad_(True)
+    base = (torch.arange(B, device="cuda") * O)[:, None]
+    sg, og = (t(s) + base).reshape(-1), (t(o) + base).reshape(-1)
+    tyf, pf = t(ty).reshape(-1), t(p).reshape(-1)
+    conf_fn = lambda: (tyf == 0).float() + (tyf == 1).float() * torch.sigmoid(st["predicates_transitive_weights"])[pf]
+    r_obj, r_p = layer_bf16_ref(st, ro, rp, sg, og, pf != 0, conf_fn, 512, 128)
+    assert_close(new_obj.float().reshape(B * O, -1), r_obj, 1e-5 + 4e-3, "new_obj vs bf16 model")   # <= 1 bf16 ulp
+    ((r_obj * t(go).reshape(B * O, -1)).sum() + (r_p * t(gp).reshape(B * T, -1)).sum()).backward()
+    assert_close(oo.grad.reshape(B * O, -1), ro.grad, 2e-2, "d_obj")
+    assert_close(pp.grad.reshape(B * T, -1), rp.grad, 2e-2, "d_pred")
+    assert_close(layer.predicates_transitive_weights.grad, st["predicates_transitive_weights"].grad, 2e-2, "d_w_trans")
+    for name, prm in layer.named_parameters():
+        if name != "predicates_transitive_weights":
+            assert_close(prm.grad, st[name].grad, 2e-2, "d " + name)
+
+
+def test_model_bf16_vs_golden(golden):
+    g = golden("sg2layout_model")
+    model = _model("bf16")
+    obj_vecs, boxes, _ = model(t(g["objs"]), t(g["triplets"]), t(g["types"]))
+    assert_close(obj_vecs.float(), g["obj_vecs"], 2e-2, "obj_vecs")      # five stacked bf16 layers
+    assert_close(boxes.float(), g["boxes_pred"], 2e-2, "boxes_pred")
+    loss = boxes.float().pow(2).sum() + (obj_vecs.float() * t(gi.model_obj_grad(obj_vecs.shape))).sum()
+    assert abs(loss.item() - float(g["loss"])) <= 2e-2 * abs(float(g["loss"]))
+    loss.backward()
+    for name, prm in model.named_parameters():
+        if name != "converse_candidates_weights":
+            assert prm.grad is not None and torch.isfinite(prm.grad).all(), name
+
+
+def test_bf16_large_batch_matches_fp32_engine():
+    """cfg2-sized ragged batch: the two engines agree to the bf16 budget (no oracle needed at this size)."""
+    from canonicalsg2im_b200.pipeline import SgToLayoutStep, HostBatch
+    vocab = synth.Vocab(42)
+    graphs = synth.make_graphs(64, 77, 3, 30, vocab, include_dummies=True)
+    hb = HostBatch(graphs, seed=1)
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        step = SgToLayoutStep(vocab, torch.device("cuda"), precision=prec, seed=0)
+        d = hb.to_device("cuda")
+        res = step.canonicalize(d)
+        canvas, loss = step.forward(d, res)
+        loss.backward()
+        outs[prec] = (canvas.detach().float(), loss.item(), step.model.gconvs[0].net1[0].weight.grad.clone(),
+                      step.model.trans_candidates_weights.grad.clone())
+    assert_close(outs["bf16"][0], outs["fp32"][0], 3e-2, "canvas")
+    assert abs(outs["bf16"][1] - outs["fp32"][1]) <= 2e-2 * abs(outs["fp32"][1])
+    # gradients summed over ~1e5 triples: mask flips average out; compare in relative L2 norm
+    for i, what in ((2, "dW1 layer 0"), (3, "d w_trans")):
+        a, b = outs["bf16"][i].double(), outs["fp32"][i].double()
+        assert ((a - b).norm() / b.norm()).item() <= 5e-2, what
