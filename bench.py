@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=128, help="graphs per GPU")
     ap.add_argument("--cpu-sample", type=int, default=8, help="graphs in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling run: cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off), "
+                         "no e2e / CPU legs; the printed numbers are not bench values")
     return ap.parse_args()
 
 
@@ -206,11 +209,15 @@ def run_ours(args):
     launches0 = L.csg_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.profile:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for _ in range(args.steps):
         loss, n_tri = step.step(d, G)
     e1.record()
     barrier()
+    if args.profile:
+        torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop() if rank == 0 else None
     launches = L.csg_launch_count() - launches0
     ops.TIMERS.clear()
@@ -223,13 +230,14 @@ def run_ours(args):
     value = world * args.batch * args.steps / sec
 
     # ---- timed region 2: end to end through the public API with HOST buffers (H2D + D2H every step)
-    for _ in range(2):
+    for _ in range(0 if args.profile else 2):
         dd = hb.to_device(dev)
         l, _ = step.step(dd, G)
         float(l.item())
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    lv = float("nan")
+    for _ in range(0 if args.profile else args.steps):
         dd = hb.to_device(dev)
         l, _ = step.step(dd, G)
         lv = float(l.item())
@@ -239,7 +247,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
     e2e_sec = float(tsec.item())
-    e2e = {"value": world * args.batch * args.steps / e2e_sec, "unit": UNIT,
+    e2e = {"value": world * args.batch * args.steps / max(e2e_sec, 1e-9), "unit": UNIT,
            "h2d_bytes_per_step": int(hb.nbytes), "d2h_bytes_per_step": 4 + 4,   # loss scalar + canon size sync
            "ms_per_step": 1e3 * e2e_sec / args.steps}
 
@@ -274,7 +282,7 @@ def run_ours(args):
                      "launches_timed": gemm_n, "share_of_step": gemm_sec / sec if sec > 0 else None},
         "loss": lv,
     }
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and not args.profile and world == 1:
         try:
             line["cpu_baseline"] = run_cpu_baseline(args.cpu_sample, os.cpu_count() or 1)
         except Exception as ex:   # the baseline is a reported number, never a reason to lose the GPU line

@@ -196,15 +196,45 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* _
   C[i] = acc;
 }
 
-// column sums (bias gradients): out[n] = sum_m X[m, n], ordered two-stage reduction
-constexpr int CS_ROWS = 256;
-__global__ void colsum_partial_kernel(const float* __restrict__ X, int M, int N, int ld, float* __restrict__ partial) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  int mbeg = blockIdx.y * CS_ROWS, mend = min(M, mbeg + CS_ROWS);
-  float acc = 0.f;
-  for (int m = mbeg; m < mend; ++m) acc += X[(size_t)m * ld + n];
-  partial[(size_t)blockIdx.y * N + n] = acc;
+// column sums (bias gradients): out[n] = sum_m X[m, n], ordered two-stage reduction.
+// Block = 32 column groups (4 columns each) x 8 row lanes; every thread keeps 4 independent
+// 16-byte loads in flight, the 8 row lanes are combined through shared memory in a fixed order.
+constexpr int CS_TX = 32, CS_TY = 8, CS_VEC = 4;
+__global__ void __launch_bounds__(CS_TX * CS_TY) colsum_partial_kernel(const float* __restrict__ X, int M, int N, int ld,
+                                                                      int rows_per_chunk, float* __restrict__ partial) {
+  __shared__ float red[CS_TY][CS_TX * CS_VEC + 4];
+  const int tx = threadIdx.x % CS_TX, ty = threadIdx.x / CS_TX;
+  const int col = (blockIdx.x * CS_TX + tx) * CS_VEC;
+  const int mbeg = blockIdx.y * rows_per_chunk, mend = min(M, mbeg + rows_per_chunk);
+  float acc[CS_VEC] = {0.f, 0.f, 0.f, 0.f};
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && col + CS_VEC <= N;
+  if (vec) {
+    int m = mbeg + ty;
+    for (; m + 3 * CS_TY < mend; m += 4 * CS_TY) {
+      float4 a = ld_f4(X + (size_t)m * ld + col), b = ld_f4(X + (size_t)(m + CS_TY) * ld + col);
+      float4 c = ld_f4(X + (size_t)(m + 2 * CS_TY) * ld + col), d = ld_f4(X + (size_t)(m + 3 * CS_TY) * ld + col);
+      acc[0] += (a.x + b.x) + (c.x + d.x); acc[1] += (a.y + b.y) + (c.y + d.y);
+      acc[2] += (a.z + b.z) + (c.z + d.z); acc[3] += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; m < mend; m += CS_TY) {
+      float4 a = ld_f4(X + (size_t)m * ld + col);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    }
+  } else {
+    for (int m = mbeg + ty; m < mend; m += CS_TY)
+      for (int j = 0; j < CS_VEC; ++j)
+        if (col + j < N) acc[j] += X[(size_t)m * ld + col + j];
+  }
+  for (int j = 0; j < CS_VEC; ++j) red[ty][tx * CS_VEC + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < CS_TX * CS_VEC) {
+    const int n = blockIdx.x * CS_TX * CS_VEC + threadIdx.x;
+    if (n < N) {
+      float s = 0.f;
+      for (int r = 0; r < CS_TY; ++r) s += red[r][threadIdx.x];
+      partial[(size_t)blockIdx.y * N + n] = s;
+    }
+  }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,6 +242,14 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int chunk
   float acc = 0.f;
   for (int c = 0; c < chunks; ++c) acc += partial[(size_t)c * N + n];
   out[n] = acc;
+}
+// number of row chunks: enough blocks to fill the SMs ~4x, at least 32 rows per chunk
+int colsum_chunks(int M, int N, int cols_per_block) {
+  int col_blocks = csg_div_up(N, cols_per_block);
+  int want = csg_div_up(4 * 148, col_blocks);
+  int maxc = csg_div_up(M, 32);
+  if (want > maxc) want = maxc;
+  return want < 1 ? 1 : want;
 }
 
 template <int AMODE, int BMODE>
@@ -262,7 +300,7 @@ CSG_API int csg_gemm_f32(int amode, int bmode, int M, int N, int K,
 
   int splits = 1;
   float* out = C;
-  if (amode == A_COL && K > 4096) {
+  if (amode == A_COL && K > 256) {
     // weight gradients: tiny [M, N], long K -> split K so that the grid covers the 148 SMs
     int tiles = csg_div_up(M, BM) * csg_div_up(N, BN);
     splits = csg_div_up(2 * csg_num_sms(), tiles);
@@ -307,18 +345,20 @@ CSG_API int csg_relu_mask_f32(const float* dy, const float* y, float* out, long 
   return 0;
 }
 
-CSG_API size_t csg_colsum_f32_workspace(int M, int N) { return (size_t)csg_div_up(M, CS_ROWS) * N * sizeof(float) + 16; }
+CSG_API size_t csg_colsum_f32_workspace(int M, int N) {
+  return (size_t)colsum_chunks(M, N, CS_TX * CS_VEC) * N * sizeof(float) + 16;
+}
 
 CSG_API int csg_colsum_f32(const float* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
                            cudaStream_t stream) {
   if (N == 0) return 0;
-  int chunks = csg_div_up(M, CS_ROWS);
+  const int chunks = colsum_chunks(M, N, CS_TX * CS_VEC);
   CSG_REQUIRE(workspace_bytes >= csg_colsum_f32_workspace(M, N), "colsum: workspace too small");
   float* partial = reinterpret_cast<float*>(workspace);
-  if (chunks > 0) {
-    colsum_partial_kernel<<<dim3(csg_div_up(N, 128), chunks), 128, 0, stream>>>(X, M, N, ld, partial);
-    CSG_CHECK_LAUNCH("csg_colsum partial");
-  }
+  const int rows_per_chunk = csg_div_up(M > 0 ? M : 1, chunks);
+  colsum_partial_kernel<<<dim3(csg_div_up(N, CS_TX * CS_VEC), chunks), CS_TX * CS_TY, 0, stream>>>(X, M, N, ld, rows_per_chunk,
+                                                                                              partial);
+  CSG_CHECK_LAUNCH("csg_colsum partial");
   colsum_final_kernel<<<csg_div_up(N, 128), 128, 0, stream>>>(partial, chunks, N, out);
   CSG_CHECK_LAUNCH("csg_colsum final");
   return 0;

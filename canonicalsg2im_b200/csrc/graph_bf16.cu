@@ -119,20 +119,52 @@ __global__ void relu_mask_bf16_kernel(const float* __restrict__ dy, const __nv_b
   if (i < n) out[i] = __float2bfloat16_rn(__bfloat162float(y[i]) > 0.f ? dy[i] : 0.f);
 }
 
-constexpr int CS_ROWS = 512;
-__global__ void colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ X, int M, int N, int ld,
-                                           float* __restrict__ partial) {
-  int n = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (n >= N) return;
-  int mbeg = blockIdx.y * CS_ROWS, mend = min(M, mbeg + CS_ROWS);
-  float a0 = 0.f, a1 = 0.f;
-  for (int m = mbeg; m < mend; ++m) {
-    uint32_t w = *reinterpret_cast<const uint32_t*>(X + (size_t)m * ld + n);
-    a0 += __uint_as_float(w << 16);
-    a1 += __uint_as_float(w & 0xFFFF0000u);
+// column sums of a bf16 matrix (bias gradients), fp32 accumulation, ordered two-stage reduction.
+// Block = 32 column groups (8 columns = one 16-byte load each) x 8 row lanes, 4 loads in flight per thread.
+constexpr int CS_TX = 32, CS_TY = 8, CS_VEC = 8;
+__global__ void __launch_bounds__(CS_TX * CS_TY) colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ X, int M, int N,
+                                                                           int ld, int rows_per_chunk,
+                                                                           float* __restrict__ partial) {
+  __shared__ float red[CS_TY][CS_TX * CS_VEC + 4];
+  const int tx = threadIdx.x % CS_TX, ty = threadIdx.x / CS_TX;
+  const int col = (blockIdx.x * CS_TX + tx) * CS_VEC;
+  const int mbeg = blockIdx.y * rows_per_chunk, mend = min(M, mbeg + rows_per_chunk);
+  float acc[CS_VEC];
+#pragma unroll
+  for (int j = 0; j < CS_VEC; ++j) acc[j] = 0.f;
+  if (col < N) {
+    int m = mbeg + ty;
+    for (; m + 3 * CS_TY < mend; m += 4 * CS_TY) {
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const uint4*>(X + (size_t)(m + u * CS_TY) * ld + col);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        unpack8(q[u], v);
+#pragma unroll
+        for (int j = 0; j < CS_VEC; ++j) acc[j] += v[j];
+      }
+    }
+    for (; m < mend; m += CS_TY) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(X + (size_t)m * ld + col), v);
+#pragma unroll
+      for (int j = 0; j < CS_VEC; ++j) acc[j] += v[j];
+    }
   }
-  partial[(size_t)blockIdx.y * N + n] = a0;
-  partial[(size_t)blockIdx.y * N + n + 1] = a1;
+#pragma unroll
+  for (int j = 0; j < CS_VEC; ++j) red[ty][tx * CS_VEC + j] = acc[j];
+  __syncthreads();
+  {
+    const int n = blockIdx.x * CS_TX * CS_VEC + threadIdx.x;
+    if (n < N) {
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < CS_TY; ++r) s += red[r][threadIdx.x];
+      partial[(size_t)blockIdx.y * N + n] = s;
+    }
+  }
 }
 __global__ void colsum_bf16_final_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,6 +172,13 @@ __global__ void colsum_bf16_final_kernel(const float* __restrict__ partial, int 
   float acc = 0.f;
   for (int c = 0; c < chunks; ++c) acc += partial[(size_t)c * N + n];
   out[n] = acc;
+}
+int colsum_bf16_chunks(int M, int N) {
+  int col_blocks = csg_div_up(N, CS_TX * CS_VEC);
+  int want = csg_div_up(4 * 148, col_blocks);
+  int maxc = csg_div_up(M, 32);
+  if (want > maxc) want = maxc;
+  return want < 1 ? 1 : want;
 }
 
 // bf16 twin of triple_bwd_assemble_kernel (graph.cu): one warp per triple, 8 columns per lane per step.
@@ -238,20 +277,22 @@ CSG_API int csg_relu_mask_bf16(const float* dy, const void* y, void* out, long l
   return 0;
 }
 
-CSG_API size_t csg_colsum_bf16_workspace(int M, int N) { return (size_t)csg_div_up(M, CS_ROWS) * N * sizeof(float) + 16; }
+CSG_API size_t csg_colsum_bf16_workspace(int M, int N) {
+  return (size_t)colsum_bf16_chunks(M, N) * N * sizeof(float) + 16;
+}
 
 CSG_API int csg_colsum_bf16(const void* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
                             cudaStream_t stream) {
   if (N == 0) return 0;
-  CSG_REQUIRE((N & 1) == 0 && (ld & 1) == 0, "colsum_bf16: N and ld must be even");
+  CSG_REQUIRE((N & 7) == 0 && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
+              "colsum_bf16: N and ld must be multiples of 8 and X 16-byte aligned");
   CSG_REQUIRE(workspace_bytes >= csg_colsum_bf16_workspace(M, N), "colsum_bf16: workspace too small");
-  int chunks = csg_div_up(M, CS_ROWS);
+  const int chunks = colsum_bf16_chunks(M, N);
+  const int rows_per_chunk = csg_div_up(M > 0 ? M : 1, chunks);
   float* partial = reinterpret_cast<float*>(workspace);
-  if (chunks > 0) {
-    colsum_bf16_partial_kernel<<<dim3(csg_div_up(N / 2, 128), chunks), 128, 0, stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(X), M, N, ld, partial);
-    CSG_CHECK_LAUNCH("csg_colsum_bf16 partial");
-  }
+  colsum_bf16_partial_kernel<<<dim3(csg_div_up(N, CS_TX * CS_VEC), chunks), CS_TX * CS_TY, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(X), M, N, ld, rows_per_chunk, partial);
+  CSG_CHECK_LAUNCH("csg_colsum_bf16 partial");
   colsum_bf16_final_kernel<<<csg_div_up(N, 128), 128, 0, stream>>>(partial, chunks, N, out);
   CSG_CHECK_LAUNCH("csg_colsum_bf16 final");
   return 0;

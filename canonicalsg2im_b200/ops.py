@@ -93,7 +93,7 @@ def gemm_f32(amode, bmode, M, N, K, A, B, out=None, bias=None, relu=False, rowsc
     need_cuda(A, B, out, bias, rowscale, mask_aux)
     L = lib()
     ws = None
-    nws = L.csg_gemm_f32_workspace(M, N, K, amode) if (amode == A_COL and K > 4096) else 0
+    nws = L.csg_gemm_f32_workspace(M, N, K, amode) if (amode == A_COL and K > 256) else 0
     if nws:
         ws = workspace(nws, dev)
     g = gather
