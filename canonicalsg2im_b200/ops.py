@@ -160,7 +160,7 @@ def gemm_bf16(M, N, K, A, B, mn_major=False, out=None, out_f32=False, bias=None,
         ptr(out), out.stride(0), int(out_f32),
         ptr(bias), int(relu), ptr(rowscale), ptr(mask_aux), (mask_aux.stride(0) if mask_aux is not None else 0),
         ptr(g.obj) if g else 0, ptr(g.pred) if g else 0, ptr(g.s_idx) if g else 0, ptr(g.o_idx) if g else 0,
-        g.din if g else 0, g.dp if g else 0, g.ldp if g else 0,
+        g.din if g else 0, g.dp if g else 0, g.ldp if g else 0, g.obj.shape[0] if g else 0,
         ptr(ws), (ws.numel() if ws is not None else 0), _stream())
     _lib.check(rc, "csg_gemm_bf16")
     if timer is not None:

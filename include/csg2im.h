@@ -106,13 +106,15 @@ int csg_colsum_f32(const float* X, int M, int N, int ld, float* out, void* works
 /* bf16 tensor-core GEMMs (tcgen05 + TMEM + TMA), fp32 accumulation.
  * mn_major = 0: C[M,N] = epi(A[M,K] B[N,K]^T), K contiguous; gather = 1 fuses the triple-input gather into A.
  * mn_major = 1: C[M,N] = A[K,M]^T B[K,N] (weight gradients, fp32 out, split-K); gather = 2 gathers B's rows.
+ * The gathered operand is the virtual row [g_obj[g_sidx[t]] | g_pred[t] | g_obj[g_oidx[t]]] (graph.py:63-66);
+ * g_obj is [g_nobj, g_din] contiguous, g_pred has row pitch g_ldp.  Object rows arrive by TMA tile::gather4.
  * A, B, mask_aux, g_obj, g_pred are bf16; bias, rowscale fp32; C is bf16 or (out_f32) fp32. */
 size_t csg_gemm_bf16_workspace(int M, int N, int K, int mn_major);
 int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
                   const void* A, int lda, const void* B, int ldb, void* C, int ldc, int out_f32,
                   const float* bias, int relu, const float* rowscale, const void* mask_aux, int ld_aux,
                   const void* g_obj, const void* g_pred, const int* g_sidx, const int* g_oidx,
-                  int g_din, int g_dp, int g_ldp,
+                  int g_din, int g_dp, int g_ldp, int g_nobj,
                   void* workspace, size_t workspace_bytes, csg_stream_t stream);
 
 /* bf16-activation twins of the pooling / assembly kernels (fp32 accumulation) + weight cast */

@@ -46,6 +46,31 @@ def test_kmajor_epilogues():
                  2e-5, "strided A")
 
 
+@pytest.mark.parametrize("M,N,K", [(777, 512, 384), (5000, 1152, 512), (40, 128, 512), (1234, 384, 512), (300, 96, 64)])
+def test_kmajor_epilogues_bf16_out(M, N, K):
+    """bf16 output path: registers -> swizzled smem -> TMA store, ReLU-mask operand prefetched by TMA."""
+    from canonicalsg2im_b200 import ops
+    A, B = _rand((M, K), 3), _rand((N, K), 4, 0.05)
+    bias = torch.randn(N, device="cuda")
+    rs = torch.rand(M, device="cuda")
+    aux = _rand((M, N), 5)
+    z = A.float() @ B.float().T
+    out = ops.gemm_bf16(M, N, K, A, B, bias=bias, relu=True, rowscale=rs)
+    assert_close(out.float(), torch.relu(z + bias) * rs[:, None], 1e-2, "bias+relu+rowscale bf16")
+    out = ops.gemm_bf16(M, N, K, A, B, mask_aux=aux)
+    ref = z * (aux.float() > 0)
+    assert_close(out.float(), ref, 1e-2, "mask bf16")
+    # the mask must be exact: masked entries are exact zeros, kept entries non-zero wherever the reference is
+    assert bool(((out.float() == 0) | (aux.float() > 0)).all())
+    # output into a column slice of a wider buffer (as new_p aliases the net1 output) + strided aux
+    wide = torch.zeros((M, N + 128), dtype=torch.bfloat16, device="cuda")
+    auxw = torch.zeros((M, N + 64), dtype=torch.bfloat16, device="cuda")
+    auxw[:, 64:] = aux
+    ops.gemm_bf16(M, N, K, A, B, out=wide[:, 64:64 + N], mask_aux=auxw[:, 64:])
+    assert_close(wide[:, 64:64 + N].float(), ref, 1e-2, "strided C / aux")
+    assert float(wide[:, :64].abs().max()) == 0 and float(wide[:, 64 + N:].abs().max()) == 0
+
+
 def _gather(NO, NT, Din, Dp, seed):
     from canonicalsg2im_b200 import ops
     g = torch.Generator("cuda").manual_seed(seed)
@@ -65,6 +90,21 @@ def test_gather_a(NT):
     ref = torch.relu(X.float() @ W.float().T + bias)
     out = ops.gemm_bf16(NT, 512, 384, None, W, out_f32=True, bias=bias, relu=True, gather=g, gather_mode=1)
     assert_close(out, ref, 2e-5, "gather A")
+    out = ops.gemm_bf16(NT, 512, 384, None, W, bias=bias, relu=True, gather=g, gather_mode=1)
+    assert_close(out.float(), ref, 1e-2, "gather A, bf16 out")
+
+
+def test_gather_a_strided_pred():
+    """pred rows that alias a wider buffer (the previous layer's [NT, 2H+Dp] output, graph.py:79-81)."""
+    from canonicalsg2im_b200 import ops
+    g, X = _gather(97, 3000, 128, 128, 12)
+    wide = _rand((3000, 1152), 13)
+    wide[:, 512:640] = g.pred
+    g2 = ops.Gather(g.obj, wide[:, 512:640], g.s_idx, g.o_idx)
+    W = _rand((512, 384), 11, 0.05)
+    ref = X.float() @ W.float().T
+    out = ops.gemm_bf16(3000, 512, 384, None, W, out_f32=True, gather=g2, gather_mode=1)
+    assert_close(out, ref, 2e-5, "gather A, strided pred")
 
 
 @pytest.mark.parametrize("M,N,K", [(512, 512, 64), (1152, 512, 3000), (128, 512, 200), (512, 384, 10000)])
