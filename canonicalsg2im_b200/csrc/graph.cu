@@ -103,15 +103,25 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(const int* __restrict__ 
   if (tid == 1023) row_ptr[n] = sums[1023];
 }
 
-// One warp per graph walks its triples in order, 32 at a time: lanes with equal keys are ranked
+// One warp (= one block) per graph walks its triples in order, 32 at a time: lanes with equal keys are ranked
 // with match_any, so perm lists every object's triples in ascending triple id (== stable sort).
-// The objects of a graph are touched by that graph's warp only, so the global cursors race-free.
-__global__ void csr_fill_kernel(const int* __restrict__ keys, const int* __restrict__ tri_off, int B,
-                                int* __restrict__ cursor, int* __restrict__ perm) {
-  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// The objects of a graph are touched by that graph's warp only; their running cursors live in shared memory
+// (falling back to the global cursor array for graphs with more than CSR_SMEM_OBJS objects).
+constexpr int CSR_SMEM_OBJS = 2048;
+__global__ void __launch_bounds__(32) csr_fill_kernel(const int* __restrict__ keys, const int* __restrict__ tri_off,
+                                                      const int* __restrict__ obj_off, int B,
+                                                      int* __restrict__ cursor, int* __restrict__ perm) {
+  __shared__ int scur[CSR_SMEM_OBJS];
+  const int g = blockIdx.x;
   if (g >= B) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x;
   const int beg = tri_off[g], end = tri_off[g + 1];
+  const int obeg = obj_off[g], nobj = obj_off[g + 1] - obeg;
+  const bool use_smem = nobj <= CSR_SMEM_OBJS;
+  if (use_smem) {
+    for (int i = lane; i < nobj; i += 32) scur[i] = cursor[obeg + i];
+    __syncwarp();
+  }
   for (int t0 = beg; t0 < end; t0 += 32) {
     int t = t0 + lane;
     bool act = t < end;
@@ -119,11 +129,13 @@ __global__ void csr_fill_kernel(const int* __restrict__ keys, const int* __restr
     unsigned peers = __match_any_sync(0xffffffffu, key);
     int rank = __popc(peers & ((1u << lane) - 1u));
     int base = 0;
-    if (act) base = cursor[key];
+    if (act) base = use_smem ? scur[key - obeg] : cursor[key];
     __syncwarp();
     if (act) {
       perm[base + rank] = t;
-      if (rank == __popc(peers) - 1) cursor[key] = base + rank + 1;
+      if (rank == __popc(peers) - 1) {
+        if (use_smem) scur[key - obeg] = base + rank + 1; else cursor[key] = base + rank + 1;
+      }
     }
     __syncwarp();
   }
@@ -262,7 +274,7 @@ __global__ void triple_bwd_assemble_kernel(const float* __restrict__ out, const 
 // d w_trans[p] += sum over type-1 triples with predicate p of dconf[t] * s(1-s), s = sigmoid(w[p]).
 // Deterministic: each warp walks a contiguous chunk in order, lanes with equal predicate are summed
 // in lane order by the group leader into warp-private bins; bins are then reduced in fixed order.
-constexpr int CONF_BWD_BLOCKS = 64;
+constexpr int CONF_BWD_BLOCKS = 256;
 __global__ void conf_bwd_partial_kernel(const float* __restrict__ dconf, const int* __restrict__ type32,
                                         const int* __restrict__ pred, int NT, int P, float* __restrict__ partial) {
   extern __shared__ float bins[];   // [warps][P]
@@ -343,7 +355,7 @@ CSG_API int csg_triple_prep_edges(const long long* edges, const long long* pred_
 
 CSG_API size_t csg_csr_workspace(int NO) { return (size_t)4 * (NO + 1) * sizeof(int); }
 
-CSG_API int csg_csr_build(const int* keys_s, const int* keys_o, const int* tri_off, int B, int NT, int NO,
+CSG_API int csg_csr_build(const int* keys_s, const int* keys_o, const int* tri_off, const int* obj_off, int B, int NT, int NO,
                           int* rowptr_s, int* perm_s, int* rowptr_o, int* perm_o,
                           void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   CSG_REQUIRE(workspace_bytes >= csg_csr_workspace(NO), "csr_build: workspace too small");
@@ -360,8 +372,8 @@ CSG_API int csg_csr_build(const int* keys_s, const int* keys_o, const int* tri_o
   csr_scan_kernel<<<1, 1024, 0, stream>>>(cnt_o, NO, rowptr_o, cur_o);
   CSG_CHECK_LAUNCH("csg_csr_build scan");
   if (NT > 0 && B > 0) {
-    csr_fill_kernel<<<csg_div_up((long long)B * 32, 256), 256, 0, stream>>>(keys_s, tri_off, B, cur_s, perm_s);
-    csr_fill_kernel<<<csg_div_up((long long)B * 32, 256), 256, 0, stream>>>(keys_o, tri_off, B, cur_o, perm_o);
+    csr_fill_kernel<<<B, 32, 0, stream>>>(keys_s, tri_off, obj_off, B, cur_s, perm_s);
+    csr_fill_kernel<<<B, 32, 0, stream>>>(keys_o, tri_off, obj_off, B, cur_o, perm_o);
     CSG_CHECK_LAUNCH("csg_csr_build fill");
   }
   return 0;

@@ -45,59 +45,110 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int co
   }
 }
 
-// One CTA of W/8 threads per object; thread j owns columns 8j..8j+7 (one 16-byte load per row).
+// Several fp32 -> bf16 casts (optionally transposed) in one launch: the 4 weight matrices of a layer and their
+// transposes are needed once per step each.
+constexpr int CAST_MAX = 16;
+struct CastJobs {
+  const float* src[CAST_MAX];
+  __nv_bfloat16* dst[CAST_MAX];
+  int rows[CAST_MAX], cols[CAST_MAX], transpose[CAST_MAX];
+  int tile_end[CAST_MAX];      // exclusive prefix of 32x32 tiles
+  int n;
+};
+__global__ void cast_bf16_multi_kernel(const CastJobs jobs) {
+  __shared__ float tile[32][33];
+  int j = 0;
+  while (j < jobs.n - 1 && (int)blockIdx.x >= jobs.tile_end[j]) ++j;
+  const int local = blockIdx.x - (j ? jobs.tile_end[j - 1] : 0);
+  const int rows = jobs.rows[j], cols = jobs.cols[j];
+  const int tcols = (cols + 31) / 32;
+  const int c0 = (local % tcols) * 32, r0 = (local / tcols) * 32;
+  const float* src = jobs.src[j];
+  __nv_bfloat16* dst = jobs.dst[j];
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    if (!jobs.transpose[j]) {
+      int r = r0 + i, c = c0 + threadIdx.x;
+      if (r < rows && c < cols) dst[(size_t)r * cols + c] = __float2bfloat16_rn(tile[i][threadIdx.x]);
+    } else {
+      int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < rows && c < cols) dst[(size_t)c * rows + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+
+// One CTA per object: TX = W/8 column threads (8 columns = one 16-byte load per row) x TY row lanes.
+// The object's incidence list (subject incidences in ascending triple id, then object incidences: the order
+// CPU scatter_add visits them, graph.py:98-99) is dealt round-robin to the row lanes, every lane keeps four
+// independent row loads in flight, and the lanes are combined in lane order: a fixed, reproducible sum.
+constexpr int SP_MAX_THREADS = 256;
 template <bool AVG>
-__global__ void segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int col_o, int W,
-                                    const int* __restrict__ rp_s, const int* __restrict__ perm_s,
-                                    const int* __restrict__ rp_o, const int* __restrict__ perm_o,
-                                    const int* __restrict__ valid, const float* __restrict__ conf,
-                                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int ldo,
-                                    float* __restrict__ cnt_out) {
+__global__ void __launch_bounds__(SP_MAX_THREADS)
+segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int col_o, int W, int TX, int TY,
+                    const int* __restrict__ rp_s, const int* __restrict__ perm_s,
+                    const int* __restrict__ rp_o, const int* __restrict__ perm_o,
+                    const int* __restrict__ valid, const float* __restrict__ conf,
+                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int ldo,
+                    float* __restrict__ cnt_out) {
+  __shared__ float red[SP_MAX_THREADS * 8];
+  __shared__ float red_cnt[SP_MAX_THREADS];
   const int o = blockIdx.x;
-  const int c = threadIdx.x * 8;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int c = tx * 8;
   const bool colok = c < W;
+  const int bs = rp_s[o], ns = rp_s[o + 1] - bs;
+  const int bo = rp_o[o], total = ns + rp_o[o + 1] - bo;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   float cnt = 0.f;
-  for (int pass = 0; pass < 2; ++pass) {
-    const int* rp = pass ? rp_o : rp_s;
-    const int* perm = pass ? perm_o : perm_s;
-    const int col = (pass ? col_o : col_s) + c;
-    const int beg = rp[o], end = rp[o + 1];
-    int j = beg;
-    for (; j + 4 <= end; j += 4) {
-      int t[4];
-      bool v[4];
-      uint4 r[4];
+  for (int e0 = ty; e0 < total; e0 += 4 * TY) {
+    uint4 r[4];
+    float w[4];
+    bool v[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        t[k] = perm[j + k];
-        v[k] = !AVG || valid[t[k]];
-        r[k] = (v[k] && colok) ? *reinterpret_cast<const uint4*>(X + (size_t)t[k] * ldx + col) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (v[k]) {
-          float f[8];
-          unpack8(r[k], f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += f[i];
-          if (AVG) cnt += conf[t[k]];
-        }
+    for (int k = 0; k < 4; ++k) {
+      const int e = e0 + k * TY;
+      v[k] = e < total;
+      r[k] = make_uint4(0, 0, 0, 0);
+      w[k] = 0.f;
+      if (v[k]) {
+        const bool subj = e < ns;
+        const int t = subj ? perm_s[bs + e] : perm_o[bo + e - ns];
+        // the row load does not wait for valid / conf (invalid rows are rare: padded batches only)
+        if (colok) r[k] = *reinterpret_cast<const uint4*>(X + (size_t)t * ldx + (subj ? col_s : col_o) + c);
+        if (AVG) { v[k] = valid[t] != 0; w[k] = conf[t]; }
       }
     }
-    for (; j < end; ++j) {
-      int t = perm[j];
-      if (AVG && !valid[t]) continue;
-      if (colok) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (v[k]) {
         float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(X + (size_t)t * ldx + col), f);
+        unpack8(r[k], f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        cnt += w[k];
       }
-      if (AVG) cnt += conf[t];
     }
+  }
+  if (TY > 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[(ty * 8 + i) * TX + tx] = acc[i];
+    if (tx == 0) red_cnt[ty] = cnt;
+    __syncthreads();
+    if (ty != 0) return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float s = 0.f;
+      for (int y = 0; y < TY; ++y) s += red[(y * 8 + i) * TX + tx];
+      acc[i] = s;
+    }
+    cnt = 0.f;
+    for (int y = 0; y < TY; ++y) cnt += red_cnt[y];
   }
   if (AVG && cnt > 0.f) {
 #pragma unroll
@@ -110,7 +161,7 @@ __global__ void segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx
     }
     if (out_bf16) *reinterpret_cast<uint4*>(out_bf16 + (size_t)o * ldo + c) = pack8(acc);
   }
-  if (AVG && threadIdx.x == 0) cnt_out[o] = cnt;
+  if (AVG && tx == 0) cnt_out[o] = cnt;
 }
 
 __global__ void relu_mask_bf16_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
@@ -166,12 +217,23 @@ __global__ void __launch_bounds__(CS_TX * CS_TY) colsum_bf16_partial_kernel(cons
     }
   }
 }
-__global__ void colsum_bf16_final_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// final pass: 32 columns x 8 chunk lanes per block, lanes combined in lane order
+__global__ void __launch_bounds__(256) colsum_bf16_final_kernel(const float* __restrict__ partial, int chunks, int N,
+                                                                float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
   float acc = 0.f;
-  for (int c = 0; c < chunks; ++c) acc += partial[(size_t)c * N + n];
-  out[n] = acc;
+  if (n < N)
+    for (int c = ty; c < chunks; c += 8) acc += partial[(size_t)c * N + n];
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += red[y][tx];
+    out[n] = s;
+  }
 }
 int colsum_bf16_chunks(int M, int N) {
   int col_blocks = csg_div_up(N, CS_TX * CS_VEC);
@@ -181,56 +243,97 @@ int colsum_bf16_chunks(int M, int N) {
   return want < 1 ? 1 : want;
 }
 
-// bf16 twin of triple_bwd_assemble_kernel (graph.cu): one warp per triple, 8 columns per lane per step.
-__global__ void triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const float* __restrict__ dS,
-                                                const __nv_bfloat16* __restrict__ d_newp, int ld_newp,
-                                                const float* __restrict__ dcnt, const int* __restrict__ s_idx,
-                                                const int* __restrict__ o_idx, const int* __restrict__ valid,
-                                                const int* __restrict__ type32, const float* __restrict__ conf,
-                                                int NT, int H, int Dp, __nv_bfloat16* __restrict__ g,
-                                                float* __restrict__ dconf) {
-  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (t >= NT) return;
-  const int lane = threadIdx.x & 31;
+// bf16 twin of triple_bwd_assemble_kernel (graph.cu): one warp per triple at a time, 8 columns per lane per step,
+// ASM_TPW consecutive triples per warp.  With CS (column sums requested: the bias gradient of net1's second
+// Linear is colsum(g)) every lane also accumulates its columns over the warp's triples; the 8 warps of a block
+// are combined through shared memory and one partial row per block is written for the ordered final pass.
+constexpr int ASM_WARPS = 8, ASM_TPW = 8, ASM_MAXI = 5;      // ASM_MAXI * 256 >= Wd
+template <bool CS>
+__global__ void __launch_bounds__(ASM_WARPS * 32)
+triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const float* __restrict__ dS,
+                                const __nv_bfloat16* __restrict__ d_newp, int ld_newp,
+                                const float* __restrict__ dcnt, const int* __restrict__ s_idx,
+                                const int* __restrict__ o_idx, const int* __restrict__ valid,
+                                const int* __restrict__ type32, const float* __restrict__ conf,
+                                int NT, int H, int Dp, __nv_bfloat16* __restrict__ g,
+                                float* __restrict__ dconf, float* __restrict__ cs_partial) {
+  __shared__ __align__(16) float cs_red[CS ? ASM_WARPS * ASM_MAXI * 256 : 4];   // per-warp column accumulators
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Wd = 2 * H + Dp;
-  const int s = s_idx[t], o = o_idx[t];
-  const bool v = valid[t] != 0;
-  const float cf = conf[t];
-  const __nv_bfloat16* orow = out + (size_t)t * Wd;
-  __nv_bfloat16* grow = g + (size_t)t * Wd;
-  float dot = 0.f;
-  for (int j = lane * 8; j < Wd; j += 256) {
-    float raw[8];
-    if (j < H || j >= H + Dp) {
-      const float* src = dS + (size_t)(j < H ? s : o) * H + (j < H ? j : j - H - Dp);
-      if (v) {
-        float4 a = ld_f4(src), b = ld_f4(src + 4);
-        raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
-      } else {
+  float* mycs = cs_red + warp * ASM_MAXI * 256;      // lane owns columns lane*8 + u*256 .. +7: no conflicts
+  if (CS) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) raw[i] = 0.f;
-      }
-    } else if (d_newp) {
-      unpack8(*reinterpret_cast<const uint4*>(d_newp + (size_t)t * ld_newp + (j - H)), raw);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) raw[i] = 0.f;
+    for (int u = 0; u < ASM_MAXI; ++u) {
+      st_f4(mycs + u * 256 + lane * 8, make_float4(0.f, 0.f, 0.f, 0.f));
+      st_f4(mycs + u * 256 + lane * 8 + 4, make_float4(0.f, 0.f, 0.f, 0.f));
     }
-    float y[8], r[8];
-    unpack8(*reinterpret_cast<const uint4*>(orow + j), y);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      dot += raw[i] * y[i];
-      r[i] = y[i] > 0.f ? raw[i] * cf : 0.f;
-    }
-    *reinterpret_cast<uint4*>(grow + j) = pack8(r);
   }
-  dot = warp_sum(dot);
-  if (lane == 0) {
-    float dc = 0.f;
-    if (type32[t] == 1 && cf > 0.f) dc = dot / cf;
-    if (v) dc += dcnt[s] + dcnt[o];
-    dconf[t] = dc;
+  const int tbeg = (blockIdx.x * ASM_WARPS + warp) * ASM_TPW;
+  for (int k = 0; k < ASM_TPW; ++k) {
+    const int t = tbeg + k;
+    if (t >= NT) break;
+    const int s = s_idx[t], o = o_idx[t];
+    const bool v = valid[t] != 0;
+    const float cf = conf[t];
+    const __nv_bfloat16* orow = out + (size_t)t * Wd;
+    __nv_bfloat16* grow = g + (size_t)t * Wd;
+    float dot = 0.f;
+#pragma unroll
+    for (int u = 0; u < ASM_MAXI; ++u) {
+      const int j = lane * 8 + u * 256;
+      if (j < Wd) {
+        float raw[8];
+        if (j < H || j >= H + Dp) {
+          const float* src = dS + (size_t)(j < H ? s : o) * H + (j < H ? j : j - H - Dp);
+          if (v) {
+            float4 a = ld_f4(src), b = ld_f4(src + 4);
+            raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) raw[i] = 0.f;
+          }
+        } else if (d_newp) {
+          unpack8(*reinterpret_cast<const uint4*>(d_newp + (size_t)t * ld_newp + (j - H)), raw);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) raw[i] = 0.f;
+        }
+        float y[8], r[8];
+        unpack8(*reinterpret_cast<const uint4*>(orow + j), y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          dot += raw[i] * y[i];
+          r[i] = y[i] > 0.f ? raw[i] * cf : 0.f;
+        }
+        const uint4 packed = pack8(r);
+        *reinterpret_cast<uint4*>(grow + j) = packed;
+        if (CS) {
+          float rb[8];
+          unpack8(packed, rb);             // sum what the GEMMs will read: the bf16-rounded values
+          float* c8 = mycs + u * 256 + lane * 8;
+          float4 a = ld_f4(c8), b = ld_f4(c8 + 4);
+          a.x += rb[0]; a.y += rb[1]; a.z += rb[2]; a.w += rb[3];
+          b.x += rb[4]; b.y += rb[5]; b.z += rb[6]; b.w += rb[7];
+          st_f4(c8, a); st_f4(c8 + 4, b);
+        }
+      }
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      float dc = 0.f;
+      if (type32[t] == 1 && cf > 0.f) dc = dot / cf;
+      if (v) dc += dcnt[s] + dcnt[o];
+      dconf[t] = dc;
+    }
+  }
+  if (CS) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < Wd; j += blockDim.x) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < ASM_WARPS; ++w) acc += cs_red[w * ASM_MAXI * 256 + j];
+      cs_partial[(size_t)blockIdx.x * Wd + j] = acc;
+    }
   }
 }
 
@@ -246,6 +349,28 @@ CSG_API int csg_cast_bf16(const float* src, int rows, int cols, int ld_src, void
   return 0;
 }
 
+// n contiguous fp32 matrices src[i] [rows[i], cols[i]] -> contiguous bf16 dst[i] ([cols, rows] when transpose[i]).
+// The pointer / size arrays are HOST arrays of length n <= 16.
+CSG_API int csg_cast_bf16_multi(int n, const void* const* src, void* const* dst, const int* rows, const int* cols,
+                                const int* transpose, cudaStream_t stream) {
+  if (n == 0) return 0;
+  CSG_REQUIRE(n > 0 && n <= CAST_MAX, "cast_bf16_multi: n=%d out of range", n);
+  CastJobs jobs;
+  jobs.n = n;
+  int total = 0;
+  for (int i = 0; i < n; ++i) {
+    jobs.src[i] = reinterpret_cast<const float*>(src[i]);
+    jobs.dst[i] = reinterpret_cast<__nv_bfloat16*>(dst[i]);
+    jobs.rows[i] = rows[i]; jobs.cols[i] = cols[i]; jobs.transpose[i] = transpose[i];
+    total += csg_div_up(rows[i], 32) * csg_div_up(cols[i], 32);
+    jobs.tile_end[i] = total;
+  }
+  if (total == 0) return 0;
+  cast_bf16_multi_kernel<<<total, dim3(32, 8), 0, stream>>>(jobs);
+  CSG_CHECK_LAUNCH("csg_cast_bf16_multi");
+  return 0;
+}
+
 CSG_API int csg_segpool_bf16(const void* X, int ldx, int col_s, int col_o, int W,
                              const int* rowptr_s, const int* perm_s, const int* rowptr_o, const int* perm_o,
                              const int* valid, const float* conf, int NO, float* out_f32, void* out_bf16, int ldo,
@@ -253,17 +378,21 @@ CSG_API int csg_segpool_bf16(const void* X, int ldx, int col_s, int col_o, int W
   if (NO == 0) return 0;
   CSG_REQUIRE((W & 7) == 0 && (ldx & 7) == 0 && (col_s & 7) == 0 && (col_o & 7) == 0 && (ldo & 7) == 0,
               "segpool_bf16: widths/offsets must be multiples of 8");
-  CSG_REQUIRE(W <= 8192, "segpool_bf16: W=%d too wide", W);
-  int threads = ((W / 8 + 31) / 32) * 32;
+  CSG_REQUIRE(W <= 8 * SP_MAX_THREADS, "segpool_bf16: W=%d too wide", W);
+  const int TX = W / 8;
+  int TY = SP_MAX_THREADS / TX;
+  if (TY > 16) TY = 16;
+  if (TY < 1) TY = 1;
+  const int threads = TX * TY;
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(X);
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   if (avg) {
     CSG_REQUIRE(valid && conf && cnt_out, "segpool_bf16(avg): valid/conf/cnt required");
-    segpool_bf16_kernel<true><<<NO, threads, 0, stream>>>(x, ldx, col_s, col_o, W, rowptr_s, perm_s, rowptr_o, perm_o,
-                                                          valid, conf, out_f32, ob, ldo, cnt_out);
+    segpool_bf16_kernel<true><<<NO, threads, 0, stream>>>(x, ldx, col_s, col_o, W, TX, TY, rowptr_s, perm_s, rowptr_o,
+                                                          perm_o, valid, conf, out_f32, ob, ldo, cnt_out);
   } else {
-    segpool_bf16_kernel<false><<<NO, threads, 0, stream>>>(x, ldx, col_s, col_o, W, rowptr_s, perm_s, rowptr_o, perm_o,
-                                                           nullptr, nullptr, out_f32, ob, ldo, nullptr);
+    segpool_bf16_kernel<false><<<NO, threads, 0, stream>>>(x, ldx, col_s, col_o, W, TX, TY, rowptr_s, perm_s, rowptr_o,
+                                                           perm_o, nullptr, nullptr, out_f32, ob, ldo, nullptr);
   }
   CSG_CHECK_LAUNCH("csg_segpool_bf16");
   return 0;
@@ -293,20 +422,48 @@ CSG_API int csg_colsum_bf16(const void* X, int M, int N, int ld, float* out, voi
   colsum_bf16_partial_kernel<<<dim3(csg_div_up(N, CS_TX * CS_VEC), chunks), CS_TX * CS_TY, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(X), M, N, ld, rows_per_chunk, partial);
   CSG_CHECK_LAUNCH("csg_colsum_bf16 partial");
-  colsum_bf16_final_kernel<<<csg_div_up(N, 128), 128, 0, stream>>>(partial, chunks, N, out);
+  colsum_bf16_final_kernel<<<csg_div_up(N, 32), 256, 0, stream>>>(partial, chunks, N, out);
   CSG_CHECK_LAUNCH("csg_colsum_bf16 final");
   return 0;
 }
 
+CSG_API size_t csg_triple_bwd_assemble_bf16_workspace(int NT, int H, int Dp) {
+  const int Wd = 2 * H + Dp;
+  size_t fused = (size_t)csg_div_up(NT > 0 ? NT : 1, ASM_WARPS * ASM_TPW) * Wd * sizeof(float) + 16;
+  size_t plain = csg_colsum_bf16_workspace(NT, Wd);
+  return fused > plain ? fused : plain;
+}
+
+// colsum_g (may be null): [2H+Dp] fp32 column sums of g, i.e. the bias gradient of net1's second Linear.
 CSG_API int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const void* d_newp, int ld_newp,
                                          const float* dcnt, const int* s_idx, const int* o_idx, const int* valid,
                                          const int* type32, const float* conf, int NT, int H, int Dp, void* g,
-                                         float* dconf, cudaStream_t stream) {
-  if (NT == 0) return 0;
+                                         float* dconf, float* colsum_g, void* workspace, size_t workspace_bytes,
+                                         cudaStream_t stream) {
+  const int Wd = 2 * H + Dp;
+  if (NT == 0) {
+    if (colsum_g) CSG_CUDA(cudaMemsetAsync(colsum_g, 0, (size_t)Wd * sizeof(float), stream));
+    return 0;
+  }
   CSG_REQUIRE((H & 7) == 0 && (Dp & 7) == 0 && (ld_newp & 7) == 0, "bwd_assemble_bf16: H, Dp, ld must be multiples of 8");
-  triple_bwd_assemble_bf16_kernel<<<csg_div_up((long long)NT * 32, 256), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(out), dS, reinterpret_cast<const __nv_bfloat16*>(d_newp), ld_newp, dcnt,
-      s_idx, o_idx, valid, type32, conf, NT, H, Dp, reinterpret_cast<__nv_bfloat16*>(g), dconf);
-  CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16");
+  CSG_REQUIRE(Wd <= ASM_MAXI * 256, "bwd_assemble_bf16: 2H+Dp=%d exceeds %d", Wd, ASM_MAXI * 256);
+  const int blocks = csg_div_up(NT, ASM_WARPS * ASM_TPW);
+  const __nv_bfloat16* o16 = reinterpret_cast<const __nv_bfloat16*>(out);
+  const __nv_bfloat16* p16 = reinterpret_cast<const __nv_bfloat16*>(d_newp);
+  __nv_bfloat16* g16 = reinterpret_cast<__nv_bfloat16*>(g);
+  if (colsum_g) {
+    CSG_REQUIRE(workspace && workspace_bytes >= csg_triple_bwd_assemble_bf16_workspace(NT, H, Dp),
+                "bwd_assemble_bf16: workspace too small");
+    float* partial = reinterpret_cast<float*>(workspace);
+    triple_bwd_assemble_bf16_kernel<true><<<blocks, ASM_WARPS * 32, 0, stream>>>(
+        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, partial);
+    CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16");
+    colsum_bf16_final_kernel<<<csg_div_up(Wd, 32), 256, 0, stream>>>(partial, blocks, Wd, colsum_g);
+    CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16 colsum");
+  } else {
+    triple_bwd_assemble_bf16_kernel<false><<<blocks, ASM_WARPS * 32, 0, stream>>>(
+        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, nullptr);
+    CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16");
+  }
   return 0;
 }

@@ -45,7 +45,7 @@ class TripleBatch:
         self.perm_o = torch.empty(max(self.NT, 1), dtype=torch.int32, device=dev)
         L = lib()
         ws = workspace(L.csg_csr_workspace(self.NO), dev)
-        rc = L.csg_csr_build(ptr(s_idx), ptr(o_idx), ptr(tri_off), self.B, self.NT, self.NO,
+        rc = L.csg_csr_build(ptr(s_idx), ptr(o_idx), ptr(tri_off), ptr(obj_off), self.B, self.NT, self.NO,
                              ptr(self.rowptr_s), ptr(self.perm_s), ptr(self.rowptr_o), ptr(self.perm_o),
                              ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "csg_csr_build")

@@ -28,6 +28,21 @@ def cast_bf16(w, transpose=False):
     return out
 
 
+def cast_bf16_multi(jobs):
+    """jobs: list of (fp32 matrix, transpose) -> list of bf16 copies, one launch."""
+    import ctypes
+    srcs = [f32c(w) for w, _ in jobs]
+    outs = [torch.empty((w.shape[1], w.shape[0]) if tr else tuple(w.shape), dtype=BF, device=w.device)
+            for w, (_, tr) in zip(srcs, jobs)]
+    n = len(jobs)
+    VP, IA = ctypes.c_void_p * n, ctypes.c_int * n
+    rc = lib().csg_cast_bf16_multi(n, VP(*[w.data_ptr() for w in srcs]), VP(*[o.data_ptr() for o in outs]),
+                                   IA(*[w.shape[0] for w in srcs]), IA(*[w.shape[1] for w in srcs]),
+                                   IA(*[int(tr) for _, tr in jobs]), _stream())
+    _lib.check(rc, "csg_cast_bf16_multi")
+    return outs
+
+
 def as_bf16_rows(x):
     """bf16 2-D tensor with unit inner stride and 16-byte aligned rows (views are kept)."""
     if x.dtype != BF:
@@ -74,7 +89,11 @@ class _TripleConvBF16(torch.autograd.Function):
         NT, NO = batch.NT, batch.NO
         ctx.in_dtypes = (obj.dtype, pred.dtype)
         obj_b, pred_b = as_bf16_rows(obj), as_bf16_rows(pred)
-        w1b, w2b, w3b, w4b = cast_bf16(w1), cast_bf16(w2), cast_bf16(w3), cast_bf16(w4)
+        need_bwd = any(ctx.needs_input_grad)
+        casts = cast_bf16_multi([(w1, False), (w2, False), (w3, False), (w4, False)] +
+                                ([(w1, True), (w2, True), (w3, True), (w4, True)] if need_bwd else []))
+        w1b, w2b, w3b, w4b = casts[:4]
+        ctx.wt = tuple(casts[4:]) if need_bwd else None
         g = Gather(obj_b, pred_b, batch.s_idx, batch.o_idx)
         conf = triple_confidence(batch, w_trans)
         Wd = 2 * H + Dpo
@@ -103,7 +122,7 @@ class _TripleConvBF16(torch.autograd.Function):
         if d_obj_out is None:
             d_obj_out = torch.zeros((NO, Dout), dtype=torch.float32, device=dev)
         # transposed bf16 weights: dy @ W needs W^T stored [in, out] so that K (= out features) is contiguous
-        w4t, w3t, w2t, w1t = (cast_bf16(w, transpose=True) for w in (w4, w3, w2, w1))
+        w1t, w2t, w3t, w4t = ctx.wt
         # ---- net2 backward
         g4 = relu_mask_bf16(d_obj_out, new_obj)
         dw4 = ops.gemm_bf16(Dout, H, NO, g4, h2, mn_major=True)
@@ -123,13 +142,15 @@ class _TripleConvBF16(torch.autograd.Function):
                              and d_newp.data_ptr() % 16 == 0) else d_newp.to(BF).contiguous()
         g = torch.empty((NT, Wd), dtype=BF, device=dev)
         dconf = torch.empty(max(NT, 1), dtype=torch.float32, device=dev)
+        db2 = torch.empty(Wd, dtype=torch.float32, device=dev)
+        ws = workspace(L.csg_triple_bwd_assemble_bf16_workspace(NT, H, Dpo), dev)
         rc = L.csg_triple_bwd_assemble_bf16(ptr(out), ptr(dS), ptr(dnp), dnp.stride(0) if dnp is not None else 0,
                                             ptr(dcnt), ptr(batch.s_idx), ptr(batch.o_idx), ptr(batch.valid),
-                                            ptr(batch.type32), ptr(conf), NT, H, Dpo, ptr(g), ptr(dconf), _stream())
+                                            ptr(batch.type32), ptr(conf), NT, H, Dpo, ptr(g), ptr(dconf), ptr(db2),
+                                            ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "csg_triple_bwd_assemble_bf16")
         # ---- net1 backward
         dw2 = ops.gemm_bf16(Wd, H, NT, g, hidden, mn_major=True)
-        db2 = colsum_bf16(g)
         dhid = ops.gemm_bf16(NT, H, Wd, g, w2t, mask_aux=hidden)
         gat = Gather(obj, pred, batch.s_idx, batch.o_idx)
         dw1 = ops.gemm_bf16(H, gat.width, NT, dhid, None, mn_major=True, gather=gat, gather_mode=2)

@@ -66,7 +66,7 @@ int csg_triple_prep_edges(const long long* edges, const long long* pred_ids, con
                           int* valid, csg_stream_t stream);
 /* stable CSR orderings by subject and by object (replace scatter_add, graph.py:98-103) */
 size_t csg_csr_workspace(int NO);
-int csg_csr_build(const int* keys_s, const int* keys_o, const int* tri_off, int B, int NT, int NO,
+int csg_csr_build(const int* keys_s, const int* keys_o, const int* tri_off, const int* obj_off, int B, int NT, int NO,
                   int* rowptr_s, int* perm_s, int* rowptr_o, int* perm_o,
                   void* workspace, size_t workspace_bytes, csg_stream_t stream);
 /* graph.py:69-74 */
@@ -120,6 +120,9 @@ int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
 /* bf16-activation twins of the pooling / assembly kernels (fp32 accumulation) + weight cast */
 int csg_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, int transpose,
                   csg_stream_t stream);
+/* n <= 16 contiguous fp32 matrices -> contiguous bf16 copies (transposed when transpose[i]); HOST arrays */
+int csg_cast_bf16_multi(int n, const void* const* src, void* const* dst, const int* rows, const int* cols,
+                        const int* transpose, csg_stream_t stream);
 int csg_segpool_bf16(const void* X, int ldx, int col_s, int col_o, int W,
                      const int* rowptr_s, const int* perm_s, const int* rowptr_o, const int* perm_o,
                      const int* valid, const float* conf, int NO, float* out_f32, void* out_bf16, int ldo,
@@ -128,10 +131,13 @@ int csg_relu_mask_bf16(const float* dy, const void* y, void* out, long long n, c
 size_t csg_colsum_bf16_workspace(int M, int N);
 int csg_colsum_bf16(const void* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
                     csg_stream_t stream);
+size_t csg_triple_bwd_assemble_bf16_workspace(int NT, int H, int Dp);
+/* colsum_g (may be NULL): [2H+Dp] fp32 column sums of g = the bias gradient of net1's second Linear, fused */
 int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const void* d_newp, int ld_newp,
                                  const float* dcnt, const int* s_idx, const int* o_idx, const int* valid,
                                  const int* type32, const float* conf, int NT, int H, int Dp, void* g,
-                                 float* dconf, csg_stream_t stream);
+                                 float* dconf, float* colsum_g, void* workspace, size_t workspace_bytes,
+                                 csg_stream_t stream);
 
 /* ---- canonicalization: sg2im/data/base_dataset.py:89-139, scripts/graphs_utils.py:15-155 ------ */
 /* pass 1: per-graph output sizes (cnt0 = type-0 edges, cnt1 = transitive edges; cnt0 = -1 flags a
