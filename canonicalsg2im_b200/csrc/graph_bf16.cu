@@ -243,13 +243,15 @@ int colsum_bf16_chunks(int M, int N) {
   return want < 1 ? 1 : want;
 }
 
-// bf16 twin of triple_bwd_assemble_kernel (graph.cu): one warp per triple at a time, 8 columns per lane per step,
-// ASM_TPW consecutive triples per warp.  With CS (column sums requested: the bias gradient of net1's second
-// Linear is colsum(g)) every lane also accumulates its columns over the warp's triples; the 8 warps of a block
-// are combined through shared memory and one partial row per block is written for the ordered final pass.
-constexpr int ASM_WARPS = 8, ASM_TPW = 8, ASM_MAXI = 5;      // ASM_MAXI * 256 >= Wd
+// bf16 twin of triple_bwd_assemble_kernel (graph.cu): one warp per triple at a time, 8 columns per lane per step;
+// the warps of the (persistent) grid take the triples round-robin.  With CS (column sums requested: the bias
+// gradient of net1's second Linear is colsum(g)) every lane also accumulates its 8 x ASM_MAXI columns in
+// registers over the warp's triples; the warps of a block are combined in warp order through shared memory and
+// one partial row per block is written for the ordered final pass (deterministic for a given grid).
+constexpr int ASM_WARPS = 8, ASM_MAXI = 5;      // ASM_MAXI * 256 >= Wd
+constexpr int ASM_CTAS_PER_SM = 3;
 template <bool CS>
-__global__ void __launch_bounds__(ASM_WARPS * 32)
+__global__ void __launch_bounds__(ASM_WARPS * 32, ASM_CTAS_PER_SM)
 triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const float* __restrict__ dS,
                                 const __nv_bfloat16* __restrict__ d_newp, int ld_newp,
                                 const float* __restrict__ dcnt, const int* __restrict__ s_idx,
@@ -257,24 +259,26 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
                                 const int* __restrict__ type32, const float* __restrict__ conf,
                                 int NT, int H, int Dp, __nv_bfloat16* __restrict__ g,
                                 float* __restrict__ dconf, float* __restrict__ cs_partial) {
-  __shared__ __align__(16) float cs_red[CS ? ASM_WARPS * ASM_MAXI * 256 : 4];   // per-warp column accumulators
+  __shared__ __align__(16) float cs_red[CS ? (ASM_WARPS / 2) * ASM_MAXI * 256 : 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Wd = 2 * H + Dp;
-  float* mycs = cs_red + warp * ASM_MAXI * 256;      // lane owns columns lane*8 + u*256 .. +7: no conflicts
-  if (CS) {
+  float cs[ASM_MAXI][8];
 #pragma unroll
-    for (int u = 0; u < ASM_MAXI; ++u) {
-      st_f4(mycs + u * 256 + lane * 8, make_float4(0.f, 0.f, 0.f, 0.f));
-      st_f4(mycs + u * 256 + lane * 8 + 4, make_float4(0.f, 0.f, 0.f, 0.f));
-    }
-  }
-  const int tbeg = (blockIdx.x * ASM_WARPS + warp) * ASM_TPW;
-  for (int k = 0; k < ASM_TPW; ++k) {
-    const int t = tbeg + k;
-    if (t >= NT) break;
-    const int s = s_idx[t], o = o_idx[t];
-    const bool v = valid[t] != 0;
-    const float cf = conf[t];
+  for (int u = 0; u < ASM_MAXI; ++u)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[u][i] = 0.f;
+  const int stride = gridDim.x * ASM_WARPS;
+  int t = blockIdx.x * ASM_WARPS + warp;
+  // scalars of the next triple are fetched one iteration ahead: the row addresses depend on them
+  int s = 0, o = 0, vi = 0, ty = 0;
+  float cf = 0.f;
+  if (t < NT) { s = s_idx[t]; o = o_idx[t]; vi = valid[t]; ty = type32[t]; cf = conf[t]; }
+  for (; t < NT; t += stride) {
+    const int tn = t + stride;
+    int s2 = 0, o2 = 0, vi2 = 0, ty2 = 0;
+    float cf2 = 0.f;
+    if (tn < NT) { s2 = s_idx[tn]; o2 = o_idx[tn]; vi2 = valid[tn]; ty2 = type32[tn]; cf2 = conf[tn]; }
+    const bool v = vi != 0;
     const __nv_bfloat16* orow = out + (size_t)t * Wd;
     __nv_bfloat16* grow = g + (size_t)t * Wd;
     float dot = 0.f;
@@ -299,7 +303,7 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
           for (int i = 0; i < 8; ++i) raw[i] = 0.f;
         }
         float y[8], r[8];
-        unpack8(*reinterpret_cast<const uint4*>(orow + j), y);
+        unpack8(__ldcs(reinterpret_cast<const uint4*>(orow + j)), y);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           dot += raw[i] * y[i];
@@ -310,31 +314,61 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
         if (CS) {
           float rb[8];
           unpack8(packed, rb);             // sum what the GEMMs will read: the bf16-rounded values
-          float* c8 = mycs + u * 256 + lane * 8;
-          float4 a = ld_f4(c8), b = ld_f4(c8 + 4);
-          a.x += rb[0]; a.y += rb[1]; a.z += rb[2]; a.w += rb[3];
-          b.x += rb[4]; b.y += rb[5]; b.z += rb[6]; b.w += rb[7];
-          st_f4(c8, a); st_f4(c8 + 4, b);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cs[u][i] += rb[i];
         }
       }
     }
     dot = warp_sum(dot);
     if (lane == 0) {
       float dc = 0.f;
-      if (type32[t] == 1 && cf > 0.f) dc = dot / cf;
+      if (ty == 1 && cf > 0.f) dc = dot / cf;
       if (v) dc += dcnt[s] + dcnt[o];
       dconf[t] = dc;
     }
+    s = s2; o = o2; vi = vi2; ty = ty2; cf = cf2;
   }
   if (CS) {
-    __syncthreads();
-    for (int j = threadIdx.x; j < Wd; j += blockDim.x) {
-      float acc = 0.f;
+    // ordered tree over the 8 warps: (w, w+4), then (w, w+2), then (w, w+1); lane owns columns lane*8 + u*256 + i
+    for (int half = ASM_WARPS / 2; half >= 1; half >>= 1) {
+      if (warp >= half && warp < 2 * half) {
+        float* dst = cs_red + (warp - half) * ASM_MAXI * 256;
 #pragma unroll
-      for (int w = 0; w < ASM_WARPS; ++w) acc += cs_red[w * ASM_MAXI * 256 + j];
-      cs_partial[(size_t)blockIdx.x * Wd + j] = acc;
+        for (int u = 0; u < ASM_MAXI; ++u) {
+          st_f4(dst + u * 256 + lane * 8, make_float4(cs[u][0], cs[u][1], cs[u][2], cs[u][3]));
+          st_f4(dst + u * 256 + lane * 8 + 4, make_float4(cs[u][4], cs[u][5], cs[u][6], cs[u][7]));
+        }
+      }
+      __syncthreads();
+      if (warp < half) {
+        const float* src = cs_red + warp * ASM_MAXI * 256;
+#pragma unroll
+        for (int u = 0; u < ASM_MAXI; ++u) {
+          float4 a = ld_f4(src + u * 256 + lane * 8), b = ld_f4(src + u * 256 + lane * 8 + 4);
+          cs[u][0] += a.x; cs[u][1] += a.y; cs[u][2] += a.z; cs[u][3] += a.w;
+          cs[u][4] += b.x; cs[u][5] += b.y; cs[u][6] += b.z; cs[u][7] += b.w;
+        }
+      }
+      __syncthreads();
+    }
+    if (warp == 0) {
+#pragma unroll
+      for (int u = 0; u < ASM_MAXI; ++u) {
+        const int j = lane * 8 + u * 256;
+        if (j < Wd) {
+          float* dst = cs_partial + (size_t)blockIdx.x * Wd + j;
+          st_f4(dst, make_float4(cs[u][0], cs[u][1], cs[u][2], cs[u][3]));
+          st_f4(dst + 4, make_float4(cs[u][4], cs[u][5], cs[u][6], cs[u][7]));
+        }
+      }
     }
   }
+}
+
+int asm_blocks(int NT) {
+  int want = csg_div_up(NT > 0 ? NT : 1, ASM_WARPS);
+  int cap = csg_num_sms() * ASM_CTAS_PER_SM;
+  return want < cap ? want : cap;
 }
 
 }  // namespace
@@ -429,7 +463,7 @@ CSG_API int csg_colsum_bf16(const void* X, int M, int N, int ld, float* out, voi
 
 CSG_API size_t csg_triple_bwd_assemble_bf16_workspace(int NT, int H, int Dp) {
   const int Wd = 2 * H + Dp;
-  size_t fused = (size_t)csg_div_up(NT > 0 ? NT : 1, ASM_WARPS * ASM_TPW) * Wd * sizeof(float) + 16;
+  size_t fused = (size_t)asm_blocks(NT) * Wd * sizeof(float) + 16;
   size_t plain = csg_colsum_bf16_workspace(NT, Wd);
   return fused > plain ? fused : plain;
 }
@@ -447,7 +481,7 @@ CSG_API int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const
   }
   CSG_REQUIRE((H & 7) == 0 && (Dp & 7) == 0 && (ld_newp & 7) == 0, "bwd_assemble_bf16: H, Dp, ld must be multiples of 8");
   CSG_REQUIRE(Wd <= ASM_MAXI * 256, "bwd_assemble_bf16: 2H+Dp=%d exceeds %d", Wd, ASM_MAXI * 256);
-  const int blocks = csg_div_up(NT, ASM_WARPS * ASM_TPW);
+  const int blocks = asm_blocks(NT);
   const __nv_bfloat16* o16 = reinterpret_cast<const __nv_bfloat16*>(out);
   const __nv_bfloat16* p16 = reinterpret_cast<const __nv_bfloat16*>(d_newp);
   __nv_bfloat16* g16 = reinterpret_cast<__nv_bfloat16*>(g);

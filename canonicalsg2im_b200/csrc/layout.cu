@@ -1,12 +1,24 @@
 // Single-pass layout compositor (boxes_to_layout / masks_to_layout) for sm_100a.
 //
-// Replaces sg2im/layout.py:12-188 of the reference: instead of materialising the
-// per-object [O, D, H, W] samples (grid_sample) and scatter-adding them, each CTA
-// owns one 8x64 pixel tile of one image's [D, H, W] canvas, builds the ordered
-// list of objects whose support intersects the tile, evaluates the separable
-// bilinear weights S_o(y, x) once per pixel (they do not depend on the channel),
-// accumulates sum_o vec[o, d] * S_o(y, x) in registers and writes every canvas
-// element exactly once with 128-bit streaming stores.
+// Replaces sg2im/layout.py:12-188 of the reference: instead of materialising the per-object
+// [O, D, H, W] samples (grid_sample) and scatter-adding them,
+//
+//   forward   a CTA (4 warps) owns a 512-pixel tile (8 rows x 64 or 4 rows x 128) of one image's [D, H, W]
+//             canvas and builds the ordered list of objects whose support intersects the tile; each warp owns a
+//             128-pixel strip, compacts the list to the objects that touch ITS strip, every lane accumulates
+//             4 pixels x 16 channels in registers (64 FMAs per weight quad + 4 broadcast vector loads from shared
+//             memory) and writes each canvas element exactly once with 128-bit streaming stores;
+//   backward  (d/dvecs) a CTA owns (image, 32 channels, a range of 256-pixel bands): a producer warp streams the
+//             incoming gradient band by band into a shared-memory ring with cp.async.bulk (1 KB per channel, fully
+//             coalesced, completion on an mbarrier), four consumer warps -- thread = (channel, 64-pixel sub-band)
+//             -- walk the objects that touch their sub-band, so the pixel weights are warp-uniform broadcasts and
+//             zero weights are skipped without divergence; per-(object, channel) sums live in shared memory and
+//             the per-range partials are combined in a fixed order by a second kernel.
+//   generic   the previous tile/butterfly backward is kept for shapes the ring cannot serve (W % 64, H*W % 256,
+//             D % 32 or unaligned gradients).
+//
+// The pixel weight of object o is separable for boxes_to_layout, S_o(y, x) = ay_o(y) * ax_o(x), and a 4-tap
+// bilinear read of the mask for masks_to_layout.
 //
 // Coordinate chain (kept operation-for-operation so that ramp pixels of small
 // boxes agree with the reference, SURVEY.md §7 "layout coordinate fidelity"):
@@ -20,11 +32,6 @@
 
 namespace {
 
-constexpr int TILE_W = 64;
-constexpr int TILE_H = 8;
-constexpr int TILE_PX = TILE_W * TILE_H;
-constexpr int NTHREADS = 256;
-
 struct LayoutParams {
   const float* vecs;     // [NO, D]
   const float* boxes;    // [NO, 4] xywh
@@ -33,21 +40,25 @@ struct LayoutParams {
   const float* lin_x;    // [W]
   const float* lin_y;    // [H]
   int N, D, H, W, M, align;
+  int TW, TH;            // tile width / height (forward: 64 x 8 or 128 x 4; generic backward: 64 x 8)
   int tiles_x, tiles_y;
   int lcap;              // object-list capacity held in shared memory
 };
+
+// unnormalised sample coordinate of ATen's grid_sampler for one axis
+__device__ __forceinline__ float axis_coord(float lin, float start, float extent, int size, int align) {
+  float u = __fdiv_rn(__fsub_rn(lin, start), extent);
+  float g = __fsub_rn(__fmul_rn(u, 2.f), 1.f);
+  if (align) return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), (float)(size - 1));
+  return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)size), 1.f), 0.5f);
+}
 
 struct Tap {
   int i0;        // index of the first tap (second is i0 + 1); -2 when both are out of range
   float w0, w1;  // bilinear weights of the two taps (NaN for degenerate boxes, as in ATen)
 };
 
-__device__ __forceinline__ Tap axis_tap(float lin, float start, float extent, int size, int align) {
-  float u = __fdiv_rn(__fsub_rn(lin, start), extent);
-  float g = __fsub_rn(__fmul_rn(u, 2.f), 1.f);
-  float ix;
-  if (align) ix = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), (float)(size - 1));
-  else       ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)size), 1.f), 0.5f);
+__device__ __forceinline__ Tap coord_tap(float ix, int size) {
   float f = floorf(ix);
   float t = __fsub_rn(ix, f);
   Tap r;
@@ -55,6 +66,28 @@ __device__ __forceinline__ Tap axis_tap(float lin, float start, float extent, in
   r.w1 = t;
   r.i0 = (f >= -2.f && f <= (float)size) ? (int)f : -2;
   return r;
+}
+
+__device__ __forceinline__ Tap axis_tap(float lin, float start, float extent, int size, int align) {
+  return coord_tap(axis_coord(lin, start, extent, size, align), size);
+}
+
+// weight of a constant-1 source sampled with zero padding (boxes_to_layout): sum of the in-range tap weights
+__device__ __forceinline__ float tap_ones(const Tap& t, int size) {
+  const bool v0 = t.i0 >= 0 && t.i0 < size, v1 = t.i0 >= -1 && t.i0 < size - 1;
+  return (v0 ? 1.f : 0.f) * t.w0 + (v1 ? 1.f : 0.f) * t.w1;
+}
+
+// 4-tap bilinear read of an S x S mask with zero padding, in ATen's nw, ne, sw, se order
+__device__ __forceinline__ float mask_weight(const float* __restrict__ m, int S, const Tap& tx, const Tap& ty) {
+  const int ix = tx.i0, iy = ty.i0;
+  const bool vx0 = ix >= 0 && ix < S, vx1 = ix >= -1 && ix < S - 1;
+  const bool vy0 = iy >= 0 && iy < S, vy1 = iy >= -1 && iy < S - 1;
+  float m00 = (vy0 && vx0) ? __ldg(m + iy * S + ix) : 0.f;
+  float m01 = (vy0 && vx1) ? __ldg(m + iy * S + ix + 1) : 0.f;
+  float m10 = (vy1 && vx0) ? __ldg(m + (iy + 1) * S + ix) : 0.f;
+  float m11 = (vy1 && vx1) ? __ldg(m + (iy + 1) * S + ix + 1) : 0.f;
+  return m00 * (tx.w0 * ty.w0) + m01 * (tx.w1 * ty.w0) + m10 * (tx.w0 * ty.w1) + m11 * (tx.w1 * ty.w1);
 }
 
 // Conservative test: can an object with (start, extent) touch linspace range [lo, hi]?
@@ -71,6 +104,551 @@ __device__ __forceinline__ bool axis_may_touch(float start, float extent, float 
   return !(mx + eps < lo || mn - eps > hi);
 }
 
+__device__ __forceinline__ bool box_poison(float4 b) {
+  // zero / NaN extents and non-finite origins give NaN weights that poison every pixel of the image
+  // (0 * NaN in grid_sample), whatever the other axis says: such objects are never culled or skipped
+  return !(b.z > 0.f || b.z < 0.f) || !(b.w > 0.f || b.w < 0.f) || !(fabsf(b.x) < INFINITY) || !(fabsf(b.y) < INFINITY);
+}
+
+// Warp 0 appends, in ascending object order, the objects of [*cursor, oend) that may touch the pixel rectangle
+// [x0, x0+TW) x [y0, y0+TH), until the list holds lcap entries.  Returns through shared memory.
+__device__ void build_list(const LayoutParams& p, int* list, int oend, int x0, int y0, int* s_cursor, int* s_count) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const int S = p.masks ? p.M : 8;
+    const float xlo = p.lin_x[x0], xhi = p.lin_x[min(x0 + p.TW, p.W) - 1];
+    const float ylo = p.lin_y[y0], yhi = p.lin_y[min(y0 + p.TH, p.H) - 1];
+    int cursor = *s_cursor, count = 0;
+    while (cursor < oend && count < p.lcap) {
+      int o = cursor + lane;
+      bool keep = false;
+      if (o < oend) {
+        float4 b = ld_f4(p.boxes + 4 * (size_t)o);
+        keep = box_poison(b) ||
+               (axis_may_touch(b.x, b.z, xlo, xhi, S, p.align) && axis_may_touch(b.y, b.w, ylo, yhi, S, p.align));
+      }
+      unsigned bal = __ballot_sync(0xffffffffu, keep);
+      int pos = count + __popc(bal & ((1u << lane) - 1u));
+      int room = p.lcap - count;
+      int total = __popc(bal);
+      if (total <= room) {
+        if (keep) list[pos] = o;
+        count += total;
+        cursor += 32;
+      } else {
+        // take only the first `room` kept objects; resume after the last one taken
+        if (keep && pos < p.lcap) list[pos] = o;
+        unsigned taken_last = __ballot_sync(0xffffffffu, keep && pos == p.lcap - 1);
+        int last_lane = __ffs(taken_last) - 1;
+        cursor += last_lane + 1;
+        count = p.lcap;
+      }
+    }
+    if (lane == 0) { *s_cursor = min(cursor, oend); *s_count = count; }
+  }
+}
+
+// ========================================================================================
+// forward: out[n, d, y, x] = sum_o vecs[o, d] * S_o(y, x)
+// ========================================================================================
+namespace fw {
+
+constexpr int NTHREADS = 128;          // 4 warps x 128-pixel strips
+constexpr int STRIP_PX = 128;
+constexpr int TILE_PX = 4 * STRIP_PX;  // 512 pixels per tile: 8 rows x 64 or 4 rows x 128
+
+struct Smem {
+  float* wS;           // [lcap][TILE_PX]   S_o(y, x) for the tile (masks_to_layout only)
+  float* vS;           // [lcap][D]         vecs of the listed objects
+  float* ax;           // [lcap][TW]        boxes: column factor; masks: column sample coordinate
+  float* ay;           // [lcap][TH]        boxes: row factor;    masks: row sample coordinate
+  int* list;           // [lcap]            object ids (global) in ascending order
+  int* flags;          // [lcap]            1 = poison (never skipped)
+  unsigned* rowmask;   // [lcap]            rows of the tile where the weight can be non-zero
+  int* nact;           // [4]
+  unsigned char* act;  // [4][lcap]         per-warp compacted list
+};
+
+__host__ __device__ inline size_t smem_floats(int lcap, int D, int TW, int TH, bool mask) {
+  return (size_t)lcap * ((mask ? TILE_PX : 0) + D + TW + TH + 3) + 4 + (size_t)lcap;   // act: 4*lcap bytes = lcap words
+}
+
+__device__ __forceinline__ Smem carve(float* base, int lcap, int D, int TW, int TH, bool mask) {
+  Smem s;
+  s.wS = base;                                  // 16B aligned: first
+  s.vS = s.wS + (mask ? (size_t)lcap * TILE_PX : 0);
+  s.ax = s.vS + (size_t)lcap * D;
+  s.ay = s.ax + (size_t)lcap * TW;
+  s.list = reinterpret_cast<int*>(s.ay + (size_t)lcap * TH);
+  s.flags = s.list + lcap;
+  s.rowmask = reinterpret_cast<unsigned*>(s.flags + lcap);
+  s.nact = reinterpret_cast<int*>(s.rowmask + lcap);
+  s.act = reinterpret_cast<unsigned char*>(s.nact + 4);
+  return s;
+}
+
+// Per-object separable factors for the tile (and, with masks, the per-pixel weights), plus the mask of rows
+// where the weight can be non-zero (anything not exactly 0, NaN included).
+template <bool HAS_MASK>
+__device__ void build_weights(const LayoutParams& p, const Smem& s, int L, int x0, int y0) {
+  const int tid = threadIdx.x;
+  const int S = HAS_MASK ? p.M : 8;
+  const int TW = p.TW, TH = p.TH;
+  for (int c = tid; c < L; c += NTHREADS) {
+    s.flags[c] = box_poison(ld_f4(p.boxes + 4 * (size_t)s.list[c])) ? 1 : 0;
+    s.rowmask[c] = 0u;
+  }
+  __syncthreads();
+  for (int i = tid; i < L * (TW + TH); i += NTHREADS) {
+    int c = i / (TW + TH), r = i % (TW + TH);
+    float4 b = ld_f4(p.boxes + 4 * (size_t)s.list[c]);
+    const bool isx = r < TW;
+    if (!isx) r -= TW;
+    const int pos = (isx ? x0 : y0) + r;
+    const int lim = isx ? p.W : p.H;
+    const float coord = axis_coord((isx ? p.lin_x : p.lin_y)[min(pos, lim - 1)], isx ? b.x : b.y, isx ? b.z : b.w, S, p.align);
+    if (HAS_MASK) {
+      (isx ? s.ax : s.ay)[c * (isx ? TW : TH) + r] = coord;
+    } else {
+      float a = tap_ones(coord_tap(coord, S), S);
+      if (pos >= lim) a = 0.f;
+      if (isx) {
+        s.ax[c * TW + r] = a;
+      } else {
+        s.ay[c * TH + r] = a;
+        if (!(a == 0.f)) atomicOr(&s.rowmask[c], 1u << r);
+      }
+    }
+  }
+  if (HAS_MASK) {
+    __syncthreads();
+    for (int i = tid; i < L * TILE_PX; i += NTHREADS) {
+      const int c = i / TILE_PX, px = i % TILE_PX;
+      const int row = px / TW, col = px % TW;
+      float w = 0.f;
+      if (x0 + col < p.W && y0 + row < p.H)
+        w = mask_weight(p.masks + (size_t)s.list[c] * S * S, S, coord_tap(s.ax[c * TW + col], S),
+                        coord_tap(s.ay[c * TH + row], S));
+      s.wS[i] = w;
+      if (!(w == 0.f)) atomicOr(&s.rowmask[c], 1u << row);
+    }
+  }
+  __syncthreads();
+}
+
+template <bool HAS_MASK, int CH>
+__global__ void __launch_bounds__(NTHREADS) layout_fwd_kernel(LayoutParams p, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem_raw[];
+  __shared__ int s_cursor, s_count;
+  const Smem s = carve(smem_raw, p.lcap, p.D, p.TW, p.TH, HAS_MASK);
+  const int n = blockIdx.y;
+  const int TW = p.TW, TH = p.TH;
+  const int x0 = (blockIdx.x % p.tiles_x) * TW, y0 = (blockIdx.x / p.tiles_x) * TH;
+  const int oend = p.obj_off[n + 1];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) s_cursor = p.obj_off[n];
+  __syncthreads();
+
+  // this lane's 4 pixels: strip `warp` = rows [warp*SR, warp*SR + SR) of the tile, SR = 128 / TW
+  const int SR = STRIP_PX / TW;
+  const int spx = lane * 4;                         // pixel offset inside the strip
+  const int row = warp * SR + spx / TW, col = spx % TW;
+  const int y = y0 + row, x = x0 + col;
+  const bool vec4 = (p.W & 3) == 0;
+  const bool active = y < p.H && x < p.W;
+  const unsigned my_rows = ((1u << SR) - 1u) << (warp * SR);
+  unsigned char* myact = s.act + warp * p.lcap;
+  bool first = true;
+  while (true) {
+    build_list(p, s.list, oend, x0, y0, &s_cursor, &s_count);
+    __syncthreads();
+    const int L = s_count;
+    const bool more = s_cursor < oend;   // read before the next build_list may advance it
+    build_weights<HAS_MASK>(p, s, L, x0, y0);
+    for (int i = tid; i < L * (p.D >> 2); i += NTHREADS) {
+      int c = i / (p.D >> 2), d4 = i % (p.D >> 2);
+      st_f4(s.vS + c * p.D + d4 * 4, ld_f4(p.vecs + (size_t)s.list[c] * p.D + d4 * 4));
+    }
+    // per-warp compaction: objects that touch this warp's strip (poisoned objects always do)
+    int na = 0;
+    for (int c0 = 0; c0 < L; c0 += 32) {
+      const int c = c0 + lane;
+      const bool keep = c < L && ((s.rowmask[c] & my_rows) != 0u || (s.flags[c] & 1));
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) myact[na + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)c;
+      na += __popc(bal);
+    }
+    __syncthreads();
+    if (active) {
+      for (int d0 = 0; d0 < p.D; d0 += CH) {
+        float acc[CH][4];
+#pragma unroll
+        for (int j = 0; j < CH; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[j][k] = 0.f;
+        for (int a = 0; a < na; ++a) {
+          const int c = myact[a];
+          float4 w;
+          if (HAS_MASK) {
+            w = ld_f4(s.wS + c * TILE_PX + warp * STRIP_PX + spx);
+          } else {
+            const float wy = s.ay[c * TH + row];
+            w = ld_f4(s.ax + c * TW + col);
+            w.x *= wy; w.y *= wy; w.z *= wy; w.w *= wy;
+          }
+          const float* vp = s.vS + c * p.D + d0;
+#pragma unroll
+          for (int j4 = 0; j4 < CH; j4 += 4) {
+            const float4 v = ld_f4(vp + j4);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              acc[j4 + j][0] = fmaf(vv[j], w.x, acc[j4 + j][0]);
+              acc[j4 + j][1] = fmaf(vv[j], w.y, acc[j4 + j][1]);
+              acc[j4 + j][2] = fmaf(vv[j], w.z, acc[j4 + j][2]);
+              acc[j4 + j][3] = fmaf(vv[j], w.w, acc[j4 + j][3]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          float* dst = out + (((size_t)n * p.D + d0 + j) * p.H + y) * p.W + x;
+          if (vec4) {
+            float4 r = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            if (!first) { float4 o = ld_f4(dst); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+            st_f4_stream(dst, r);
+          } else {
+            for (int k = 0; k < 4 && x + k < p.W; ++k) dst[k] = first ? acc[j][k] : dst[k] + acc[j][k];
+          }
+        }
+      }
+    }
+    first = false;
+    __syncthreads();
+    if (!more) break;
+  }
+}
+
+}  // namespace fw
+
+// ========================================================================================
+// backward wrt vecs, ring version: dvecs[o, d] = sum_{y, x} dout[n, d, y, x] * S_o(y, x)
+// ========================================================================================
+namespace bw {
+
+constexpr int DC = 32;                 // channels per CTA
+constexpr int BAND = 256;              // pixels per band (1 KB per channel)
+constexpr int SUBS = 4;                // consumer warps = 64-pixel sub-bands
+constexpr int SUB_PX = BAND / SUBS;
+constexpr int CSTRIDE = BAND + 4;      // floats between channels of a stage: lanes (= channels) hit distinct banks
+constexpr int STAGES = 2;
+constexpr int STAGE_FLOATS = DC * CSTRIDE;
+constexpr int NCONS = SUBS * 32;
+constexpr int NTHREADS = NCONS + 32;   // + producer warp
+
+struct Params {
+  LayoutParams p;
+  const float* dout;
+  float* partial;        // [splits][NO][D]
+  const float* axg;      // [NO][W]  boxes: column factor; masks: column sample coordinate   (layout_tables_kernel)
+  const float* ayg;      // [NO][H]
+  const int* rng;        // [NO][4]  xmin, xmax, ymin, ymax: outside, the weight is exactly zero (max < min: nowhere)
+  int NO, splits, bands_per_item, cblocks;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("csg layout_bwd: mbarrier timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCONS) : "memory"); }
+
+struct Smem {
+  float* stage;     // [STAGES][DC][CSTRIDE]
+  float* acc;       // [lcap][SUBS][DC]
+  float* ax;        // [lcap][W]   boxes: column factor; masks: column sample coordinate
+  float* ay;        // [lcap][H]   boxes: row factor;    masks: row sample coordinate
+  float* wS;        // [lcap][BAND] masks only: weights of the current band
+  int* rng;         // [lcap][4]   xmin, xmax, ymin, ymax
+  unsigned char* act;  // [SUBS][lcap]
+  unsigned long long* bars;   // full[STAGES], empty[STAGES], tables
+};
+
+__host__ __device__ inline size_t smem_bytes(int lcap, int H, int W, bool mask) {
+  size_t f = (size_t)STAGES * STAGE_FLOATS + (size_t)lcap * SUBS * DC + (size_t)lcap * (W + H) +
+             (mask ? (size_t)lcap * BAND : 0) + (size_t)lcap * 4 + (size_t)lcap /* act */;
+  return f * 4 + (2 * STAGES + 1) * 8 + 16;
+}
+
+__device__ __forceinline__ Smem carve(float* base, int lcap, int H, int W, bool mask) {
+  Smem s;
+  s.stage = base;
+  s.acc = s.stage + (size_t)STAGES * STAGE_FLOATS;
+  s.ax = s.acc + (size_t)lcap * SUBS * DC;
+  s.ay = s.ax + (size_t)lcap * W;
+  s.wS = s.ay + (size_t)lcap * H;
+  s.rng = reinterpret_cast<int*>(s.wS + (mask ? (size_t)lcap * BAND : 0));
+  s.act = reinterpret_cast<unsigned char*>(s.rng + 4 * lcap);
+  uintptr_t b = reinterpret_cast<uintptr_t>(s.act + (size_t)SUBS * lcap);
+  s.bars = reinterpret_cast<unsigned long long*>((b + 7) & ~(uintptr_t)7);
+  return s;
+}
+
+// One block per object: ax[o][W], ay[o][H] (boxes: separable weight factors; masks: sample coordinates) and the
+// column / row intervals outside of which the weight of the object is exactly zero.
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(128) layout_tables_kernel(LayoutParams p, int NO, float* __restrict__ axg,
+                                                            float* __restrict__ ayg, int* __restrict__ rng) {
+  __shared__ int r[4];
+  const int o = blockIdx.x;
+  const int S = HAS_MASK ? p.M : 8;
+  const float4 b = ld_f4(p.boxes + 4 * (size_t)o);
+  const bool poison = box_poison(b);
+  if (threadIdx.x == 0) {
+    r[0] = poison ? 0 : p.W;  r[1] = poison ? p.W - 1 : -1;
+    r[2] = poison ? 0 : p.H;  r[3] = poison ? p.H - 1 : -1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.W + p.H; i += blockDim.x) {
+    const bool isx = i < p.W;
+    const int k = isx ? i : i - p.W;
+    const float coord = axis_coord((isx ? p.lin_x : p.lin_y)[k], isx ? b.x : b.y, isx ? b.z : b.w, S, p.align);
+    float val;
+    bool touched;
+    if (HAS_MASK) {
+      val = coord;
+      touched = !(coord <= -1.f) && !(coord >= (float)S);          // some tap in range (NaN counts as touched)
+    } else {
+      val = tap_ones(coord_tap(coord, S), S);
+      touched = !(val == 0.f);
+    }
+    (isx ? axg + (size_t)o * p.W : ayg + (size_t)o * p.H)[k] = val;
+    if (touched) {
+      atomicMin(&r[isx ? 0 : 2], k);
+      atomicMax(&r[isx ? 1 : 3], k);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) rng[4 * (size_t)o + threadIdx.x] = r[threadIdx.x];
+}
+
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(NTHREADS) layout_bwd_ring_kernel(Params q) {
+  extern __shared__ __align__(16) float smem_raw[];
+  const LayoutParams& p = q.p;
+  const Smem s = carve(smem_raw, p.lcap, p.H, p.W, HAS_MASK);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x % q.splits;
+  const int cblk = (blockIdx.x / q.splits) % q.cblocks;
+  const int n = blockIdx.x / (q.splits * q.cblocks);
+  const int obeg = p.obj_off[n], oend = p.obj_off[n + 1];
+  const int On = oend - obeg;
+  const int b0 = split * q.bands_per_item, nb = q.bands_per_item;
+  const int nchunks = (On + p.lcap - 1) / p.lcap;
+  const int S = HAS_MASK ? p.M : 8;
+  const size_t plane = (size_t)p.H * p.W;
+  float* my_partial = q.partial + ((size_t)split * q.NO + obeg) * p.D + cblk * DC;   // [On][D] slice, DC wide
+
+  const uint32_t full0 = smem_u32(s.bars), empty0 = smem_u32(s.bars + STAGES), tab = smem_u32(s.bars + 2 * STAGES);
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, NCONS);
+    }
+    mbar_init(tab, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == SUBS) {
+    // ---------------- producer: one 1 KB bulk copy per channel per band
+    const float* src0 = q.dout + ((size_t)n * p.D + cblk * DC + lane) * plane + (size_t)b0 * BAND;
+    int it = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      for (int b = 0; b < nb; ++b, ++it) {
+        const int st = it % STAGES;
+        if (it >= STAGES) mbar_wait(empty0 + 8 * st, ((it / STAGES) - 1) & 1);
+        if (lane == 0) mbar_arrive_expect_tx(full0 + 8 * st, DC * BAND * 4);
+        __syncwarp();
+        bulk_load(smem_u32(s.stage + (size_t)st * STAGE_FLOATS + lane * CSTRIDE), src0 + (size_t)b * BAND, BAND * 4,
+                  full0 + 8 * st);
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers: thread = (channel lane, sub-band warp)
+  const int sub = warp;
+  unsigned char* myact = s.act + sub * p.lcap;
+  int it = 0;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int cbeg = obeg + ch * p.lcap;
+    const int L = min(p.lcap, oend - cbeg);
+    // per-object tables of this chunk (separable factors / sample coordinates and the non-zero intervals),
+    // precomputed by layout_tables_kernel: three bulk copies
+    if (tid == 0) {
+      const uint32_t bx = L * p.W * 4, by = L * p.H * 4, br = L * 16;
+      mbar_arrive_expect_tx(tab, bx + by + br);
+      bulk_load(smem_u32(s.ax), q.axg + (size_t)cbeg * p.W, bx, tab);
+      bulk_load(smem_u32(s.ay), q.ayg + (size_t)cbeg * p.H, by, tab);
+      bulk_load(smem_u32(s.rng), q.rng + (size_t)cbeg * 4, br, tab);
+    }
+    for (int i = tid; i < L * SUBS * DC; i += NCONS) s.acc[i] = 0.f;
+    mbar_wait(tab, ch & 1);
+    consumer_sync();
+
+    for (int b = 0; b < nb; ++b, ++it) {
+      const int st = it % STAGES;
+      const int pix0 = (b0 + b) * BAND + sub * SUB_PX;      // first pixel of this warp's sub-band
+      const int row = pix0 / p.W, col0 = pix0 % p.W;
+      if (HAS_MASK) {
+        // weights of this band for the objects that touch it (others are never read)
+        const int bpix = (b0 + b) * BAND;
+        for (int i = tid; i < L * BAND; i += NCONS) {
+          const int c = i / BAND, px = i % BAND;
+          const int y = (bpix + px) / p.W, x = (bpix + px) % p.W;
+          float w = 0.f;
+          const int4 r4 = *reinterpret_cast<const int4*>(s.rng + 4 * c);
+          if (y >= r4.z && y <= r4.w && x >= r4.x && x <= r4.y)
+            w = mask_weight(p.masks + (size_t)(cbeg + c) * S * S, S, coord_tap(s.ax[c * p.W + x], S),
+                            coord_tap(s.ay[c * p.H + y], S));
+          s.wS[i] = w;
+        }
+        consumer_sync();
+      }
+      // objects touching this sub-band, in ascending order
+      int na = 0;
+      for (int c0 = 0; c0 < L; c0 += 32) {
+        const int c = c0 + lane;
+        bool keep = false;
+        if (c < L) {
+          const int4 r4 = *reinterpret_cast<const int4*>(s.rng + 4 * c);
+          keep = row >= r4.z && row <= r4.w && r4.x <= col0 + SUB_PX - 1 && r4.y >= col0;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) myact[na + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)c;
+        na += __popc(bal);
+      }
+      __syncwarp();
+      mbar_wait(full0 + 8 * st, (it / STAGES) & 1);
+      const float* gch = s.stage + (size_t)st * STAGE_FLOATS + lane * CSTRIDE + sub * SUB_PX;
+      for (int a = 0; a < na; ++a) {
+        const int c = myact[a];
+        const int2 xr = *reinterpret_cast<const int2*>(s.rng + 4 * c);
+        const int g0 = max(xr.x - col0, 0) >> 2, g1 = min(xr.y - col0, SUB_PX - 1) >> 2;
+        const float* wrow = HAS_MASK ? s.wS + c * BAND + sub * SUB_PX : s.ax + c * p.W + col0;
+        float a0 = 0.f, a1 = 0.f;
+        int gi = g0;
+        for (; gi + 1 <= g1; gi += 2) {
+          const float4 ga = ld_f4(gch + 4 * gi), wa = ld_f4(wrow + 4 * gi);
+          const float4 gb = ld_f4(gch + 4 * gi + 4), wb = ld_f4(wrow + 4 * gi + 4);
+          a0 = fmaf(ga.x, wa.x, a0); a0 = fmaf(ga.y, wa.y, a0); a0 = fmaf(ga.z, wa.z, a0); a0 = fmaf(ga.w, wa.w, a0);
+          a1 = fmaf(gb.x, wb.x, a1); a1 = fmaf(gb.y, wb.y, a1); a1 = fmaf(gb.z, wb.z, a1); a1 = fmaf(gb.w, wb.w, a1);
+        }
+        if (gi <= g1) {
+          const float4 ga = ld_f4(gch + 4 * gi), wa = ld_f4(wrow + 4 * gi);
+          a0 = fmaf(ga.x, wa.x, a0); a0 = fmaf(ga.y, wa.y, a0); a0 = fmaf(ga.z, wa.z, a0); a0 = fmaf(ga.w, wa.w, a0);
+        }
+        float sum = a0 + a1;
+        if (!HAS_MASK) sum *= s.ay[c * p.H + row];
+        s.acc[(c * SUBS + sub) * DC + lane] += sum;
+      }
+      mbar_arrive(empty0 + 8 * st);
+      if (HAS_MASK) consumer_sync();      // wS is rebuilt for the next band
+    }
+    consumer_sync();
+    for (int i = tid; i < L * DC; i += NCONS) {
+      const int c = i / DC, d = i % DC;
+      float v = 0.f;
+#pragma unroll
+      for (int u = 0; u < SUBS; ++u) v += s.acc[(c * SUBS + u) * DC + d];
+      my_partial[(size_t)(ch * p.lcap + c) * p.D + d] = v;
+    }
+    consumer_sync();
+  }
+}
+
+__global__ void layout_bwd_sum_splits_kernel(const float* __restrict__ partial, float* __restrict__ dvecs,
+                                             long long n, int splits) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += partial[(size_t)s * n + i];
+  dvecs[i] = acc;
+}
+
+int pick_splits(int N, int D, int H, int W) {
+  const int nbands = (H * W) / BAND;
+  const long long base = (long long)N * (D / DC);
+  const long long want = 6LL * 2 * csg_num_sms();
+  int s = 1;
+  while (s * 2 <= nbands && nbands % (s * 2) == 0 && base * s < want) s *= 2;
+  return s;
+}
+
+int pick_lcap(int max_objs, int H, int W, bool mask) {
+  int lcap = max_objs > 0 ? max_objs : 16;
+  lcap = (lcap + 3) & ~3;
+  if (lcap < 4) lcap = 4;
+  if (lcap > 64) lcap = 64;
+  while (lcap > 4 && smem_bytes(lcap, H, W, mask) > 110 * 1024) lcap -= 4;   // two CTAs per SM
+  return lcap;
+}
+
+bool shape_ok(int D, int H, int W) {
+  return (W % 64) == 0 && (H % 4) == 0 && ((long long)H * W) % BAND == 0 && (D % DC) == 0 &&
+         smem_bytes(4, H, W, true) <= 200 * 1024;
+}
+size_t workspace_bytes(int N, int NO, int D, int H, int W) {
+  return ((size_t)pick_splits(N, D, H, W) * NO * D + (size_t)NO * (W + H) + (size_t)NO * 4) * 4 + 256;
+}
+bool eligible(const float* dout, int D, int H, int W) {
+  return shape_ok(D, H, W) && (reinterpret_cast<uintptr_t>(dout) & 15) == 0;
+}
+
+}  // namespace bw
+
+// ========================================================================================
+// generic backward wrt vecs (any shape): per-tile partial[tile][o_local][d], then an ordered sum over tiles
+// ========================================================================================
+namespace gen {
+
+constexpr int TILE_W = 64;
+constexpr int TILE_H = 8;
+constexpr int TILE_PX = TILE_W * TILE_H;
+constexpr int NTHREADS = 256;
+
 struct Smem {
   int* list;     // [lcap]            object ids (global) in ascending order
   int* ci;       // [lcap][TILE_W]    first column tap
@@ -78,7 +656,7 @@ struct Smem {
   int* ri;       // [lcap][TILE_H]
   float* rw;     // [lcap][TILE_H][2]
   float* wS;     // [lcap][TILE_PX]   S_o(y, x) for the tile
-  float* vS;     // [lcap][D]         (forward: vecs; backward: per-object accumulators)
+  float* vS;     // [lcap][D]         per-object accumulators
 };
 
 __device__ __forceinline__ Smem carve(float* base, int lcap, int D) {
@@ -96,49 +674,6 @@ __device__ __forceinline__ Smem carve(float* base, int lcap, int D) {
 size_t smem_bytes(int lcap, int D) {
   return sizeof(float) * ((size_t)lcap * TILE_PX + (size_t)lcap * D + (size_t)lcap * TILE_W * 2 +
                           (size_t)lcap * TILE_H * 2 + (size_t)lcap * TILE_W + (size_t)lcap * TILE_H + lcap);
-}
-
-// Warp 0 appends, in ascending object order, the objects of [*cursor, oend) that may touch
-// the tile, until the list holds lcap entries.  Returns through shared memory.
-__device__ void build_list(const LayoutParams& p, const Smem& s, int oend, int x0, int y0,
-                           int* s_cursor, int* s_count) {
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    const int S = p.masks ? p.M : 8;
-    const float xlo = p.lin_x[x0], xhi = p.lin_x[min(x0 + TILE_W, p.W) - 1];
-    const float ylo = p.lin_y[y0], yhi = p.lin_y[min(y0 + TILE_H, p.H) - 1];
-    int cursor = *s_cursor, count = 0;
-    while (cursor < oend && count < p.lcap) {
-      int o = cursor + lane;
-      bool keep = false;
-      if (o < oend) {
-        float4 b = ld_f4(p.boxes + 4 * (size_t)o);
-        // zero / NaN extents and non-finite origins give NaN weights that poison every pixel of the image
-        // (0 * NaN in grid_sample), whatever the other axis says: never cull those
-        const bool poison = !(b.z > 0.f || b.z < 0.f) || !(b.w > 0.f || b.w < 0.f) ||
-                            !(fabsf(b.x) < INFINITY) || !(fabsf(b.y) < INFINITY);
-        keep = poison ||
-               (axis_may_touch(b.x, b.z, xlo, xhi, S, p.align) && axis_may_touch(b.y, b.w, ylo, yhi, S, p.align));
-      }
-      unsigned bal = __ballot_sync(0xffffffffu, keep);
-      int pos = count + __popc(bal & ((1u << lane) - 1u));
-      int room = p.lcap - count;
-      int total = __popc(bal);
-      if (total <= room) {
-        if (keep) s.list[pos] = o;
-        count += total;
-        cursor += 32;
-      } else {
-        // take only the first `room` kept objects; resume after the last one taken
-        if (keep && pos < p.lcap) s.list[pos] = o;
-        unsigned taken_last = __ballot_sync(0xffffffffu, keep && pos == p.lcap - 1);
-        int last_lane = __ffs(taken_last) - 1;
-        cursor += last_lane + 1;
-        count = p.lcap;
-      }
-    }
-    if (lane == 0) { *s_cursor = min(cursor, oend); *s_count = count; }
-  }
 }
 
 template <bool HAS_MASK>
@@ -168,116 +703,16 @@ __device__ void build_weights(const LayoutParams& p, const Smem& s, int L, int x
   for (int i = tid; i < L * TILE_PX; i += NTHREADS) {
     int c = i / TILE_PX, px = i % TILE_PX;
     int row = px / TILE_W, col = px % TILE_W;
-    int ix = s.ci[c * TILE_W + col], iy = s.ri[c * TILE_H + row];
-    float wx0 = s.cw[(c * TILE_W + col) * 2], wx1 = s.cw[(c * TILE_W + col) * 2 + 1];
-    float wy0 = s.rw[(c * TILE_H + row) * 2], wy1 = s.rw[(c * TILE_H + row) * 2 + 1];
-    bool vx0 = ix >= 0 && ix < S, vx1 = ix >= -1 && ix < S - 1;
-    bool vy0 = iy >= 0 && iy < S, vy1 = iy >= -1 && iy < S - 1;
+    Tap tx, ty;
+    tx.i0 = s.ci[c * TILE_W + col]; tx.w0 = s.cw[(c * TILE_W + col) * 2]; tx.w1 = s.cw[(c * TILE_W + col) * 2 + 1];
+    ty.i0 = s.ri[c * TILE_H + row]; ty.w0 = s.rw[(c * TILE_H + row) * 2]; ty.w1 = s.rw[(c * TILE_H + row) * 2 + 1];
     float w;
-    if (HAS_MASK) {
-      const float* m = p.masks + (size_t)s.list[c] * S * S;
-      float m00 = (vy0 && vx0) ? __ldg(m + iy * S + ix) : 0.f;
-      float m01 = (vy0 && vx1) ? __ldg(m + iy * S + ix + 1) : 0.f;
-      float m10 = (vy1 && vx0) ? __ldg(m + (iy + 1) * S + ix) : 0.f;
-      float m11 = (vy1 && vx1) ? __ldg(m + (iy + 1) * S + ix + 1) : 0.f;
-      // nw, ne, sw, se order of ATen's bilinear
-      w = m00 * (wx0 * wy0) + m01 * (wx1 * wy0) + m10 * (wx0 * wy1) + m11 * (wx1 * wy1);
-    } else {
-      float ax = (vx0 ? 1.f : 0.f) * wx0 + (vx1 ? 1.f : 0.f) * wx1;
-      float ay = (vy0 ? 1.f : 0.f) * wy0 + (vy1 ? 1.f : 0.f) * wy1;
-      w = ax * ay;
-    }
+    if (HAS_MASK) w = mask_weight(p.masks + (size_t)s.list[c] * S * S, S, tx, ty);
+    else w = tap_ones(tx, S) * tap_ones(ty, S);
     s.wS[i] = w;
   }
 }
 
-// ----------------------------------------------------------------------------------------
-// forward: out[n, d, y, x] = sum_o vecs[o, d] * S_o(y, x)
-// ----------------------------------------------------------------------------------------
-template <bool HAS_MASK>
-__global__ void __launch_bounds__(NTHREADS) layout_fwd_kernel(LayoutParams p, float* __restrict__ out) {
-  extern __shared__ __align__(16) float smem_raw[];
-  __shared__ int s_cursor, s_count;
-  const Smem s = carve(smem_raw, p.lcap, p.D);
-  const int n = blockIdx.y;
-  const int x0 = (blockIdx.x % p.tiles_x) * TILE_W, y0 = (blockIdx.x / p.tiles_x) * TILE_H;
-  const int oend = p.obj_off[n + 1];
-  const int tid = threadIdx.x;
-  if (tid == 0) s_cursor = p.obj_off[n];
-  __syncthreads();
-
-  const int q = tid & 127, half = tid >> 7;
-  const int row = q >> 4, col4 = (q & 15) * 4;
-  const int y = y0 + row, x = x0 + col4;
-  const bool vec4 = (p.W & 3) == 0;
-  const bool active = y < p.H && x < p.W;
-  bool first = true;
-  while (true) {
-    build_list(p, s, oend, x0, y0, &s_cursor, &s_count);
-    __syncthreads();
-    const int L = s_count;
-    const bool more = s_cursor < oend;   // read before the next build_list may advance it
-    build_weights<HAS_MASK>(p, s, L, x0, y0);
-    for (int i = tid; i < L * p.D; i += NTHREADS) {
-      int c = i / p.D, d = i % p.D;
-      s.vS[i] = p.vecs[(size_t)s.list[c] * p.D + d];
-    }
-    __syncthreads();
-    if (active) {
-      for (int dg = half * 4; dg < p.D; dg += 8) {
-        float acc[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) acc[j][k] = 0.f;
-        const int nd = min(4, p.D - dg);
-        if (nd == 4) {
-          for (int c = 0; c < L; ++c) {
-            float4 w = ld_f4(s.wS + c * TILE_PX + q * 4);
-            float4 v = ld_f4(s.vS + c * p.D + dg);
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              acc[j][0] = fmaf(vv[j], w.x, acc[j][0]);
-              acc[j][1] = fmaf(vv[j], w.y, acc[j][1]);
-              acc[j][2] = fmaf(vv[j], w.z, acc[j][2]);
-              acc[j][3] = fmaf(vv[j], w.w, acc[j][3]);
-            }
-          }
-        } else {
-          for (int c = 0; c < L; ++c) {
-            float4 w = ld_f4(s.wS + c * TILE_PX + q * 4);
-            for (int j = 0; j < nd; ++j) {
-              float vj = s.vS[c * p.D + dg + j];
-              acc[j][0] = fmaf(vj, w.x, acc[j][0]);
-              acc[j][1] = fmaf(vj, w.y, acc[j][1]);
-              acc[j][2] = fmaf(vj, w.z, acc[j][2]);
-              acc[j][3] = fmaf(vj, w.w, acc[j][3]);
-            }
-          }
-        }
-        for (int j = 0; j < nd; ++j) {
-          float* dst = out + (((size_t)n * p.D + dg + j) * p.H + y) * p.W + x;
-          if (vec4) {
-            float4 r = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-            if (!first) { float4 o = ld_f4(dst); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
-            st_f4_stream(dst, r);
-          } else {
-            for (int k = 0; k < 4 && x + k < p.W; ++k) dst[k] = first ? acc[j][k] : dst[k] + acc[j][k];
-          }
-        }
-      }
-    }
-    first = false;
-    __syncthreads();
-    if (!more) break;
-  }
-}
-
-// ----------------------------------------------------------------------------------------
-// backward wrt vecs: dvecs[o, d] = sum_{y, x} dout[n, d, y, x] * S_o(y, x)
-// Pass 1 (per tile): partial[tile][o_local][d]; pass 2: ordered sum over the tiles of an image.
-// ----------------------------------------------------------------------------------------
 constexpr int BWD_CH = 8;   // objects whose 8 weights per pixel slice are kept in registers
 
 template <bool HAS_MASK>
@@ -300,10 +735,10 @@ __global__ void __launch_bounds__(NTHREADS) layout_bwd_vecs_kernel(LayoutParams 
   const int slice = tid & 63, cg = tid >> 6;       // 64 slices of 8 px, 4 channel groups
   const int row = slice >> 3, col8 = (slice & 7) * 8;
   const int y = y0 + row, x = x0 + col8;
-  const bool vec4 = (p.W & 3) == 0;
+  const bool vec4 = (p.W & 3) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0;
   const bool rowok = y < p.H;
   while (true) {
-    build_list(p, s, oend, x0, y0, &s_cursor, &s_count);
+    build_list(p, s.list, oend, x0, y0, &s_cursor, &s_count);
     __syncthreads();
     const int L = s_count;
     const bool more = s_cursor < oend;
@@ -406,24 +841,34 @@ __global__ void obj_img_kernel(const int* __restrict__ obj_off, int N, int* __re
   for (int o = obj_off[n] + threadIdx.x; o < obj_off[n + 1]; o += blockDim.x) obj_img[o] = n;
 }
 
-int pick_lcap(int max_objs, int D, size_t extra = 0) {
+int pick_lcap(int max_objs, int D) {
   int lcap = max_objs > 0 ? max_objs : 16;
   if (lcap < 4) lcap = 4;
   if (lcap > 48) lcap = 48;
-  while (lcap > 4 && smem_bytes(lcap, D) + extra > 200 * 1024) lcap -= 4;
+  while (lcap > 4 && smem_bytes(lcap, D) > 200 * 1024) lcap -= 4;
   return lcap;
 }
 
+size_t workspace_bytes(int NO, int D, int H, int W) {
+  size_t tiles = (size_t)csg_div_up(W, TILE_W) * csg_div_up(H, TILE_H);
+  return tiles * (size_t)NO * D * sizeof(float) + (size_t)(NO + 1) * sizeof(int) + 256;
+}
+
+}  // namespace gen
+
 int fill_params(LayoutParams& p, const float* vecs, const float* boxes, const float* masks, const int* obj_off,
-                const float* lin_x, const float* lin_y, int N, int D, int H, int W, int M, int align,
-                int max_objs) {
+                const float* lin_x, const float* lin_y, int N, int D, int H, int W, int M, int align) {
   CSG_REQUIRE(N >= 0 && D > 0 && H > 0 && W > 0, "layout: bad sizes N=%d D=%d H=%d W=%d", N, D, H, W);
   CSG_REQUIRE(masks == nullptr || M > 0, "layout: masks given but M=%d", M);
   CSG_REQUIRE((D & 3) == 0, "layout: D=%d must be a multiple of 4", D);
   p.vecs = vecs; p.boxes = boxes; p.masks = masks; p.obj_off = obj_off; p.lin_x = lin_x; p.lin_y = lin_y;
   p.N = N; p.D = D; p.H = H; p.W = W; p.M = M; p.align = align;
-  p.tiles_x = csg_div_up(W, TILE_W); p.tiles_y = csg_div_up(H, TILE_H);
-  p.lcap = pick_lcap(max_objs, D);
+  return 0;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t smem) {
+  CSG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return 0;
 }
 
@@ -436,25 +881,43 @@ CSG_API int csg_layout_fwd(const float* vecs, const float* boxes, const float* m
                            const float* lin_x, const float* lin_y, float* out, int N, int D, int H, int W,
                            int M, int align_corners, int max_objs_per_image, cudaStream_t stream) {
   LayoutParams p;
-  if (int rc = fill_params(p, vecs, boxes, masks, obj_off, lin_x, lin_y, N, D, H, W, M, align_corners,
-                           max_objs_per_image)) return rc;
+  if (int rc = fill_params(p, vecs, boxes, masks, obj_off, lin_x, lin_y, N, D, H, W, M, align_corners)) return rc;
   if (N == 0) return 0;
-  size_t smem = smem_bytes(p.lcap, D);
+  p.TW = W <= 64 ? 64 : 128;
+  p.TH = fw::TILE_PX / p.TW;
+  p.tiles_x = csg_div_up(W, p.TW); p.tiles_y = csg_div_up(H, p.TH);
+  int lcap = max_objs_per_image > 0 ? max_objs_per_image : 16;
+  lcap = (lcap + 3) & ~3;
+  if (lcap < 4) lcap = 4;
+  if (lcap > 64) lcap = 64;
+  // keep at least three CTAs per SM resident
+  while (lcap > 4 && fw::smem_floats(lcap, D, p.TW, p.TH, masks != nullptr) * 4 > 72 * 1024) lcap -= 4;
+  p.lcap = lcap;
+  const size_t smem = fw::smem_floats(lcap, D, p.TW, p.TH, masks != nullptr) * 4;
+  CSG_REQUIRE(smem <= 220 * 1024, "layout fwd: D=%d needs %zu bytes of shared memory", D, smem);
+  const bool vec_store = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  CSG_REQUIRE(vec_store, "layout fwd: out must be 16-byte aligned");
   dim3 grid(p.tiles_x * p.tiles_y, N);
-  if (masks) {
-    CSG_CUDA(cudaFuncSetAttribute(layout_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layout_fwd_kernel<true><<<grid, NTHREADS, smem, stream>>>(p, out);
-  } else {
-    CSG_CUDA(cudaFuncSetAttribute(layout_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layout_fwd_kernel<false><<<grid, NTHREADS, smem, stream>>>(p, out);
-  }
+  const bool wide = (D % 16) == 0;
+#define CSG_FWD_LAUNCH(MASK, CH)                                                          \
+  do {                                                                                    \
+    if (int rc = set_smem(fw::layout_fwd_kernel<MASK, CH>, smem)) return rc;              \
+    fw::layout_fwd_kernel<MASK, CH><<<grid, fw::NTHREADS, smem, stream>>>(p, out);        \
+  } while (0)
+  if (masks) { if (wide) CSG_FWD_LAUNCH(true, 16); else CSG_FWD_LAUNCH(true, 4); }
+  else       { if (wide) CSG_FWD_LAUNCH(false, 16); else CSG_FWD_LAUNCH(false, 4); }
+#undef CSG_FWD_LAUNCH
   CSG_CHECK_LAUNCH("csg_layout_fwd");
   return 0;
 }
 
-CSG_API size_t csg_layout_bwd_vecs_workspace(int NO, int D, int H, int W) {
-  size_t tiles = (size_t)csg_div_up(W, TILE_W) * csg_div_up(H, TILE_H);
-  return tiles * (size_t)NO * D * sizeof(float) + (size_t)(NO + 1) * sizeof(int) + 256;
+CSG_API size_t csg_layout_bwd_vecs_workspace(int N, int NO, int D, int H, int W) {
+  size_t need = gen::workspace_bytes(NO, D, H, W);
+  if (bw::shape_ok(D, H, W)) {
+    size_t ring = bw::workspace_bytes(N, NO, D, H, W);
+    if (ring > need) need = ring;
+  }
+  return need;
 }
 
 CSG_API int csg_layout_bwd_vecs(const float* dout, const float* boxes, const float* masks, const int* obj_off,
@@ -462,26 +925,59 @@ CSG_API int csg_layout_bwd_vecs(const float* dout, const float* boxes, const flo
                                 int H, int W, int M, int align_corners, int max_objs_per_image,
                                 void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   LayoutParams p;
-  if (int rc = fill_params(p, nullptr, boxes, masks, obj_off, lin_x, lin_y, N, D, H, W, M, align_corners,
-                           max_objs_per_image)) return rc;
+  if (int rc = fill_params(p, nullptr, boxes, masks, obj_off, lin_x, lin_y, N, D, H, W, M, align_corners)) return rc;
   if (N == 0 || NO == 0) return 0;
-  CSG_REQUIRE(workspace_bytes >= csg_layout_bwd_vecs_workspace(NO, D, H, W), "layout bwd: workspace too small");
-  const int tiles = p.tiles_x * p.tiles_y;
+  CSG_REQUIRE(workspace_bytes >= csg_layout_bwd_vecs_workspace(N, NO, D, H, W), "layout bwd: workspace too small");
   float* partial = reinterpret_cast<float*>(workspace);
+  if (bw::eligible(dout, D, H, W)) {
+    bw::Params q;
+    q.p = p;
+    q.p.TW = W; q.p.TH = H; q.p.tiles_x = q.p.tiles_y = 1;
+    q.p.lcap = bw::pick_lcap(max_objs_per_image, H, W, masks != nullptr);
+    q.dout = dout; q.partial = partial; q.NO = NO;
+    q.splits = bw::pick_splits(N, D, H, W);
+    q.bands_per_item = (H * W) / bw::BAND / q.splits;
+    q.cblocks = D / bw::DC;
+    float* axg = partial + (size_t)q.splits * NO * D;
+    float* ayg = axg + (size_t)NO * W;
+    int* rng = reinterpret_cast<int*>(ayg + (size_t)NO * H);
+    q.axg = axg; q.ayg = ayg; q.rng = rng;
+    if (masks) bw::layout_tables_kernel<true><<<NO, 128, 0, stream>>>(q.p, NO, axg, ayg, rng);
+    else       bw::layout_tables_kernel<false><<<NO, 128, 0, stream>>>(q.p, NO, axg, ayg, rng);
+    CSG_CHECK_LAUNCH("csg_layout_bwd_vecs tables");
+    const size_t smem = bw::smem_bytes(q.p.lcap, H, W, masks != nullptr);
+    const int grid = N * q.cblocks * q.splits;
+    if (masks) {
+      if (int rc = set_smem(bw::layout_bwd_ring_kernel<true>, smem)) return rc;
+      bw::layout_bwd_ring_kernel<true><<<grid, bw::NTHREADS, smem, stream>>>(q);
+    } else {
+      if (int rc = set_smem(bw::layout_bwd_ring_kernel<false>, smem)) return rc;
+      bw::layout_bwd_ring_kernel<false><<<grid, bw::NTHREADS, smem, stream>>>(q);
+    }
+    CSG_CHECK_LAUNCH("csg_layout_bwd_vecs ring");
+    const long long n = (long long)NO * D;
+    bw::layout_bwd_sum_splits_kernel<<<csg_div_up(n, 256), 256, 0, stream>>>(partial, dvecs, n, q.splits);
+    CSG_CHECK_LAUNCH("csg_layout_bwd_vecs sum");
+    return 0;
+  }
+  p.TW = gen::TILE_W; p.TH = gen::TILE_H;
+  p.tiles_x = csg_div_up(W, gen::TILE_W); p.tiles_y = csg_div_up(H, gen::TILE_H);
+  p.lcap = gen::pick_lcap(max_objs_per_image, D);
+  const int tiles = p.tiles_x * p.tiles_y;
   int* obj_img = reinterpret_cast<int*>(partial + (size_t)tiles * NO * D);
-  size_t smem = smem_bytes(p.lcap, D);
+  size_t smem = gen::smem_bytes(p.lcap, D);
   dim3 grid(tiles, N);
-  obj_img_kernel<<<N, 64, 0, stream>>>(obj_off, N, obj_img);
+  gen::obj_img_kernel<<<N, 64, 0, stream>>>(obj_off, N, obj_img);
   if (masks) {
-    CSG_CUDA(cudaFuncSetAttribute(layout_bwd_vecs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layout_bwd_vecs_kernel<true><<<grid, NTHREADS, smem, stream>>>(p, dout, partial);
+    if (int rc = set_smem(gen::layout_bwd_vecs_kernel<true>, smem)) return rc;
+    gen::layout_bwd_vecs_kernel<true><<<grid, gen::NTHREADS, smem, stream>>>(p, dout, partial);
   } else {
-    CSG_CUDA(cudaFuncSetAttribute(layout_bwd_vecs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layout_bwd_vecs_kernel<false><<<grid, NTHREADS, smem, stream>>>(p, dout, partial);
+    if (int rc = set_smem(gen::layout_bwd_vecs_kernel<false>, smem)) return rc;
+    gen::layout_bwd_vecs_kernel<false><<<grid, gen::NTHREADS, smem, stream>>>(p, dout, partial);
   }
   CSG_CHECK_LAUNCH("csg_layout_bwd_vecs");
-  layout_bwd_reduce_kernel<<<csg_div_up((long long)NO * D, 256), 256, 0, stream>>>(partial, obj_off, obj_img, dvecs,
-                                                                                  NO, D, tiles);
+  gen::layout_bwd_reduce_kernel<<<csg_div_up((long long)NO * D, 256), 256, 0, stream>>>(partial, obj_off, obj_img, dvecs,
+                                                                                       NO, D, tiles);
   CSG_CHECK_LAUNCH("csg_layout_bwd_reduce");
   return 0;
 }

@@ -65,7 +65,7 @@ class _LayoutFn(torch.autograd.Function):
         lin_x, lin_y = _linspace(W, dout.device), _linspace(H, dout.device)
         if ctx.needs_input_grad[0]:
             dvecs = torch.empty((NO, D), dtype=torch.float32, device=dout.device)
-            ws = workspace(L.csg_layout_bwd_vecs_workspace(NO, D, H, W), dout.device)
+            ws = workspace(L.csg_layout_bwd_vecs_workspace(N, NO, D, H, W), dout.device)
             rc = L.csg_layout_bwd_vecs(ptr(dout), ptr(boxes), ptr(masks), ptr(obj_off), ptr(lin_x), ptr(lin_y),
                                        ptr(dvecs), N, NO, D, H, W, M, align, max_objs, ptr(ws), ws.numel(), _stream())
             _lib.check(rc, "csg_layout_bwd_vecs")

@@ -45,7 +45,7 @@ long long csg_launch_count(void);   /* kernel-launch sites passed since the libr
 int csg_layout_fwd(const float* vecs, const float* boxes, const float* masks, const int* obj_off,
                    const float* lin_x, const float* lin_y, float* out, int N, int D, int H, int W,
                    int M, int align_corners, int max_objs_per_image, csg_stream_t stream);
-size_t csg_layout_bwd_vecs_workspace(int NO, int D, int H, int W);
+size_t csg_layout_bwd_vecs_workspace(int N, int NO, int D, int H, int W);
 /* dvecs[o, d] = sum_{y, x} dout[n(o), d, y, x] * S_o(y, x)  (autograd of the above wrt vecs) */
 int csg_layout_bwd_vecs(const float* dout, const float* boxes, const float* masks, const int* obj_off,
                         const float* lin_x, const float* lin_y, float* dvecs, int N, int NO, int D,
