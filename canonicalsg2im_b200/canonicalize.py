@@ -92,12 +92,13 @@ def add_learnt_triplets_batched(triplets, tri_off, obj_off, num_rel, meta_ids, c
     args = (ptr(tr), ptr(tri_off), ptr(obj_off), B, ptr(uniforms) if learned_converse else 0, ptr(cdf_t), ptr(vals_t),
             ncand, num_rel, meta[0], meta[1], int(learned_converse), int(learned_transitivity), int(max_objs_per_graph))
     _lib.check(L.csg_canon_count(*args, ptr(cnt[0]), ptr(cnt[1]), ptr(conv_counts), _stream()), "csg_canon_count")
-    if B and int(cnt[0, :B].min().item()) < 0:
+    out_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    summary = torch.empty(2, dtype=torch.int32, device=dev)
+    _lib.check(L.csg_canon_offsets(ptr(cnt[0]), ptr(cnt[1]), B, ptr(out_off), ptr(summary), _stream()),
+               "csg_canon_offsets")
+    total, min_cnt0 = summary.tolist()         # sizes the output allocation (the one host sync per batch)
+    if B and min_cnt0 < 0:
         raise _lib.CsgError("canonicalize: a graph has more objects than max_objs_per_graph=%d" % max_objs_per_graph)
-    out_off = torch.zeros(B + 1, dtype=torch.int32, device=dev)
-    if B:
-        out_off[1:] = torch.cumsum((cnt[0, :B] + cnt[1, :B]).to(torch.int64), 0).to(torch.int32)
-    total = int(out_off[-1].item())            # sizes the output allocation (one host sync per batch)
     out_t = torch.empty((max(total, 1), 3), dtype=torch.int64, device=dev)
     out_ty = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
     _lib.check(L.csg_canon_emit(*args, ptr(out_off), ptr(out_t), ptr(out_ty), _stream()), "csg_canon_emit")

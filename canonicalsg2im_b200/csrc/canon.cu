@@ -320,6 +320,54 @@ CSG_API int csg_canon_emit(const long long* triplets, const int* tri_off, const 
   return 0;
 }
 
+// out_off[B+1] = exclusive scan of cnt0 + cnt1; summary[0] = total, summary[1] = min(cnt0) (negative = a graph
+// exceeded max_objs_per_graph).  One block; the only host read of the canonicalization is `summary`.
+namespace {
+__global__ void __launch_bounds__(1024) canon_offsets_kernel(const int* __restrict__ cnt0, const int* __restrict__ cnt1,
+                                                             int B, int* __restrict__ out_off, int* __restrict__ summary) {
+  __shared__ int sums[1024];
+  __shared__ int mins[32];
+  const int tid = threadIdx.x;
+  const int per = (B + 1023) / 1024;
+  const int beg = min(tid * per, B), end = min(beg + per, B);
+  int local = 0, mn = 0x7fffffff;
+  for (int i = beg; i < end; ++i) {
+    local += max(cnt0[i], 0) + cnt1[i];
+    mn = min(mn, cnt0[i]);
+  }
+  sums[tid] = local;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    int v = tid >= off ? sums[tid - off] : 0;
+    __syncthreads();
+    sums[tid] += v;
+    __syncthreads();
+  }
+  int run = sums[tid] - local;
+  for (int i = beg; i < end; ++i) {
+    out_off[i] = run;
+    run += max(cnt0[i], 0) + cnt1[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if ((tid & 31) == 0) mins[tid >> 5] = mn;
+  __syncthreads();
+  if (tid == 0) {
+    int m = mins[0];
+    for (int i = 1; i < 32; ++i) m = min(m, mins[i]);
+    out_off[B] = sums[1023];
+    summary[0] = sums[1023];
+    summary[1] = B > 0 ? m : 0;
+  }
+}
+}  // namespace
+
+CSG_API int csg_canon_offsets(const int* cnt0, const int* cnt1, int B, int* out_off, int* summary, cudaStream_t stream) {
+  canon_offsets_kernel<<<1, 1024, 0, stream>>>(cnt0, cnt1, B, out_off, summary);
+  CSG_CHECK_LAUNCH("csg_canon_offsets");
+  return 0;
+}
+
 // closure (reduce = 0) or minimal graph (reduce = 1) of G adjacency matrices [G, n, n] (uint8 0/1).
 CSG_API int csg_canon_closure(const unsigned char* adj, int G, int n, int reduce, unsigned char* out,
                               cudaStream_t stream) {

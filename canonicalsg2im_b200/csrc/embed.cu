@@ -1,0 +1,221 @@
+// Embedding lookups of Sg2LayoutModel.forward (sg2im/model.py:108-109, sg2im/attribute_embed.py:38-48) and the
+// masked box regression loss that seeds the backward pass (sg2im/pix2pix_model.py:72-85), for sm_100a.
+//
+//   csg_embed_fwd   out[r, :] = table[idx[r], :]  written as fp32 or straight as bf16 (the operand type of the
+//                   tensor-core GCN), so the [NT, E] fp32 predicate rows are never materialised;
+//   csg_embed_bwd   dtable[v, :] = sum_{r: idx[r] = v} dout[r, :]  -- deterministic: every single-warp block walks a
+//                   contiguous range of rows in order, accumulating into a private [V, E] table in shared memory;
+//                   the per-block tables are then summed in block order (torch's embedding backward sorts the
+//                   indices with a radix sort per call and accumulates with atomics);
+//   csg_box_loss    mean smooth-L1 over the coordinates of real boxes (gt >= 0) and its gradient, one block.
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+__device__ __forceinline__ float4 load_row4(const void* base, size_t elem, bool bf16) {
+  if (bf16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem);
+}
+
+// one warp per row, 4 columns per lane per step
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict__ table, const long long* __restrict__ idx,
+                                                        long long idx_stride, int n, int V, int E,
+                                                        void* __restrict__ out, int ld_out, int out_bf16) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  const int lane = threadIdx.x & 31;
+  long long v = idx[(size_t)r * idx_stride];
+  if (v < 0 || v >= V) v = 0;                        // caller validates; never read out of bounds
+  const float* src = table + (size_t)v * E;
+  for (int c = lane * 4; c < E; c += 128) {
+    const float4 x = ld_f4(src + c);
+    if (out_bf16) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(x.x, x.y), b = __floats2bfloat162_rn(x.z, x.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&a);
+      u.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)r * ld_out + c) = u;
+    } else {
+      st_f4(reinterpret_cast<float*>(out) + (size_t)r * ld_out + c, x);
+    }
+  }
+}
+
+constexpr int EB_UNROLL = 4;
+// block b (one warp) owns rows [b * rows_per_block, ...) and vocabulary slice [v0, v0 + Vc)
+__global__ void __launch_bounds__(32) embed_bwd_partial_kernel(const void* __restrict__ dout, int ld, int in_bf16,
+                                                               const long long* __restrict__ idx, long long idx_stride,
+                                                               int n, int rows_per_block, int v0, int Vc, int E,
+                                                               float* __restrict__ partial) {
+  extern __shared__ __align__(16) float acc[];     // [Vc][E]
+  const int lane = threadIdx.x;
+  for (int i = lane * 4; i < Vc * E; i += 128) st_f4(acc + i, make_float4(0.f, 0.f, 0.f, 0.f));
+  __syncwarp();
+  const int rbeg = blockIdx.x * rows_per_block, rend = min(rbeg + rows_per_block, n);
+  for (int c = lane * 4; c < E; c += 128) {
+    for (int r0 = rbeg; r0 < rend; r0 += EB_UNROLL) {
+      float4 x[EB_UNROLL];
+      int v[EB_UNROLL];
+#pragma unroll
+      for (int u = 0; u < EB_UNROLL; ++u) {
+        const int r = r0 + u;
+        v[u] = -1;
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rend) {
+          const long long vv = idx[(size_t)r * idx_stride] - v0;
+          if (vv >= 0 && vv < Vc) {
+            v[u] = (int)vv;
+            x[u] = load_row4(dout, (size_t)r * ld + c, in_bf16 != 0);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < EB_UNROLL; ++u) {
+        if (v[u] >= 0) {
+          float* a = acc + (size_t)v[u] * E + c;
+          float4 s = ld_f4(a);
+          s.x += x[u].x; s.y += x[u].y; s.z += x[u].z; s.w += x[u].w;
+          st_f4(a, s);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  float* dst = partial + (size_t)blockIdx.x * Vc * E;
+  for (int i = lane * 4; i < Vc * E; i += 128) st_f4(dst + i, ld_f4(acc + i));
+}
+
+__global__ void embed_bwd_final_kernel(const float* __restrict__ partial, int blocks, int cells, float* __restrict__ dtable) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cells) return;
+  float a0 = 0.f, a1 = 0.f;
+  int b = 0;
+  for (; b + 1 < blocks; b += 2) {
+    a0 += partial[(size_t)b * cells + i];
+    a1 += partial[(size_t)(b + 1) * cells + i];
+  }
+  if (b < blocks) a0 += partial[(size_t)b * cells + i];
+  dtable[i] = a0 + a1;
+}
+
+constexpr int EB_SMEM_MAX = 96 * 1024;
+struct EbPlan { int Vc, blocks, rows_per_block; };
+EbPlan embed_bwd_plan(int n, int V, int E) {
+  EbPlan p;
+  p.Vc = EB_SMEM_MAX / (E * 4);
+  if (p.Vc > V) p.Vc = V;
+  if (p.Vc < 1) p.Vc = 1;
+  const int per_sm = (200 * 1024) / (p.Vc * E * 4 + 1024);
+  int cap = csg_num_sms() * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+  int want = csg_div_up(n > 0 ? n : 1, 64);
+  p.blocks = want < cap ? want : cap;
+  p.rows_per_block = csg_div_up(n > 0 ? n : 1, p.blocks);
+  p.rows_per_block = (p.rows_per_block + EB_UNROLL - 1) / EB_UNROLL * EB_UNROLL;
+  p.blocks = csg_div_up(n > 0 ? n : 1, p.rows_per_block);
+  return p;
+}
+
+__device__ __forceinline__ float block_sum_1024(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < 32) {
+    t = red[threadIdx.x];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+__global__ void __launch_bounds__(1024) box_loss_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int n,
+                                                        float* __restrict__ loss, float* __restrict__ dpred) {
+  __shared__ float red[33];
+  float cnt = 0.f, sum = 0.f;
+  for (int r = threadIdx.x; r < n; r += 1024) {
+    const float4 g = ld_f4(gt + 4 * (size_t)r), p = ld_f4(pred + 4 * (size_t)r);
+    if (g.x >= 0.f && g.y >= 0.f && g.z >= 0.f && g.w >= 0.f) {
+      cnt += 1.f;
+      const float d[4] = {p.x - g.x, p.y - g.y, p.z - g.z, p.w - g.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = fabsf(d[k]);
+        sum += a < 1.f ? 0.5f * d[k] * d[k] : a - 0.5f;
+      }
+    }
+  }
+  const float total_cnt = block_sum_1024(cnt, red);
+  const float total = block_sum_1024(sum, red);
+  const float scale = total_cnt > 0.f ? 1.f / (4.f * total_cnt) : 0.f;
+  if (threadIdx.x == 0) loss[0] = total * scale;
+  for (int r = threadIdx.x; r < n; r += 1024) {
+    const float4 g = ld_f4(gt + 4 * (size_t)r), p = ld_f4(pred + 4 * (size_t)r);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.x >= 0.f && g.y >= 0.f && g.z >= 0.f && g.w >= 0.f) {
+      const float d[4] = {p.x - g.x, p.y - g.y, p.z - g.z, p.w - g.w};
+      float q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) q[k] = (fabsf(d[k]) < 1.f ? d[k] : (d[k] > 0.f ? 1.f : -1.f)) * scale;
+      o = make_float4(q[0], q[1], q[2], q[3]);
+    }
+    st_f4(dpred + 4 * (size_t)r, o);
+  }
+}
+
+}  // namespace
+
+CSG_API int csg_embed_fwd(const float* table, const long long* idx, long long idx_stride, int n, int V, int E,
+                          void* out, int ld_out, int out_bf16, cudaStream_t stream) {
+  if (n == 0) return 0;
+  CSG_REQUIRE(V > 0 && E > 0 && (E & 3) == 0 && (ld_out & 3) == 0, "embed_fwd: E=%d / ld=%d must be multiples of 4", E, ld_out);
+  embed_fwd_kernel<<<csg_div_up((long long)n * 32, 256), 256, 0, stream>>>(table, idx, idx_stride, n, V, E, out, ld_out,
+                                                                          out_bf16);
+  CSG_CHECK_LAUNCH("csg_embed_fwd");
+  return 0;
+}
+
+CSG_API size_t csg_embed_bwd_workspace(int n, int V, int E) {
+  const EbPlan p = embed_bwd_plan(n, V, E);
+  return (size_t)p.blocks * p.Vc * E * sizeof(float) + 256;
+}
+
+// dtable [V, E] fp32 is fully written (rows of unused ids are zero).  dout: fp32 or bf16 rows with leading dimension ld.
+CSG_API int csg_embed_bwd(const void* dout, int ld, int in_bf16, const long long* idx, long long idx_stride, int n,
+                          int V, int E, float* dtable, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  CSG_REQUIRE(V > 0 && E > 0 && (E & 3) == 0 && (ld & 3) == 0, "embed_bwd: E=%d / ld=%d must be multiples of 4", E, ld);
+  CSG_REQUIRE(workspace_bytes >= csg_embed_bwd_workspace(n, V, E), "embed_bwd: workspace too small");
+  if (n == 0) {
+    CSG_CUDA(cudaMemsetAsync(dtable, 0, (size_t)V * E * sizeof(float), stream));
+    return 0;
+  }
+  const EbPlan p = embed_bwd_plan(n, V, E);
+  float* partial = reinterpret_cast<float*>(workspace);
+  const size_t smem = (size_t)p.Vc * E * sizeof(float);
+  CSG_CUDA(cudaFuncSetAttribute(embed_bwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int v0 = 0; v0 < V; v0 += p.Vc) {
+    const int vc = V - v0 < p.Vc ? V - v0 : p.Vc;
+    embed_bwd_partial_kernel<<<p.blocks, 32, (size_t)vc * E * sizeof(float), stream>>>(dout, ld, in_bf16, idx, idx_stride, n,
+                                                                                      p.rows_per_block, v0, vc, E, partial);
+    CSG_CHECK_LAUNCH("csg_embed_bwd partial");
+    embed_bwd_final_kernel<<<csg_div_up((long long)vc * E, 256), 256, 0, stream>>>(partial, p.blocks, vc * E,
+                                                                                  dtable + (size_t)v0 * E);
+    CSG_CHECK_LAUNCH("csg_embed_bwd final");
+  }
+  return 0;
+}
+
+// loss[0] = mean over the 4 coordinates of the rows with gt >= 0 of smooth_l1(pred - gt); dpred = d loss / d pred.
+CSG_API int csg_box_loss(const float* pred, const float* gt, int n, float* loss, float* dpred, cudaStream_t stream) {
+  box_loss_kernel<<<1, 1024, 0, stream>>>(pred, gt, n, loss, dpred);
+  CSG_CHECK_LAUNCH("csg_box_loss");
+  return 0;
+}

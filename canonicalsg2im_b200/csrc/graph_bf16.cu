@@ -277,7 +277,14 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
     const int tn = t + stride;
     int s2 = 0, o2 = 0, vi2 = 0, ty2 = 0;
     float cf2 = 0.f;
-    if (tn < NT) { s2 = s_idx[tn]; o2 = o_idx[tn]; vi2 = valid[tn]; ty2 = type32[tn]; cf2 = conf[tn]; }
+    if (tn < NT) {
+      s2 = s_idx[tn]; o2 = o_idx[tn]; vi2 = valid[tn]; ty2 = type32[tn]; cf2 = conf[tn];
+      // pull the next row of `out` (the only DRAM-resident operand) into L2 while this one is processed
+      const __nv_bfloat16* nrow = out + (size_t)tn * Wd;
+#pragma unroll
+      for (int u = 0; u < ASM_MAXI; ++u)
+        if (lane * 8 + u * 256 < Wd) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + lane * 8 + u * 256));
+    }
     const bool v = vi != 0;
     const __nv_bfloat16* orow = out + (size_t)t * Wd;
     __nv_bfloat16* grow = g + (size_t)t * Wd;

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from . import synth
 from .canonicalize import add_learnt_triplets_batched, converse_tables
 from .layout import layout_batched
-from .model import Sg2LayoutModel, get_conv_converse
+from .model import Sg2LayoutModel, get_conv_converse, masked_box_loss
 from .parallel import BucketedGradAllReduce
 
 
@@ -97,8 +97,7 @@ class SgToLayoutStep:
         # canvas from GT boxes, as training does (train.py:358, generator.py:81-96); the __image__ dummy
         # has box -1 and contributes exact zeros, so no object filtering pass is needed
         canvas = layout_batched(obj_vecs, d["boxes"], d["obj_off"], self.H, self.W, max_objs_per_image=d["max_objs"])
-        real = (d["boxes"] >= 0).all(-1)
-        loss = F.smooth_l1_loss(boxes_pred[real], d["boxes"][real])      # pix2pix_model.py:72-85
+        loss = masked_box_loss(boxes_pred, d["boxes"])                   # pix2pix_model.py:72-85
         return canvas, loss
 
     def step(self, d, canvas_grad):

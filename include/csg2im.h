@@ -139,6 +139,18 @@ int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const void* d
                                  float* dconf, float* colsum_g, void* workspace, size_t workspace_bytes,
                                  csg_stream_t stream);
 
+/* ---- embeddings + box loss around the GCN: sg2im/model.py:108-109, sg2im/attribute_embed.py:38-48,
+ *      sg2im/pix2pix_model.py:72-85 --------------------------------------------------------------- */
+/* out[r, 0:E] = table[idx[r * idx_stride], :]  (out fp32 or bf16 rows with leading dimension ld_out) */
+int csg_embed_fwd(const float* table, const long long* idx, long long idx_stride, int n, int V, int E,
+                  void* out, int ld_out, int out_bf16, csg_stream_t stream);
+size_t csg_embed_bwd_workspace(int n, int V, int E);
+/* dtable[v, :] = sum_{r: idx[r] = v} dout[r, :]  (deterministic; dout fp32 or bf16; dtable fully written) */
+int csg_embed_bwd(const void* dout, int ld, int in_bf16, const long long* idx, long long idx_stride, int n,
+                  int V, int E, float* dtable, void* workspace, size_t workspace_bytes, csg_stream_t stream);
+/* loss[0] = mean smooth-L1 over the coordinates of rows with gt >= 0; dpred [n, 4] = d loss / d pred */
+int csg_box_loss(const float* pred, const float* gt, int n, float* loss, float* dpred, csg_stream_t stream);
+
 /* ---- canonicalization: sg2im/data/base_dataset.py:89-139, scripts/graphs_utils.py:15-155 ------ */
 /* pass 1: per-graph output sizes (cnt0 = type-0 edges, cnt1 = transitive edges; cnt0 = -1 flags a
  * graph with more than max_objs_per_graph objects) and conv_counts [B, P, P+1] */
@@ -146,6 +158,9 @@ int csg_canon_count(const long long* triplets, const int* tri_off, const int* ob
                     const double* uniforms, const double* cdf, const int* vals, int ncand,
                     int P, int meta0, int meta1, int learned_converse, int learned_transitivity,
                     int max_objs_per_graph, int* cnt0, int* cnt1, int* conv_counts, csg_stream_t stream);
+/* between the passes: out_off[B+1] = exclusive scan of cnt0 + cnt1; summary[0] = total rows, summary[1] = min(cnt0)
+ * (the one host read of a canonicalization: it sizes the output allocation) */
+int csg_canon_offsets(const int* cnt0, const int* cnt1, int B, int* out_off, int* summary, csg_stream_t stream);
 /* pass 2: emit [s, p, o] int64 rows + edge types at out_off[g] (exclusive scan of cnt0 + cnt1) */
 int csg_canon_emit(const long long* triplets, const int* tri_off, const int* obj_off, int B,
                    const double* uniforms, const double* cdf, const int* vals, int ncand,
