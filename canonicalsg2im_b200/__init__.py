@@ -4,6 +4,7 @@ roeiherz/CanonicalSg2Im, behind the reference's own Python operator surface.
     from canonicalsg2im_b200 import GraphTripleConv, GraphTripleConvNet, Sg2LayoutModel
     from canonicalsg2im_b200 import boxes_to_layout, masks_to_layout, layout_batched
     from canonicalsg2im_b200 import add_learnt_triplets, add_learnt_triplets_batched
+    from canonicalsg2im_b200 import crop_bbox, crop_bbox_batch
 
 Everything computes in ``libcsg2im.so`` (hand-written CUDA, C ABI in ``include/csg2im.h``); importing
 the operators without the built library, or calling them on CPU tensors, raises.
@@ -12,7 +13,8 @@ from . import synth  # noqa: F401  (host-side synthetic inputs; no kernels)
 
 __all__ = ["synth", "GraphTripleConv", "GraphTripleConvNet", "TripleBatch", "Sg2LayoutModel", "get_conv_converse",
            "boxes_to_layout", "masks_to_layout", "layout_batched", "add_learnt_triplets",
-           "add_learnt_triplets_batched", "converse_tables", "closure"]
+           "add_learnt_triplets_batched", "converse_tables", "closure", "crop_bbox", "crop_bbox_batch",
+           "crop_bbox_ragged"]
 
 _LAZY = {
     "GraphTripleConv": "graph", "GraphTripleConvNet": "graph", "TripleBatch": "graph",
@@ -20,6 +22,7 @@ _LAZY = {
     "boxes_to_layout": "layout", "masks_to_layout": "layout", "layout_batched": "layout",
     "add_learnt_triplets": "canonicalize", "add_learnt_triplets_batched": "canonicalize",
     "converse_tables": "canonicalize", "closure": "canonicalize",
+    "crop_bbox": "bilinear", "crop_bbox_batch": "bilinear", "crop_bbox_ragged": "bilinear",
 }
 
 

@@ -71,12 +71,10 @@ class _LayoutFn(torch.autograd.Function):
             _lib.check(rc, "csg_layout_bwd_vecs")
         need_geom = ctx.needs_input_grad[1] or (ctx.needs_input_grad[2] and ctx.masks_float)
         if need_geom:
-            if not hasattr(L, "csg_layout_bwd_geom"):
-                raise NotImplementedError("gradients wrt boxes / masks need csg_layout_bwd_geom")
-            dboxes = torch.zeros((NO, 4), dtype=torch.float32, device=dout.device)
+            dboxes = torch.empty((NO, 4), dtype=torch.float32, device=dout.device)
             want_dm = ctx.needs_input_grad[2] and ctx.masks_float
-            dmasks = torch.zeros_like(masks) if want_dm else None
-            ws = workspace(L.csg_layout_bwd_geom_workspace(NO, D, H, W, M), dout.device)
+            dmasks = torch.empty_like(masks) if want_dm else None
+            ws = workspace(L.csg_layout_bwd_geom_workspace(NO), dout.device)
             rc = L.csg_layout_bwd_geom(ptr(dout), ptr(vecs), ptr(boxes), ptr(masks), ptr(obj_off), ptr(lin_x),
                                        ptr(lin_y), ptr(dboxes), ptr(dmasks), N, NO, D, H, W, M, align,
                                        ptr(ws), ws.numel(), _stream())
@@ -116,11 +114,36 @@ def _occlude(vecs, boxes, masks, off, H, W, align_corners):
     NO, D = vecs_c.shape
     N, M = off.numel() - 1, masks_c.shape[1]
     out = torch.empty((N, D, H, W), dtype=torch.float32, device=vecs.device)
-    ws = workspace(L.csg_layout_occlude_workspace(NO), vecs.device)
+    ws = workspace(L.csg_layout_occlude_workspace(N, NO), vecs.device)
     lin_x, lin_y = _linspace(W, vecs.device), _linspace(H, vecs.device)
     rc = L.csg_layout_occlude_fwd(ptr(vecs_c), ptr(boxes_c), ptr(masks_c), ptr(off), ptr(lin_x), ptr(lin_y), ptr(out),
                                   N, NO, D, H, W, M, int(align_corners), ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "csg_layout_occlude_fwd")
+    return out
+
+
+def _boxes_to_grid(boxes, H, W):
+    """``sg2im/layout.py:80-112``: boxes [O, 4] xywh -> sampling grid [O, H, W, 2] in [-1, 1].  The
+    compositor kernels evaluate this chain per pixel and never materialise the grid; the function is
+    kept for callers that feed ``F.grid_sample`` themselves (elementwise torch ops on the caller's device)."""
+    need_cuda(boxes)
+    O = boxes.size(0)
+    b = boxes.view(O, 4, 1, 1)
+    X = (_linspace(W, boxes.device).view(1, 1, W).to(boxes) - b[:, 0]) / b[:, 2]
+    Y = (_linspace(H, boxes.device).view(1, H, 1).to(boxes) - b[:, 1]) / b[:, 3]
+    return torch.stack([X.expand(O, H, W), Y.expand(O, H, W)], dim=3).mul(2).sub(1)
+
+
+def _pool_samples(samples, pooling="sum"):
+    """``sg2im/layout.py:156-188``: samples [O, D, H, W] of ONE image -> [1, D, H, W].  Only used by callers
+    that already hold materialised samples; ``boxes_to_layout`` / ``masks_to_layout`` never build them."""
+    need_cuda(samples)
+    O = samples.size(0)
+    out = samples.sum(dim=0, keepdim=True)
+    if pooling == "avg":
+        out = out / max(O, 1)
+    elif pooling != "sum":
+        raise ValueError('Invalid pooling "%s"' % pooling)
     return out
 
 

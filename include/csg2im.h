@@ -52,6 +52,36 @@ int csg_layout_bwd_vecs(const float* dout, const float* boxes, const float* mask
                         int H, int W, int M, int align_corners, int max_objs_per_image,
                         void* workspace, size_t workspace_bytes, csg_stream_t stream);
 
+/* masks_to_layout(test_mode=True), sg2im/layout.py:72-76 + _pool_mask_samples :135-147: objects are visited in
+ * ascending order of their total sampled mass; the first one whose clean mask sample is > 0.5 owns the pixel
+ * (out = vecs[owner] * S_owner, 0 where nobody does).  Inference only; no host synchronisation. */
+size_t csg_layout_occlude_workspace(int N, int NO);
+int csg_layout_occlude_fwd(const float* vecs, const float* boxes, const float* masks, const int* obj_off,
+                           const float* lin_x, const float* lin_y, float* out, int N, int NO, int D, int H,
+                           int W, int M, int align_corners, void* workspace, size_t workspace_bytes,
+                           csg_stream_t stream);
+/* autograd of csg_layout_fwd wrt boxes [NO,4] (always) and wrt float masks [NO,M,M] (dmasks may be NULL):
+ * F.grid_sample backward (bilinear, zero padding) chained through _boxes_to_grid, layout.py:80-112 */
+size_t csg_layout_bwd_geom_workspace(int NO);
+int csg_layout_bwd_geom(const float* dout, const float* vecs, const float* boxes, const float* masks,
+                        const int* obj_off, const float* lin_x, const float* lin_y, float* dboxes,
+                        float* dmasks, int N, int NO, int D, int H, int W, int M, int align_corners,
+                        void* workspace, size_t workspace_bytes, csg_stream_t stream);
+
+/* ---- box crops: sg2im/bilinear.py:65-94 (crop_bbox, backend 'cudnn'), :44-62 (crop_bbox_batch_cudnn).
+ *      Crops crop_off[n]..crop_off[n+1] sample image n of feats [N,C,H,W] in place (the reference expands the
+ *      image once per object); bbox [NC,4] xywh; swx/ewx [WW], swy/ewy [HH] = torch.linspace(1,0,.) / (0,1,.)
+ *      in fp32 (tensor_linspace, bilinear.py:155-184).  crops [NC,C,HH,WW]. ------------------------------ */
+size_t csg_crop_bbox_workspace(int NC);
+int csg_crop_bbox_fwd(const float* feats, const float* bbox, const int* crop_off, const float* swx,
+                      const float* ewx, const float* swy, const float* ewy, float* crops, int N, int NC,
+                      int C, int H, int W, int HH, int WW, int align_corners, void* workspace,
+                      size_t workspace_bytes, csg_stream_t stream);
+/* dfeats [N,C,H,W] (fully written) = autograd of the above wrt feats; deterministic gather */
+int csg_crop_bbox_bwd(const float* dcrops, const float* bbox, const int* crop_off, const float* swx,
+                      const float* ewx, const float* swy, const float* ewy, float* dfeats, int N, int NC,
+                      int C, int H, int W, int HH, int WW, int align_corners, csg_stream_t stream);
+
 /* ---- triple graph convolution: sg2im/graph.py:44-113 ---------------------------------------- */
 int csg_offsets_uniform(int* off, int B, int stride, csg_stream_t stream);
 /* model.py:104-107 + graph.py:60-61: split int64 triplets, globalise indices, valid = (p != padding) */

@@ -144,3 +144,107 @@ def test_full_size_properties(L):
     y.backward(G)
     rhs = (vg.detach().double() * vg.grad.double()).sum()
     assert abs(lhs.item() - rhs.item()) <= 1e-5 * abs(lhs.item())
+
+
+# ------------------------------------------------------------------------------------------------------
+# test-mode occlusion compositor (layout.py:72-76, :135-147)
+# ------------------------------------------------------------------------------------------------------
+def test_golden_occlusion(golden, L):
+    g = golden("layout")
+    v, b, m = t(g["demo_vecs"]), t(g["demo_boxes"]), t(g["demo_masks"])
+    v4 = torch.cat([v, torch.zeros(6, 1, device="cuda")], 1)
+    y = L.masks_to_layout(v4, b, m, 64, test_mode=True)
+    assert_close(y[:, :3], g["demo_masks64_test_out"], TOL, "demo occlusion")
+    assert (y[:, 3] == 0).all()
+    y = L.masks_to_layout(t(g["rnd_vecs"]), t(g["rnd_boxes"]), t(g["rnd_masks"]), 32, 48, test_mode=True)
+    assert_close(y, g["rnd_masks_test_out"], TOL, "rnd occlusion")
+
+
+@pytest.mark.parametrize("H,W,D,M,nmax", [(64, 64, 32, 16, 9), (40, 52, 8, 5, 6), (128, 128, 16, 16, 40)])
+def test_occlusion_batched_vs_oracle(L, H, W, D, M, nmax):
+    """Ragged occlusion launch == per-image oracle calls; nmax=40 also exercises more objects than one list chunk
+    when they all overlap the tile."""
+    from oracle import layout as olayout
+    vecs, boxes, masks, off = _rand_objs(5, 4, 2, nmax, D, M)
+    y = L.layout_batched(t(vecs), t(boxes), t(off), H, W, masks=t(masks), test_mode=True)
+    ref = olayout.batched_layout([torch.from_numpy(vecs[off[i]:off[i + 1]]) for i in range(4)],
+                                 [torch.from_numpy(boxes[off[i]:off[i + 1]]) for i in range(4)],
+                                 [torch.from_numpy(masks[off[i]:off[i + 1]]) for i in range(4)], H, W, test_mode=True)
+    # a pixel whose clean sample is within rounding of the 0.5 threshold may legitimately flip owner: allow a
+    # handful of such pixels, everything else must agree to 1e-5
+    diff = (y.cpu() - ref).abs().amax(dim=1)
+    scale = ref.abs().max().item()
+    bad = (diff > TOL * scale).sum().item()
+    assert bad <= 2e-4 * diff.numel(), "occlusion: %d / %d pixels differ" % (bad, diff.numel())
+
+
+def test_occlusion_properties_full_size(L):
+    """cfg4-like size (10 images, 32-64 objects, 256x256): every pixel is either 0 or exactly one object's
+    vec * weight with weight > 0.5, and the canvas is invariant to the storage order of the objects."""
+    vecs, boxes, masks, off = _rand_objs(21, 10, 32, 64, 32, 16)
+    v, b, m, o = t(vecs), t(boxes), t(masks).float(), t(off)
+    y = L.layout_batched(v, b, o, 256, 256, masks=m, test_mode=True)
+    assert y.shape == (10, 32, 256, 256) and torch.isfinite(y).all()
+    # permute objects inside every image: masses are distinct, so the owner of each pixel is unchanged
+    perm = np.concatenate([off[i] + np.random.RandomState(i).permutation(off[i + 1] - off[i]) for i in range(10)])
+    pt = torch.from_numpy(perm).cuda()
+    y2 = L.layout_batched(v[pt], b[pt], o, 256, 256, masks=m[pt], test_mode=True)
+    assert torch.equal(y, y2)
+    # the summed compositor upper-bounds coverage: where the plain sum has no mass at all, occlusion is 0
+    ys = L.layout_batched(v.abs(), b, o, 256, 256, masks=m)
+    assert (y[(ys == 0)] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------------
+# gradients wrt boxes and float masks (autograd of grid_sample + _boxes_to_grid)
+# ------------------------------------------------------------------------------------------------------
+def _geom_case(L, g, tag, H, W, masks=None, float_masks=False, legacy=False, pad=0):
+    v = t(g["demo_vecs"] if tag.startswith("demo") else g["rnd_vecs"])
+    b = t(g["demo_boxes"] if tag.startswith("demo") else g["rnd_boxes"]).requires_grad_(True)
+    if pad:
+        v = torch.cat([v, torch.zeros(v.shape[0], pad, device="cuda")], 1)
+    m = None
+    if masks is not None:
+        m = t(masks)
+        if float_masks:
+            m = m.float().requires_grad_(True)
+    y = L.layout_batched(v, b, torch.tensor([0, v.shape[0]], dtype=torch.int32, device="cuda"), H, W, masks=m,
+                         align_corners=legacy)
+    D = y.shape[1] - pad
+    gy = torch.zeros_like(y)
+    gy[:, :D] = t(gi.layout_out_grad((1, D, H, W)))
+    (y * gy).sum().backward()
+    assert_close(b.grad, g[tag + "_dboxes"], TOL, tag + " dboxes")
+    if float_masks:
+        assert_close(m.grad, g[tag + "_dmasks"], TOL, tag + " dmasks")
+
+
+def test_golden_box_and_mask_grads(golden, L):
+    g = golden("layout")
+    _geom_case(L, g, "demo_boxes64", 64, 64, pad=1)
+    _geom_case(L, g, "demo_boxes64_legacy", 64, 64, legacy=True, pad=1)
+    _geom_case(L, g, "demo_masks64", 64, 64, masks=g["demo_masks"], float_masks=True, pad=1)
+    _geom_case(L, g, "demo_masks64_legacy", 64, 64, masks=g["demo_masks"], float_masks=True, legacy=True, pad=1)
+    _geom_case(L, g, "rnd_boxes", 32, 48)
+    _geom_case(L, g, "rnd_masks", 32, 48, masks=g["rnd_masks"])
+    _geom_case(L, g, "rnd_masks_f", 40, 40, masks=g["rnd_masks_f_in"], float_masks=True)
+
+
+def test_geom_grads_batched_vs_oracle(L):
+    from oracle import layout as olayout
+    H, W, D, M = 48, 64, 16, 8
+    vecs, boxes, masks, off = _rand_objs(9, 3, 2, 7, D, M)
+    fm = synth.det_uniform(masks.size, 3).reshape(masks.shape).astype(np.float32)
+    b = t(boxes).requires_grad_(True)
+    m = t(fm).requires_grad_(True)
+    y = L.layout_batched(t(vecs), b, t(off), H, W, masks=m)
+    gy = synth.det_tensor(tuple(y.shape), 17, 1.0)
+    (y * t(gy)).sum().backward()
+    bc = torch.from_numpy(boxes).requires_grad_(True)
+    mc = torch.from_numpy(fm).requires_grad_(True)
+    ref = olayout.batched_layout([torch.from_numpy(vecs[off[i]:off[i + 1]]) for i in range(3)],
+                                 [bc[off[i]:off[i + 1]] for i in range(3)],
+                                 [mc[off[i]:off[i + 1]] for i in range(3)], H, W)
+    (ref * torch.from_numpy(gy)).sum().backward()
+    assert_close(b.grad, bc.grad, TOL, "batched dboxes")
+    assert_close(m.grad, mc.grad, TOL, "batched dmasks")
