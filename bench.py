@@ -38,7 +38,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CSG_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("CSG_PRECISION", "bf16"), choices=["fp32", "bf16"],
+                    help="bf16 = tcgen05 tensor-core engine (north_star: bf16 MLP, fp32 accumulate, 1e-2 rel); "
+                         "fp32 = the 1e-5 parity engine")
     ap.add_argument("--batch", type=int, default=128, help="graphs per GPU")
     ap.add_argument("--cpu-sample", type=int, default=8, help="graphs in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -165,6 +167,51 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def layout_roofline(d, G, pk, iters=20):
+    """The layout compositor pair of this workload timed alone (CUDA events on the launching stream; the 268 MB
+    canvas and its gradient exceed the 126 MB L2, so every launch streams from / to HBM).  Algorithmic bytes:
+    forward = one write of N*D*H*W*4, backward = one read of the same."""
+    from canonicalsg2im_b200 import _lib
+    from canonicalsg2im_b200.layout import _linspace
+    from canonicalsg2im_b200.ops import lib, ptr, workspace, _stream
+    L = lib()
+    dev = G.device
+    N, D, H, W = G.shape
+    boxes, off = d["boxes"].float().contiguous(), d["obj_off"]
+    NO = boxes.shape[0]
+    vecs = torch.randn((NO, D), device=dev)
+    out = torch.empty_like(G)
+    dv = torch.empty((NO, D), device=dev)
+    lx, ly = _linspace(W, dev), _linspace(H, dev)
+    ws = workspace(L.csg_layout_bwd_vecs_workspace(N, NO, D, H, W), dev)
+    mo = int(d["max_objs"])
+
+    def fwd():
+        _lib.check(L.csg_layout_fwd(ptr(vecs), ptr(boxes), 0, ptr(off), ptr(lx), ptr(ly), ptr(out), N, D, H, W, 0, 0, mo,
+                                    _stream()), "csg_layout_fwd")
+
+    def bwd():
+        _lib.check(L.csg_layout_bwd_vecs(ptr(G), ptr(boxes), 0, ptr(off), ptr(lx), ptr(ly), ptr(dv), N, NO, D, H, W, 0, 0,
+                                         mo, ptr(ws), ws.numel(), _stream()), "csg_layout_bwd_vecs")
+    res = {}
+    nbytes = N * D * H * W * 4
+    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) * 1e-3 / iters
+        res[name] = {"us": sec * 1e6, "achieved": nbytes / sec / 1e9, "frac": nbytes / sec / 1e9 / pk["hbm"]}
+    return {"kernel": "layout_fwd_kernel / layout_bwd_ring_kernel (boxes_to_layout %dx%dx%dx%d)" % (N, D, H, W),
+            "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"], "peak_source": pk["src"] + " copy bandwidth",
+            "bytes_per_launch": nbytes, "fwd": res["fwd"], "bwd": res["bwd"]}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from canonicalsg2im_b200 import _lib, ops
@@ -255,6 +302,7 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    hbm = None if args.profile else layout_roofline(d, G, pk)
     n_obj = int(hb.obj_off[-1])
     peak_tf = pk["tf_sustained"]
     ach_tf = gemm_flops / gemm_sec / 1e12 if gemm_sec > 0 else 0.0
@@ -280,6 +328,7 @@ def run_ours(args):
                      "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": ach_tf / peak_tf, "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
                      "launches_timed": gemm_n, "share_of_step": gemm_sec / sec if sec > 0 else None},
+        "roofline_hbm": hbm,
         "loss": lv,
     }
     if not args.no_cpu_baseline and not args.profile and world == 1:
