@@ -201,6 +201,8 @@ __global__ void __launch_bounds__(NTHREADS) layout_fwd_kernel(LayoutParams p, fl
     }
     __syncthreads();
     if (active) {
+      const size_t plane = (size_t)p.H * p.W;
+      float* dst = out + (size_t)n * p.D * plane + (size_t)y * p.W + x;      // channel 0 of this lane's pixels
       for (int d0 = 0; d0 < p.D; d0 += CH) {
         float acc[CH][4];
 #pragma unroll
@@ -231,15 +233,23 @@ __global__ void __launch_bounds__(NTHREADS) layout_fwd_kernel(LayoutParams p, fl
             }
           }
         }
+        if (vec4 && first) {
+          // the common case: every canvas element is written exactly once, 16 bytes per lane, 512 contiguous
+          // bytes per warp and channel
 #pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          float* dst = out + (((size_t)n * p.D + d0 + j) * p.H + y) * p.W + x;
-          if (vec4) {
-            float4 r = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-            if (!first) { float4 o = ld_f4(dst); r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
-            st_f4_stream(dst, r);
-          } else {
-            for (int k = 0; k < 4 && x + k < p.W; ++k) dst[k] = first ? acc[j][k] : dst[k] + acc[j][k];
+          for (int j = 0; j < CH; ++j, dst += plane)
+            st_f4_stream(dst, make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j, dst += plane) {
+            if (vec4) {
+              float4 r = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+              float4 o = ld_f4(dst);
+              r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+              st_f4_stream(dst, r);
+            } else {
+              for (int k = 0; k < 4 && x + k < p.W; ++k) dst[k] = first ? acc[j][k] : dst[k] + acc[j][k];
+            }
           }
         }
       }
@@ -430,6 +440,9 @@ __global__ void __launch_bounds__(NTHREADS) layout_bwd_ring_kernel(Params q) {
   }
 
   // ---------------- consumers: thread = (channel lane, sub-band warp)
+  // The 64 gradient values of (channel, sub-band) are copied to registers once per band and the stage is handed
+  // back to the producer at once.  Weights are warp-uniform broadcasts; quarters of the sub-band outside an
+  // object's columns are skipped without divergence.
   const int sub = warp;
   unsigned char* myact = s.act + sub * p.lcap;
   int it = 0;
@@ -483,32 +496,39 @@ __global__ void __launch_bounds__(NTHREADS) layout_bwd_ring_kernel(Params q) {
       }
       __syncwarp();
       mbar_wait(full0 + 8 * st, (it / STAGES) & 1);
-      const float* gch = s.stage + (size_t)st * STAGE_FLOATS + lane * CSTRIDE + sub * SUB_PX;
+      float4 g[SUB_PX / 4];
+      {
+        const float* gch = s.stage + (size_t)st * STAGE_FLOATS + lane * CSTRIDE + sub * SUB_PX;
+#pragma unroll
+        for (int i = 0; i < SUB_PX / 4; ++i) g[i] = ld_f4(gch + 4 * i);
+      }
+      mbar_arrive(empty0 + 8 * st);          // the stage is free as soon as the registers hold it
+#pragma unroll 1
       for (int a = 0; a < na; ++a) {
         const int c = myact[a];
         const int2 xr = *reinterpret_cast<const int2*>(s.rng + 4 * c);
-        const int g0 = max(xr.x - col0, 0) >> 2, g1 = min(xr.y - col0, SUB_PX - 1) >> 2;
         const float* wrow = HAS_MASK ? s.wS + c * BAND + sub * SUB_PX : s.ax + c * p.W + col0;
-        float a0 = 0.f, a1 = 0.f;
-        int gi = g0;
-        for (; gi + 1 <= g1; gi += 2) {
-          const float4 ga = ld_f4(gch + 4 * gi), wa = ld_f4(wrow + 4 * gi);
-          const float4 gb = ld_f4(gch + 4 * gi + 4), wb = ld_f4(wrow + 4 * gi + 4);
-          a0 = fmaf(ga.x, wa.x, a0); a0 = fmaf(ga.y, wa.y, a0); a0 = fmaf(ga.z, wa.z, a0); a0 = fmaf(ga.w, wa.w, a0);
-          a1 = fmaf(gb.x, wb.x, a1); a1 = fmaf(gb.y, wb.y, a1); a1 = fmaf(gb.z, wb.z, a1); a1 = fmaf(gb.w, wb.w, a1);
+        float sum = 0.f;
+#pragma unroll
+        for (int qd = 0; qd < SUB_PX / 16; ++qd) {
+          if (xr.x <= col0 + 16 * qd + 15 && xr.y >= col0 + 16 * qd) {
+            const float4 w0 = ld_f4(wrow + 16 * qd), w1 = ld_f4(wrow + 16 * qd + 4);
+            const float4 w2 = ld_f4(wrow + 16 * qd + 8), w3 = ld_f4(wrow + 16 * qd + 12);
+            const float4 g0 = g[4 * qd], g1 = g[4 * qd + 1], g2 = g[4 * qd + 2], g3 = g[4 * qd + 3];
+            float t0 = g0.x * w0.x, t1 = g1.x * w1.x, t2 = g2.x * w2.x, t3 = g3.x * w3.x;
+            t0 = fmaf(g0.y, w0.y, t0); t1 = fmaf(g1.y, w1.y, t1); t2 = fmaf(g2.y, w2.y, t2); t3 = fmaf(g3.y, w3.y, t3);
+            t0 = fmaf(g0.z, w0.z, t0); t1 = fmaf(g1.z, w1.z, t1); t2 = fmaf(g2.z, w2.z, t2); t3 = fmaf(g3.z, w3.z, t3);
+            t0 = fmaf(g0.w, w0.w, t0); t1 = fmaf(g1.w, w1.w, t1); t2 = fmaf(g2.w, w2.w, t2); t3 = fmaf(g3.w, w3.w, t3);
+            sum += (t0 + t1) + (t2 + t3);
+          }
         }
-        if (gi <= g1) {
-          const float4 ga = ld_f4(gch + 4 * gi), wa = ld_f4(wrow + 4 * gi);
-          a0 = fmaf(ga.x, wa.x, a0); a0 = fmaf(ga.y, wa.y, a0); a0 = fmaf(ga.z, wa.z, a0); a0 = fmaf(ga.w, wa.w, a0);
-        }
-        float sum = a0 + a1;
         if (!HAS_MASK) sum *= s.ay[c * p.H + row];
         s.acc[(c * SUBS + sub) * DC + lane] += sum;
       }
-      mbar_arrive(empty0 + 8 * st);
       if (HAS_MASK) consumer_sync();      // wS is rebuilt for the next band
     }
     consumer_sync();
+    // combine the four sub-band warps in a fixed order
     for (int i = tid; i < L * DC; i += NCONS) {
       const int c = i / DC, d = i % DC;
       float v = 0.f;
