@@ -248,8 +248,6 @@ def run_ours(args):
     barrier()
 
     # ---- timed region 1: inputs resident in HBM
-    timer = ops.KernelTimer()
-    ops.TIMERS["gemm"] = timer
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -267,9 +265,23 @@ def run_ours(args):
         torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop() if rank == 0 else None
     launches = L.csg_launch_count() - launches0
-    ops.TIMERS.clear()
     sec = e0.elapsed_time(e1) * 1e-3
-    gemm_flops, gemm_sec, gemm_n = timer.summary()
+    # ---- instrumented pass (not the headline): the same K steps with CUDA events around every GEMM / layout /
+    # pooling entry point on the launching stream (csg_prof_*), for the roofline objects
+    import ctypes
+    prof = (ctypes.c_double * 24)()
+    L.csg_prof_enable(1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(0 if args.profile else args.steps):
+        step.step(d, G)
+    p1.record()
+    torch.cuda.synchronize()
+    L.csg_prof_collect(prof)
+    L.csg_prof_enable(0)
+    prof_sec = p0.elapsed_time(p1) * 1e-3
+    cls = 1 if args.precision == "fp32" else 0
+    gemm_flops, gemm_sec, gemm_n = prof[cls * 3], prof[cls * 3 + 1], int(prof[cls * 3 + 2])
     tsec = torch.tensor([sec], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
@@ -327,7 +339,9 @@ def run_ours(args):
         "roofline": {"kernel": "net1/net2 GEMMs (%s)" % ("gemm_f32_kernel" if args.precision == "fp32" else "gemm_tc_kernel"),
                      "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": ach_tf / peak_tf, "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
-                     "launches_timed": gemm_n, "share_of_step": gemm_sec / sec if sec > 0 else None},
+                     "launches_timed": gemm_n, "share_of_step": gemm_sec / prof_sec if prof_sec > 0 else None,
+                     "note": "measured in a separate instrumented pass of the same %d steps (%.3f ms/step)"
+                             % (args.steps, 1e3 * prof_sec / args.steps)},
         "roofline_hbm": hbm,
         "loss": lv,
     }

@@ -33,3 +33,58 @@ CSG_API const char* csg_last_error(void) { return g_err; }
 CSG_API void csg_clear_error(void) { g_err[0] = 0; }
 CSG_API int csg_version(void) { return 100; }   // 0.1.0
 CSG_API int csg_device_sms(void) { return csg_num_sms(); }
+
+// ------------------------------------------------------------------------------------------------
+// live timing of kernel classes (bench.py's roofline legs).  Off by default; when on, every instrumented
+// entry point records two CUDA events on ITS stream; csg_prof_collect synchronises them and sums per class.
+// ------------------------------------------------------------------------------------------------
+#include <mutex>
+#include <vector>
+namespace {
+struct ProfRec { cudaEvent_t e0, e1; int cls; double work; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;
+std::vector<ProfRec> g_prof_pool;
+int g_prof_on = 0;
+}  // namespace
+
+CsgProfScope::CsgProfScope(int cls, double work, cudaStream_t s) : slot(-1), stream(s) {
+  if (!__atomic_load_n(&g_prof_on, __ATOMIC_RELAXED)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  if (!g_prof_pool.empty()) { r = g_prof_pool.back(); g_prof_pool.pop_back(); }
+  else if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  r.cls = cls; r.work = work;
+  cudaEventRecord(r.e0, s);
+  slot = (int)g_prof_recs.size();
+  g_prof_recs.push_back(r);
+}
+CsgProfScope::~CsgProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot < (int)g_prof_recs.size()) cudaEventRecord(g_prof_recs[slot].e1, stream);
+}
+
+CSG_API int csg_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof_recs) g_prof_pool.push_back(r);
+  g_prof_recs.clear();
+  __atomic_store_n(&g_prof_on, on ? 1 : 0, __ATOMIC_RELAXED);
+  return 0;
+}
+// out: HOST array [CSG_PROF_CLASSES][3] = {work, seconds, scopes} per class; clears the records.
+CSG_API int csg_prof_collect(double* out) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < CSG_PROF_CLASSES * 3; ++i) out[i] = 0.0;
+  for (auto& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      out[r.cls * 3 + 0] += r.work;
+      out[r.cls * 3 + 1] += (double)ms * 1e-3;
+      out[r.cls * 3 + 2] += 1.0;
+    }
+    g_prof_pool.push_back(r);
+  }
+  g_prof_recs.clear();
+  return 0;
+}

@@ -40,6 +40,17 @@ void csg_count_launch();
     }                                                                               \
   } while (0)
 
+// Optional live timing of kernel classes (csg_prof_enable / csg_prof_collect): CUDA events recorded on the
+// launching stream around the launches of one entry point.  Disabled = one relaxed load per call.
+struct CsgProfScope {
+  int slot;
+  cudaStream_t stream;
+  CsgProfScope(int cls, double work, cudaStream_t s);
+  ~CsgProfScope();
+};
+enum { CSG_PROF_GEMM_BF16 = 0, CSG_PROF_GEMM_F32 = 1, CSG_PROF_LAYOUT_FWD = 2, CSG_PROF_LAYOUT_BWD = 3,
+       CSG_PROF_POOL = 4, CSG_PROF_ASSEMBLE = 5, CSG_PROF_CANON = 6, CSG_PROF_CLASSES = 8 };
+
 static inline int csg_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int csg_num_sms();   // SM count of the current device (cached per device)

@@ -1,0 +1,284 @@
+// Native executor of one GraphTripleConv layer (sg2im/graph.py:44-113) on the bf16 tensor-core engine.
+//
+// The reference runs a layer as ~13*B small ATen launches from Python; the per-stage C ABI of this library
+// (csg_gemm_bf16, csg_segpool_bf16, ...) already collapses that to ~30 launches per layer and direction, but
+// issuing them one ctypes call at a time leaves the GPU idle more than half of the step.  Here the whole launch
+// sequence of a layer's forward (7 launches) or backward (~24) is issued by ONE call from C++, on the caller's
+// stream, out of caller-owned memory:
+//
+//   saved      activations kept for backward + the bf16 copies of the weights (csg_gconv_bf16_saved_bytes)
+//   workspace  scratch that is dead when the call returns on the stream (csg_gconv_bf16_workspace)
+//
+// Dataflow (identical to canonicalsg2im_b200/graph_tc.py, which remains as the staged form used by the tests):
+//   forward   cast weights -> conf (graph.py:69-74) -> F1 (gather fused, graph.py:63-67) -> F2 (+bias, ReLU, x conf)
+//             -> CSR pooling (graph.py:83-107) -> net2 (graph.py:110)
+//   backward  net2 dW/db/dX -> pooling backward -> assemble d(net1 pre-activation) (+ db2, dconf) -> dW2, dhidden,
+//             dW1 (re-gathers its operand), db1, dX -> segmented sums of dX onto objects -> d w_trans
+#include "common.cuh"
+#include "csg2im.h"
+#include <cuda_bf16.h>
+
+namespace {
+
+struct Dims {
+  int NT, NO, Din, Dp, H, Dout, Dpo, P;
+  int K1() const { return 2 * Din + Dp; }
+  int Wd() const { return 2 * H + Dpo; }
+};
+
+inline Dims read_dims(const int* d) { return Dims{d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]}; }
+
+inline size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// ---- layout of `saved`
+struct Saved {
+  size_t w1b, w2b, w3b, w4b, w1t, w2t, w3t, w4t, conf, hidden, out, pooled32, pooled16, cnt, h2, total;
+};
+Saved plan_saved(const Dims& d, bool need_bwd) {
+  Saved s;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
+  const size_t e1 = (size_t)d.H * d.K1() * 2, e2 = (size_t)d.Wd() * d.H * 2, e3 = (size_t)d.H * d.H * 2,
+               e4 = (size_t)d.Dout * d.H * 2;
+  s.w1b = take(e1); s.w2b = take(e2); s.w3b = take(e3); s.w4b = take(e4);
+  s.w1t = take(need_bwd ? e1 : 0); s.w2t = take(need_bwd ? e2 : 0); s.w3t = take(need_bwd ? e3 : 0);
+  s.w4t = take(need_bwd ? e4 : 0);
+  s.conf = take((size_t)(d.NT > 0 ? d.NT : 1) * 4);
+  s.hidden = take((size_t)d.NT * d.H * 2);
+  s.out = take((size_t)d.NT * d.Wd() * 2);
+  s.pooled32 = take((size_t)d.NO * d.H * 4);
+  s.pooled16 = take((size_t)d.NO * d.H * 2);
+  s.cnt = take((size_t)d.NO * 4);
+  s.h2 = take((size_t)d.NO * d.H * 2);
+  s.total = o + 256;
+  return s;
+}
+
+// ---- layout of the backward workspace
+struct Work {
+  size_t g4, dh2, dpooled, dS, dcnt, g, dconf, dhid, splitk, small, splitk_bytes, small_bytes, total;
+};
+Work plan_work(const Dims& d) {
+  Work w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
+  auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
+  w.g4 = take((size_t)d.NO * d.Dout * 2);
+  w.dh2 = take((size_t)d.NO * d.H * 2);
+  w.dpooled = take((size_t)d.NO * d.H * 4);
+  w.dS = take((size_t)d.NO * d.H * 4);
+  w.dcnt = take((size_t)d.NO * 4);
+  w.g = take((size_t)d.NT * d.Wd() * 2);
+  w.dconf = take((size_t)(d.NT > 0 ? d.NT : 1) * 4);
+  w.dhid = take((size_t)d.NT * d.H * 2);
+  size_t sk = csg_gemm_bf16_workspace(d.Dout, d.H, d.NO, 1);
+  sk = mx(sk, csg_gemm_bf16_workspace(d.H, d.H, d.NO, 1));
+  sk = mx(sk, csg_gemm_bf16_workspace(d.Wd(), d.H, d.NT, 1));
+  sk = mx(sk, csg_gemm_bf16_workspace(d.H, d.K1(), d.NT, 1));
+  w.splitk_bytes = sk;
+  w.splitk = take(sk);
+  size_t sm = csg_colsum_bf16_workspace(d.NO, d.Dout);
+  sm = mx(sm, csg_colsum_bf16_workspace(d.NO, d.H));
+  sm = mx(sm, csg_colsum_bf16_workspace(d.NT, d.H));
+  sm = mx(sm, csg_triple_bwd_assemble_bf16_workspace(d.NT, d.H, d.Dpo));
+  sm = mx(sm, csg_conf_bwd_workspace(d.P));
+  w.small_bytes = sm;
+  w.small = take(sm);
+  w.total = o + 256;
+  return w;
+}
+
+inline uint8_t* align256(void* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 255) & ~(uintptr_t)255);
+}
+
+int check_dims(const Dims& d) {
+  CSG_REQUIRE(d.NT >= 0 && d.NO >= 0 && d.P > 0, "gconv_bf16: bad sizes NT=%d NO=%d P=%d", d.NT, d.NO, d.P);
+  CSG_REQUIRE(d.Din > 0 && d.Dp > 0 && d.H > 0 && d.Dout > 0 && d.Dpo > 0 && d.Din % 64 == 0 && d.Dp % 64 == 0 &&
+              d.H % 64 == 0 && d.Dout % 64 == 0 && d.Dpo % 64 == 0,
+              "gconv_bf16: feature widths must be positive multiples of 64 (Din=%d Dp=%d H=%d Dout=%d Dpo=%d)",
+              d.Din, d.Dp, d.H, d.Dout, d.Dpo);
+  return 0;
+}
+
+// out = bf16(y > 0 ? dy : 0) with dy fp32 or bf16 (ReLU backward of the layer output, graph.py:110)
+template <bool DY_BF16>
+__global__ void relu_mask_out_kernel(const void* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                     __nv_bfloat16* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = DY_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[i])
+                          : reinterpret_cast<const float*>(dy)[i];
+  out[i] = __float2bfloat16_rn(__bfloat162float(y[i]) > 0.f ? v : 0.f);
+}
+
+#define CSG_TRY(call)            \
+  do {                           \
+    if (int rc__ = (call)) return rc__; \
+  } while (0)
+
+}  // namespace
+
+CSG_API size_t csg_gconv_bf16_saved_bytes(const int* dims, int need_bwd) {
+  return plan_saved(read_dims(dims), need_bwd != 0).total;
+}
+CSG_API size_t csg_gconv_bf16_out_offset(const int* dims, int need_bwd) {
+  return plan_saved(read_dims(dims), need_bwd != 0).out;
+}
+CSG_API size_t csg_gconv_bf16_workspace(const int* dims) { return plan_work(read_dims(dims)).total; }
+
+// dims (HOST): {NT, NO, Din, Dp, H, Dout, Dpo, P}.  params (HOST array of 9 device pointers, fp32): w1 [H, 2Din+Dp],
+// b1, w2 [2H+Dpo, H], b2, w3 [H, H], b3, w4 [Dout, H], b4, w_trans [P].  index (HOST array of 9 device pointers,
+// int32): s_idx, o_idx, pred_id, type32, valid [NT]; rowptr_s [NO+1], perm_s [NT], rowptr_o, perm_o.
+// obj [NO, Din] bf16 contiguous; pred [NT, Dp] bf16 with row pitch ldp; new_obj [NO, Dout] bf16 (written);
+// `saved` must be 256-byte aligned; new_p = saved + csg_gconv_bf16_out_offset, rows of pitch 2H+Dpo, columns H..H+Dpo.
+CSG_API int csg_gconv_bf16_fwd(const int* dims, const void* obj, const void* pred, int ldp,
+                               const void* const* params, const void* const* index, int need_bwd, void* saved,
+                               size_t saved_bytes, void* new_obj, csg_stream_t stream) {
+  const Dims d = read_dims(dims);
+  CSG_TRY(check_dims(d));
+  const Saved s = plan_saved(d, need_bwd != 0);
+  CSG_REQUIRE(saved && saved_bytes >= s.total && (reinterpret_cast<uintptr_t>(saved) & 255) == 0,
+              "gconv_bf16_fwd: `saved` must be 256-byte aligned and hold %zu bytes", s.total);
+  uint8_t* sv = reinterpret_cast<uint8_t*>(saved);
+  const float* w[4] = {(const float*)params[0], (const float*)params[2], (const float*)params[4], (const float*)params[6]};
+  const float* b[4] = {(const float*)params[1], (const float*)params[3], (const float*)params[5], (const float*)params[7]};
+  const float* w_trans = (const float*)params[8];
+  const int* s_idx = (const int*)index[0];
+  const int* o_idx = (const int*)index[1];
+  const int* pred_id = (const int*)index[2];
+  const int* type32 = (const int*)index[3];
+  const int* valid = (const int*)index[4];
+  const int *rowptr_s = (const int*)index[5], *perm_s = (const int*)index[6], *rowptr_o = (const int*)index[7],
+            *perm_o = (const int*)index[8];
+  const int K1 = d.K1(), Wd = d.Wd();
+  // ---- bf16 copies of the weights (+ transposes for the dX-type GEMMs of backward), one launch
+  {
+    const void* src[8] = {w[0], w[1], w[2], w[3], w[0], w[1], w[2], w[3]};
+    void* dst[8] = {sv + s.w1b, sv + s.w2b, sv + s.w3b, sv + s.w4b, sv + s.w1t, sv + s.w2t, sv + s.w3t, sv + s.w4t};
+    const int rows[8] = {d.H, Wd, d.H, d.Dout, d.H, Wd, d.H, d.Dout};
+    const int cols[8] = {K1, d.H, d.H, d.H, K1, d.H, d.H, d.H};
+    const int tr[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+    CSG_TRY(csg_cast_bf16_multi(need_bwd ? 8 : 4, src, dst, rows, cols, tr, stream));
+  }
+  float* conf = reinterpret_cast<float*>(sv + s.conf);
+  CSG_TRY(csg_triple_conf(type32, pred_id, w_trans, d.NT, conf, stream));
+  // ---- net1 on the gathered triple rows
+  CSG_TRY(csg_gemm_bf16(0, 1, d.NT, d.H, K1, nullptr, 0, sv + s.w1b, K1, sv + s.hidden, d.H, 0, b[0], 1, nullptr, nullptr, 0,
+                        obj, pred, s_idx, o_idx, d.Din, d.Dp, ldp, d.NO, nullptr, 0, stream));
+  CSG_TRY(csg_gemm_bf16(0, 0, d.NT, Wd, d.H, sv + s.hidden, d.H, sv + s.w2b, d.H, sv + s.out, Wd, 0, b[1], 1, conf, nullptr, 0,
+                        nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, stream));
+  // ---- confidence-weighted average onto objects
+  CSG_TRY(csg_segpool_bf16(sv + s.out, Wd, 0, d.H + d.Dpo, d.H, rowptr_s, perm_s, rowptr_o, perm_o, valid, conf, d.NO,
+                           reinterpret_cast<float*>(sv + s.pooled32), sv + s.pooled16, d.H,
+                           reinterpret_cast<float*>(sv + s.cnt), 1, stream));
+  // ---- net2
+  CSG_TRY(csg_gemm_bf16(0, 0, d.NO, d.H, d.H, sv + s.pooled16, d.H, sv + s.w3b, d.H, sv + s.h2, d.H, 0, b[2], 1, nullptr,
+                        nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, stream));
+  CSG_TRY(csg_gemm_bf16(0, 0, d.NO, d.Dout, d.H, sv + s.h2, d.H, sv + s.w4b, d.H, new_obj, d.Dout, 0, b[3], 1, nullptr,
+                        nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, stream));
+  return 0;
+}
+
+// Backward of the call above.  d_new_obj [NO, Dout] (fp32, or bf16 when d_new_obj_bf16; NULL = zero),
+// d_new_p [NT, Dpo] bf16 with row pitch ld_dnewp (NULL = zero).  Written: dobj [NO, Din] (fp32, or bf16 when
+// dobj_bf16), dX [NT, 2Din+Dp] bf16 (its columns Din..Din+Dp are d pred), dparams (fp32, contiguous, in this order:
+// dw1 [H, 2Din+Dp], db1 [H], dw2 [2H+Dpo, H], db2, dw3 [H, H], db3, dw4 [Dout, H], db4, dw_trans [P]).
+CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pred, int ldp,
+                               const void* const* params, const void* const* index,
+                               const void* d_new_obj, int d_new_obj_bf16, const void* d_new_p, int ld_dnewp,
+                               const void* saved, const void* new_obj, void* dobj, int dobj_bf16, void* dX,
+                               float* dparams, void* workspace, size_t workspace_bytes, csg_stream_t stream) {
+  const Dims d = read_dims(dims);
+  CSG_TRY(check_dims(d));
+  const Saved s = plan_saved(d, true);
+  const Work w = plan_work(d);
+  CSG_REQUIRE(saved && (reinterpret_cast<uintptr_t>(saved) & 255) == 0, "gconv_bf16_bwd: `saved` must be 256-byte aligned");
+  CSG_REQUIRE(workspace && workspace_bytes >= w.total, "gconv_bf16_bwd: workspace of %zu bytes needed", w.total);
+  const uint8_t* sv = reinterpret_cast<const uint8_t*>(saved);
+  uint8_t* ws = align256(workspace);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const float* w_trans = (const float*)params[8];
+  const int* s_idx = (const int*)index[0];
+  const int* o_idx = (const int*)index[1];
+  const int* pred_id = (const int*)index[2];
+  const int* type32 = (const int*)index[3];
+  const int* valid = (const int*)index[4];
+  const int *rowptr_s = (const int*)index[5], *perm_s = (const int*)index[6], *rowptr_o = (const int*)index[7],
+            *perm_o = (const int*)index[8];
+  const int K1 = d.K1(), Wd = d.Wd(), H = d.H, NT = d.NT, NO = d.NO, Dout = d.Dout;
+  // flat parameter gradients
+  float* dw1 = dparams;
+  float* db1 = dw1 + (size_t)H * K1;
+  float* dw2 = db1 + H;
+  float* db2 = dw2 + (size_t)Wd * H;
+  float* dw3 = db2 + Wd;
+  float* db3 = dw3 + (size_t)H * H;
+  float* dw4 = db3 + H;
+  float* db4 = dw4 + (size_t)Dout * H;
+  float* dwt = db4 + Dout;
+  CSG_REQUIRE((reinterpret_cast<uintptr_t>(dparams) & 15) == 0, "gconv_bf16_bwd: dparams must be 16-byte aligned");
+
+  void* g4 = ws + w.g4;
+  void* dh2 = ws + w.dh2;
+  float* dpooled = reinterpret_cast<float*>(ws + w.dpooled);
+  float* dS = reinterpret_cast<float*>(ws + w.dS);
+  float* dcnt = reinterpret_cast<float*>(ws + w.dcnt);
+  void* g = ws + w.g;
+  float* dconf = reinterpret_cast<float*>(ws + w.dconf);
+  void* dhid = ws + w.dhid;
+  void* splitk = ws + w.splitk;
+  void* small = ws + w.small;
+  const void* hidden = sv + s.hidden;
+  const void* out = sv + s.out;
+  const void* h2 = sv + s.h2;
+  const void* pooled16 = sv + s.pooled16;
+  const float* conf = reinterpret_cast<const float*>(sv + s.conf);
+
+#define GEMM(mn, gather, M, N, K, A, lda, B, ldb, C, ldc, f32, mask, ldm)                                            \
+  CSG_TRY(csg_gemm_bf16(mn, gather, M, N, K, A, lda, B, ldb, C, ldc, f32, nullptr, 0, nullptr, mask, ldm,            \
+                        (gather) ? obj : nullptr, (gather) ? pred : nullptr, (gather) ? s_idx : nullptr,             \
+                        (gather) ? o_idx : nullptr, (gather) ? d.Din : 0, (gather) ? d.Dp : 0, (gather) ? ldp : 0,   \
+                        (gather) ? NO : 0, splitk, w.splitk_bytes, stream))
+
+  // ---- net2 backward (graph.py:110)
+  const long long n4 = (long long)NO * Dout;
+  if (n4 > 0) {
+    if (!d_new_obj) {
+      CSG_CUDA(cudaMemsetAsync(g4, 0, (size_t)n4 * 2, st));
+    } else if (d_new_obj_bf16) {
+      relu_mask_out_kernel<true><<<csg_div_up(n4, 256), 256, 0, st>>>(d_new_obj, (const __nv_bfloat16*)new_obj,
+                                                                      (__nv_bfloat16*)g4, n4);
+      CSG_CHECK_LAUNCH("csg_gconv_bf16_bwd relu mask");
+    } else {
+      relu_mask_out_kernel<false><<<csg_div_up(n4, 256), 256, 0, st>>>(d_new_obj, (const __nv_bfloat16*)new_obj,
+                                                                       (__nv_bfloat16*)g4, n4);
+      CSG_CHECK_LAUNCH("csg_gconv_bf16_bwd relu mask");
+    }
+  }
+  GEMM(1, 0, Dout, H, NO, g4, Dout, h2, H, dw4, H, 1, nullptr, 0);
+  CSG_TRY(csg_colsum_bf16(g4, NO, Dout, Dout, db4, small, w.small_bytes, stream));
+  GEMM(0, 0, NO, H, Dout, g4, Dout, sv + s.w4t, Dout, dh2, H, 0, h2, H);
+  GEMM(1, 0, H, H, NO, dh2, H, pooled16, H, dw3, H, 1, nullptr, 0);
+  CSG_TRY(csg_colsum_bf16(dh2, NO, H, H, db3, small, w.small_bytes, stream));
+  GEMM(0, 0, NO, H, H, dh2, H, sv + s.w3t, H, dpooled, H, 1, nullptr, 0);
+  // ---- pooling backward (graph.py:83-107)
+  CSG_TRY(csg_pool_bwd_obj(dpooled, reinterpret_cast<const float*>(sv + s.pooled32),
+                           reinterpret_cast<const float*>(sv + s.cnt), NO, H, dS, dcnt, stream));
+  CSG_TRY(csg_triple_bwd_assemble_bf16(out, dS, d_new_p, d_new_p ? ld_dnewp : 0, dcnt, s_idx, o_idx, valid, type32, conf,
+                                       NT, H, d.Dpo, g, dconf, db2, small, w.small_bytes, stream));
+  // ---- net1 backward (graph.py:63-67)
+  GEMM(1, 0, Wd, H, NT, g, Wd, hidden, H, dw2, H, 1, nullptr, 0);
+  GEMM(0, 0, NT, H, Wd, g, Wd, sv + s.w2t, Wd, dhid, H, 0, hidden, H);
+  GEMM(1, 2, H, K1, NT, dhid, H, nullptr, 0, dw1, K1, 1, nullptr, 0);
+  CSG_TRY(csg_colsum_bf16(dhid, NT, H, H, db1, small, w.small_bytes, stream));
+  GEMM(0, 0, NT, K1, H, dhid, H, sv + s.w1t, H, dX, K1, 0, nullptr, 0);
+#undef GEMM
+  // ---- gather backward: segmented sums of dX over ALL triples onto their subject / object rows
+  CSG_TRY(csg_segpool_bf16(dX, K1, 0, d.Din + d.Dp, d.Din, rowptr_s, perm_s, rowptr_o, perm_o, nullptr, nullptr, NO,
+                           dobj_bf16 ? nullptr : reinterpret_cast<float*>(dobj), dobj_bf16 ? dobj : nullptr, d.Din, nullptr,
+                           0, stream));
+  // ---- confidence backward (graph.py:69-74)
+  CSG_TRY(csg_conf_bwd(dconf, type32, pred_id, w_trans, NT, d.P, dwt, small, w.small_bytes, stream));
+  return 0;
+}

@@ -279,6 +279,7 @@ CSG_API int csg_gemm_f32(int amode, int bmode, int M, int N, int K,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (M == 0 || N == 0) return 0;
   CSG_REQUIRE(M > 0 && N > 0 && K >= 0, "gemm_f32: bad sizes M=%d N=%d K=%d", M, N, K);
+  CsgProfScope prof(CSG_PROF_GEMM_F32, 2.0 * M * N * K, stream);
   GemmParams p;
   p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;
   p.bias = bias; p.relu = relu; p.rowscale = rowscale; p.mask_aux = mask_aux; p.ld_aux = ld_aux;

@@ -693,11 +693,37 @@ int pick_bn(int N) {
   return 64;
 }
 
+// split-K plan of the MN-major (weight-gradient) GEMMs: one work item per CTA (a second wave would double the time)
+void mn_split_plan(int M, int N, int K, int BN, int& kb_per_split, int& nsplits) {
+  const int tiles = csg_div_up(M, BLOCK_M) * csg_div_up(N, BN);
+  const int kb_total = csg_div_up(K, BLOCK_K);
+  int splits = csg_num_sms() / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > 64) splits = 64;
+  if (splits > kb_total) splits = kb_total;
+  kb_per_split = csg_div_up(kb_total, splits);
+  nsplits = csg_div_up(kb_total, kb_per_split);
+}
+
+int mn_pick_bn(int N, int gather) {
+  if (gather == 2) return (N % 192 == 0) ? 192 : (N % 128 == 0 ? 128 : 64);
+  return pick_bn(N);
+}
+
 }  // namespace
 
+// bytes of split-K partials for an MN-major GEMM of this shape on the current device (gathered-B GEMMs may pick a
+// narrower tile: the larger of the two plans is returned)
 CSG_API size_t csg_gemm_bf16_workspace(int M, int N, int K, int mn_major) {
-  if (!mn_major) return 0;
-  return (size_t)64 * M * N * sizeof(float);
+  if (!mn_major || M <= 0 || N <= 0 || K <= 0) return 0;
+  size_t need = 0;
+  for (int gather = 0; gather <= 2; gather += 2) {
+    int kbs, ns;
+    mn_split_plan(M, N, K, mn_pick_bn(N, gather), kbs, ns);
+    const size_t b = ns > 1 ? (size_t)ns * M * N * sizeof(float) : 0;
+    if (b > need) need = b;
+  }
+  return need;
 }
 
 // mn_major = 0:  C[M,N] = epi(A[M,K] * B[N,K]^T)        A, B row-major with K contiguous (bf16)
@@ -713,7 +739,12 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
                           int g_din, int g_dp, int g_ldp, int g_nobj,
                           void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (M == 0 || N == 0) return 0;
+  if (K == 0 && mn_major && out_f32 && M > 0 && N > 0) {      // empty reduction (no triples): the gradient is zero
+    CSG_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, stream));
+    return 0;
+  }
   CSG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: bad sizes M=%d N=%d K=%d", M, N, K);
+  CsgProfScope prof(CSG_PROF_GEMM_BF16, 2.0 * M * N * K, stream);
   CSG_REQUIRE(N % 32 == 0, "gemm_bf16: N=%d must be a multiple of 32", N);
   CSG_REQUIRE((ldc % 8) == 0 || out_f32, "gemm_bf16: bf16 ldc must be a multiple of 8");
   CSG_REQUIRE(!out_f32 || (ldc % 4) == 0, "gemm_bf16: fp32 ldc must be a multiple of 4");
@@ -731,10 +762,8 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
                 "gemm_bf16: gather mode / shape mismatch");
   }
   if (p.mask_aux) CSG_REQUIRE(ld_aux % 8 == 0, "gemm_bf16: ld_aux must be a multiple of 8");
-  int BN = pick_bn(N);
-  if (gather == 2) {   // a gathered 64-column chunk must not straddle two source segments: guaranteed by %64 dims
-    BN = (N % 192 == 0) ? 192 : (N % 128 == 0 ? 128 : 64);
-  }
+  // a gathered 64-column chunk must not straddle two source segments: guaranteed by %64 dims
+  const int BN = mn_pick_bn(N, gather);
   p.m_tiles = csg_div_up(M, BLOCK_M);
   p.n_tiles = csg_div_up(N, BN);
   p.kb_total = csg_div_up(K, BLOCK_K);
@@ -772,13 +801,7 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
   } else {
     CSG_REQUIRE(out_f32, "gemm_bf16: MN-major (weight-gradient) GEMMs write fp32");
     CSG_REQUIRE(!bias && !relu && !rowscale && !mask_aux, "gemm_bf16: MN-major GEMMs have no epilogue");
-    int tiles = p.m_tiles * p.n_tiles;
-    int splits = csg_num_sms() / tiles;          // one work item per CTA: a second wave would double the time
-    if (splits < 1) splits = 1;
-    if (splits > 64) splits = 64;
-    if (splits > p.kb_total) splits = p.kb_total;
-    p.kb_per_split = csg_div_up(p.kb_total, splits);
-    p.splits = csg_div_up(p.kb_total, p.kb_per_split);
+    mn_split_plan(M, N, K, BN, p.kb_per_split, p.splits);
     if (p.splits > 1) {
       CSG_REQUIRE(ldc == N, "gemm_bf16: split-K output must be contiguous");
       CSG_REQUIRE(workspace && workspace_bytes >= (size_t)p.splits * M * N * sizeof(float), "gemm_bf16: workspace too small");

@@ -824,6 +824,7 @@ CSG_API int csg_layout_fwd(const float* vecs, const float* boxes, const float* m
   LayoutParams p;
   if (int rc = fill_params(p, vecs, boxes, masks, obj_off, lin_x, lin_y, N, D, H, W, M, align_corners)) return rc;
   if (N == 0) return 0;
+  CsgProfScope prof(CSG_PROF_LAYOUT_FWD, 4.0 * N * D * H * W, stream);
   p.TW = W <= 64 ? 64 : 128;
   p.TH = fw::TILE_PX / p.TW;
   p.tiles_x = csg_div_up(W, p.TW); p.tiles_y = csg_div_up(H, p.TH);
@@ -868,6 +869,7 @@ CSG_API int csg_layout_bwd_vecs(const float* dout, const float* boxes, const flo
   LayoutParams p;
   if (int rc = fill_params(p, nullptr, boxes, masks, obj_off, lin_x, lin_y, N, D, H, W, M, align_corners)) return rc;
   if (N == 0 || NO == 0) return 0;
+  CsgProfScope prof(CSG_PROF_LAYOUT_BWD, 4.0 * N * D * H * W, stream);
   CSG_REQUIRE(workspace_bytes >= csg_layout_bwd_vecs_workspace(N, NO, D, H, W), "layout bwd: workspace too small");
   float* partial = reinterpret_cast<float*>(workspace);
   if (bw::eligible(dout, D, H, W)) {

@@ -50,6 +50,16 @@ class TripleBatch:
                              ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "csg_csr_build")
 
+    def index_array(self):
+        """HOST array of the 9 device pointers csg_gconv_bf16_fwd/bwd take (include/csg2im.h)."""
+        arr = getattr(self, "_index_array", None)
+        if arr is None:
+            import ctypes
+            ts = (self.s_idx, self.o_idx, self.pred, self.type32, self.valid, self.rowptr_s, self.perm_s,
+                  self.rowptr_o, self.perm_o)
+            arr = self._index_array = (ctypes.c_void_p * 9)(*[t.data_ptr() for t in ts])
+        return arr
+
     # ---- constructors
     @staticmethod
     def _alloc(NT, dev):

@@ -9,6 +9,9 @@ Same dataflow as ``graph._TripleConvF32`` with every GEMM on tcgen05 (csrc/gemm_
 Activations between layers stay bf16; weight gradients, pooling sums and confidences are fp32.
 Tolerance vs the fp32 reference: 1e-2 relative (north_star).
 """
+import ctypes
+import os
+
 import torch
 
 from . import _lib
@@ -172,12 +175,107 @@ class _TripleConvBF16(torch.autograd.Function):
         return None, None, None, dobj, dpred, dw1, db1, dw2, db2, dw3, db3, dw4, db4, dwt
 
 
-def triple_conv(batch, obj, pred, params, w_trans, hidden_dim, pred_out_dim):
+# --------------------------------------------------------------------------------------------
+# native layer executor (csrc/gconv_engine.cu): the same launch sequence, issued by ONE call per direction
+# --------------------------------------------------------------------------------------------
+_WS = {}      # device -> reusable scratch (dead once the call has returned on the stream)
+
+
+def _scratch(nbytes, dev):
+    buf = _WS.get(dev)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=dev)
+        _WS[dev] = buf
+    return buf
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+class _TripleConvEngine(torch.autograd.Function):
+    """One GraphTripleConv layer through csg_gconv_bf16_fwd / csg_gconv_bf16_bwd."""
+
+    @staticmethod
+    def forward(ctx, batch, H, Dpo, obj, pred, w1, b1, w2, b2, w3, b3, w4, b4, w_trans):
+        L = lib()
+        dev = obj.device
+        ctx.in_dtypes = (obj.dtype, pred.dtype)
+        obj_b, pred_b = as_bf16_rows(obj), as_bf16_rows(pred)
+        if not obj_b.is_contiguous():
+            obj_b = obj_b.contiguous()
+        params = [f32c(p.detach()) for p in (w1, b1, w2, b2, w3, b3, w4, b4, w_trans)]
+        Dout, P = w4.shape[0], w_trans.numel()
+        dims = (ctypes.c_int * 8)(batch.NT, batch.NO, obj_b.shape[1], pred_b.shape[1], H, Dout, Dpo, P)
+        need_bwd = int(any(ctx.needs_input_grad))
+        nsaved = L.csg_gconv_bf16_saved_bytes(dims, need_bwd)
+        saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
+        new_obj = torch.empty((batch.NO, Dout), dtype=BF, device=dev)
+        index = batch.index_array()
+        rc = L.csg_gconv_bf16_fwd(dims, ptr(obj_b), ptr(pred_b), pred_b.stride(0), _ptr_array(params), index, need_bwd,
+                                  ptr(saved), nsaved, ptr(new_obj), _stream())
+        _lib.check(rc, "csg_gconv_bf16_fwd")
+        Wd = 2 * H + Dpo
+        off = L.csg_gconv_bf16_out_offset(dims, need_bwd)
+        out = saved[off:off + batch.NT * Wd * 2].view(BF).view(batch.NT, Wd)
+        new_p = out[:, H:H + Dpo]
+        ctx.batch, ctx.dims, ctx.params = batch, dims, params
+        ctx.save_for_backward(obj_b, pred_b, saved, new_obj)
+        ctx.set_materialize_grads(False)
+        return new_obj, new_p
+
+    @staticmethod
+    def backward(ctx, d_obj_out, d_newp):
+        obj, pred, saved, new_obj = ctx.saved_tensors
+        batch, dims, params = ctx.batch, ctx.dims, ctx.params
+        NT, NO, Din, Dp, H, Dout, Dpo, P = list(dims)
+        K1, Wd = 2 * Din + Dp, 2 * H + Dpo
+        dev = obj.device
+        L = lib()
+        if d_obj_out is not None:
+            if d_obj_out.dtype not in (torch.float32, BF):
+                d_obj_out = d_obj_out.float()
+            d_obj_out = d_obj_out.contiguous()
+        if d_newp is not None and not (d_newp.dtype == BF and d_newp.stride(-1) == 1 and d_newp.stride(0) % 8 == 0
+                                       and d_newp.data_ptr() % 16 == 0):
+            d_newp = d_newp.to(BF).contiguous()
+        obj_bf16 = ctx.in_dtypes[0] == BF
+        dobj = torch.empty((NO, Din), dtype=BF if obj_bf16 else torch.float32, device=dev)
+        dX = torch.empty((NT, K1), dtype=BF, device=dev)
+        sizes = (H * K1, H, Wd * H, Wd, H * H, H, Dout * H, Dout, P)
+        dparams = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        nws = L.csg_gconv_bf16_workspace(dims)
+        ws = _scratch(nws, dev)
+        rc = L.csg_gconv_bf16_bwd(dims, ptr(obj), ptr(pred), pred.stride(0), _ptr_array(params), batch.index_array(),
+                                  ptr(d_obj_out), int(d_obj_out is not None and d_obj_out.dtype == BF),
+                                  ptr(d_newp), d_newp.stride(0) if d_newp is not None else 0,
+                                  ptr(saved), ptr(new_obj), ptr(dobj), int(obj_bf16), ptr(dX), ptr(dparams),
+                                  ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "csg_gconv_bf16_bwd")
+        dw1, db1, dw2, db2, dw3, db3, dw4, db4, dwt = torch.split(dparams, sizes)
+        if not obj_bf16 and ctx.in_dtypes[0] != torch.float32:
+            dobj = dobj.to(ctx.in_dtypes[0])
+        dpred = dX[:, Din:Din + Dp]
+        if ctx.in_dtypes[1] != BF:
+            dpred = dpred.to(ctx.in_dtypes[1])
+        return (None, None, None, dobj, dpred, dw1.view(H, K1), db1, dw2.view(Wd, H), db2, dw3.view(H, H), db3,
+                dw4.view(Dout, H), db4, dwt)
+
+
+USE_ENGINE = os.environ.get("CSG_STAGED", "0") != "1"     # CSG_STAGED=1: one ctypes call per stage (debugging)
+
+
+def triple_conv(batch, obj, pred, params, w_trans, hidden_dim, pred_out_dim, staged=None):
     din, dp = obj.shape[1], pred.shape[1]
-    if din % 64 or dp % 64 or hidden_dim % 64 or pred_out_dim % 64:
+    dout = params[6].shape[0]
+    if din % 64 or dp % 64 or hidden_dim % 64 or pred_out_dim % 64 or dout % 64:
         raise _lib.CsgError("precision='bf16' needs feature widths that are multiples of 64 "
-                            "(got Din=%d Dp=%d H=%d Dp_out=%d); use precision='fp32'" % (din, dp, hidden_dim, pred_out_dim))
-    return _TripleConvBF16.apply(batch, hidden_dim, pred_out_dim, obj, pred, *params, w_trans)
+                            "(got Din=%d Dp=%d H=%d Dout=%d Dp_out=%d); use precision='fp32'"
+                            % (din, dp, hidden_dim, dout, pred_out_dim))
+    if staged is None:
+        staged = not USE_ENGINE
+    fn = _TripleConvBF16 if staged else _TripleConvEngine
+    return fn.apply(batch, hidden_dim, pred_out_dim, obj, pred, *params, w_trans)
 
 
 def dense_mlp2(x, w0, b0, w1, b1, final_relu):

@@ -36,6 +36,12 @@ void csg_clear_error(void);
 int csg_version(void);
 int csg_device_sms(void);
 long long csg_launch_count(void);   /* kernel-launch sites passed since the library was loaded */
+/* Live timing of kernel classes (measurement aid, off by default): while enabled, the instrumented entry points
+ * record CUDA events on their stream.  csg_prof_collect fills a HOST array [8][3] = {work, seconds, calls} per
+ * class (0 bf16 GEMMs: FLOP, 1 fp32 GEMMs: FLOP, 2 layout fwd: bytes, 3 layout bwd: bytes, 4 pooling: bytes,
+ * 5 backward assemble: bytes) and clears the records; it synchronises on the recorded events. */
+int csg_prof_enable(int on);
+int csg_prof_collect(double* out);
 
 /* ---- layout compositor: sg2im/layout.py:12-45 (boxes_to_layout), :48-77 (masks_to_layout),
  *      :80-112 (_boxes_to_grid), :156-188 (_pool_samples), batched over images as the caller
@@ -168,6 +174,31 @@ int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const void* d
                                  const int* type32, const float* conf, int NT, int H, int Dp, void* g,
                                  float* dconf, float* colsum_g, void* workspace, size_t workspace_bytes,
                                  csg_stream_t stream);
+
+/* ---- one GraphTripleConv layer (sg2im/graph.py:44-113) per call on the bf16 engine: the launch sequence of the
+ *      stages above issued natively, out of caller-owned `saved` (activations kept for backward + bf16 weights)
+ *      and `workspace` (scratch).  dims (HOST int[8]) = {NT, NO, Din, Dp, H, Dout, Dpo, P}; all widths % 64 == 0.
+ *      params (HOST array of 9 device pointers, fp32): net1.0.weight [H, 2Din+Dp], net1.0.bias, net1.2.weight
+ *      [2H+Dpo, H], net1.2.bias, net2.0.weight [H, H], net2.0.bias, net2.2.weight [Dout, H], net2.2.bias,
+ *      predicates_transitive_weights [P].  index (HOST array of 9 device pointers, int32): s_idx, o_idx, pred_id,
+ *      type32, valid [NT] (csg_triple_prep) and rowptr_s, perm_s, rowptr_o, perm_o (csg_csr_build). ---------- */
+size_t csg_gconv_bf16_saved_bytes(const int* dims, int need_bwd);
+size_t csg_gconv_bf16_out_offset(const int* dims, int need_bwd);   /* byte offset in `saved` of net1's output [NT, 2H+Dpo] bf16 */
+size_t csg_gconv_bf16_workspace(const int* dims);
+/* obj [NO, Din] bf16 contiguous, pred [NT, Dp] bf16 rows of pitch ldp -> new_obj [NO, Dout] bf16; new_p_vecs are
+ * columns H..H+Dpo of the [NT, 2H+Dpo] matrix at saved + csg_gconv_bf16_out_offset.  `saved` 256-byte aligned. */
+int csg_gconv_bf16_fwd(const int* dims, const void* obj, const void* pred, int ldp,
+                       const void* const* params, const void* const* index, int need_bwd, void* saved,
+                       size_t saved_bytes, void* new_obj, csg_stream_t stream);
+/* d_new_obj [NO, Dout] fp32 or (d_new_obj_bf16) bf16, NULL = 0; d_new_p [NT, Dpo] bf16 rows of pitch ld_dnewp,
+ * NULL = 0.  Writes dobj [NO, Din] fp32 or (dobj_bf16) bf16, dX [NT, 2Din+Dp] bf16 (columns Din..Din+Dp = d pred)
+ * and dparams: fp32, contiguous, 16-byte aligned, in the order of `params` (dw1, db1, dw2, db2, dw3, db3, dw4,
+ * db4, dw_trans). */
+int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pred, int ldp,
+                       const void* const* params, const void* const* index,
+                       const void* d_new_obj, int d_new_obj_bf16, const void* d_new_p, int ld_dnewp,
+                       const void* saved, const void* new_obj, void* dobj, int dobj_bf16, void* dX,
+                       float* dparams, void* workspace, size_t workspace_bytes, csg_stream_t stream);
 
 /* ---- embeddings + box loss around the GCN: sg2im/model.py:108-109, sg2im/attribute_embed.py:38-48,
  *      sg2im/pix2pix_model.py:72-85 --------------------------------------------------------------- */

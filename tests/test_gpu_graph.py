@@ -234,3 +234,41 @@ def test_bf16_large_batch_matches_fp32_engine():
     for i, what in ((2, "dW1 layer 0"), (3, "d w_trans")):
         a, b = outs["bf16"][i].double(), outs["fp32"][i].double()
         assert ((a - b).norm() / b.norm()).item() <= 5e-2, what
+
+
+def test_native_layer_executor_is_bitwise_the_staged_path():
+    """csg_gconv_bf16_fwd/bwd issue exactly the launch sequence of the staged (one ctypes call per stage) layer:
+    outputs and every gradient must be bit-identical, on padded golden inputs and on a ragged batch with a
+    strided predicate operand (the previous layer's net1 output)."""
+    from canonicalsg2im_b200 import graph_tc
+    from canonicalsg2im_b200.graph import TripleBatch
+    obj, pred, s, o, p, ty = gi.layer_inputs()
+    B, O, T = obj.shape[0], obj.shape[1], pred.shape[1]
+    layer = _layer("bf16")
+    batch = TripleBatch.from_padded_edges(t(np.stack([s, o], -1)), t(p) != 0, t(ty), t(p), O)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    wide = torch.randn((B * T, 1152), device="cuda", generator=gen).bfloat16()
+    cases = [(t(obj).reshape(B * O, -1), t(pred).reshape(B * T, -1)),                 # fp32 inputs (layer 0 style)
+             (t(obj).reshape(B * O, -1).bfloat16(), wide[:, 512:640])]               # bf16 inputs, strided pred view
+    for oi, pi in cases:
+        res = []
+        for staged in (True, False):
+            layer.zero_grad()
+            ov = oi.clone().requires_grad_(True)
+            pv = pi.detach().clone() if pi.is_contiguous() else pi
+            wide.grad = None
+            if not pi.is_contiguous():
+                base = wide.clone().requires_grad_(True)
+                pv = base[:, 512:640]
+            else:
+                pv = pv.requires_grad_(True)
+                base = pv
+            a, b = graph_tc.triple_conv(batch, ov, pv, layer.layer_params(), layer.predicates_transitive_weights,
+                                        512, 128, staged=staged)
+            ga = torch.randn(a.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9)).to(a.dtype)
+            gb = torch.randn(b.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(10)).to(b.dtype)
+            torch.autograd.backward([a, b], [ga, gb])
+            grads = [q.grad.clone() for q in layer.parameters()]
+            res.append([a.detach().clone(), b.detach().clone(), ov.grad.clone(), base.grad.clone()] + grads)
+        for x, y in zip(*res):
+            assert x.dtype == y.dtype and torch.equal(x, y)
