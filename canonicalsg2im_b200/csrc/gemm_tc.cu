@@ -20,18 +20,20 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // bf16 elements = 128 bytes = one swizzle row
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 192;              // producer, MMA, 4 epilogue warps
-constexpr int GATHER_WARPS = 4;               // extra warps 6-9 of the gather variants (8 issuing lanes each)
+constexpr int NUM_THREADS = 320;              // producer, MMA, 8 epilogue warps
+constexpr int GATHER_WARPS = 4;               // extra warps 10-13 of the gather variants (8 issuing lanes each)
+constexpr int FIRST_GATHER_WARP = 10;
 constexpr int ACC_STRIDE = 256;                   // TMEM columns per accumulator stage
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;                      // two per TMEM lane quarter: one warp per scheduler cannot hide its own latencies
 constexpr int CHUNK_N = 64;                       // epilogue chunk: 64 bf16 columns = one 128-byte swizzle row
 constexpr int CHUNK_BYTES = 32 * CHUNK_N * 2;     // per-warp staging buffer: 32 rows x 128 bytes
 constexpr size_t SMEM_LIMIT = 232448;             // 227 KB opt-in maximum per CTA
@@ -41,8 +43,8 @@ enum { G_NONE = 0, G_A = 1, G_B = 2 };
 struct TcParams {
   int M, N, K;                 // K = reduction length (rows of the MN-major operands)
   int m_tiles, n_tiles, splits, kb_per_split, kb_total;
-  int stages, cbufs;           // smem ring depth; staging buffers per epilogue warp (1 or 2)
-  int tma_epi;                 // bf16 output through swizzled smem + TMA store (K-major kernels)
+  int stages;                  // smem ring depth
+  int smem_epi;                // bf16 output through the swizzled smem staging tile + coalesced stores (K-major kernels)
   void* C;                     // [splits][M][ldc] (splits > 1: fp32 partials)
   int ldc, out_f32;
   const float* bias;           // [N]
@@ -54,6 +56,7 @@ struct TcParams {
   const int* g_sidx;
   const int* g_oidx;
   int g_din, g_dp, g_rows;
+  int debug;                   // scratch/bench_gemm.py only: 1 = no operand loads, 2 = no MMAs, 4 = no epilogue work
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -79,14 +82,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps instead of hanging the GPU box.
+// Bounded wait: a protocol bug traps instead of hanging the GPU box.  The report lives in one out-of-line function so
+// that the many wait sites stay small (instruction cache) and keep no printf argument buffers on their stacks.
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("csg gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("csg gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (++spins > (1u << 26)) mbar_timeout(bar, parity);
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -103,20 +108,40 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
       : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
-               : "memory");
+// cta_group::2 forms: the destination is this CTA's shared memory, the mbarrier lives in the pair's leader CTA
+// (bar is a shared::cluster address obtained with mapa).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
 }
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_gather4_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int r0, int r1, int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -139,6 +164,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// cta_group::2 forms (CTA pair: one MMA of M = 256 spans both SMs, each CTA holds half of B)
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this CTA-relative address in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -177,24 +225,22 @@ struct __align__(8) Barriers {
   uint64_t empty[MAX_STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t aux_full[EPI_WARPS][2];
   uint32_t tmem_base;
 };
 
 // Shared-memory plan (offsets from the 1024-byte aligned base):
-//   [A ring: stages x 16 KB][B ring: stages x BN*128 B][C staging: 4 warps x cbufs x 4 KB]
+//   [A ring: stages x 16 KB][B ring: stages x BN*128 B][C staging: 4 warps x 4 KB]
 //   [aux staging: 4 warps x 2 x 4 KB][bias: 4 warps x BN floats][barriers]
 struct SmemPlan {
-  uint32_t b, c, aux, bias, bars, total;
+  uint32_t b, c, bias, bars, total;
 };
-__host__ __device__ inline SmemPlan smem_plan(int BN, int stages, int cbufs, bool tma_epi, bool has_aux) {
+__host__ __device__ inline SmemPlan smem_plan(int BN, int b_rows, int stages, bool smem_epi) {
   SmemPlan s;
   s.b = (uint32_t)stages * A_STAGE_BYTES;
-  s.c = s.b + (uint32_t)stages * BN * 128;
-  s.aux = s.c + (tma_epi ? EPI_WARPS * cbufs * CHUNK_BYTES : 0);
-  s.bias = s.aux + ((tma_epi && has_aux) ? EPI_WARPS * 2 * CHUNK_BYTES : 0);
-  s.bars = s.bias + (tma_epi ? EPI_WARPS * BN * 4 : 0);
-  s.total = s.bars + (uint32_t)sizeof(Barriers) + 1024;      // + alignment slack
+  s.c = s.b + (uint32_t)stages * b_rows * 128;
+  s.bias = s.c + (smem_epi ? EPI_WARPS * CHUNK_BYTES : 0);
+  s.bars = s.bias + (smem_epi ? 2 * BN * 4 : 0);             // bias of the current n-tile, double-buffered by tile parity
+  s.total = s.bars + (uint32_t)sizeof(Barriers);
   return s;
 }
 
@@ -206,18 +252,35 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ bool bf16_pos(uint32_t h) { return h != 0 && h < 0x8000u; }
 
 // tmA/tmB: operand maps (in the gather variants the gathered operand's slot holds the object-row table,
-// box {64, 1}); tmP: predicate rows of the fused gather; tmC/tmX: output / ReLU-mask operand, box {64, 32}.
-template <int BN, bool MN, int GATHER>
+// box {64, 1}); tmP: predicate rows of the fused gather.
+//
+// CG = 2 (K-major variants only): the kernel runs as clusters of two CTAs on one TPC.  A pair owns a 256 x BN tile:
+// each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), the leader (cluster rank 0) issues
+// tcgen05.mma.cta_group::2 (M = 256) which reads both halves of B across the pair, and each CTA's TMEM receives the
+// accumulators of its own 128 rows.  This halves the B bytes every SM has to ingest per MMA cycle, which is what
+// bounds the 1-CTA kernel (ncu r01d: 47 % tensor-pipe active with L2 and DRAM far from saturated).
+// Pair protocol: all TMA loads of both CTAs complete on the LEADER's full[] barrier; the leader's commits are
+// multicast to empty[] / tmem_full[] of both CTAs; both CTAs' epilogue warps arrive on the leader's tmem_empty[].
+template <int BN, bool MN, int GATHER, int CG>
 __global__ void __launch_bounds__(NUM_THREADS + (GATHER != G_NONE ? GATHER_WARPS * 32 : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmC,
-               const __grid_constant__ CUtensorMap tmX, const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024-byte alignment
-  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  constexpr int B_STAGE = BN * BLOCK_K * 2;
-  const bool has_aux = p.mask_aux != nullptr;
-  const SmemPlan plan = smem_plan(BN, p.stages, p.cbufs, p.tma_epi != 0, has_aux);
+               const __grid_constant__ CUtensorMap tmP, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];             // SWIZZLE_128B needs 1024-byte alignment
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* base_ptr = smem_raw;
+  if ((base & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("csg gemm_tc: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  static_assert(CG == 1 || !MN, "CTA pairs are implemented for the K-major kernels");
+  constexpr int B_ROWS = BN / CG;                   // rows of the B tile staged by this CTA
+  constexpr int B_STAGE = B_ROWS * BLOCK_K * 2;
+  constexpr int TILE_M = BLOCK_M * CG;              // rows of C per work item (pair tile when CG = 2)
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int worker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nworkers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const bool has_aux = GATHER == G_NONE && p.mask_aux != nullptr;   // the gathered GEMMs never take a ReLU mask
+  const SmemPlan plan = smem_plan(BN, B_ROWS, p.stages, p.smem_epi != 0);
   const uint32_t sA = base, sB = base + plan.b;
   Barriers* bars = reinterpret_cast<Barriers*>(base_ptr + plan.bars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -231,27 +294,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bars->tmem_full[s]), 1);
-      mbar_init(smem_u32(&bars->tmem_empty[s]), EPI_WARPS);
+      mbar_init(smem_u32(&bars->tmem_empty[s]), EPI_WARPS * CG);
     }
-    for (int w = 0; w < EPI_WARPS; ++w)
-      for (int s = 0; s < 2; ++s) mbar_init(smem_u32(&bars->aux_full[w][s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (GATHER != G_NONE) tma_prefetch_desc(&tmP);
-    if (p.tma_epi) tma_prefetch_desc(&tmC);
-    if (p.tma_epi && has_aux) tma_prefetch_desc(&tmX);
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(&bars->tmem_base), 512);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_pair(smem_u32(&bars->tmem_base), 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(smem_u32(&bars->tmem_base), 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();     // barriers of BOTH CTAs are initialised past this point
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  // shared::cluster address of a barrier of the pair's leader (identity for the 1-CTA kernel)
+  auto leader = [&](const uint64_t* bar) -> uint32_t { return CG == 2 ? mapa(smem_u32(bar), 0u) : smem_u32(bar); };
 
   auto decode = [&](int tile, int& mt, int& nt, int& sp) {
     nt = tile % p.n_tiles;
@@ -268,17 +329,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================================================================== producer (one lane): tile loads
     if (lane == 0) {
       int stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += nworkers) {
         int mt, nt, sp, kb0, kb1;
         decode(tile, mt, nt, sp);
         kb_range(sp, kb0, kb1);
+        const int m0 = mt * TILE_M + (int)cta_rank * BLOCK_M;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
-          const uint32_t fb = smem_u32(&bars->full[stage]);
-          // the whole stage is accounted here; bytes gathered by warps 6-9 may land before or after this arrive
-          mbar_arrive_expect_tx(fb, A_STAGE_BYTES + B_STAGE);
+          const uint32_t fb = leader(&bars->full[stage]);
+          // the whole stage (of both CTAs of a pair) is accounted here by the leader; bytes gathered by warps 6-9 or
+          // loaded by the peer CTA may land before or after this arrive
+          if (p.debug & 1) {
+            if (CG == 1 || cta_rank == 0) mbar_arrive(smem_u32(&bars->full[stage]));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          if (CG == 1 || cta_rank == 0) mbar_arrive_expect_tx(smem_u32(&bars->full[stage]), CG * (A_STAGE_BYTES + B_STAGE));
           const uint32_t a_dst = sA + stage * A_STAGE_BYTES, b_dst = sB + stage * B_STAGE;
-          if (!MN) {
+          if (!MN && CG == 2) {
+            if (GATHER == G_NONE) tma_load_2d_pair(a_dst, &tmA, fb, kb * BLOCK_K, m0);
+            else {
+              const int c0 = kb * BLOCK_K;
+              if (c0 >= p.g_din && c0 < p.g_din + p.g_dp) tma_load_2d_pair(a_dst, &tmP, fb, c0 - p.g_din, m0);
+            }
+            tma_load_2d_pair(b_dst, &tmB, fb, kb * BLOCK_K, nt * BN + (int)cta_rank * B_ROWS);
+          } else if (!MN) {
             // K-major: rows = M (or N), 64 contiguous k elements per 128-byte row
             if (GATHER == G_NONE) tma_load_2d(a_dst, &tmA, fb, kb * BLOCK_K, mt * BLOCK_M);
             else {
@@ -299,15 +374,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= FIRST_GATHER_WARP) {
     // ================================================================== gather producers (warps 6-9, lanes 0-7)
     // Object rows of the virtual operand arrive by TMA tile::gather4 (4 rows x 128 bytes per instruction, written
     // in the same 128-byte swizzle as a tile load).  A TMA instruction takes warp-uniform operands, so a warp
     // issues them one lane at a time: the work is spread over 4 warps x 8 lanes.
     if (GATHER != G_NONE && lane < 8) {
-      const int gl = (warp - 6) * 8 + lane;          // 0..31
+      const int gl = (warp - FIRST_GATHER_WARP) * 8 + lane;          // 0..31
       int stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += nworkers) {
         int mt, nt, sp, kb0, kb1;
         decode(tile, mt, nt, sp);
         kb_range(sp, kb0, kb1);
@@ -316,7 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           int si[4], oi[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int t = mt * BLOCK_M + 4 * gl + i;
+            const int t = mt * TILE_M + (int)cta_rank * BLOCK_M + 4 * gl + i;
             const bool ok = t < p.g_rows;
             si[i] = ok ? __ldg(p.g_sidx + t) : 0;
             oi[i] = ok ? __ldg(p.g_oidx + t) : 0;
@@ -326,10 +401,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool seg_s = c0 < p.g_din, seg_o = c0 >= p.g_din + p.g_dp;
             if (seg_s || seg_o) {
               mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
-              const uint32_t fb = smem_u32(&bars->full[stage]);
+              const uint32_t fb = leader(&bars->full[stage]);
               const uint32_t dst = sA + stage * A_STAGE_BYTES + gl * 512;
-              if (seg_s) tma_gather4(dst, &tmA, fb, c0, si[0], si[1], si[2], si[3]);
-              else tma_gather4(dst, &tmA, fb, c0 - p.g_din - p.g_dp, oi[0], oi[1], oi[2], oi[3]);
+              if (CG == 2) {
+                if (seg_s) tma_gather4_pair(dst, &tmA, fb, c0, si[0], si[1], si[2], si[3]);
+                else tma_gather4_pair(dst, &tmA, fb, c0 - p.g_din - p.g_dp, oi[0], oi[1], oi[2], oi[3]);
+              } else {
+                if (seg_s) tma_gather4(dst, &tmA, fb, c0, si[0], si[1], si[2], si[3]);
+                else tma_gather4(dst, &tmA, fb, c0 - p.g_din - p.g_dp, oi[0], oi[1], oi[2], oi[3]);
+              }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -382,14 +462,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BN, MN, MN);
+    if (lane == 0 && cta_rank == 0) {
       int stage = 0, phase = 0, it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
         int mt, nt, sp, kb0, kb1;
         decode(tile, mt, nt, sp);
         kb_range(sp, kb0, kb1);
         const int as = it & 1, aphase = (it >> 1) & 1;
+        // the last n-tile may be narrower than BN: issue MMAs of its real width (N % 32 == 0 is required by the host
+        // side; an MMA of N = 192 costs as much as N = 256, which is why BN is 256 with a narrow tail and not 192)
+        const int mma_n = (!MN && CG == 1) ? min(BN, p.N - nt * BN) : BN;
+        const uint32_t idesc = make_idesc(TILE_M, mma_n, MN, MN);
         mbar_wait(smem_u32(&bars->tmem_empty[as]), aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
@@ -407,73 +490,96 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               ad = make_desc(a_base + k * 2048, 8192, 1024);
               bd = make_desc(b_base + k * 2048, 8192, 1024);
             }
-            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (p.debug & 2) continue;
+            if (CG == 2) umma_bf16_pair(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(smem_u32(&bars->empty[stage]));        // frees the smem slot when these MMAs retire
-          if (kb == kb1 - 1) umma_commit(smem_u32(&bars->tmem_full[as]));
+          if (CG == 2) {
+            umma_commit_pair(smem_u32(&bars->empty[stage]));   // frees the slot in both CTAs when these MMAs retire
+            if (kb == kb1 - 1) umma_commit_pair(smem_u32(&bars->tmem_full[as]));
+          } else {
+            umma_commit(smem_u32(&bars->empty[stage]));        // frees the smem slot when these MMAs retire
+            if (kb == kb1 - 1) umma_commit(smem_u32(&bars->tmem_full[as]));
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (kb1 <= kb0) umma_commit(smem_u32(&bars->tmem_full[as]));   // empty k range (never scheduled)
+        if (kb1 <= kb0) {                                      // empty k range (never scheduled)
+          if (CG == 2) umma_commit_pair(smem_u32(&bars->tmem_full[as])); else umma_commit(smem_u32(&bars->tmem_full[as]));
+        }
       }
     }
-  } else if (warp < 6) {
-    // ================================================================== epilogue (warps 2-5)
+  } else if (warp < FIRST_GATHER_WARP) {
+    // ================================================================== epilogue (warps 2-9)
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int ew = warp - 2;                      // 0..7
+    const int half = ew >> 2;                     // the two warps of a quarter take alternate 64-column chunks
     int it = 0;
-    if (!MN && p.tma_epi) {
-      // bf16 output: registers -> swizzled smem -> TMA store, 64 columns at a time, this warp's 32 rows only
-      const uint32_t sC = base + plan.c + q * p.cbufs * CHUNK_BYTES;
-      const uint32_t sX = base + plan.aux + q * 2 * CHUNK_BYTES;
-      float* sbias = reinterpret_cast<float*>(base_ptr + plan.bias) + q * BN;
-      const uint32_t sw = (uint32_t)(lane & 7) << 4;           // 128B swizzle: 16-byte chunk j of row r sits at j ^ (r & 7)
+    if (!MN && p.smem_epi) {
+      // bf16 output, 64 columns at a time: registers (one row per lane) -> bias / ReLU / row scale -> this warp's
+      // swizzled 32 x 128 B staging tile -> registers in the coalesced layout (one instruction = 4 rows x 128 B) ->
+      // ReLU mask (the mask operand is read with the same coalesced addressing, one chunk ahead) -> 16-byte global
+      // stores.  Stores are fire-and-forget: no epilogue warp ever waits for a write to drain.
+      const uint32_t sC = base + plan.c + ew * CHUNK_BYTES;
+      float* sbias_all = reinterpret_cast<float*>(base_ptr + plan.bias);
+      const int etid = threadIdx.x - 64;                      // 0..255 among the epilogue threads
+      const uint32_t sw = (uint32_t)(lane & 7) << 4;           // 128B swizzle: 16-byte piece j of row r sits at j ^ (r & 7)
       const uint32_t row_off = (uint32_t)lane * 128;
-      uint32_t gc = 0;                                          // chunks stored so far (staging buffer parity)
-      uint32_t xc = 0;                                          // aux chunks consumed so far
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int crow = lane >> 3, cpiece = lane & 7;           // coalesced layout: rows i*4 + crow, 16-byte piece cpiece
+      __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
+      auto load_mask = [&](uint4 (&ax)[8], int row0, int col) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = row0 + i * 4 + crow;
+          ax[i] = (r < p.M && col < p.N) ? __ldg(reinterpret_cast<const uint4*>(p.mask_aux + (size_t)r * p.ld_aux + col))
+                                         : make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
         int mt, nt, sp;
         decode(tile, mt, nt, sp);
         const int as = it & 1, aphase = (it >> 1) & 1;
-        const int row0 = mt * BLOCK_M + q * 32;
+        const int row0 = mt * TILE_M + (int)cta_rank * BLOCK_M + q * 32;
         const int row = row0 + lane;
         const int ncols = min(BN, p.N - nt * BN);
         const int nchunks = (ncols + CHUNK_N - 1) / CHUNK_N;
         const bool warp_rows = row0 < p.M;
-        if (has_aux && lane == 0 && warp_rows) {
-          for (int c = 0; c < min(2, nchunks); ++c) {
-            const uint32_t xb = smem_u32(&bars->aux_full[q][(xc + c) & 1]);
-            mbar_arrive_expect_tx(xb, CHUNK_BYTES);
-            tma_load_2d(sX + ((xc + c) & 1) * CHUNK_BYTES, &tmX, xb, nt * BN + c * CHUNK_N, row0);
-          }
-        }
+        const float* sbias = sbias_all + (it & 1) * BN;
         if (p.bias) {
-          for (int j = lane; j < BN; j += 32) sbias[j] = (nt * BN + j < p.N) ? __ldg(p.bias + nt * BN + j) : 0.f;
+          // one copy per CTA, filled by the 256 epilogue threads; the buffer of tile it-1 may still be in use by a
+          // slower warp, the one of tile it-2 cannot (every warp has passed the barrier of tile it-1 since)
+          for (int j = etid; j < BN; j += EPI_WARPS * 32)
+            sbias_all[(it & 1) * BN + j] = (nt * BN + j < p.N) ? __ldg(p.bias + nt * BN + j) : 0.f;
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
         }
         const float rs = (p.rowscale && row < p.M) ? __ldg(p.rowscale + row) : 1.f;
-        __syncwarp();
         mbar_wait(smem_u32(&bars->tmem_full[as]), aphase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
+        const int my_last = ((nchunks - 1 - half) & ~1) + half;      // last chunk of this warp (< half: it has none)
+        if ((p.debug & 4) || my_last < half) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (CG == 2) mbar_arrive_cluster(leader(&bars->tmem_empty[as])); else mbar_arrive(smem_u32(&bars->tmem_empty[as])); }
+          continue;
+        }
 #pragma unroll 1
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = half; c < nchunks; c += 2) {
           uint32_t r0[32], r1[32];
           tmem_ld32(t_row + c * CHUNK_N, r0);
           tmem_ld32(t_row + c * CHUNK_N + 32, r1);
-          const uint32_t cbuf = sC + (p.cbufs == 2 ? (gc & 1) : 0) * CHUNK_BYTES;
-          if (warp_rows) {
-            // the TMA store that last read this staging buffer must have drained it
-            if (lane == 0) { if (p.cbufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
-            if (has_aux) mbar_wait(smem_u32(&bars->aux_full[q][xc & 1]), (xc >> 1) & 1);
-          }
-          __syncwarp();
+          const int col = nt * BN + c * CHUNK_N + cpiece * 8;  // first column of this lane's 16-byte piece
+          // ReLU-mask operand of this chunk, in the coalesced layout of the final stores: needed only after the math
+          // and the staging round trip below, which cover its latency
+          uint4 ax[8];
+          if (has_aux && warp_rows) load_mask(ax, row0, col);
           tmem_ld_wait();
-          if (c == nchunks - 1) {
+          if (c == my_last) {
             // accumulator fully read: hand the TMEM stage back before the math / stores of the last chunk
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[as]));
+            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(leader(&bars->tmem_empty[as])); else mbar_arrive(smem_u32(&bars->tmem_empty[as])); }
           }
           if (warp_rows) {
-            const uint32_t xbuf = sX + (xc & 1) * CHUNK_BYTES;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               float v[32];
@@ -497,52 +603,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 const uint32_t off = row_off + ((((uint32_t)(h * 4 + j4)) << 4) ^ sw);
-                if (has_aux) {
-                  uint4 a;
-                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(xbuf + off));
-                  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    if (!bf16_pos(w[e] & 0xFFFFu)) v[j4 * 8 + e * 2] = 0.f;
-                    if (!bf16_pos(w[e] >> 16)) v[j4 * 8 + e * 2 + 1] = 0.f;
-                  }
-                }
                 const uint32_t u0 = pack_bf16(v[j4 * 8], v[j4 * 8 + 1]), u1 = pack_bf16(v[j4 * 8 + 2], v[j4 * 8 + 3]);
                 const uint32_t u2 = pack_bf16(v[j4 * 8 + 4], v[j4 * 8 + 5]), u3 = pack_bf16(v[j4 * 8 + 6], v[j4 * 8 + 7]);
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(cbuf + off), "r"(u0), "r"(u1), "r"(u2), "r"(u3) : "memory");
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sC + off), "r"(u0), "r"(u1), "r"(u2), "r"(u3) : "memory");
               }
             }
-            fence_proxy_async();                   // generic-proxy smem writes -> visible to the TMA store
             __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmC, cbuf, nt * BN + c * CHUNK_N, row0);
-              bulk_commit();
-              if (has_aux && c + 2 < nchunks) {    // every lane has read aux buffer (xc & 1): refill it
-                const uint32_t xb = smem_u32(&bars->aux_full[q][xc & 1]);
-                mbar_arrive_expect_tx(xb, CHUNK_BYTES);
-                tma_load_2d(xbuf, &tmX, xb, nt * BN + (c + 2) * CHUNK_N, row0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rl = i * 4 + crow;
+              uint4 o;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                           : "r"(sC + (uint32_t)rl * 128 + ((uint32_t)(cpiece ^ (rl & 7)) << 4)));
+              if (has_aux) {
+                const uint32_t a[4] = {ax[i].x, ax[i].y, ax[i].z, ax[i].w};
+                uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!bf16_pos(a[e] & 0xFFFFu)) w[e] &= 0xFFFF0000u;
+                  if (!bf16_pos(a[e] >> 16)) w[e] &= 0x0000FFFFu;
+                }
+                o = make_uint4(w[0], w[1], w[2], w[3]);
               }
+              if (row0 + rl < p.M && col < p.N)
+                *reinterpret_cast<uint4*>(Cb + (size_t)(row0 + rl) * p.ldc + col) = o;
             }
-            ++gc;
-            if (has_aux) ++xc;
+            __syncwarp();                        // the staging tile is rewritten by the next chunk
           }
         }
       }
-      if (lane == 0) bulk_wait<0>();
     } else {
       // fp32 output (split-K partials, small fp32 results): direct 16-byte stores, 32 columns at a time
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
         int mt, nt, sp;
         decode(tile, mt, nt, sp);
         const int as = it & 1, aphase = (it >> 1) & 1;
         mbar_wait(smem_u32(&bars->tmem_full[as]), aphase);
         tc_fence_after();
-        const int row = mt * BLOCK_M + q * 32 + lane;
+        const int row = mt * TILE_M + (int)cta_rank * BLOCK_M + q * 32 + lane;
         const bool rowok = row < p.M;
         const float rs = (p.rowscale && rowok) ? p.rowscale[row] : 1.f;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half; c < BN / 32; c += 2) {
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           tmem_ld_wait();
@@ -599,14 +702,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[as]));
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(leader(&bars->tmem_empty[as])); else mbar_arrive(smem_u32(&bars->tmem_empty[as])); }
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // no CTA leaves while its peer can still touch its smem / TMEM
+  if (warp == 2) { if (CG == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 __global__ void splitk_reduce_tc_kernel(const float* __restrict__ partial, float* __restrict__ C, long long MN, int splits) {
@@ -652,36 +755,60 @@ int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, 
 }
 
 struct Maps {
-  CUtensorMap a, b, p, c, x;
+  CUtensorMap a, b, p;
 };
 
-template <int BN, bool MN, int GATHER>
+template <int BN, bool MN, int GATHER, int CG>
 int launch(const Maps& m, const TcParams& p, cudaStream_t stream) {
-  const size_t smem = smem_plan(BN, p.stages, p.cbufs, p.tma_epi != 0, p.mask_aux != nullptr).total;
+  const size_t smem = smem_plan(BN, BN / CG, p.stages, p.smem_epi != 0).total;
   CSG_REQUIRE(smem <= SMEM_LIMIT, "gemm_tc: shared-memory plan of %zu bytes exceeds the limit", smem);
   static bool configured = false;
   if (!configured) {
-    CSG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    CSG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN, GATHER, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     configured = true;
   }
-  int tiles = p.m_tiles * p.n_tiles * p.splits;
-  int grid = tiles < csg_num_sms() ? tiles : csg_num_sms();
-  gemm_tc_kernel<BN, MN, GATHER><<<grid, NUM_THREADS + (GATHER != G_NONE ? GATHER_WARPS * 32 : 0), smem, stream>>>(m.a, m.b, m.p, m.c, m.x, p);
+  const int tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int nthreads = NUM_THREADS + (GATHER != G_NONE ? GATHER_WARPS * 32 : 0);
+  if (CG == 1) {
+    const int grid = tiles < csg_num_sms() ? tiles : csg_num_sms();
+    gemm_tc_kernel<BN, MN, GATHER, CG><<<grid, nthreads, smem, stream>>>(m.a, m.b, m.p, p);
+  } else {
+    // one CTA pair (cluster of 2 on one TPC) per work item, persistent over the pair tiles
+    const int pairs = csg_num_sms() / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+    cfg.blockDim = dim3(nthreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CSG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MN, GATHER, CG>, m.a, m.b, m.p, p));
+  }
   CSG_CHECK_LAUNCH("csg_gemm_bf16");
   return 0;
 }
 
-template <bool MN, int GATHER>
+template <bool MN, int GATHER, int CG>
 int launch_bn(int BN, const Maps& m, const TcParams& p, cudaStream_t stream) {
   switch (BN) {
-    case 64: return launch<64, MN, GATHER>(m, p, stream);
-    case 128: return launch<128, MN, GATHER>(m, p, stream);
-    case 192: return launch<192, MN, GATHER>(m, p, stream);
-    case 256: return launch<256, MN, GATHER>(m, p, stream);
+    case 64: return launch<64, MN, GATHER, CG>(m, p, stream);
+    case 128: return launch<128, MN, GATHER, CG>(m, p, stream);
+    case 192: return launch<192, MN, GATHER, CG>(m, p, stream);
+    case 256: return launch<256, MN, GATHER, CG>(m, p, stream);
   }
   csg_set_error("gemm_tc: unsupported BLOCK_N %d", BN);
   return 1;
 }
+
+// CTA-pair policy of the K-major GEMMs: -1 = automatic (pairs once M fills every SM at least twice), 0 = never,
+// 1 = whenever the shape allows it (tests)
+int g_pair_mode = -1;
+
+// K-major kernels: 256-wide tiles with a narrower last tile (the MMA of the tail uses its real width)
+int kmajor_pick_bn(int N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }
 
 int pick_bn(int N) {
   if (N % 256 == 0) return 256;
@@ -711,6 +838,8 @@ int mn_pick_bn(int N, int gather) {
 }
 
 }  // namespace
+
+CSG_API void csg_gemm_bf16_set_pair_mode(int mode) { g_pair_mode = mode; }
 
 // bytes of split-K partials for an MN-major GEMM of this shape on the current device (gathered-B GEMMs may pick a
 // narrower tile: the larger of the two plans is returned)
@@ -755,6 +884,7 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
   p.mask_aux = reinterpret_cast<const __nv_bfloat16*>(mask_aux); p.ld_aux = ld_aux;
   p.g_sidx = g_sidx; p.g_oidx = g_oidx; p.g_din = g_din; p.g_dp = g_dp;
   p.g_rows = mn_major ? K : M;
+  { const char* dbg = getenv("CSG_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   if (gather) {
     CSG_REQUIRE(g_obj && g_pred && g_sidx && g_oidx && g_nobj > 0, "gemm_bf16: gather sources missing");
     CSG_REQUIRE(g_din % 64 == 0 && g_dp % 64 == 0 && g_ldp % 8 == 0, "gemm_bf16: gather dims must be multiples of 64");
@@ -762,9 +892,14 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
                 "gemm_bf16: gather mode / shape mismatch");
   }
   if (p.mask_aux) CSG_REQUIRE(ld_aux % 8 == 0, "gemm_bf16: ld_aux must be a multiple of 8");
+  CSG_REQUIRE(!(gather && mask_aux), "gemm_bf16: the gathered GEMMs take no ReLU mask");
   // a gathered 64-column chunk must not straddle two source segments: guaranteed by %64 dims
-  const int BN = mn_pick_bn(N, gather);
-  p.m_tiles = csg_div_up(M, BLOCK_M);
+  const int BN = mn_major ? mn_pick_bn(N, gather) : kmajor_pick_bn(N);
+  // CTA pairs (cta_group::2): K-major only; each CTA stages BN/2 rows of B, so BN/2 must keep the 8-row swizzle atoms
+  const bool pair = !mn_major && (BN % 32 == 0) && csg_num_sms() >= 2 &&
+                    (g_pair_mode == 1 || (g_pair_mode < 0 && M >= 2 * BLOCK_M * csg_num_sms()));
+  const int CG = pair ? 2 : 1;
+  p.m_tiles = csg_div_up(M, BLOCK_M * CG);
   p.n_tiles = csg_div_up(N, BN);
   p.kb_total = csg_div_up(K, BLOCK_K);
   p.splits = 1;
@@ -772,9 +907,8 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
   Maps maps;
   memset(&maps, 0, sizeof(maps));
   void* out = C;
-  p.tma_epi = 0;
+  p.smem_epi = 0;
   p.stages = 4;
-  p.cbufs = 1;
   if (!mn_major) {
     CSG_REQUIRE(K % 8 == 0, "gemm_bf16: K=%d must be a multiple of 8", K);
     if (gather == 1) {
@@ -784,20 +918,15 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
     } else {
       if (int rc = make_map(&maps.a, A, K, M, (uint64_t)lda * 2, BLOCK_M)) return rc;
     }
-    if (int rc = make_map(&maps.b, B, K, N, (uint64_t)ldb * 2, BN)) return rc;
-    p.tma_epi = (!out_f32 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) ? 1 : 0;
-    if (p.tma_epi) {
-      if (int rc = make_map(&maps.c, C, N, M, (uint64_t)ldc * 2, 32)) return rc;
-      if (p.mask_aux) { if (int rc = make_map(&maps.x, mask_aux, N, M, (uint64_t)ld_aux * 2, 32)) return rc; }
-    }
-    // deepest ring that fits, then double-buffered staging if it still fits
-    const bool aux = p.mask_aux != nullptr;
-    int best_s = 0, best_c = 1;
-    for (int st = 4; st >= 2 && !best_s; --st)
-      for (int cb = 2; cb >= 1; --cb)
-        if (smem_plan(BN, st, cb, p.tma_epi != 0, aux).total <= SMEM_LIMIT) { best_s = st; best_c = cb; break; }
+    if (int rc = make_map(&maps.b, B, K, N, (uint64_t)ldb * 2, BN / CG)) return rc;
+    p.smem_epi = (!out_f32 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                  (!mask_aux || (reinterpret_cast<uintptr_t>(mask_aux) & 15) == 0)) ? 1 : 0;
+    // deepest ring that fits
+    int best_s = 0;
+    for (int st = (pair ? 6 : 5); st >= 2 && !best_s; --st)
+      if (smem_plan(BN, BN / CG, st, p.smem_epi != 0).total <= SMEM_LIMIT) best_s = st;
     CSG_REQUIRE(best_s > 0, "gemm_bf16: no shared-memory plan fits BN=%d", BN);
-    p.stages = best_s; p.cbufs = best_c;
+    p.stages = best_s;
   } else {
     CSG_REQUIRE(out_f32, "gemm_bf16: MN-major (weight-gradient) GEMMs write fp32");
     CSG_REQUIRE(!bias && !relu && !rowscale && !mask_aux, "gemm_bf16: MN-major GEMMs have no epilogue");
@@ -814,11 +943,12 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
     } else {
       if (int rc = make_map(&maps.b, B, N, K, (uint64_t)ldb * 2, 64)) return rc;
     }
-    p.stages = smem_plan(BN, 5, 1, false, false).total <= SMEM_LIMIT ? 5 : 4;
+    p.stages = smem_plan(BN, BN, 5, false).total <= SMEM_LIMIT ? 5 : 4;
   }
   int rc;
-  if (!mn_major) rc = gather == 1 ? launch_bn<false, G_A>(BN, maps, p, stream) : launch_bn<false, G_NONE>(BN, maps, p, stream);
-  else rc = gather == 2 ? launch_bn<true, G_B>(BN, maps, p, stream) : launch_bn<true, G_NONE>(BN, maps, p, stream);
+  if (!mn_major && pair) rc = gather == 1 ? launch_bn<false, G_A, 2>(BN, maps, p, stream) : launch_bn<false, G_NONE, 2>(BN, maps, p, stream);
+  else if (!mn_major) rc = gather == 1 ? launch_bn<false, G_A, 1>(BN, maps, p, stream) : launch_bn<false, G_NONE, 1>(BN, maps, p, stream);
+  else rc = gather == 2 ? launch_bn<true, G_B, 1>(BN, maps, p, stream) : launch_bn<true, G_NONE, 1>(BN, maps, p, stream);
   if (rc) return rc;
   if (p.splits > 1) {
     long long MN = (long long)M * N;

@@ -9,6 +9,16 @@ from tests.util import assert_close
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[0, 1], ids=["cta1", "cta_pair"], autouse=True)
+def pair_mode(request):
+    """Every test runs on the 1-CTA kernels and on the CTA-pair (tcgen05 cta_group::2) kernels; the automatic
+    policy (pairs once M >= 2 * 128 * #SMs) is restored afterwards and exercised by test_pair_auto_large."""
+    from canonicalsg2im_b200.ops import lib
+    lib().csg_gemm_bf16_set_pair_mode(request.param)
+    yield request.param
+    lib().csg_gemm_bf16_set_pair_mode(-1)
+
+
 def _rand(shape, seed, scale=1.0):
     g = torch.Generator("cuda").manual_seed(seed)
     return (torch.randn(shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
@@ -123,3 +133,30 @@ def test_gather_b(NT):
     ref = dh.float().T @ X.float()
     out = ops.gemm_bf16(512, 384, NT, dh, None, mn_major=True, gather=g, gather_mode=2)
     assert_close(out, ref, 2e-5, "gather B")
+
+
+def test_pair_auto_large(pair_mode):
+    """Bench-sized K-major GEMMs (M = 117 321 triples: odd number of 128-row tiles, so the last pair has an empty
+    peer CTA) with the automatic pair policy: F2-type epilogue and the masked dX-type, many tiles per pair."""
+    if pair_mode == 0:
+        pytest.skip("automatic policy runs once")
+    from canonicalsg2im_b200 import ops
+    from canonicalsg2im_b200.ops import lib
+    lib().csg_gemm_bf16_set_pair_mode(-1)
+    M = 117321
+    A, B = _rand((M, 512), 40), _rand((1152, 512), 41, 0.05)
+    bias = torch.randn(1152, device="cuda")
+    rs = torch.rand(M, device="cuda")
+    out = ops.gemm_bf16(M, 1152, 512, A, B, bias=bias, relu=True, rowscale=rs)
+    ref = torch.relu(A.float() @ B.float().T + bias) * rs[:, None]
+    assert_close(out.float(), ref, 1e-2, "F2 shape, pairs")
+    del ref
+    aux = _rand((M, 512), 42)
+    B2 = _rand((512, 1152), 43, 0.05)
+    out2 = ops.gemm_bf16(M, 512, 1152, out, B2, mask_aux=aux)
+    ref2 = (out.float() @ B2.float().T) * (aux.float() > 0)
+    assert_close(out2.float(), ref2, 1e-2, "dhid shape, pairs")
+    g, X = _gather(2349, M, 128, 128, 44)
+    W = _rand((512, 384), 45, 0.05)
+    out3 = ops.gemm_bf16(M, 512, 384, None, W, bias=bias[:512].contiguous(), relu=True, gather=g, gather_mode=1)
+    assert_close(out3.float(), torch.relu(X.float() @ W.float().T + bias[:512]), 1e-2, "F1 shape, pairs")
