@@ -56,14 +56,23 @@ class CanonResult:
                 for b in range(len(off) - 1)]
 
 
-def add_learnt_triplets_batched(triplets, tri_off, obj_off, num_rel, meta_ids, conv_weights=None,
-                                learned_converse=False, learned_transitivity=False, uniforms=None,
-                                max_objs_per_graph=None, tables=None):
-    """Canonicalise B graphs at once.
+class CanonPlan:
+    """First half of a batched canonicalization (sizes counted, output offsets scanned, sizes on their way to the
+    host): what :func:`canon_count_async` returns and :func:`canon_emit` consumes."""
 
-    triplets [NTin, 3] int64 (graph-local ids, any order, duplicates allowed), tri_off / obj_off [B+1]
-    int32 (CUDA), ``uniforms`` [>= NTin] float64 (CUDA): the k-th converse draw of graph g is
-    ``uniforms[tri_off[g] + k]``.  Returns a :class:`CanonResult` (device tensors)."""
+    def __init__(self, args, keep, B, out_off, conv_counts, summary_host, event, max_objs):
+        self.args, self.keep, self.B = args, keep, B
+        self.out_off, self.conv_counts = out_off, conv_counts
+        self.summary_host, self.event, self.max_objs = summary_host, event, max_objs
+
+
+def canon_count_async(triplets, tri_off, obj_off, num_rel, meta_ids, conv_weights=None,
+                      learned_converse=False, learned_transitivity=False, uniforms=None,
+                      max_objs_per_graph=None, tables=None):
+    """Counting pass of :func:`add_learnt_triplets_batched` without a host synchronisation: launches
+    ``csg_canon_count`` + the offset scan and an asynchronous copy of the two summary integers into pinned host
+    memory.  A data pipeline calls this for batch i+1 while batch i trains, so that :func:`canon_emit` finds the
+    sizes already on the host and the launch queue never drains."""
     need_cuda(triplets, tri_off, obj_off, uniforms)
     dev = triplets.device
     L = lib()
@@ -96,13 +105,38 @@ def add_learnt_triplets_batched(triplets, tri_off, obj_off, num_rel, meta_ids, c
     summary = torch.empty(2, dtype=torch.int32, device=dev)
     _lib.check(L.csg_canon_offsets(ptr(cnt[0]), ptr(cnt[1]), B, ptr(out_off), ptr(summary), _stream()),
                "csg_canon_offsets")
-    total, min_cnt0 = summary.tolist()         # sizes the output allocation (the one host sync per batch)
-    if B and min_cnt0 < 0:
-        raise _lib.CsgError("canonicalize: a graph has more objects than max_objs_per_graph=%d" % max_objs_per_graph)
+    summary_host = torch.empty(2, dtype=torch.int32, pin_memory=True)
+    summary_host.copy_(summary, non_blocking=True)
+    event = torch.cuda.Event()
+    event.record()
+    keep = (tr, tri_off, obj_off, uniforms, cdf_t, vals_t, cnt, summary)     # device buffers the emit pass reads
+    return CanonPlan(args, keep, B, out_off, conv_counts, summary_host, event, max_objs_per_graph)
+
+
+def canon_emit(plan):
+    """Second half: waits (on the host) for the sizes of ``plan`` -- already there when the plan was launched a step
+    ahead --, allocates the output and launches ``csg_canon_emit``.  Returns a :class:`CanonResult`."""
+    plan.event.synchronize()                   # sizes the output allocation (the one host wait per batch)
+    total, min_cnt0 = plan.summary_host.tolist()
+    if plan.B and min_cnt0 < 0:
+        raise _lib.CsgError("canonicalize: a graph has more objects than max_objs_per_graph=%d" % plan.max_objs)
+    dev = plan.out_off.device
     out_t = torch.empty((max(total, 1), 3), dtype=torch.int64, device=dev)
     out_ty = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
-    _lib.check(L.csg_canon_emit(*args, ptr(out_off), ptr(out_t), ptr(out_ty), _stream()), "csg_canon_emit")
-    return CanonResult(out_t[:total], out_ty[:total], out_off, conv_counts[:B])
+    _lib.check(lib().csg_canon_emit(*plan.args, ptr(plan.out_off), ptr(out_t), ptr(out_ty), _stream()), "csg_canon_emit")
+    return CanonResult(out_t[:total], out_ty[:total], plan.out_off, plan.conv_counts[:plan.B])
+
+
+def add_learnt_triplets_batched(triplets, tri_off, obj_off, num_rel, meta_ids, conv_weights=None,
+                                learned_converse=False, learned_transitivity=False, uniforms=None,
+                                max_objs_per_graph=None, tables=None):
+    """Canonicalise B graphs at once.
+
+    triplets [NTin, 3] int64 (graph-local ids, any order, duplicates allowed), tri_off / obj_off [B+1]
+    int32 (CUDA), ``uniforms`` [>= NTin] float64 (CUDA): the k-th converse draw of graph g is
+    ``uniforms[tri_off[g] + k]``.  Returns a :class:`CanonResult` (device tensors)."""
+    return canon_emit(canon_count_async(triplets, tri_off, obj_off, num_rel, meta_ids, conv_weights, learned_converse,
+                                        learned_transitivity, uniforms, max_objs_per_graph, tables))
 
 
 def add_learnt_triplets(triplets, O, num_rel, meta_ids, conv_weights=None, learned_converse=False,

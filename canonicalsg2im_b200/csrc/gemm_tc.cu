@@ -803,8 +803,9 @@ int launch_bn(int BN, const Maps& m, const TcParams& p, cudaStream_t stream) {
   return 1;
 }
 
-// CTA-pair policy of the K-major GEMMs: -1 = automatic (pairs once M fills every SM at least twice), 0 = never,
-// 1 = whenever the shape allows it (tests)
+// CTA-pair policy of the K-major GEMMs: -1 = automatic (pairs once M fills every SM at least twice and the reduction
+// is long, K >= 1024: measured 132 vs 136 us on the dhid shape, while short-K shapes are 3-5 % faster on single CTAs),
+// 0 = never, 1 = whenever the shape allows it (tests)
 int g_pair_mode = -1;
 
 // K-major kernels: 256-wide tiles with a narrower last tile (the MMA of the tail uses its real width)
@@ -897,7 +898,7 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
   const int BN = mn_major ? mn_pick_bn(N, gather) : kmajor_pick_bn(N);
   // CTA pairs (cta_group::2): K-major only; each CTA stages BN/2 rows of B, so BN/2 must keep the 8-row swizzle atoms
   const bool pair = !mn_major && (BN % 32 == 0) && csg_num_sms() >= 2 &&
-                    (g_pair_mode == 1 || (g_pair_mode < 0 && M >= 2 * BLOCK_M * csg_num_sms()));
+                    (g_pair_mode == 1 || (g_pair_mode < 0 && M >= 2 * BLOCK_M * csg_num_sms() && K >= 1024));
   const int CG = pair ? 2 : 1;
   p.m_tiles = csg_div_up(M, BLOCK_M * CG);
   p.n_tiles = csg_div_up(N, BN);

@@ -11,7 +11,7 @@ import torch
 import torch.nn.functional as F
 
 from . import synth
-from .canonicalize import add_learnt_triplets_batched, converse_tables
+from .canonicalize import canon_count_async, canon_emit, converse_tables
 from .layout import layout_batched
 from .model import Sg2LayoutModel, get_conv_converse, masked_box_loss
 from .parallel import BucketedGradAllReduce
@@ -86,10 +86,18 @@ class SgToLayoutStep:
         cdf, vals = converse_tables(W, self.vocab.num_preds, self.vocab.meta_ids)
         self.tables = (torch.from_numpy(cdf).to(self.device), torch.from_numpy(vals).to(self.device))
 
+    def prefetch(self, d):
+        """Launch the counting pass of the canonicalization of batch ``d`` now (no host wait); ``step(d, ...)``
+        later finds the output sizes on the host.  The reference canonicalizes in DataLoader workers ahead of the
+        training step (base_dataset.py:89-139 inside ``__getitem__``); this is the same look-ahead on the device."""
+        d["_canon_plan"] = canon_count_async(d["triplets"], d["tri_off"], d["obj_off"], self.vocab.num_preds,
+                                             self.vocab.meta_ids, None, self.flags[0], self.flags[1], d["uniforms"],
+                                             max_objs_per_graph=d["max_objs"], tables=self.tables)
+
     def canonicalize(self, d):
-        return add_learnt_triplets_batched(d["triplets"], d["tri_off"], d["obj_off"], self.vocab.num_preds,
-                                           self.vocab.meta_ids, None, self.flags[0], self.flags[1], d["uniforms"],
-                                           max_objs_per_graph=d["max_objs"], tables=self.tables)
+        if d.get("_canon_plan") is None:
+            self.prefetch(d)
+        return canon_emit(d.pop("_canon_plan"))
 
     def forward(self, d, res):
         obj_vecs, boxes_pred = self.model.forward_ragged(d["objs"], res.triplets, res.triplet_type, res.tri_off,
@@ -100,8 +108,12 @@ class SgToLayoutStep:
         loss = masked_box_loss(boxes_pred, d["boxes"])                   # pix2pix_model.py:72-85
         return canvas, loss
 
-    def step(self, d, canvas_grad):
+    def step(self, d, canvas_grad, prefetch=None):
+        """One training step on batch ``d``.  ``prefetch``: the batch of the NEXT step (may be ``d`` itself); its
+        canonicalization counting pass is enqueued right behind this step's emit pass."""
         res = self.canonicalize(d)
+        if prefetch is not None:
+            self.prefetch(prefetch)
         canvas, loss = self.forward(d, res)
         torch.autograd.backward([canvas, loss], [canvas_grad, None])
         if self.reducer is not None:

@@ -153,7 +153,8 @@ int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
                   int g_din, int g_dp, int g_ldp, int g_nobj,
                   void* workspace, size_t workspace_bytes, csg_stream_t stream);
 /* CTA-pair policy of the K-major GEMMs (tcgen05.mma.cta_group::2, 256 x N pair tiles, each CTA stages half of B):
- * -1 automatic (default: pairs once M >= 2 * 128 * #SMs), 0 never, 1 whenever the shape allows.  Process-wide. */
+ * -1 automatic (default: pairs once M >= 2 * 128 * #SMs and K >= 1024), 0 never, 1 whenever the shape allows.
+ * Process-wide. */
 void csg_gemm_bf16_set_pair_mode(int mode);
 
 /* bf16-activation twins of the pooling / assembly kernels (fp32 accumulation) + weight cast */

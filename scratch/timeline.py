@@ -22,11 +22,11 @@ step = SgToLayoutStep(vocab, dev, precision=prec, seed=0)
 G = torch.randn((128, 128, 64, 64), device=dev) * 1e-3
 d = hb.to_device(dev)
 for _ in range(5):
-    step.step(d, G)
+    step.step(d, G, prefetch=d)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
-        step.step(d, G)
+        step.step(d, G, prefetch=d)
     torch.cuda.synchronize()
 path = os.path.join(tempfile.gettempdir(), "trace.json")
 prof.export_chrome_trace(path)
