@@ -24,6 +24,7 @@ _C2CT = {
     "int": ctypes.c_int,
     "long long": ctypes.c_longlong,
     "size_t": ctypes.c_size_t,
+    "double": ctypes.c_double,
     "void": None,
     "csg_stream_t": ctypes.c_void_p,
 }

@@ -48,6 +48,24 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
   }
 }
 
+// one-hot rows [n, ld] bf16 (ld >= V, a multiple of 8): row r is 1.0 at column idx[r] and 0 elsewhere.  With it the table
+// gradient of a large bf16 lookup is the tensor-core product onehot^T dout (csg_gemm_bf16, mn_major): exact products,
+// fp32 accumulation in a fixed split-K order, i.e. a deterministic segmented sum at GEMM speed.
+__global__ void __launch_bounds__(256) onehot_bf16_kernel(const long long* __restrict__ idx, long long idx_stride, int n,
+                                                          int V, int ld, uint4* __restrict__ out) {
+  const int per_row = ld >> 3;                                    // 16-byte pieces per row
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * per_row) return;
+  const int r = (int)(i / per_row), c8 = (int)(i % per_row) * 8;
+  const long long v = idx[(size_t)r * idx_stride];
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (v >= c8 && v < c8 + 8 && v < V) {
+    const int k = (int)(v - c8);
+    w[k >> 1] = (k & 1) ? 0x3F800000u : 0x00003F80u;              // bf16 1.0 = 0x3F80
+  }
+  out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 constexpr int EB_UNROLL = 4;
 // block b (one warp) owns rows [b * rows_per_block, ...) and vocabulary slice [v0, v0 + Vc)
 __global__ void __launch_bounds__(32) embed_bwd_partial_kernel(const void* __restrict__ dout, int ld, int in_bf16,
@@ -210,6 +228,17 @@ CSG_API int csg_embed_bwd(const void* dout, int ld, int in_bf16, const long long
                                                                                   dtable + (size_t)v0 * E);
     CSG_CHECK_LAUNCH("csg_embed_bwd final");
   }
+  return 0;
+}
+
+CSG_API int csg_onehot_bf16(const long long* idx, long long idx_stride, int n, int V, void* out, int ld,
+                            cudaStream_t stream) {
+  if (n == 0) return 0;
+  CSG_REQUIRE(V > 0 && ld >= V && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "onehot_bf16: ld=%d must be a multiple of 8 and >= V=%d, out 16-byte aligned", ld, V);
+  const long long pieces = (long long)n * (ld >> 3);
+  onehot_bf16_kernel<<<csg_div_up(pieces, 256), 256, 0, stream>>>(idx, idx_stride, n, V, ld, reinterpret_cast<uint4*>(out));
+  CSG_CHECK_LAUNCH("csg_onehot_bf16");
   return 0;
 }
 

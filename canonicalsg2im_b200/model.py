@@ -50,6 +50,14 @@ class _EmbedFn(torch.autograd.Function):
         if dout.stride(-1) != 1 or dout.stride(0) % 4 != 0 or dout.data_ptr() % 16 != 0:
             dout = dout.contiguous()
         L = lib()
+        if (dout.dtype == torch.bfloat16 and n >= 8192 and E % 32 == 0 and dout.stride(0) % 8 == 0
+                and dout.data_ptr() % 16 == 0):
+            # large bf16 lookups (the predicate rows of the tensor-core engine): dtable = onehot^T dout on tcgen05
+            from .ops import gemm_bf16
+            ld = (V + 63) // 64 * 64
+            onehot = torch.empty((n, ld), dtype=torch.bfloat16, device=dout.device)
+            _lib.check(L.csg_onehot_bf16(ptr(idx), idx.stride(0), n, V, ptr(onehot), ld, _stream()), "csg_onehot_bf16")
+            return gemm_bf16(ld, E, n, onehot, dout, mn_major=True)[:V], None, None
         dtable = torch.empty((V, E), dtype=torch.float32, device=dout.device)
         ws = workspace(L.csg_embed_bwd_workspace(n, V, E), dout.device)
         rc = L.csg_embed_bwd(ptr(dout), dout.stride(0) if n else E, int(dout.dtype == torch.bfloat16), ptr(idx),

@@ -14,6 +14,7 @@ from . import synth
 from .canonicalize import canon_count_async, canon_emit, converse_tables
 from .layout import layout_batched
 from .model import Sg2LayoutModel, get_conv_converse, masked_box_loss
+from .optim import FusedAdam
 from .parallel import BucketedGradAllReduce
 
 
@@ -77,7 +78,7 @@ class SgToLayoutStep:
                        + [self.model.trans_candidates_weights])
         self.reducer = BucketedGradAllReduce(buckets) if distributed else None
         params = [p for p in self.model.parameters() if p is not self.model.converse_candidates_weights]
-        self.opt = torch.optim.Adam(params, lr=lr, fused=True)
+        self.opt = FusedAdam(params, lr=lr)                      # torch.optim.Adam arithmetic, one multi-tensor launch
 
     def refresh_tables(self):
         """The reference pushes the symmetrised converse weights into the dataset every step

@@ -213,6 +213,17 @@ size_t csg_embed_bwd_workspace(int n, int V, int E);
 /* dtable[v, :] = sum_{r: idx[r] = v} dout[r, :]  (deterministic; dout fp32 or bf16; dtable fully written) */
 int csg_embed_bwd(const void* dout, int ld, int in_bf16, const long long* idx, long long idx_stride, int n,
                   int V, int E, float* dtable, void* workspace, size_t workspace_bytes, csg_stream_t stream);
+/* out[r, :] = one-hot(idx[r]) as bf16 rows of pitch ld (>= V, multiple of 8): operand of the tensor-core form of the
+ * table gradient, dtable = onehot^T dout through csg_gemm_bf16(mn_major = 1). */
+int csg_onehot_bf16(const long long* idx, long long idx_stride, int n, int V, void* out, int ld, csg_stream_t stream);
+/* Multi-tensor Adam (torch.optim.Adam arithmetic, amsgrad off): updates `count` fp32 tensors in place in
+ * ceil(count / 48) launches.  params / grads / exp_avg / exp_avg_sq / numel are HOST arrays (device pointers, element
+ * counts); step >= 1 is the update index used for the bias corrections.  The reference's training loop
+ * (scripts/train.py) calls torch.optim.Adam.step() at this point. */
+int csg_adam_multi(int count, void* const* params, const void* const* grads, void* const* exp_avg,
+                   void* const* exp_avg_sq, const int* numel, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int step, csg_stream_t stream);
+
 /* loss[0] = mean smooth-L1 over the coordinates of rows with gt >= 0; dpred [n, 4] = d loss / d pred */
 int csg_box_loss(const float* pred, const float* gt, int n, float* loss, float* dpred, csg_stream_t stream);
 

@@ -52,6 +52,27 @@ def test_embedding_strided_index_and_bf16():
     assert torch.equal(w.grad, w2.grad)
 
 
+def test_embedding_bwd_large_bf16_tensor_core_path():
+    """n >= 8192 bf16 gradient rows: dtable = onehot^T dout on the tcgen05 MN-major GEMM (exact products, fp32
+    accumulation): 1e-5 against an fp32 index_add of the same bf16 values, deterministic, unused ids exactly zero."""
+    from canonicalsg2im_b200.model import embedding_lookup
+    rng = np.random.RandomState(9)
+    V, E, n = 51, 128, 117321
+    trip = rng.randint(0, V - 1, size=(n, 3)).astype(np.int64)       # id V-1 never used
+    table = synth.det_tensor((V, E), 6, 1.0)
+    wide = t(synth.det_tensor((n, 3 * E), 8, 1.0)).to(torch.bfloat16)
+    grads = []
+    for _ in range(2):
+        w = t(table).requires_grad_(True)
+        embedding_lookup(w, t(trip)[:, 1], torch.bfloat16).backward(wide[:, E:2 * E])
+        grads.append(w.grad)
+    gref = torch.zeros(V, E, dtype=torch.float64).index_add_(0, torch.from_numpy(trip[:, 1]),
+                                                             wide[:, E:2 * E].double().cpu()).float()
+    assert_close(grads[0], gref, 1e-5, "dtable, tensor-core path")
+    assert torch.equal(grads[0], grads[1])
+    assert float(grads[0][V - 1].abs().max()) == 0.0
+
+
 def test_model_embeddings_match_torch_modules():
     """AttributeEmbeddings with several attributes + attribute_fc_gen (CLEVR layout, attribute_embed.py:18-48)."""
     from canonicalsg2im_b200.model import AttributeEmbeddings
