@@ -28,68 +28,109 @@ def shard_by_cost(costs, world_size):
 
 
 class BucketedGradAllReduce:
-    """Flat per-bucket gradient buffers whose slices ARE the parameters' ``.grad`` (no copies);
-    a bucket is all-reduced asynchronously once every parameter in it has accumulated its gradient.
+    """Bucketed, overlapped all-reduce of the weight gradients, in place on the buffers the backward kernels wrote.
 
-    buckets: list of lists of parameters, in the order their gradients become final during
-    backward (last layer first).  ``finish()`` waits for the collectives and averages."""
+    buckets: list of lists of parameters, in the order their gradients become final during backward (last layer
+    first).  A post-accumulate hook counts a bucket's gradients; once all are final the bucket is all-reduced
+    asynchronously (NCCL: ``ReduceOp.AVG``, no separate scaling pass) while the remaining layers run backward:
+
+      * if the bucket's ``.grad`` tensors tile one contiguous region of a common base buffer -- the case of a
+        ``GraphTripleConv`` layer, whose executor writes all eight weight / bias gradients into one flat buffer
+        (``graph_tc._TripleConvEngine.backward``) -- that region itself is reduced: no flat copy, no accumulate
+        pass, nothing to zero between steps;
+      * otherwise the gradients are packed into a temporary flat buffer, reduced, and unpacked in ``finish()``.
+
+    ``finish()`` waits for the collectives; ``zero()`` drops the gradients (``set_to_none``)."""
 
     def __init__(self, buckets, group=None, average=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.average = average
-        self.flats, self.params, self.pending, self.handles = [], [], [], []
+        backend = dist.get_backend(group) if dist.is_initialized() else ""
+        self.native_avg = average and backend == "nccl"
+        self.params, self.pending = [], []
         self._bucket_of = {}
+        self._inflight = []          # (handle, region, unpack list or None)
+        self.in_place_buckets = 0    # statistics of the last step (tests / bench)
         seen = set()
         for bi, params in enumerate(buckets):
             params = [p for p in params if p.requires_grad and id(p) not in seen]
             seen.update(id(p) for p in params)
-            if not params:
-                self.flats.append(None)
-                self.params.append([])
-                self.pending.append(0)
-                continue
-            n = sum(p.numel() for p in params)
-            flat = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
-            off = 0
             for p in params:
-                p.grad = flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
                 self._bucket_of[id(p)] = bi
                 if self.world > 1:
                     p.register_post_accumulate_grad_hook(self._hook)
-            self.flats.append(flat)
             self.params.append(params)
             self.pending.append(len(params))
         self._count = list(self.pending)
+
+    @staticmethod
+    def _contiguous_region(grads):
+        """The 1-D tensor covering exactly the given gradients if they tile one region of a common storage
+        (autograd hands over the producer's views, so ``.grad`` shares the storage of the flat buffer the backward
+        kernels wrote)."""
+        g0 = grads[0]
+        st = g0.untyped_storage()
+        esz = g0.element_size()
+        spans = []
+        for g in grads:
+            if (g.untyped_storage().data_ptr() != st.data_ptr() or not g.is_contiguous() or g.dtype != g0.dtype
+                    or g.device != g0.device):
+                return None
+            spans.append((g.data_ptr(), g.data_ptr() + g.numel() * esz))
+        spans.sort()
+        for (a0, a1), (b0, b1) in zip(spans[:-1], spans[1:]):
+            if a1 != b0:
+                return None
+        off = (spans[0][0] - st.data_ptr()) // esz
+        n = (spans[-1][1] - spans[0][0]) // esz
+        return torch.empty(0, dtype=g0.dtype, device=g0.device).set_(st, off, (n,), (1,))
+
+    def _launch(self, bi):
+        grads = [p.grad for p in self.params[bi] if p.grad is not None]
+        if not grads:
+            return
+        op = dist.ReduceOp.AVG if self.native_avg else dist.ReduceOp.SUM
+        region = self._contiguous_region(grads)
+        unpack = None
+        if region is None:
+            region = torch.cat([g.reshape(-1) for g in grads])
+            unpack = grads
+        else:
+            self.in_place_buckets += 1
+        h = dist.all_reduce(region, op=op, group=self.group, async_op=True)
+        self._inflight.append((h, region, unpack))
 
     def _hook(self, p):
         bi = self._bucket_of[id(p)]
         self._count[bi] -= 1
         if self._count[bi] == 0:
-            self.handles.append(dist.all_reduce(self.flats[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._launch(bi)
 
     def finish(self):
         """Wait for outstanding all-reduces; launch the ones whose hooks did not all fire (unused params)."""
         if self.world > 1:
             for bi, c in enumerate(self._count):
-                if c != 0 and self.flats[bi] is not None:
-                    self.handles.append(dist.all_reduce(self.flats[bi], op=dist.ReduceOp.SUM, group=self.group,
-                                                        async_op=True))
-            for h in self.handles:
+                if c != 0 and self.params[bi]:
+                    self._launch(bi)
+            for h, region, unpack in self._inflight:
                 h.wait()
-            if self.average:
-                for f in self.flats:
-                    if f is not None:
-                        f.div_(self.world)
-        self.handles = []
+                if self.average and not self.native_avg:
+                    region.div_(self.world)
+                if unpack is not None:
+                    off = 0
+                    for g in unpack:
+                        g.copy_(region[off:off + g.numel()].view_as(g))
+                        off += g.numel()
+        self._inflight = []
         self._count = list(self.pending)
 
     def zero(self):
-        for f in self.flats:
-            if f is not None:
-                f.zero_()
+        self.in_place_buckets = 0
+        for params in self.params:
+            for p in params:
+                p.grad = None
 
     @property
     def nbytes(self):
-        return sum(f.numel() * f.element_size() for f in self.flats if f is not None)
+        return sum(p.numel() * p.element_size() for params in self.params for p in params)

@@ -60,3 +60,48 @@ def test_bucketed_allreduce_equals_mean_of_shard_grads():
             assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
         for a, b in zip(out[rank + world], ref):
             assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
+
+
+class _FlatGrads(torch.autograd.Function):
+    """Gradients handed to autograd as views of ONE flat buffer, as the native layer executor does."""
+
+    @staticmethod
+    def forward(ctx, x, a, b):
+        ctx.save_for_backward(x)
+        return (x @ a).sum() + (x.sum(0) * b).sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        flat = torch.empty(6 * 4 + 6)
+        da, db = torch.split(flat, [24, 6])
+        da.view(6, 4).copy_(x.sum(0)[:, None].expand(6, 4) * g)
+        db.copy_(x.sum(0) * g)
+        return None, da.view(6, 4), db
+
+
+def _worker_in_place(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, b = torch.nn.Parameter(torch.ones(6, 4)), torch.nn.Parameter(torch.ones(6))
+    red = BucketedGradAllReduce([[a, b]])
+    x = torch.arange(24, dtype=torch.float32).view(4, 6) / 10 + rank
+    for _ in range(2):
+        _FlatGrads.apply(x, a, b).backward()
+        red.finish()
+        out[rank] = (a.grad.clone(), b.grad.clone(), red.in_place_buckets)
+        red.zero()
+    dist.destroy_process_group()
+
+
+def test_bucket_reduced_in_place_on_the_producers_flat_buffer():
+    world, port = 2, 29613
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_in_place, args=(world, port, out), nprocs=world, join=True)
+    xs = [torch.arange(24, dtype=torch.float32).view(4, 6) / 10 + r for r in range(world)]
+    db = sum(x.sum(0) for x in xs) / world
+    for rank in range(world):
+        ga, gb, n_in_place = out[rank]
+        assert n_in_place == 1                      # no pack / unpack copies for this bucket
+        assert torch.allclose(gb, db, rtol=1e-6) and torch.allclose(ga, db[:, None].expand(6, 4), rtol=1e-6)
