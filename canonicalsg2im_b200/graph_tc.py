@@ -278,7 +278,59 @@ def triple_conv(batch, obj, pred, params, w_trans, hidden_dim, pred_out_dim, sta
     return fn.apply(batch, hidden_dim, pred_out_dim, obj, pred, *params, w_trans)
 
 
+class _DenseMLP2BF16(torch.autograd.Function):
+    """box_net (model.py:58-60) on the bf16 engine: Linear(D, H) + ReLU on tcgen05, the 4-wide Linear(H, 4) head as a
+    row-dot kernel (csrc/head_bf16.cu); the backward head kernel folds the ReLU mask and writes dh in bf16."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w1, b1):
+        L = lib()
+        xb = as_bf16_rows(x)
+        M, (H, D), nout = xb.shape[0], w0.shape, w1.shape[0]
+        need_bwd = any(ctx.needs_input_grad)
+        casts = cast_bf16_multi([(w0, False)] + ([(w0, True)] if need_bwd else []))
+        h = ops.gemm_bf16(M, H, D, xb, casts[0], bias=f32c(b0), relu=True)
+        y = torch.empty((M, nout), dtype=torch.float32, device=xb.device)
+        w1c = f32c(w1.detach())
+        _lib.check(L.csg_head_fwd(ptr(h), h.stride(0), ptr(w1c), ptr(f32c(b1.detach())), M, H, nout, ptr(y), _stream()),
+                   "csg_head_fwd")
+        ctx.save_for_backward(xb, h, w1c)
+        ctx.w0t = casts[1] if need_bwd else None
+        ctx.x_dtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, h, w1c = ctx.saved_tensors
+        L = lib()
+        M, H = h.shape
+        D, nout = xb.shape[1], w1c.shape[0]
+        dev = xb.device
+        dy = f32c(dy)
+        dh = torch.empty((M, H), dtype=BF, device=dev)
+        dw1 = torch.empty((nout, H), dtype=torch.float32, device=dev)
+        db1 = torch.empty(nout, dtype=torch.float32, device=dev)
+        ws = workspace(L.csg_head_bwd_workspace(M, H, nout), dev)
+        _lib.check(L.csg_head_bwd(ptr(dy), ptr(h), h.stride(0), ptr(w1c), M, H, nout, ptr(dh), dh.stride(0), ptr(dw1),
+                                  ptr(db1), ptr(ws), ws.numel(), _stream()), "csg_head_bwd")
+        dw0 = ops.gemm_bf16(H, D, M, dh, xb, mn_major=True)
+        db0 = colsum_bf16(dh)
+        dx = ops.gemm_bf16(M, D, H, dh, ctx.w0t)
+        if ctx.x_dtype != BF:
+            dx = dx.to(ctx.x_dtype)
+        return dx, dw0, db0, dw1, db1
+
+
 def dense_mlp2(x, w0, b0, w1, b1, final_relu):
+    """box_net (model.py:58-60).  Feature widths that fit the tensor-core tiles and a head of <= 8 outputs run on
+    ``_DenseMLP2BF16``; anything else on the fp32 engine."""
+    if (not final_relu and w1.shape[0] <= 8 and w0.shape[0] % 64 == 0 and w0.shape[1] % 64 == 0
+            and w0.shape[0] * w1.shape[0] * 4 <= 48 * 1024):
+        return _DenseMLP2BF16.apply(x, w0, b0, w1, b1)
+    return _dense_mlp2_f32(x, w0, b0, w1, b1, final_relu)
+
+
+def _dense_mlp2_f32(x, w0, b0, w1, b1, final_relu):
     """box_net (model.py:58-60): M = #objects, output width 4 -- too small to matter; it runs on the fp32 engine."""
     from .graph import _DenseMLP2F32
     return _DenseMLP2F32.apply(x.float() if x.dtype != torch.float32 else x, w0, b0, w1, b1, final_relu)

@@ -216,6 +216,15 @@ int csg_embed_bwd(const void* dout, int ld, int in_bf16, const long long* idx, l
 /* out[r, :] = one-hot(idx[r]) as bf16 rows of pitch ld (>= V, multiple of 8): operand of the tensor-core form of the
  * table gradient, dtable = onehot^T dout through csg_gemm_bf16(mn_major = 1). */
 int csg_onehot_bf16(const long long* idx, long long idx_stride, int n, int V, void* out, int ld, csg_stream_t stream);
+/* Narrow output head (box_net's Linear(H, 4), model.py:58-60) of the bf16 engine: y = h w^T + b forward; backward
+ * writes dh = (h > 0) * (dy w) as bf16 (the first layer's ReLU folded in), dw = dy^T h and db = colsum(dy) in fp32,
+ * deterministically.  h / dh bf16 with pitches ldh / lddh, nout <= 8. */
+int csg_head_fwd(const void* h, int ldh, const float* w, const float* b, int M, int K, int nout, float* y,
+                 csg_stream_t stream);
+size_t csg_head_bwd_workspace(int M, int K, int nout);
+int csg_head_bwd(const float* dy, const void* h, int ldh, const float* w, int M, int K, int nout, void* dh, int lddh,
+                 float* dw, float* db, void* workspace, size_t workspace_bytes, csg_stream_t stream);
+
 /* Multi-tensor Adam (torch.optim.Adam arithmetic, amsgrad off): updates `count` fp32 tensors in place in
  * ceil(count / 48) launches.  params / grads / exp_avg / exp_avg_sq / numel are HOST arrays (device pointers, element
  * counts); step >= 1 is the update index used for the bias corrections.  The reference's training loop

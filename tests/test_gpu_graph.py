@@ -272,3 +272,35 @@ def test_native_layer_executor_is_bitwise_the_staged_path():
             res.append([a.detach().clone(), b.detach().clone(), ov.grad.clone(), base.grad.clone()] + grads)
         for x, y in zip(*res):
             assert x.dtype == y.dtype and torch.equal(x, y)
+
+
+def test_box_net_bf16_head_vs_fp32_reference():
+    """box_net (model.py:58-60) on the bf16 engine: tcgen05 first layer + the 4-wide row-dot head (csrc/head_bf16.cu),
+    forward and all five gradients against torch fp32 on the same bf16-rounded operands: 1e-2 relative (north_star's
+    bf16 budget); run-to-run bitwise reproducible."""
+    from canonicalsg2im_b200 import graph_tc
+    torch.manual_seed(3)
+    M, D, H = 2349, 128, 512
+    x = torch.randn(M, D, device="cuda").to(torch.bfloat16)
+    w0 = (torch.randn(H, D, device="cuda") * 0.1).requires_grad_(True)
+    b0 = (torch.randn(H, device="cuda") * 0.1).requires_grad_(True)
+    w1 = (torch.randn(4, H, device="cuda") * 0.1).requires_grad_(True)
+    b1 = (torch.randn(4, device="cuda") * 0.1).requires_grad_(True)
+    gy = torch.randn(M, 4, device="cuda")
+    outs = []
+    for _ in range(2):
+        xx = x.clone().requires_grad_(True)
+        y = graph_tc.dense_mlp2(xx, w0, b0, w1, b1, False)
+        grads = torch.autograd.grad(y, [xx, w0, b0, w1, b1], gy)
+        outs.append((y.detach(), [g.detach() for g in grads]))
+    # reference with the engine's operand rounding (bf16 x and w0, fp32 accumulation), as tests/bf16_ref.py does for the
+    # GCN layers: an fp32-weight reference flips the ReLU of a few hundred near-zero pre-activations, which says
+    # nothing about the kernels
+    xr = x.float().requires_grad_(True)
+    w0r = w0.detach().to(torch.bfloat16).float().requires_grad_(True)
+    yr = torch.relu(xr @ w0r.t() + b0) @ w1.t() + b1
+    gr = torch.autograd.grad(yr, [xr, w0r, b0, w1, b1], gy)
+    assert_close(outs[0][0], yr, 1e-2, "box_net y")
+    for name, a, b in zip(["dx", "dw0", "db0", "dw1", "db1"], outs[0][1], gr):
+        assert_close(a.float(), b, 1e-2, "box_net " + name)
+    assert torch.equal(outs[0][0], outs[1][0]) and all(torch.equal(a, b) for a, b in zip(outs[0][1], outs[1][1]))
