@@ -63,7 +63,7 @@ def main():
     tag = sys.argv[1]
     out = ["# ncu summary `%s`" % tag, "",
            "Per-launch times below come from `ncu --metrics gpu__time_duration.sum --clock-control none` over "
-           "`python bench.py --steps 2 --warmup 1` (cold-cache, serialised: compare SHARES).", ""]
+           "`python bench.py --steps 1 --warmup 3 --profile` (one profiled step; cold-cache, serialised: compare SHARES).", ""]
     agg = launches(tag)
     if agg:
         total = sum(v[1] for v in agg.values())
