@@ -61,6 +61,23 @@ __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<fl
 __device__ __forceinline__ void st_f4_stream(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 __device__ __forceinline__ float4 ld_f4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 
+// s = p[0] + p[stride] + ... + p[(n-1)*stride] in exactly that order, with the loads issued U at a time (the ordered
+// "final" passes of the deterministic reductions are latency-bound on their dependent load -> add chain otherwise)
+template <int U>
+__device__ __forceinline__ float ordered_sum(const float* __restrict__ p, size_t stride, int n) {
+  float s = 0.f;
+  int b = 0;
+  for (; b + U <= n; b += U) {
+    float x[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) x[i] = p[(size_t)(b + i) * stride];
+#pragma unroll
+    for (int i = 0; i < U; ++i) s += x[i];
+  }
+  for (; b < n; ++b) s += p[(size_t)b * stride];
+  return s;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

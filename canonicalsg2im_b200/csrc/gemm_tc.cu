@@ -715,9 +715,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 __global__ void splitk_reduce_tc_kernel(const float* __restrict__ partial, float* __restrict__ C, long long MN, int splits) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= MN) return;
-  float acc = 0.f;
-  for (int z = 0; z < splits; ++z) acc += partial[(size_t)z * MN + i];
-  C[i] = acc;
+  C[i] = ordered_sum<8>(partial + i, (size_t)MN, splits);
 }
 
 // ------------------------------------------------------------------------------------------ host

@@ -108,12 +108,18 @@ __global__ void __launch_bounds__(1024) csr_scan_kernel(const int* __restrict__ 
 // The objects of a graph are touched by that graph's warp only; their running cursors live in shared memory
 // (falling back to the global cursor array for graphs with more than CSR_SMEM_OBJS objects).
 constexpr int CSR_SMEM_OBJS = 2048;
-__global__ void __launch_bounds__(32) csr_fill_kernel(const int* __restrict__ keys, const int* __restrict__ tri_off,
-                                                      const int* __restrict__ obj_off, int B,
-                                                      int* __restrict__ cursor, int* __restrict__ perm) {
+// Blocks [0, B) fill the by-subject ordering, blocks [B, 2B) the by-object ordering (one launch for both).
+__global__ void __launch_bounds__(32) csr_fill_kernel(const int* __restrict__ keys_s, const int* __restrict__ keys_o,
+                                                      const int* __restrict__ tri_off, const int* __restrict__ obj_off, int B,
+                                                      int* __restrict__ cursor_s, int* __restrict__ cursor_o,
+                                                      int* __restrict__ perm_s, int* __restrict__ perm_o) {
   __shared__ int scur[CSR_SMEM_OBJS];
-  const int g = blockIdx.x;
+  const bool second = blockIdx.x >= B;
+  const int g = second ? blockIdx.x - B : blockIdx.x;
   if (g >= B) return;
+  const int* __restrict__ keys = second ? keys_o : keys_s;
+  int* __restrict__ cursor = second ? cursor_o : cursor_s;
+  int* __restrict__ perm = second ? perm_o : perm_s;
   const int lane = threadIdx.x;
   const int beg = tri_off[g], end = tri_off[g + 1];
   const int obeg = obj_off[g], nobj = obj_off[g + 1] - obeg;
@@ -122,10 +128,12 @@ __global__ void __launch_bounds__(32) csr_fill_kernel(const int* __restrict__ ke
     for (int i = lane; i < nobj; i += 32) scur[i] = cursor[obeg + i];
     __syncwarp();
   }
+  int key_next = beg + lane < end ? keys[beg + lane] : 0;        // keys are fetched one 32-triple step ahead
   for (int t0 = beg; t0 < end; t0 += 32) {
     int t = t0 + lane;
     bool act = t < end;
-    int key = act ? keys[t] : -1 - lane;
+    int key = act ? key_next : -1 - lane;
+    if (t + 32 < end) key_next = keys[t + 32];
     unsigned peers = __match_any_sync(0xffffffffu, key);
     int rank = __popc(peers & ((1u << lane) - 1u));
     int base = 0;
@@ -312,8 +320,7 @@ __global__ void conf_bwd_final_kernel(const float* __restrict__ partial, const f
                                       int blocks, float* __restrict__ dw) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += partial[b * P + p];
+  const float s = ordered_sum<16>(partial + p, (size_t)P, blocks);
   float sg = 1.f / (1.f + expf(-w_trans[p]));
   dw[p] = s * sg * (1.f - sg);
 }
@@ -372,8 +379,7 @@ CSG_API int csg_csr_build(const int* keys_s, const int* keys_o, const int* tri_o
   csr_scan_kernel<<<1, 1024, 0, stream>>>(cnt_o, NO, rowptr_o, cur_o);
   CSG_CHECK_LAUNCH("csg_csr_build scan");
   if (NT > 0 && B > 0) {
-    csr_fill_kernel<<<B, 32, 0, stream>>>(keys_s, tri_off, obj_off, B, cur_s, perm_s);
-    csr_fill_kernel<<<B, 32, 0, stream>>>(keys_o, tri_off, obj_off, B, cur_o, perm_o);
+    csr_fill_kernel<<<2 * B, 32, 0, stream>>>(keys_s, keys_o, tri_off, obj_off, B, cur_s, cur_o, perm_s, perm_o);
     CSG_CHECK_LAUNCH("csg_csr_build fill");
   }
   return 0;

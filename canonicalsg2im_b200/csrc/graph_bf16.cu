@@ -224,8 +224,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_final_kernel(const float* __r
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
   float acc = 0.f;
-  if (n < N)
-    for (int c = ty; c < chunks; c += 8) acc += partial[(size_t)c * N + n];
+  if (n < N && ty < chunks) acc = ordered_sum<8>(partial + (size_t)ty * N + n, (size_t)8 * N, (chunks - ty + 7) / 8);
   red[ty][tx] = acc;
   __syncthreads();
   if (ty == 0 && n < N) {

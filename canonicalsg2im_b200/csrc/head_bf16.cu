@@ -84,8 +84,7 @@ __global__ void head_bwd_final_kernel(const float* __restrict__ partial, int blo
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int cells = NOUT * K + HEAD_MAX_OUT;
   if (i >= cells) return;
-  float a = 0.f;
-  for (int b = 0; b < blocks; ++b) a += partial[(size_t)b * cells + i];
+  const float a = ordered_sum<16>(partial + i, (size_t)cells, blocks);
   if (i < NOUT * K) dw[i] = a;
   else if (i - NOUT * K < NOUT) db[i - NOUT * K] = a;
 }

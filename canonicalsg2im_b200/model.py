@@ -50,7 +50,7 @@ class _EmbedFn(torch.autograd.Function):
         if dout.stride(-1) != 1 or dout.stride(0) % 4 != 0 or dout.data_ptr() % 16 != 0:
             dout = dout.contiguous()
         L = lib()
-        if (dout.dtype == torch.bfloat16 and n >= 8192 and E % 32 == 0 and dout.stride(0) % 8 == 0
+        if (dout.dtype == torch.bfloat16 and n >= 1024 and E % 32 == 0 and dout.stride(0) % 8 == 0
                 and dout.data_ptr() % 16 == 0):
             # large bf16 lookups (the predicate rows of the tensor-core engine): dtable = onehot^T dout on tcgen05
             from .ops import gemm_bf16
