@@ -96,7 +96,9 @@ segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int
                     float* __restrict__ cnt_out) {
   __shared__ float red[SP_MAX_THREADS * 8];
   __shared__ float red_cnt[SP_MAX_THREADS];
-  const int o = blockIdx.x;
+  // objects are visited last-to-first: X was just written front-to-back by the producing GEMM and is larger than L2, so
+  // its tail is what is still cached; walking forwards would evict that tail before reaching it
+  const int o = gridDim.x - 1 - blockIdx.x;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int c = tx * 8;
   const bool colok = c < W;

@@ -77,6 +77,7 @@ namespace fw {
 constexpr int NTHREADS = 128;          // 4 warps x 128-pixel strips
 constexpr int STRIP_PX = 128;
 constexpr int TILE_PX = 4 * STRIP_PX;  // 512 pixels per tile: 8 rows x 64 or 4 rows x 128
+constexpr int ORDER_MAX_N = 512;       // batches up to this many images are served heaviest-first
 
 struct Smem {
   float* wS;           // [lcap][TILE_PX]   S_o(y, x) for the tile (masks_to_layout only)
@@ -162,7 +163,26 @@ __global__ void __launch_bounds__(NTHREADS) layout_fwd_kernel(LayoutParams p, fl
   extern __shared__ __align__(16) float smem_raw[];
   __shared__ int s_cursor, s_count;
   const Smem s = carve(smem_raw, p.lcap, p.D, p.TW, p.TH, HAS_MASK);
-  const int n = blockIdx.y;
+  // Images are served heaviest first (most objects first; CTAs are dispatched in blockIdx.y order), so that the
+  // partial last wave of CTAs consists of the cheapest tiles: blockIdx.y is a rank, not an image index.
+  __shared__ int s_cnt[ORDER_MAX_N];
+  __shared__ int s_img;
+  int n = blockIdx.y;
+  if (p.N <= ORDER_MAX_N) {
+    for (int i = threadIdx.x; i < p.N; i += NTHREADS) s_cnt[i] = p.obj_off[i + 1] - p.obj_off[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.N; i += NTHREADS) {
+      const int ci = s_cnt[i];
+      int rank = 0;
+      for (int j = 0; j < p.N; ++j) {
+        const int cj = s_cnt[j];
+        rank += (cj > ci || (cj == ci && j < i)) ? 1 : 0;
+      }
+      if (rank == (int)blockIdx.y) s_img = i;
+    }
+    __syncthreads();
+    n = s_img;
+  }
   const int TW = p.TW, TH = p.TH;
   const int x0 = (blockIdx.x % p.tiles_x) * TW, y0 = (blockIdx.x / p.tiles_x) * TH;
   const int oend = p.obj_off[n + 1];
