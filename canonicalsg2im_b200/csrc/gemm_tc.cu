@@ -806,8 +806,15 @@ int launch_bn(int BN, const Maps& m, const TcParams& p, cudaStream_t stream) {
 // 0 = never, 1 = whenever the shape allows it (tests)
 int g_pair_mode = -1;
 
-// K-major kernels: 256-wide tiles with a narrower last tile (the MMA of the tail uses its real width)
-int kmajor_pick_bn(int N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }
+// K-major kernels: 256-wide tiles with a narrower last tile
+// (the MMA of the tail uses its real width); short M (the per-object GEMMs of net2 / box_net) takes narrower tiles until
+// every SM has one
+int kmajor_pick_bn(int M, int N) {
+  int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  const int m_tiles = csg_div_up(M, BLOCK_M);
+  while (bn > 64 && m_tiles * csg_div_up(N, bn) < csg_num_sms()) bn >>= 1;
+  return bn;
+}
 
 int pick_bn(int N) {
   if (N % 256 == 0) return 256;
@@ -893,7 +900,7 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
   if (p.mask_aux) CSG_REQUIRE(ld_aux % 8 == 0, "gemm_bf16: ld_aux must be a multiple of 8");
   CSG_REQUIRE(!(gather && mask_aux), "gemm_bf16: the gathered GEMMs take no ReLU mask");
   // a gathered 64-column chunk must not straddle two source segments: guaranteed by %64 dims
-  const int BN = mn_major ? mn_pick_bn(N, gather) : kmajor_pick_bn(N);
+  const int BN = mn_major ? mn_pick_bn(N, gather) : kmajor_pick_bn(M, N);
   // CTA pairs (cta_group::2): K-major only; each CTA stages BN/2 rows of B, so BN/2 must keep the 8-row swizzle atoms
   const bool pair = !mn_major && (BN % 32 == 0) && csg_num_sms() >= 2 &&
                     (g_pair_mode == 1 || (g_pair_mode < 0 && M >= 2 * BLOCK_M * csg_num_sms() && K >= 1024));
