@@ -28,6 +28,14 @@
 //   ix = ((g + 1) / 2) * (S - 1)      align_corners=True (torch <= 1.2 behaviour)
 // with S = 8 for boxes_to_layout (layout.py:34) and S = M for masks_to_layout.
 #include "layout_common.cuh"
+#include <stdlib.h>
+
+// tensor-core backward (layout_bwd_tc.cu)
+bool csg_layout_bwd_tc_eligible(const float* dout, int N, int D, int H, int W, int max_objs);
+size_t csg_layout_bwd_tc_partial_floats(int N, int NO, int D, int H, int W, int max_objs);
+int csg_layout_bwd_tc_launch(const float* dout, const float* masks, const int* obj_off, const float* axg, const float* ayg,
+                             float* partial, float* dvecs, int N, int NO, int D, int H, int W, int M, int max_objs,
+                             cudaStream_t stream);
 
 namespace {
 
@@ -879,6 +887,10 @@ CSG_API size_t csg_layout_bwd_vecs_workspace(int N, int NO, int D, int H, int W)
     size_t ring = bw::workspace_bytes(N, NO, D, H, W);
     if (ring > need) need = ring;
   }
+  if (N > 0 && (D % 128) == 0 && (W % 32) == 0) {
+    size_t tc = (csg_layout_bwd_tc_partial_floats(N, NO, D, H, W, 16) + (size_t)NO * (W + H) + (size_t)NO * 4) * 4 + 256;
+    if (tc > need) need = tc;
+  }
   return need;
 }
 
@@ -892,7 +904,26 @@ CSG_API int csg_layout_bwd_vecs(const float* dout, const float* boxes, const flo
   CsgProfScope prof(CSG_PROF_LAYOUT_BWD, 4.0 * N * D * H * W, stream);
   CSG_REQUIRE(workspace_bytes >= csg_layout_bwd_vecs_workspace(N, NO, D, H, W), "layout bwd: workspace too small");
   float* partial = reinterpret_cast<float*>(workspace);
-  if (bw::eligible(dout, D, H, W)) {
+  // CSG_LAYOUT_BWD = tc | ring | generic forces a path (benchmarks).  Default: the ring kernel.  The tcgen05 3xTF32
+  // contraction (layout_bwd_tc.cu) is bit-compatible with the 1e-5 contract and streams the gradient at 4.9 TB/s when
+  // its MMAs are switched off, but a kind::tf32 MMA of M = 128 with a narrow N costs ~180 cycles whatever N is, and
+  // the 8 it needs per 32-pixel tile make it MMA-bound at 112 us on the cfg2 canvas (ring kernel: 98 us).
+  static const char* force = getenv("CSG_LAYOUT_BWD");
+  const bool want_tc = force && force[0] == 't';
+  if (want_tc && csg_layout_bwd_tc_eligible(dout, N, D, H, W, max_objs_per_image)) {
+    // tcgen05 path: dvecs = S * dout^T per image on the tensor cores (layout_bwd_tc.cu); tables as for the ring kernel
+    LayoutParams tp = p;
+    tp.TW = W; tp.TH = H; tp.tiles_x = tp.tiles_y = 1; tp.lcap = 0;
+    float* axg = partial + csg_layout_bwd_tc_partial_floats(N, NO, D, H, W, max_objs_per_image);
+    float* ayg = axg + (size_t)NO * W;
+    int* rng = reinterpret_cast<int*>(ayg + (size_t)NO * H);
+    if (masks) bw::layout_tables_kernel<true><<<NO, 128, 0, stream>>>(tp, NO, axg, ayg, rng);
+    else       bw::layout_tables_kernel<false><<<NO, 128, 0, stream>>>(tp, NO, axg, ayg, rng);
+    CSG_CHECK_LAUNCH("csg_layout_bwd_vecs tables");
+    return csg_layout_bwd_tc_launch(dout, masks, obj_off, axg, ayg, partial, dvecs, N, NO, D, H, W, M, max_objs_per_image,
+                                    stream);
+  }
+  if ((!force || force[0] != 'g') && bw::eligible(dout, D, H, W)) {
     bw::Params q;
     q.p = p;
     q.p.TW = W; q.p.TH = H; q.p.tiles_x = q.p.tiles_y = 1;

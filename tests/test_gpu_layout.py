@@ -248,3 +248,43 @@ def test_geom_grads_batched_vs_oracle(L):
     (ref * torch.from_numpy(gy)).sum().backward()
     assert_close(b.grad, bc.grad, TOL, "batched dboxes")
     assert_close(m.grad, mc.grad, TOL, "batched dmasks")
+
+
+def test_tensor_core_backward_path_matches_ring_path():
+    """layout_bwd_tc.cu (tcgen05 kind::tf32, 3-term split) is selected with CSG_LAYOUT_BWD=tc (read once per process,
+    hence the subprocess): its d/dvecs must agree with the default ring kernel to the fp32 contract (1e-5) for boxes
+    and masks, including an image without objects."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch
+        sys.path.insert(0, %r)
+        from canonicalsg2im_b200 import synth
+        from canonicalsg2im_b200.layout import layout_batched
+        vocab = synth.Vocab(0)
+        gs = [synth.make_graph(900 + i, 3, 20, vocab, include_dummies=False, mask_size=16) for i in range(9)]
+        boxes = np.concatenate([g.boxes for g in gs]); masks = np.concatenate([g.masks for g in gs]).astype(np.float32)
+        off = np.concatenate([[0], np.cumsum([len(g.boxes) for g in gs])]).astype(np.int32)
+        off = np.insert(off, 4, off[4])                      # an empty image in the middle
+        N, mo = len(off) - 1, int(np.diff(off).max())
+        out = {}
+        for use_masks in (False, True):
+            v = torch.from_numpy(synth.det_tensor((len(boxes), 128), 5, 1.0)).cuda().requires_grad_(True)
+            y = layout_batched(v, torch.from_numpy(boxes).cuda(), torch.from_numpy(off).cuda(), 64, 64,
+                               masks=torch.from_numpy(masks).cuda() if use_masks else None, max_objs_per_image=mo)
+            g = torch.from_numpy(synth.det_tensor(tuple(y.shape), 6, 1.0)).cuda()
+            y.backward(g)
+            out[use_masks] = v.grad.cpu().numpy()
+        np.savez(sys.argv[1], boxes=out[False], masks=out[True])
+    """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import tempfile
+    res = {}
+    with tempfile.TemporaryDirectory() as td:
+        for mode in ("ring", "tc"):
+            path = os.path.join(td, mode + ".npz")
+            env = dict(os.environ, CSG_LAYOUT_BWD=mode)
+            subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+            res[mode] = dict(np.load(path))
+    for k in ("boxes", "masks"):
+        a, b = res["tc"][k], res["ring"][k]
+        assert np.isfinite(a).all()
+        assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max(), k
