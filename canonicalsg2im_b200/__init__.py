@@ -3,7 +3,7 @@ roeiherz/CanonicalSg2Im, behind the reference's own Python operator surface.
 
     from canonicalsg2im_b200 import GraphTripleConv, GraphTripleConvNet, Sg2LayoutModel
     from canonicalsg2im_b200 import boxes_to_layout, masks_to_layout, layout_batched
-    from canonicalsg2im_b200 import add_learnt_triplets, add_learnt_triplets_batched
+    from canonicalsg2im_b200 import add_learnt_triplets, add_learnt_triplets_batched, add_location_triplets_batched
     from canonicalsg2im_b200 import crop_bbox, crop_bbox_batch
 
 Everything computes in ``libcsg2im.so`` (hand-written CUDA, C ABI in ``include/csg2im.h``); importing
@@ -13,15 +13,16 @@ from . import synth  # noqa: F401  (host-side synthetic inputs; no kernels)
 
 __all__ = ["synth", "GraphTripleConv", "GraphTripleConvNet", "TripleBatch", "Sg2LayoutModel", "get_conv_converse",
            "boxes_to_layout", "masks_to_layout", "layout_batched", "add_learnt_triplets",
-           "add_learnt_triplets_batched", "converse_tables", "closure", "crop_bbox", "crop_bbox_batch",
-           "crop_bbox_ragged"]
+           "add_learnt_triplets_batched", "add_location_triplets_batched", "canon_count_async", "canon_emit",
+           "converse_tables", "closure", "crop_bbox", "crop_bbox_batch", "crop_bbox_ragged", "FusedAdam"]
 
 _LAZY = {
     "GraphTripleConv": "graph", "GraphTripleConvNet": "graph", "TripleBatch": "graph",
     "Sg2LayoutModel": "model", "get_conv_converse": "model",
     "boxes_to_layout": "layout", "masks_to_layout": "layout", "layout_batched": "layout",
     "add_learnt_triplets": "canonicalize", "add_learnt_triplets_batched": "canonicalize",
-    "converse_tables": "canonicalize", "closure": "canonicalize",
+    "add_location_triplets_batched": "canonicalize", "canon_count_async": "canonicalize", "canon_emit": "canonicalize",
+    "converse_tables": "canonicalize", "closure": "canonicalize", "FusedAdam": "optim",
     "crop_bbox": "bilinear", "crop_bbox_batch": "bilinear", "crop_bbox_ragged": "bilinear",
 }
 

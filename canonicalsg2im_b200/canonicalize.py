@@ -139,6 +139,45 @@ def add_learnt_triplets_batched(triplets, tri_off, obj_off, num_rel, meta_ids, c
                                         learned_transitivity, uniforms, max_objs_per_graph, tables))
 
 
+AUGMENTED_RELATIONS = ("__below__", "__above__", "__left of__", "__right of__", "__inside__", "__surrounding__")
+
+
+def add_location_triplets_batched(boxes, obj_centers, objs, obj_off, image_obj_id, pred_ids, max_objs_per_graph=None):
+    """``BaseDataset.add_location_triplets`` (base_dataset.py:35-87) for a whole flat batch on the device.
+
+    boxes [NO, 4] xywh float32, obj_centers [NO, 2] float32, objs [NO] or [NO, A] int64 class ids (column 0 is used),
+    obj_off [B+1] int32 (all CUDA); ``pred_ids`` maps the six augmented relation names to predicate ids.  Returns
+    ``(triplets [T, 3] int64 with graph-local ids, tri_off [B+1] int32)``: per graph, the rows the reference appends to
+    ``triplets`` (relation by relation in ``augmented_relations`` order, each reduced by ``triplets_to_minimal``)."""
+    need_cuda(boxes, obj_centers, objs, obj_off)
+    dev = boxes.device
+    L = lib()
+    B = obj_off.numel() - 1
+    bx = boxes.to(torch.float32).contiguous()
+    cen = obj_centers.to(torch.float32).contiguous()
+    ob = objs.to(torch.int64)
+    if ob.dim() == 2:
+        ob = ob[:, 0]
+    off = obj_off.to(torch.int32).contiguous()
+    if max_objs_per_graph is None:
+        max_objs_per_graph = int((off[1:] - off[:-1]).max().item()) if B else 1
+    import ctypes
+    pid = (ctypes.c_int * 6)(*[int(pred_ids[name]) for name in AUGMENTED_RELATIONS])
+    cnt = torch.zeros((2, max(B, 1)), dtype=torch.int32, device=dev)
+    args = (ptr(bx), ptr(cen), ptr(ob), ob.stride(0) if ob.numel() else 1, ptr(off), B, int(image_obj_id), pid,
+            int(max(max_objs_per_graph, 1)))
+    _lib.check(L.csg_location_count(*args, ptr(cnt[0]), _stream()), "csg_location_count")
+    out_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    summary = torch.empty(2, dtype=torch.int32, device=dev)
+    _lib.check(L.csg_canon_offsets(ptr(cnt[0]), ptr(cnt[1]), B, ptr(out_off), ptr(summary), _stream()), "csg_canon_offsets")
+    total, min_cnt = summary.tolist()
+    if B and min_cnt < 0:
+        raise _lib.CsgError("location triplets: a graph has more objects than max_objs_per_graph=%d" % max_objs_per_graph)
+    out = torch.empty((max(total, 1), 3), dtype=torch.int64, device=dev)
+    _lib.check(L.csg_location_emit(*args, ptr(out_off), ptr(out), _stream()), "csg_location_emit")
+    return out[:total], out_off
+
+
 def add_learnt_triplets(triplets, O, num_rel, meta_ids, conv_weights=None, learned_converse=False,
                         learned_transitivity=False, uniforms=None, device="cuda"):
     """Single-graph form mirroring ``BaseDataset.add_learnt_triplets(triplets, O)`` (base_dataset.py:89):

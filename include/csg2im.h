@@ -216,6 +216,19 @@ int csg_embed_bwd(const void* dout, int ld, int in_bf16, const long long* idx, l
 /* out[r, :] = one-hot(idx[r]) as bf16 rows of pitch ld (>= V, multiple of 8): operand of the tensor-core form of the
  * table gradient, dtable = onehot^T dout through csg_gemm_bf16(mn_major = 1). */
 int csg_onehot_bf16(const long long* idx, long long idx_stride, int n, int V, void* out, int ld, csg_stream_t stream);
+/* Geometric ("location") triplets (sg2im/data/base_dataset.py:35-87): for every ordered pair of real objects (class id
+ * != image_id, graphs with a single object have none) the box predicates below / above / left of / right of / inside /
+ * surrounding, each relation reduced to its minimal graph when it has >= 3 edges (graphs_utils.py:64-71), emitted
+ * relation by relation in row-major order.  pred_ids: HOST array of the six predicate ids in that order.  Two passes
+ * around csg_canon_offsets (pass a zero array as its cnt1): csg_location_count fills cnt[B], csg_location_emit writes
+ * the [T, 3] int64 (s, p, o) rows (graph-local ids) at out_off[g].  max_objs >= the largest graph. */
+int csg_location_count(const float* boxes, const float* centers, const long long* objs, long long objs_stride,
+                       const int* obj_off, int B, long long image_id, const int* pred_ids, int max_objs, int* cnt,
+                       csg_stream_t stream);
+int csg_location_emit(const float* boxes, const float* centers, const long long* objs, long long objs_stride,
+                      const int* obj_off, int B, long long image_id, const int* pred_ids, int max_objs,
+                      const int* out_off, long long* out_triplets, csg_stream_t stream);
+
 /* Narrow output head (box_net's Linear(H, 4), model.py:58-60) of the bf16 engine: y = h w^T + b forward; backward
  * writes dh = (h > 0) * (dy w) as bf16 (the first layer's ReLU folded in), dw = dy^T h and db = colsum(dy) in fp32,
  * deterministically.  h / dh bf16 with pitches ldh / lddh, nout <= 8. */

@@ -96,3 +96,60 @@ def test_properties_large():
     assert torch.equal(C.closure(m), C.closure(dag))
     reach = (torch.linalg.matrix_power((dag.float() + torch.eye(n, device="cuda")), n) > 0)
     assert torch.equal(C.closure(dag).bool() | torch.eye(n, device="cuda").bool(), reach)
+
+
+# ---------------------------------------------------------------------------- location triplets (base_dataset.py:35-87)
+def _centers(g):
+    n_real = len(g.centers)
+    return np.concatenate([g.centers, np.zeros((len(g.boxes) - n_real, 2), np.float32)]).astype(np.float32)
+
+
+def _gpu_location(graphs, vocab, max_objs=None):
+    from canonicalsg2im_b200 import canonicalize as C
+    boxes = np.concatenate([g.boxes for g in graphs]).astype(np.float32)
+    cen = np.concatenate([_centers(g) for g in graphs])
+    objs = np.concatenate([g.objs for g in graphs]).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum([len(g.boxes) for g in graphs])]).astype(np.int32)
+    trip, tri_off = C.add_location_triplets_batched(t(boxes), t(cen), t(objs), t(off), vocab.image_obj_id, vocab.pred_ids,
+                                                    max_objs_per_graph=max_objs)
+    trip, tri_off = trip.cpu().numpy(), tri_off.cpu().numpy()
+    return [trip[tri_off[i]:tri_off[i + 1]] for i in range(len(graphs))]
+
+
+def test_location_triplets_golden(golden):
+    """The reference's own output (location + dummy triplets of the golden graphs, oracle/make_golden.py) bit for bit."""
+    from oracle import canon as ocanon
+    gd = golden("canon")
+    for c in range(int(gd["num_cases"])):
+        nb, na, n0, n1, dummies, clevr = [int(x) for x in gd["c%d_spec" % c][:6]]
+        vocab = synth.Vocab(nb, num_attributes=na)
+        g = synth.make_graph(int(gd["c%d_spec" % c][8]), n0, n1, vocab, include_dummies=bool(dummies),
+                             box_mode="clevr" if clevr else "coco")
+        loc = _gpu_location([g], vocab)[0]
+        dummy = ocanon.add_dummy_triplets(g.objs[:, 0], vocab.image_obj_id, vocab.in_image_id,
+                                          include_dummies=len(g.boxes) > len(g.centers))
+        got = np.concatenate([loc, np.array(dummy, dtype=np.int64).reshape(-1, 3)])
+        assert (got == gd["c%d_base" % c]).all()
+
+
+@pytest.mark.parametrize("n_min,n_max,mode", [(1, 4, "coco"), (3, 30, "coco"), (32, 64, "clevr"), (60, 100, "coco")])
+def test_location_triplets_batched_equal_oracle(n_min, n_max, mode):
+    """Ragged batches (single-object graphs, VG-sized graphs, CLEVR-sized graphs of 32-64 objects, > 64 objects = more
+    than one bitset word per row) against the oracle port, graph by graph, bit-exact."""
+    from oracle import canon as ocanon
+    vocab = synth.Vocab(0)
+    graphs = [synth.make_graph(5000 + 31 * n_max + i, n_min, n_max, vocab, include_dummies=(i % 3 != 0), box_mode=mode)
+              for i in range(24)]
+    got = _gpu_location(graphs, vocab)
+    for g, trip in zip(graphs, got):
+        ref = np.array(ocanon.add_location_triplets(g.boxes, _centers(g), g.objs[:, 0], vocab.image_obj_id, vocab.pred_ids),
+                       dtype=np.int64).reshape(-1, 3)
+        assert trip.shape == ref.shape and (trip == ref).all()
+
+
+def test_location_triplets_oversize_graph_is_reported():
+    from canonicalsg2im_b200 import _lib
+    vocab = synth.Vocab(0)
+    graphs = [synth.make_graph(77, 10, 12, vocab, include_dummies=True)]
+    with pytest.raises(_lib.CsgError):
+        _gpu_location(graphs, vocab, max_objs=4)
