@@ -234,9 +234,9 @@ struct __align__(8) Barriers {
 struct SmemPlan {
   uint32_t b, c, bias, bars, total;
 };
-__host__ __device__ inline SmemPlan smem_plan(int BN, int b_rows, int stages, bool smem_epi) {
+__host__ __device__ inline SmemPlan smem_plan(int BN, int b_rows, int stages, bool smem_epi, int mt = 1) {
   SmemPlan s;
-  s.b = (uint32_t)stages * A_STAGE_BYTES;
+  s.b = (uint32_t)stages * mt * A_STAGE_BYTES;
   s.c = s.b + (uint32_t)stages * b_rows * 128;
   s.bias = s.c + (smem_epi ? EPI_WARPS * CHUNK_BYTES : 0);
   s.bars = s.bias + (smem_epi ? 2 * BN * 4 : 0);             // bias of the current n-tile, double-buffered by tile parity
@@ -261,7 +261,11 @@ __device__ __forceinline__ bool bf16_pos(uint32_t h) { return h != 0 && h < 0x80
 // bounds the 1-CTA kernel (ncu r01d: 47 % tensor-pipe active with L2 and DRAM far from saturated).
 // Pair protocol: all TMA loads of both CTAs complete on the LEADER's full[] barrier; the leader's commits are
 // multicast to empty[] / tmem_full[] of both CTAs; both CTAs' epilogue warps arrive on the leader's tmem_empty[].
-template <int BN, bool MN, int GATHER, int CG>
+//
+// MT > 1 (gathered-B weight gradient dW1 only): one CTA owns MT 128-row m sub-tiles of the output for one 128-column
+// n-tile, i.e. MT accumulators side by side in TMEM.  The gathered operand (the TMA gather4 issue rate is what bounds
+// this GEMM) is then staged once per k-block for MT * 128 rows of M instead of once per 128-row m-tile.
+template <int BN, bool MN, int GATHER, int CG, int MT>
 __global__ void __launch_bounds__(NUM_THREADS + (GATHER != G_NONE ? GATHER_WARPS * 32 : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmP, const TcParams p) {
@@ -273,14 +277,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __trap();
   }
   static_assert(CG == 1 || !MN, "CTA pairs are implemented for the K-major kernels");
+  static_assert(MT == 1 || (MN && GATHER == G_B && CG == 1 && MT * BN <= 512), "MT > 1: gathered-B MN-major kernels only");
+  constexpr int A_STAGE = MT * A_STAGE_BYTES;        // bytes of the A tile(s) of one stage
   constexpr int B_ROWS = BN / CG;                   // rows of the B tile staged by this CTA
   constexpr int B_STAGE = B_ROWS * BLOCK_K * 2;
-  constexpr int TILE_M = BLOCK_M * CG;              // rows of C per work item (pair tile when CG = 2)
+  constexpr int TILE_M = BLOCK_M * CG * MT;         // rows of C per work item (pair tile when CG = 2)
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const int worker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int nworkers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const bool has_aux = GATHER == G_NONE && p.mask_aux != nullptr;   // the gathered GEMMs never take a ReLU mask
-  const SmemPlan plan = smem_plan(BN, B_ROWS, p.stages, p.smem_epi != 0);
+  const SmemPlan plan = smem_plan(BN, B_ROWS, p.stages, p.smem_epi != 0, MT);
   const uint32_t sA = base, sB = base + plan.b;
   Barriers* bars = reinterpret_cast<Barriers*>(base_ptr + plan.bars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -344,8 +350,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
-          if (CG == 1 || cta_rank == 0) mbar_arrive_expect_tx(smem_u32(&bars->full[stage]), CG * (A_STAGE_BYTES + B_STAGE));
-          const uint32_t a_dst = sA + stage * A_STAGE_BYTES, b_dst = sB + stage * B_STAGE;
+          if (CG == 1 || cta_rank == 0) mbar_arrive_expect_tx(smem_u32(&bars->full[stage]), CG * (A_STAGE + B_STAGE));
+          const uint32_t a_dst = sA + stage * A_STAGE, b_dst = sB + stage * B_STAGE;
           if (!MN && CG == 2) {
             if (GATHER == G_NONE) tma_load_2d_pair(a_dst, &tmA, fb, kb * BLOCK_K, m0);
             else {
@@ -363,7 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(b_dst, &tmB, fb, kb * BLOCK_K, nt * BN);
           } else {
             // MN-major: rows = k (64 per block), one [64 k x 64 mn] box per 64-wide chunk
-            for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(a_dst + c * 8192, &tmA, fb, mt * BLOCK_M + c * 64, kb * BLOCK_K);
+            for (int c = 0; c < MT * BLOCK_M / 64; ++c) tma_load_2d(a_dst + c * 8192, &tmA, fb, mt * TILE_M + c * 64, kb * BLOCK_K);
             for (int c = 0; c < BN / 64; ++c) {
               const int n0 = nt * BN + c * 64;
               if (GATHER == G_NONE) tma_load_2d(b_dst + c * 8192, &tmB, fb, n0, kb * BLOCK_K);
@@ -402,7 +408,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (seg_s || seg_o) {
               mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
               const uint32_t fb = leader(&bars->full[stage]);
-              const uint32_t dst = sA + stage * A_STAGE_BYTES + gl * 512;
+              const uint32_t dst = sA + stage * A_STAGE + gl * 512;
               if (CG == 2) {
                 if (seg_s) tma_gather4_pair(dst, &tmA, fb, c0, si[0], si[1], si[2], si[3]);
                 else tma_gather4_pair(dst, &tmA, fb, c0 - p.g_din - p.g_dp, oi[0], oi[1], oi[2], oi[3]);
@@ -472,27 +478,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // the last n-tile may be narrower than BN: issue MMAs of its real width (N % 32 == 0 is required by the host
         // side; an MMA of N = 192 costs as much as N = 256, which is why BN is 256 with a narrow tail and not 192)
         const int mma_n = (!MN && CG == 1) ? min(BN, p.N - nt * BN) : BN;
-        const uint32_t idesc = make_idesc(TILE_M, mma_n, MN, MN);
+        const uint32_t idesc = make_idesc(BLOCK_M * CG, mma_n, MN, MN);
         mbar_wait(smem_u32(&bars->tmem_empty[as]), aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bars->full[stage]), phase);
           tc_fence_after();
-          const uint32_t a_base = sA + stage * A_STAGE_BYTES, b_base = sB + stage * B_STAGE;
+          const uint32_t a_base = sA + stage * A_STAGE, b_base = sB + stage * B_STAGE;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            uint64_t ad, bd;
-            if (!MN) {
-              ad = make_desc(a_base + k * 32, 16, 1024);
-              bd = make_desc(b_base + k * 32, 16, 1024);
-            } else {
-              ad = make_desc(a_base + k * 2048, 8192, 1024);
-              bd = make_desc(b_base + k * 2048, 8192, 1024);
+          for (int mi = 0; mi < MT; ++mi) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              uint64_t ad, bd;
+              if (!MN) {
+                ad = make_desc(a_base + k * 32, 16, 1024);
+                bd = make_desc(b_base + k * 32, 16, 1024);
+              } else {
+                ad = make_desc(a_base + mi * A_STAGE_BYTES + k * 2048, 8192, 1024);
+                bd = make_desc(b_base + k * 2048, 8192, 1024);
+              }
+              if (p.debug & 2) continue;
+              if (CG == 2) umma_bf16_pair(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem + mi * BN, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
-            if (p.debug & 2) continue;
-            if (CG == 2) umma_bf16_pair(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if (CG == 2) {
             umma_commit_pair(smem_u32(&bars->empty[stage]));   // frees the slot in both CTAs when these MMAs retire
@@ -640,12 +649,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int as = it & 1, aphase = (it >> 1) & 1;
         mbar_wait(smem_u32(&bars->tmem_full[as]), aphase);
         tc_fence_after();
-        const int row = mt * TILE_M + (int)cta_rank * BLOCK_M + q * 32 + lane;
-        const bool rowok = row < p.M;
-        const float rs = (p.rowscale && rowok) ? p.rowscale[row] : 1.f;
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
 #pragma unroll 1
-        for (int c = half; c < BN / 32; c += 2) {
+        for (int ci = half; ci < MT * (BN / 32); ci += 2) {
+          const int mi = ci / (BN / 32), c = ci % (BN / 32);          // m sub-tile (MT > 1), 32-column group
+          const int row = mt * TILE_M + (int)cta_rank * BLOCK_M + mi * BLOCK_M + q * 32 + lane;
+          const bool rowok = row < p.M;
+          const float rs = (p.rowscale && rowok) ? p.rowscale[row] : 1.f;
+          const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE + mi * BN;
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           tmem_ld_wait();
@@ -756,20 +766,20 @@ struct Maps {
   CUtensorMap a, b, p;
 };
 
-template <int BN, bool MN, int GATHER, int CG>
+template <int BN, bool MN, int GATHER, int CG, int MT = 1>
 int launch(const Maps& m, const TcParams& p, cudaStream_t stream) {
-  const size_t smem = smem_plan(BN, BN / CG, p.stages, p.smem_epi != 0).total;
+  const size_t smem = smem_plan(BN, BN / CG, p.stages, p.smem_epi != 0, MT).total;
   CSG_REQUIRE(smem <= SMEM_LIMIT, "gemm_tc: shared-memory plan of %zu bytes exceeds the limit", smem);
   static bool configured = false;
   if (!configured) {
-    CSG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN, GATHER, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    CSG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN, GATHER, CG, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     configured = true;
   }
   const int tiles = p.m_tiles * p.n_tiles * p.splits;
   const int nthreads = NUM_THREADS + (GATHER != G_NONE ? GATHER_WARPS * 32 : 0);
   if (CG == 1) {
     const int grid = tiles < csg_num_sms() ? tiles : csg_num_sms();
-    gemm_tc_kernel<BN, MN, GATHER, CG><<<grid, nthreads, smem, stream>>>(m.a, m.b, m.p, p);
+    gemm_tc_kernel<BN, MN, GATHER, CG, MT><<<grid, nthreads, smem, stream>>>(m.a, m.b, m.p, p);
   } else {
     // one CTA pair (cluster of 2 on one TPC) per work item, persistent over the pair tiles
     const int pairs = csg_num_sms() / 2;
@@ -783,7 +793,7 @@ int launch(const Maps& m, const TcParams& p, cudaStream_t stream) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CSG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MN, GATHER, CG>, m.a, m.b, m.p, p));
+    CSG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MN, GATHER, CG, MT>, m.a, m.b, m.p, p));
   }
   CSG_CHECK_LAUNCH("csg_gemm_bf16");
   return 0;
@@ -827,8 +837,8 @@ int pick_bn(int N) {
 }
 
 // split-K plan of the MN-major (weight-gradient) GEMMs: one work item per CTA (a second wave would double the time)
-void mn_split_plan(int M, int N, int K, int BN, int& kb_per_split, int& nsplits) {
-  const int tiles = csg_div_up(M, BLOCK_M) * csg_div_up(N, BN);
+void mn_split_plan(int M, int N, int K, int BN, int& kb_per_split, int& nsplits, int mt = 1) {
+  const int tiles = csg_div_up(M, BLOCK_M * mt) * csg_div_up(N, BN);
   const int kb_total = csg_div_up(K, BLOCK_K);
   int splits = csg_num_sms() / tiles;
   if (splits < 1) splits = 1;
@@ -838,7 +848,14 @@ void mn_split_plan(int M, int N, int K, int BN, int& kb_per_split, int& nsplits)
   nsplits = csg_div_up(kb_total, kb_per_split);
 }
 
-int mn_pick_bn(int N, int gather) {
+// gathered-B weight gradient with 128-column n-tiles: GB_MT m sub-tiles (accumulators) per CTA, so that the gathered
+// operand is staged once per k-block for GB_MT * 128 rows of M.  (GB_MT = 4 halves the gathers again but leaves room
+// for only two 80 KB stages and measured no faster than GB_MT = 1; 2 keeps a 4-stage ring.)
+constexpr int GB_MT = 2;
+bool mn_gather_mt4(int M, int N, int gather) { return gather == 2 && (M % (GB_MT * BLOCK_M)) == 0 && (N % 128) == 0; }
+
+int mn_pick_bn(int M, int N, int gather) {
+  if (mn_gather_mt4(M, N, gather)) return 128;
   if (gather == 2) return (N % 192 == 0) ? 192 : (N % 128 == 0 ? 128 : 64);
   return pick_bn(N);
 }
@@ -854,7 +871,7 @@ CSG_API size_t csg_gemm_bf16_workspace(int M, int N, int K, int mn_major) {
   size_t need = 0;
   for (int gather = 0; gather <= 2; gather += 2) {
     int kbs, ns;
-    mn_split_plan(M, N, K, mn_pick_bn(N, gather), kbs, ns);
+    mn_split_plan(M, N, K, mn_pick_bn(M, N, gather), kbs, ns, mn_gather_mt4(M, N, gather) ? GB_MT : 1);
     const size_t b = ns > 1 ? (size_t)ns * M * N * sizeof(float) : 0;
     if (b > need) need = b;
   }
@@ -900,12 +917,13 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
   if (p.mask_aux) CSG_REQUIRE(ld_aux % 8 == 0, "gemm_bf16: ld_aux must be a multiple of 8");
   CSG_REQUIRE(!(gather && mask_aux), "gemm_bf16: the gathered GEMMs take no ReLU mask");
   // a gathered 64-column chunk must not straddle two source segments: guaranteed by %64 dims
-  const int BN = mn_major ? mn_pick_bn(N, gather) : kmajor_pick_bn(M, N);
+  const int BN = mn_major ? mn_pick_bn(M, N, gather) : kmajor_pick_bn(M, N);
+  const int MT = (mn_major && mn_gather_mt4(M, N, gather)) ? GB_MT : 1;
   // CTA pairs (cta_group::2): K-major only; each CTA stages BN/2 rows of B, so BN/2 must keep the 8-row swizzle atoms
   const bool pair = !mn_major && (BN % 32 == 0) && csg_num_sms() >= 2 &&
                     (g_pair_mode == 1 || (g_pair_mode < 0 && M >= 2 * BLOCK_M * csg_num_sms() && K >= 1024));
   const int CG = pair ? 2 : 1;
-  p.m_tiles = csg_div_up(M, BLOCK_M * CG);
+  p.m_tiles = csg_div_up(M, BLOCK_M * CG * MT);
   p.n_tiles = csg_div_up(N, BN);
   p.kb_total = csg_div_up(K, BLOCK_K);
   p.splits = 1;
@@ -936,7 +954,7 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
   } else {
     CSG_REQUIRE(out_f32, "gemm_bf16: MN-major (weight-gradient) GEMMs write fp32");
     CSG_REQUIRE(!bias && !relu && !rowscale && !mask_aux, "gemm_bf16: MN-major GEMMs have no epilogue");
-    mn_split_plan(M, N, K, BN, p.kb_per_split, p.splits);
+    mn_split_plan(M, N, K, BN, p.kb_per_split, p.splits, MT);
     if (p.splits > 1) {
       CSG_REQUIRE(ldc == N, "gemm_bf16: split-K output must be contiguous");
       CSG_REQUIRE(workspace && workspace_bytes >= (size_t)p.splits * M * N * sizeof(float), "gemm_bf16: workspace too small");
@@ -949,11 +967,15 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
     } else {
       if (int rc = make_map(&maps.b, B, N, K, (uint64_t)ldb * 2, 64)) return rc;
     }
-    p.stages = smem_plan(BN, BN, 5, false).total <= SMEM_LIMIT ? 5 : 4;
+    p.stages = 5;
+    while (p.stages > 2 && smem_plan(BN, BN, p.stages, false, MT).total > SMEM_LIMIT) --p.stages;
+    CSG_REQUIRE(MT == 1 || p.m_tiles * p.n_tiles * p.splits <= csg_num_sms(),
+                "gemm_bf16: the multi-accumulator weight-gradient kernel needs one work item per CTA");
   }
   int rc;
   if (!mn_major && pair) rc = gather == 1 ? launch_bn<false, G_A, 2>(BN, maps, p, stream) : launch_bn<false, G_NONE, 2>(BN, maps, p, stream);
   else if (!mn_major) rc = gather == 1 ? launch_bn<false, G_A, 1>(BN, maps, p, stream) : launch_bn<false, G_NONE, 1>(BN, maps, p, stream);
+  else if (MT == GB_MT) rc = launch<128, true, G_B, 1, GB_MT>(maps, p, stream);
   else rc = gather == 2 ? launch_bn<true, G_B, 1>(BN, maps, p, stream) : launch_bn<true, G_NONE, 1>(BN, maps, p, stream);
   if (rc) return rc;
   if (p.splits > 1) {

@@ -282,7 +282,7 @@ __global__ void triple_bwd_assemble_kernel(const float* __restrict__ out, const 
 // d w_trans[p] += sum over type-1 triples with predicate p of dconf[t] * s(1-s), s = sigmoid(w[p]).
 // Deterministic: each warp walks a contiguous chunk in order, lanes with equal predicate are summed
 // in lane order by the group leader into warp-private bins; bins are then reduced in fixed order.
-constexpr int CONF_BWD_BLOCKS = 64;    // partial rows summed in order by the final pass (one block per 1.8 k triples at cfg2)
+constexpr int CONF_BWD_BLOCKS = 256;   // (64 blocks made the partial pass 3x slower: each warp walks its triples serially)
 __global__ void conf_bwd_partial_kernel(const float* __restrict__ dconf, const int* __restrict__ type32,
                                         const int* __restrict__ pred, int NT, int P, float* __restrict__ partial) {
   extern __shared__ float bins[];   // [warps][P]

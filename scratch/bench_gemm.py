@@ -53,3 +53,11 @@ if __name__ == "__main__":
                     continue
                 t = timeit(fn)
                 print("dbg=%d pair=%d %-22s %7.1f us  %7.1f TFLOP/s" % (dbg, mode, name, t * 1e6, fl / t / 1e12), flush=True)
+
+# gathered-B weight gradient dW1 = dhid^T [obj[s] | pred | obj[o]]  (M = 512, N = 384, K = triples)
+if os.environ.get("CSG_BENCH_DW1"):
+    os.environ["CSG_GEMM_DEBUG"] = "0"
+    dh = rnd((NT, 512), 0.1)
+    fn = lambda: ops.gemm_bf16(512, 384, NT, dh, None, mn_major=True, gather=ga, gather_mode=2)
+    t = timeit(fn)
+    print("dW1 gatherB 512x384xNT  %7.1f us  %7.1f TFLOP/s" % (t * 1e6, 2.0 * 512 * 384 * NT / t / 1e12), flush=True)
