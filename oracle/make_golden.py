@@ -46,6 +46,7 @@ def import_reference():
 sys.path.insert(0, ROOT)
 from canonicalsg2im_b200 import synth  # noqa: E402
 from oracle import canon as ocanon, graph as ograph, layout as olayout  # noqa: E402
+from tests import golden_inputs as gi  # noqa: E402
 
 
 def t(x):
@@ -402,6 +403,37 @@ def gen_layout(rlayout, rbil):
     print("layout fixtures:", len(out), "arrays")
 
 
+def gen_collate():
+    """packed_coco.py:385-478 / packed_vg.py:147-229 on seeded samples (the dataset modules import h5py / PIL /
+    pycocotools at module level: absent here, stubbed, never called by the collate functions)."""
+    for name in ("h5py", "PIL", "PIL.Image", "torchvision", "torchvision.transforms", "pycocotools", "pycocotools.mask",
+                 "skimage", "skimage.transform", "imageio", "cv2"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    import sg2im.data.packed_coco as pc
+    import sg2im.data.packed_vg as pv
+    from oracle import collate as ocollate
+    out = {}
+    for ci, (fn, with_masks, na, seed) in enumerate([(pc.coco_collate_fn, True, 1, 3), (pv.vg_collate_fn, False, 1, 4),
+                                                      (pc.coco_collate_fn, False, 3, 5)]):
+        vocab = synth.Vocab(0, num_attributes=na)
+        rv = {"pred_name_to_idx": vocab.pred_ids}
+        samples = gi.collate_samples(vocab, seed, 5, with_masks, 6)
+        ref = fn(rv, samples)
+        mine = ocollate.padded_collate(rv, samples, with_masks=fn is pc.coco_collate_fn)
+        for k, (a, b) in enumerate(zip(ref, mine)):
+            assert (a is None and b is None) or (a.dtype == b.dtype and torch.equal(a, b)), ("oracle collate", ci, k)
+        out["c%d_spec" % ci] = np.array([int(with_masks), na, seed, int(fn is pc.coco_collate_fn)])
+        for k, a in enumerate(ref):
+            if a is not None:
+                out["c%d_out%d" % (ci, k)] = a.numpy()
+    out["num_cases"] = np.array(3)
+    np.savez_compressed(os.path.join(OUT, "collate.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -410,6 +442,7 @@ def main():
     gen_gconv(rgraph)
     gen_model(rmodel)
     gen_layout(rlayout, rbil)
+    gen_collate()
     for f in sorted(os.listdir(OUT)):
         print("%-28s %8.1f KB" % (f, os.path.getsize(os.path.join(OUT, f)) / 1024))
 

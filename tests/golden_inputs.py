@@ -61,3 +61,26 @@ def layout_out_grad(shape):
 
 def crop_out_grad(shape):
     return synth.det_tensor(tuple(shape), 32, 1.0)
+
+
+def collate_samples(vocab, seed, num, with_masks, P):
+    """Per-sample tuples as the reference datasets' ``__getitem__`` returns them (packed_coco.py:373-383), seeded:
+    ``(img, objs: dict attribute -> LongTensor[O], boxes, triplets, conv_counts, triplet_type, masks or None, image_id)``."""
+    import torch
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+    samples = []
+    graphs = synth.make_graphs(num, seed, 1, 9, vocab, include_dummies=True, mask_size=4 if with_masks else 0)
+    for i, g in enumerate(graphs):
+        O = len(g.boxes)
+        img = t(synth.det_tensor((3, 4, 4), seed * 31 + i, 1.0))
+        objs = {"a%d" % k: t(g.objs[:, k].astype(np.int64)) for k in range(g.objs.shape[1])}
+        trip = t(g.triplets.astype(np.int64))
+        ty = t((synth.det_uniform(len(g.triplets), seed * 7 + i) < 0.3).astype(np.int64))
+        cc = t(synth.det_tensor((P, P + 1), seed * 13 + i, 1.0).astype(np.float64))
+        masks = None
+        if with_masks:
+            m = np.zeros((O, 4, 4), np.int64)
+            m[:len(g.masks)] = g.masks
+            masks = t(m)
+        samples.append((img, objs, t(g.boxes.astype(np.float32)), trip, cc, ty, masks, 1000 + i))
+    return samples

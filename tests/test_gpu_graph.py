@@ -341,3 +341,22 @@ def test_cfg5_scale_ragged_batch_is_sum_of_its_shards():
     for i, what in ((2, "dW1 layer 0"), (3, "d w_trans")):
         s = a[i] + b[i]
         assert ((whole[i] - s).norm() / s.norm()).item() <= 1e-3, what
+
+
+def test_ragged_collate_batch_runs_the_model_like_the_padded_batch():
+    """collate.ragged_collate_fn -> Sg2LayoutModel.forward_ragged equals the reference-shaped padded batch
+    (collate.ragged_to_padded -> Sg2LayoutModel.forward) on the real object rows."""
+    from canonicalsg2im_b200.collate import ragged_collate_fn, ragged_to_padded
+    vocab = synth.Vocab(0)
+    samples = gi.collate_samples(vocab, 21, 6, False, vocab.num_preds)
+    rb = ragged_collate_fn(None, samples)
+    model = _model()
+    d = rb.to("cuda")
+    vecs_r, boxes_r = model.forward_ragged(d["objs"], d["triplets"], d["triplet_type"], d["tri_off"], d["obj_off"])
+    _, objs_p, _, trip_p, _, types_p, _, _ = ragged_to_padded(rb, vocab.padding_id)
+    vecs_p, boxes_p, _ = model(objs_p.cuda(), trip_p.cuda(), types_p.cuda())
+    off = rb["obj_off"].tolist()
+    sel_v = torch.cat([vecs_p[b, :off[b + 1] - off[b]] for b in range(rb["B"])])
+    sel_b = torch.cat([boxes_p[b, :off[b + 1] - off[b]] for b in range(rb["B"])])
+    assert_close(vecs_r, sel_v, 1e-6, "ragged collate vs padded collate: obj_vecs")
+    assert_close(boxes_r, sel_b, 1e-6, "ragged collate vs padded collate: boxes")
