@@ -316,6 +316,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();     // barriers of BOTH CTAs are initialised past this point
   tc_fence_after();
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no
+  // global memory and may run while the previous kernel of the stream drains; its results are visible past this point.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = bars->tmem_base;
   // shared::cluster address of a barrier of the pair's leader (identity for the 1-CTA kernel)
   auto leader = [&](const uint64_t* bar) -> uint32_t { return CG == 2 ? mapa(smem_u32(bar), 0u) : smem_u32(bar); };
@@ -779,7 +782,17 @@ int launch(const Maps& m, const TcParams& p, cudaStream_t stream) {
   const int nthreads = NUM_THREADS + (GATHER != G_NONE ? GATHER_WARPS * 32 : 0);
   if (CG == 1) {
     const int grid = tiles < csg_num_sms() ? tiles : csg_num_sms();
-    gemm_tc_kernel<BN, MN, GATHER, CG, MT><<<grid, nthreads, smem, stream>>>(m.a, m.b, m.p, p);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(nthreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see griddepcontrol.wait in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CSG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MN, GATHER, CG, MT>, m.a, m.b, m.p, p));
   } else {
     // one CTA pair (cluster of 2 on one TPC) per work item, persistent over the pair tiles
     const int pairs = csg_num_sms() / 2;
@@ -789,10 +802,12 @@ int launch(const Maps& m, const TcParams& p, cudaStream_t stream) {
     cfg.blockDim = dim3(nthreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
     CSG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MN, GATHER, CG, MT>, m.a, m.b, m.p, p));
   }
   CSG_CHECK_LAUNCH("csg_gemm_bf16");
