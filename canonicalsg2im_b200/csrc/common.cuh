@@ -53,6 +53,23 @@ enum { CSG_PROF_GEMM_BF16 = 0, CSG_PROF_GEMM_F32 = 1, CSG_PROF_LAYOUT_FWD = 2, C
 
 static inline int csg_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (PDL): a kernel launched through csg_launch_pdl may be scheduled while the previous
+// kernel of the stream is still draining; it must execute CSG_PDL_WAIT() before its first global-memory access (a
+// no-op when the kernel was launched the ordinary way).  Hides ~1-2 us of launch latency per kernel in the ~200-launch
+// training step.
+#define CSG_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+template <typename... KArgs, typename... Args>
+static inline cudaError_t csg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                         Args... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int csg_num_sms();   // SM count of the current device (cached per device)
 
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }

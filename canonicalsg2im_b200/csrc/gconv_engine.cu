@@ -105,6 +105,7 @@ int check_dims(const Dims& d) {
 template <bool DY_BF16>
 __global__ void relu_mask_out_kernel(const void* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                      __nv_bfloat16* __restrict__ out, long long n) {
+  CSG_PDL_WAIT();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = DY_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[i])
@@ -247,12 +248,12 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
     if (!d_new_obj) {
       CSG_CUDA(cudaMemsetAsync(g4, 0, (size_t)n4 * 2, st));
     } else if (d_new_obj_bf16) {
-      relu_mask_out_kernel<true><<<csg_div_up(n4, 256), 256, 0, st>>>(d_new_obj, (const __nv_bfloat16*)new_obj,
-                                                                      (__nv_bfloat16*)g4, n4);
+      CSG_CUDA(csg_launch_pdl(relu_mask_out_kernel<true>, dim3(csg_div_up(n4, 256)), dim3(256), 0, st, d_new_obj, (const __nv_bfloat16*)new_obj,
+                                                                      (__nv_bfloat16*)g4, n4));
       CSG_CHECK_LAUNCH("csg_gconv_bf16_bwd relu mask");
     } else {
-      relu_mask_out_kernel<false><<<csg_div_up(n4, 256), 256, 0, st>>>(d_new_obj, (const __nv_bfloat16*)new_obj,
-                                                                       (__nv_bfloat16*)g4, n4);
+      CSG_CUDA(csg_launch_pdl(relu_mask_out_kernel<false>, dim3(csg_div_up(n4, 256)), dim3(256), 0, st, d_new_obj, (const __nv_bfloat16*)new_obj,
+                                                                       (__nv_bfloat16*)g4, n4));
       CSG_CHECK_LAUNCH("csg_gconv_bf16_bwd relu mask");
     }
   }

@@ -726,6 +726,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 __global__ void splitk_reduce_tc_kernel(const float* __restrict__ partial, float* __restrict__ C, long long MN, int splits) {
+  CSG_PDL_WAIT();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= MN) return;
   C[i] = ordered_sum<8>(partial + i, (size_t)MN, splits);
@@ -995,8 +996,8 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
   if (rc) return rc;
   if (p.splits > 1) {
     long long MN = (long long)M * N;
-    splitk_reduce_tc_kernel<<<csg_div_up(MN, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(p.C),
-                                                                     reinterpret_cast<float*>(out), MN, p.splits);
+    CSG_CUDA(csg_launch_pdl(splitk_reduce_tc_kernel, dim3(csg_div_up(MN, 256)), dim3(256), 0, stream, reinterpret_cast<const float*>(p.C),
+                                                                     reinterpret_cast<float*>(out), MN, p.splits));
     CSG_CHECK_LAUNCH("csg_gemm_bf16 split-K reduce");
   }
   return 0;

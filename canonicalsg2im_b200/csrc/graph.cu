@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(32) csr_fill_kernel(const int* __restrict__ ke
 
 __global__ void triple_conf_kernel(const int* __restrict__ type32, const int* __restrict__ pred,
                                    const float* __restrict__ w_trans, int NT, float* __restrict__ conf) {
+  CSG_PDL_WAIT();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= NT) return;
   int ty = type32[t];
@@ -215,6 +216,7 @@ __global__ void segpool_kernel(const float* __restrict__ X, int ldx, int col_s, 
 __global__ void pool_bwd_obj_kernel(const float* __restrict__ dpooled, const float* __restrict__ pooled,
                                     const float* __restrict__ cnt, int W, float* __restrict__ dS,
                                     float* __restrict__ dcnt) {
+  CSG_PDL_WAIT();
   const int o = blockIdx.x;
   const float c = cnt[o];
   const bool nz = c > 0.f;
@@ -285,6 +287,7 @@ __global__ void triple_bwd_assemble_kernel(const float* __restrict__ out, const 
 constexpr int CONF_BWD_BLOCKS = 256;   // (64 blocks made the partial pass 3x slower: each warp walks its triples serially)
 __global__ void conf_bwd_partial_kernel(const float* __restrict__ dconf, const int* __restrict__ type32,
                                         const int* __restrict__ pred, int NT, int P, float* __restrict__ partial) {
+  CSG_PDL_WAIT();
   extern __shared__ float bins[];   // [warps][P]
   const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < warps * P; i += blockDim.x) bins[i] = 0.f;
@@ -318,6 +321,7 @@ __global__ void conf_bwd_partial_kernel(const float* __restrict__ dconf, const i
 }
 __global__ void conf_bwd_final_kernel(const float* __restrict__ partial, const float* __restrict__ w_trans, int P,
                                       int blocks, float* __restrict__ dw) {
+  CSG_PDL_WAIT();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const float s = ordered_sum<16>(partial + p, (size_t)P, blocks);
@@ -388,7 +392,7 @@ CSG_API int csg_csr_build(const int* keys_s, const int* keys_o, const int* tri_o
 CSG_API int csg_triple_conf(const int* type32, const int* pred, const float* w_trans, int NT, float* conf,
                             cudaStream_t stream) {
   if (NT == 0) return 0;
-  triple_conf_kernel<<<csg_div_up(NT, 256), 256, 0, stream>>>(type32, pred, w_trans, NT, conf);
+  CSG_CUDA(csg_launch_pdl(triple_conf_kernel, dim3(csg_div_up(NT, 256)), dim3(256), 0, stream, type32, pred, w_trans, NT, conf));
   CSG_CHECK_LAUNCH("csg_triple_conf");
   return 0;
 }
@@ -419,7 +423,7 @@ CSG_API int csg_segpool_f32(const float* X, int ldx, int col_s, int col_o, int W
 CSG_API int csg_pool_bwd_obj(const float* dpooled, const float* pooled, const float* cnt, int NO, int W,
                              float* dS, float* dcnt, cudaStream_t stream) {
   if (NO == 0) return 0;
-  pool_bwd_obj_kernel<<<NO, 128, 0, stream>>>(dpooled, pooled, cnt, W, dS, dcnt);
+  CSG_CUDA(csg_launch_pdl(pool_bwd_obj_kernel, dim3(NO), dim3(128), 0, stream, dpooled, pooled, cnt, W, dS, dcnt));
   CSG_CHECK_LAUNCH("csg_pool_bwd_obj");
   return 0;
 }
@@ -444,10 +448,10 @@ CSG_API int csg_conf_bwd(const float* dconf, const int* type32, const int* pred,
   CSG_REQUIRE(P > 0 && P <= 4096, "conf_bwd: P=%d out of range", P);
   float* partial = reinterpret_cast<float*>(workspace);
   const int threads = 128;
-  conf_bwd_partial_kernel<<<CONF_BWD_BLOCKS, threads, (threads / 32) * P * sizeof(float), stream>>>(
-      dconf, type32, pred, NT, P, partial);
+  CSG_CUDA(csg_launch_pdl(conf_bwd_partial_kernel, dim3(CONF_BWD_BLOCKS), dim3(threads), (threads / 32) * P * sizeof(float), stream, 
+      dconf, type32, pred, NT, P, partial));
   CSG_CHECK_LAUNCH("csg_conf_bwd partial");
-  conf_bwd_final_kernel<<<csg_div_up(P, 128), 128, 0, stream>>>(partial, w_trans, P, CONF_BWD_BLOCKS, dw);
+  CSG_CUDA(csg_launch_pdl(conf_bwd_final_kernel, dim3(csg_div_up(P, 128)), dim3(128), 0, stream, partial, w_trans, P, CONF_BWD_BLOCKS, dw));
   CSG_CHECK_LAUNCH("csg_conf_bwd final");
   return 0;
 }

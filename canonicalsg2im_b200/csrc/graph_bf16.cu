@@ -56,6 +56,7 @@ struct CastJobs {
   int n;
 };
 __global__ void cast_bf16_multi_kernel(const CastJobs jobs) {
+  CSG_PDL_WAIT();
   __shared__ float tile[32][33];
   int j = 0;
   while (j < jobs.n - 1 && (int)blockIdx.x >= jobs.tile_end[j]) ++j;
@@ -94,6 +95,7 @@ segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int
                     const int* __restrict__ valid, const float* __restrict__ conf,
                     float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int ldo,
                     float* __restrict__ cnt_out) {
+  CSG_PDL_WAIT();
   __shared__ float red[SP_MAX_THREADS * 8];
   __shared__ float red_cnt[SP_MAX_THREADS];
   // objects are visited last-to-first: X was just written front-to-back by the producing GEMM and is larger than L2, so
@@ -178,6 +180,7 @@ constexpr int CS_TX = 32, CS_TY = 8, CS_VEC = 8;
 __global__ void __launch_bounds__(CS_TX * CS_TY) colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ X, int M, int N,
                                                                            int ld, int rows_per_chunk,
                                                                            float* __restrict__ partial) {
+  CSG_PDL_WAIT();
   __shared__ float red[CS_TY][CS_TX * CS_VEC + 4];
   const int tx = threadIdx.x % CS_TX, ty = threadIdx.x / CS_TX;
   const int col = (blockIdx.x * CS_TX + tx) * CS_VEC;
@@ -222,6 +225,7 @@ __global__ void __launch_bounds__(CS_TX * CS_TY) colsum_bf16_partial_kernel(cons
 // final pass: 32 columns x 8 chunk lanes per block, lanes combined in lane order
 __global__ void __launch_bounds__(256) colsum_bf16_final_kernel(const float* __restrict__ partial, int chunks, int N,
                                                                 float* __restrict__ out) {
+  CSG_PDL_WAIT();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
@@ -260,6 +264,7 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
                                 const int* __restrict__ type32, const float* __restrict__ conf,
                                 int NT, int H, int Dp, __nv_bfloat16* __restrict__ g,
                                 float* __restrict__ dconf, float* __restrict__ cs_partial) {
+  CSG_PDL_WAIT();
   __shared__ __align__(16) float cs_red[CS ? (ASM_WARPS / 2) * ASM_MAXI * 256 : 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Wd = 2 * H + Dp;
@@ -408,7 +413,7 @@ CSG_API int csg_cast_bf16_multi(int n, const void* const* src, void* const* dst,
     jobs.tile_end[i] = total;
   }
   if (total == 0) return 0;
-  cast_bf16_multi_kernel<<<total, dim3(32, 8), 0, stream>>>(jobs);
+  CSG_CUDA(csg_launch_pdl(cast_bf16_multi_kernel, dim3(total), dim3(dim3(32, 8)), 0, stream, jobs));
   CSG_CHECK_LAUNCH("csg_cast_bf16_multi");
   return 0;
 }
@@ -430,11 +435,11 @@ CSG_API int csg_segpool_bf16(const void* X, int ldx, int col_s, int col_o, int W
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   if (avg) {
     CSG_REQUIRE(valid && conf && cnt_out, "segpool_bf16(avg): valid/conf/cnt required");
-    segpool_bf16_kernel<true><<<NO, threads, 0, stream>>>(x, ldx, col_s, col_o, W, TX, TY, rowptr_s, perm_s, rowptr_o,
-                                                          perm_o, valid, conf, out_f32, ob, ldo, cnt_out);
+    CSG_CUDA(csg_launch_pdl(segpool_bf16_kernel<true>, dim3(NO), dim3(threads), 0, stream, x, ldx, col_s, col_o, W, TX, TY, rowptr_s, perm_s, rowptr_o,
+                                                          perm_o, valid, conf, out_f32, ob, ldo, cnt_out));
   } else {
-    segpool_bf16_kernel<false><<<NO, threads, 0, stream>>>(x, ldx, col_s, col_o, W, TX, TY, rowptr_s, perm_s, rowptr_o,
-                                                           perm_o, nullptr, nullptr, out_f32, ob, ldo, nullptr);
+    CSG_CUDA(csg_launch_pdl(segpool_bf16_kernel<false>, dim3(NO), dim3(threads), 0, stream, x, ldx, col_s, col_o, W, TX, TY, rowptr_s, perm_s, rowptr_o,
+                                                           perm_o, nullptr, nullptr, out_f32, ob, ldo, nullptr));
   }
   CSG_CHECK_LAUNCH("csg_segpool_bf16");
   return 0;
@@ -461,10 +466,10 @@ CSG_API int csg_colsum_bf16(const void* X, int M, int N, int ld, float* out, voi
   const int chunks = colsum_bf16_chunks(M, N);
   const int rows_per_chunk = csg_div_up(M > 0 ? M : 1, chunks);
   float* partial = reinterpret_cast<float*>(workspace);
-  colsum_bf16_partial_kernel<<<dim3(csg_div_up(N, CS_TX * CS_VEC), chunks), CS_TX * CS_TY, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(X), M, N, ld, rows_per_chunk, partial);
+  CSG_CUDA(csg_launch_pdl(colsum_bf16_partial_kernel, dim3(dim3(csg_div_up(N, CS_TX * CS_VEC), chunks)), dim3(CS_TX * CS_TY), 0, stream, 
+      reinterpret_cast<const __nv_bfloat16*>(X), M, N, ld, rows_per_chunk, partial));
   CSG_CHECK_LAUNCH("csg_colsum_bf16 partial");
-  colsum_bf16_final_kernel<<<csg_div_up(N, 32), 256, 0, stream>>>(partial, chunks, N, out);
+  CSG_CUDA(csg_launch_pdl(colsum_bf16_final_kernel, dim3(csg_div_up(N, 32)), dim3(256), 0, stream, partial, chunks, N, out));
   CSG_CHECK_LAUNCH("csg_colsum_bf16 final");
   return 0;
 }
@@ -497,14 +502,14 @@ CSG_API int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const
     CSG_REQUIRE(workspace && workspace_bytes >= csg_triple_bwd_assemble_bf16_workspace(NT, H, Dp),
                 "bwd_assemble_bf16: workspace too small");
     float* partial = reinterpret_cast<float*>(workspace);
-    triple_bwd_assemble_bf16_kernel<true><<<blocks, ASM_WARPS * 32, 0, stream>>>(
-        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, partial);
+    CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream, 
+        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, partial));
     CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16");
-    colsum_bf16_final_kernel<<<csg_div_up(Wd, 32), 256, 0, stream>>>(partial, blocks, Wd, colsum_g);
+    CSG_CUDA(csg_launch_pdl(colsum_bf16_final_kernel, dim3(csg_div_up(Wd, 32)), dim3(256), 0, stream, partial, blocks, Wd, colsum_g));
     CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16 colsum");
   } else {
-    triple_bwd_assemble_bf16_kernel<false><<<blocks, ASM_WARPS * 32, 0, stream>>>(
-        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, nullptr);
+    CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<false>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream, 
+        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, nullptr));
     CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16");
   }
   return 0;
