@@ -69,6 +69,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int* to
 
 template <bool EMIT>
 __global__ void __launch_bounds__(CTHREADS) canon_kernel(CanonParams p) {
+  CSG_PDL_WAIT();
   extern __shared__ __align__(16) u64 bits[];
   __shared__ int scratch[CTHREADS];
   const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -297,7 +298,7 @@ CSG_API int csg_canon_count(const long long* triplets, const int* tri_off, const
   p.out_off = nullptr; p.out_triplets = nullptr; p.out_type = nullptr;
   CSG_CUDA(cudaMemsetAsync(conv_counts, 0, (size_t)B * P * (P + 1) * sizeof(int), stream));
   CSG_CUDA(cudaFuncSetAttribute(canon_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  canon_kernel<false><<<B, CTHREADS, smem, stream>>>(p);
+  CSG_CUDA(csg_launch_pdl(canon_kernel<false>, dim3(B), dim3(CTHREADS), smem, stream, p));
   CSG_CHECK_LAUNCH("csg_canon_count");
   return 0;
 }
@@ -315,7 +316,7 @@ CSG_API int csg_canon_emit(const long long* triplets, const int* tri_off, const 
   p.cnt0 = nullptr; p.cnt1 = nullptr; p.conv_counts = nullptr;
   p.out_off = out_off; p.out_triplets = out_triplets; p.out_type = out_type;
   CSG_CUDA(cudaFuncSetAttribute(canon_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  canon_kernel<true><<<B, CTHREADS, smem, stream>>>(p);
+  CSG_CUDA(csg_launch_pdl(canon_kernel<true>, dim3(B), dim3(CTHREADS), smem, stream, p));
   CSG_CHECK_LAUNCH("csg_canon_emit");
   return 0;
 }
@@ -325,6 +326,7 @@ CSG_API int csg_canon_emit(const long long* triplets, const int* tri_off, const 
 namespace {
 __global__ void __launch_bounds__(1024) canon_offsets_kernel(const int* __restrict__ cnt0, const int* __restrict__ cnt1,
                                                              int B, int* __restrict__ out_off, int* __restrict__ summary) {
+  CSG_PDL_WAIT();
   __shared__ int sums[1024];
   __shared__ int mins[32];
   const int tid = threadIdx.x;
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(1024) canon_offsets_kernel(const int* __restri
 }  // namespace
 
 CSG_API int csg_canon_offsets(const int* cnt0, const int* cnt1, int B, int* out_off, int* summary, cudaStream_t stream) {
-  canon_offsets_kernel<<<1, 1024, 0, stream>>>(cnt0, cnt1, B, out_off, summary);
+  CSG_CUDA(csg_launch_pdl(canon_offsets_kernel, dim3(1), dim3(1024), 0, stream, cnt0, cnt1, B, out_off, summary));
   CSG_CHECK_LAUNCH("csg_canon_offsets");
   return 0;
 }

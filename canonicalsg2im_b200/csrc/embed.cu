@@ -28,6 +28,7 @@ __device__ __forceinline__ float4 load_row4(const void* base, size_t elem, bool 
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict__ table, const long long* __restrict__ idx,
                                                         long long idx_stride, int n, int V, int E,
                                                         void* __restrict__ out, int ld_out, int out_bf16) {
+  CSG_PDL_WAIT();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= n) return;
   const int lane = threadIdx.x & 31;
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
 // fp32 accumulation in a fixed split-K order, i.e. a deterministic segmented sum at GEMM speed.
 __global__ void __launch_bounds__(256) onehot_bf16_kernel(const long long* __restrict__ idx, long long idx_stride, int n,
                                                           int V, int ld, uint4* __restrict__ out) {
+  CSG_PDL_WAIT();
   const int per_row = ld >> 3;                                    // 16-byte pieces per row
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * per_row) return;
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(32) embed_bwd_partial_kernel(const void* __res
                                                                const long long* __restrict__ idx, long long idx_stride,
                                                                int n, int rows_per_block, int v0, int Vc, int E,
                                                                float* __restrict__ partial) {
+  CSG_PDL_WAIT();
   extern __shared__ __align__(16) float acc[];     // [Vc][E]
   const int lane = threadIdx.x;
   for (int i = lane * 4; i < Vc * E; i += 128) st_f4(acc + i, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(32) embed_bwd_partial_kernel(const void* __res
 }
 
 __global__ void embed_bwd_final_kernel(const float* __restrict__ partial, int blocks, int cells, float* __restrict__ dtable) {
+  CSG_PDL_WAIT();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cells) return;
   float a0 = 0.f, a1 = 0.f;
@@ -157,6 +161,7 @@ __device__ __forceinline__ float block_sum_1024(float v, float* red) {
 
 __global__ void __launch_bounds__(1024) box_loss_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int n,
                                                         float* __restrict__ loss, float* __restrict__ dpred) {
+  CSG_PDL_WAIT();
   __shared__ float red[33];
   float cnt = 0.f, sum = 0.f;
   for (int r = threadIdx.x; r < n; r += 1024) {
@@ -195,8 +200,8 @@ CSG_API int csg_embed_fwd(const float* table, const long long* idx, long long id
                           void* out, int ld_out, int out_bf16, cudaStream_t stream) {
   if (n == 0) return 0;
   CSG_REQUIRE(V > 0 && E > 0 && (E & 3) == 0 && (ld_out & 3) == 0, "embed_fwd: E=%d / ld=%d must be multiples of 4", E, ld_out);
-  embed_fwd_kernel<<<csg_div_up((long long)n * 32, 256), 256, 0, stream>>>(table, idx, idx_stride, n, V, E, out, ld_out,
-                                                                          out_bf16);
+  CSG_CUDA(csg_launch_pdl(embed_fwd_kernel, dim3(csg_div_up((long long)n * 32, 256)), dim3(256), 0, stream, table, idx, idx_stride, n, V, E, out, ld_out,
+                                                                          out_bf16));
   CSG_CHECK_LAUNCH("csg_embed_fwd");
   return 0;
 }
@@ -221,11 +226,11 @@ CSG_API int csg_embed_bwd(const void* dout, int ld, int in_bf16, const long long
   CSG_CUDA(cudaFuncSetAttribute(embed_bwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (int v0 = 0; v0 < V; v0 += p.Vc) {
     const int vc = V - v0 < p.Vc ? V - v0 : p.Vc;
-    embed_bwd_partial_kernel<<<p.blocks, 32, (size_t)vc * E * sizeof(float), stream>>>(dout, ld, in_bf16, idx, idx_stride, n,
-                                                                                      p.rows_per_block, v0, vc, E, partial);
+    CSG_CUDA(csg_launch_pdl(embed_bwd_partial_kernel, dim3(p.blocks), dim3(32), (size_t)vc * E * sizeof(float), stream, dout, ld, in_bf16, idx, idx_stride, n,
+                                                                                      p.rows_per_block, v0, vc, E, partial));
     CSG_CHECK_LAUNCH("csg_embed_bwd partial");
-    embed_bwd_final_kernel<<<csg_div_up((long long)vc * E, 256), 256, 0, stream>>>(partial, p.blocks, vc * E,
-                                                                                  dtable + (size_t)v0 * E);
+    CSG_CUDA(csg_launch_pdl(embed_bwd_final_kernel, dim3(csg_div_up((long long)vc * E, 256)), dim3(256), 0, stream, partial, p.blocks, vc * E,
+                                                                                  dtable + (size_t)v0 * E));
     CSG_CHECK_LAUNCH("csg_embed_bwd final");
   }
   return 0;
@@ -237,14 +242,14 @@ CSG_API int csg_onehot_bf16(const long long* idx, long long idx_stride, int n, i
   CSG_REQUIRE(V > 0 && ld >= V && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
               "onehot_bf16: ld=%d must be a multiple of 8 and >= V=%d, out 16-byte aligned", ld, V);
   const long long pieces = (long long)n * (ld >> 3);
-  onehot_bf16_kernel<<<csg_div_up(pieces, 256), 256, 0, stream>>>(idx, idx_stride, n, V, ld, reinterpret_cast<uint4*>(out));
+  CSG_CUDA(csg_launch_pdl(onehot_bf16_kernel, dim3(csg_div_up(pieces, 256)), dim3(256), 0, stream, idx, idx_stride, n, V, ld, reinterpret_cast<uint4*>(out)));
   CSG_CHECK_LAUNCH("csg_onehot_bf16");
   return 0;
 }
 
 // loss[0] = mean over the 4 coordinates of the rows with gt >= 0 of smooth_l1(pred - gt); dpred = d loss / d pred.
 CSG_API int csg_box_loss(const float* pred, const float* gt, int n, float* loss, float* dpred, cudaStream_t stream) {
-  box_loss_kernel<<<1, 1024, 0, stream>>>(pred, gt, n, loss, dpred);
+  CSG_CUDA(csg_launch_pdl(box_loss_kernel, dim3(1), dim3(1024), 0, stream, pred, gt, n, loss, dpred));
   CSG_CHECK_LAUNCH("csg_box_loss");
   return 0;
 }

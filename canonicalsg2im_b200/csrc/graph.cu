@@ -31,6 +31,7 @@ __global__ void triple_prep_kernel(const long long* __restrict__ triplets, const
                                    int NT, int T_pad, int O_pad, int padding_id,
                                    int* __restrict__ s_idx, int* __restrict__ o_idx, int* __restrict__ pred,
                                    int* __restrict__ type32, int* __restrict__ valid) {
+  CSG_PDL_WAIT();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= NT) return;
   int base;
@@ -71,6 +72,7 @@ __global__ void offsets_uniform_kernel(int* __restrict__ off, int B, int stride)
 // ---------------------------------------------------------------- CSR
 __global__ void csr_hist_kernel(const int* __restrict__ ks, const int* __restrict__ ko, int NT,
                                 int* __restrict__ cnt_s, int* __restrict__ cnt_o) {
+  CSG_PDL_WAIT();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= NT) return;
   atomicAdd(&cnt_s[ks[t]], 1);   // integer atomics: the result does not depend on order
@@ -80,6 +82,7 @@ __global__ void csr_hist_kernel(const int* __restrict__ ks, const int* __restric
 // single-CTA exclusive scan of n counts -> row_ptr[n+1]; also copies the starts into cursor[n]
 __global__ void __launch_bounds__(1024) csr_scan_kernel(const int* __restrict__ cnt, int n, int* __restrict__ row_ptr,
                                                         int* __restrict__ cursor) {
+  CSG_PDL_WAIT();
   __shared__ int sums[1024];
   const int tid = threadIdx.x;
   const int per = (n + 1023) / 1024;
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(32) csr_fill_kernel(const int* __restrict__ ke
                                                       const int* __restrict__ tri_off, const int* __restrict__ obj_off, int B,
                                                       int* __restrict__ cursor_s, int* __restrict__ cursor_o,
                                                       int* __restrict__ perm_s, int* __restrict__ perm_o) {
+  CSG_PDL_WAIT();
   __shared__ int scur[CSR_SMEM_OBJS];
   const bool second = blockIdx.x >= B;
   const int g = second ? blockIdx.x - B : blockIdx.x;
@@ -345,8 +349,8 @@ CSG_API int csg_triple_prep(const long long* triplets, const long long* triplet_
                             int* s_idx, int* o_idx, int* pred, int* type32, int* valid, cudaStream_t stream) {
   if (NT == 0) return 0;
   CSG_REQUIRE(T_pad > 0 || (tri_off && obj_off), "triple_prep: ragged mode needs offsets");
-  triple_prep_kernel<<<csg_div_up(NT, 256), 256, 0, stream>>>(triplets, triplet_type, tri_off, obj_off, B, NT, T_pad,
-                                                              O_pad, padding_id, s_idx, o_idx, pred, type32, valid);
+  CSG_CUDA(csg_launch_pdl(triple_prep_kernel, dim3(csg_div_up(NT, 256)), dim3(256), 0, stream, triplets, triplet_type, tri_off, obj_off, B, NT, T_pad,
+                                                              O_pad, padding_id, s_idx, o_idx, pred, type32, valid));
   CSG_CHECK_LAUNCH("csg_triple_prep");
   return 0;
 }
@@ -376,14 +380,14 @@ CSG_API int csg_csr_build(const int* keys_s, const int* keys_o, const int* tri_o
   int* cur_o = cur_s + (NO + 1);
   CSG_CUDA(cudaMemsetAsync(cnt_s, 0, (size_t)2 * (NO + 1) * sizeof(int), stream));
   if (NT > 0) {
-    csr_hist_kernel<<<csg_div_up(NT, 256), 256, 0, stream>>>(keys_s, keys_o, NT, cnt_s, cnt_o);
+    CSG_CUDA(csg_launch_pdl(csr_hist_kernel, dim3(csg_div_up(NT, 256)), dim3(256), 0, stream, keys_s, keys_o, NT, cnt_s, cnt_o));
     CSG_CHECK_LAUNCH("csg_csr_build hist");
   }
-  csr_scan_kernel<<<1, 1024, 0, stream>>>(cnt_s, NO, rowptr_s, cur_s);
-  csr_scan_kernel<<<1, 1024, 0, stream>>>(cnt_o, NO, rowptr_o, cur_o);
+  CSG_CUDA(csg_launch_pdl(csr_scan_kernel, dim3(1), dim3(1024), 0, stream, cnt_s, NO, rowptr_s, cur_s));
+  CSG_CUDA(csg_launch_pdl(csr_scan_kernel, dim3(1), dim3(1024), 0, stream, cnt_o, NO, rowptr_o, cur_o));
   CSG_CHECK_LAUNCH("csg_csr_build scan");
   if (NT > 0 && B > 0) {
-    csr_fill_kernel<<<2 * B, 32, 0, stream>>>(keys_s, keys_o, tri_off, obj_off, B, cur_s, cur_o, perm_s, perm_o);
+    CSG_CUDA(csg_launch_pdl(csr_fill_kernel, dim3(2 * B), dim3(32), 0, stream, keys_s, keys_o, tri_off, obj_off, B, cur_s, cur_o, perm_s, perm_o));
     CSG_CHECK_LAUNCH("csg_csr_build fill");
   }
   return 0;

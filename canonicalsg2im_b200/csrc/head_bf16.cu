@@ -16,6 +16,7 @@ constexpr int HB_ROWS = 32;            // rows per block of the backward kernel
 __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ h, int ldh, const float* __restrict__ w,
                                                        const float* __restrict__ b, int M, int K, int NOUT,
                                                        float* __restrict__ y) {
+  CSG_PDL_WAIT();
   extern __shared__ __align__(16) float ws[];          // [NOUT][K]
   for (int i = threadIdx.x; i < NOUT * K; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ h, int ldh,
                                                        const float* __restrict__ w, int M, int K, int NOUT,
                                                        __nv_bfloat16* __restrict__ dh, int lddh, float* __restrict__ partial) {
+  CSG_PDL_WAIT();
   __shared__ float sdy[HB_ROWS][HEAD_MAX_OUT];
   const int r0 = blockIdx.x * HB_ROWS, nr = min(HB_ROWS, M - r0);
   for (int i = threadIdx.x; i < HB_ROWS * HEAD_MAX_OUT; i += blockDim.x) {
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 
 __global__ void head_bwd_final_kernel(const float* __restrict__ partial, int blocks, int K, int NOUT, float* __restrict__ dw,
                                       float* __restrict__ db) {
+  CSG_PDL_WAIT();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int cells = NOUT * K + HEAD_MAX_OUT;
   if (i >= cells) return;
@@ -100,7 +103,7 @@ CSG_API int csg_head_fwd(const void* h, int ldh, const float* w, const float* b,
   CSG_REQUIRE(smem <= 48 * 1024, "head_fwd: weight [%d, %d] does not fit shared memory", nout, K);
   int blocks = csg_div_up(M, 8);
   if (blocks > 4 * csg_num_sms()) blocks = 4 * csg_num_sms();
-  head_fwd_kernel<<<blocks, 256, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(h), ldh, w, b, M, K, nout, y);
+  CSG_CUDA(csg_launch_pdl(head_fwd_kernel, dim3(blocks), dim3(256), smem, stream, reinterpret_cast<const __nv_bfloat16*>(h), ldh, w, b, M, K, nout, y));
   CSG_CHECK_LAUNCH("csg_head_fwd");
   return 0;
 }
@@ -121,11 +124,11 @@ CSG_API int csg_head_bwd(const float* dy, const void* h, int ldh, const float* w
   CSG_REQUIRE(workspace && workspace_bytes >= csg_head_bwd_workspace(M, K, nout), "head_bwd: workspace too small");
   const int blocks = csg_div_up(M, HB_ROWS);
   float* partial = reinterpret_cast<float*>(workspace);
-  head_bwd_kernel<<<blocks, 256, 0, stream>>>(dy, reinterpret_cast<const __nv_bfloat16*>(h), ldh, w, M, K, nout,
-                                              reinterpret_cast<__nv_bfloat16*>(dh), lddh, partial);
+  CSG_CUDA(csg_launch_pdl(head_bwd_kernel, dim3(blocks), dim3(256), 0, stream, dy, reinterpret_cast<const __nv_bfloat16*>(h), ldh, w, M, K, nout,
+                                              reinterpret_cast<__nv_bfloat16*>(dh), lddh, partial));
   CSG_CHECK_LAUNCH("csg_head_bwd");
   const int cells = nout * K + HEAD_MAX_OUT;
-  head_bwd_final_kernel<<<csg_div_up(cells, 256), 256, 0, stream>>>(partial, blocks, K, nout, dw, db);
+  CSG_CUDA(csg_launch_pdl(head_bwd_final_kernel, dim3(csg_div_up(cells, 256)), dim3(256), 0, stream, partial, blocks, K, nout, dw, db));
   CSG_CHECK_LAUNCH("csg_head_bwd final");
   return 0;
 }

@@ -389,6 +389,7 @@ __device__ __forceinline__ Smem carve(float* base, int lcap, int H, int W, bool 
 template <bool HAS_MASK>
 __global__ void __launch_bounds__(128) layout_tables_kernel(LayoutParams p, int NO, float* __restrict__ axg,
                                                             float* __restrict__ ayg, int* __restrict__ rng) {
+  CSG_PDL_WAIT();
   __shared__ int r[4];
   const int o = blockIdx.x;
   const int S = HAS_MASK ? p.M : 8;
@@ -424,6 +425,7 @@ __global__ void __launch_bounds__(128) layout_tables_kernel(LayoutParams p, int 
 
 template <bool HAS_MASK>
 __global__ void __launch_bounds__(NTHREADS) layout_bwd_ring_kernel(Params q) {
+  CSG_PDL_WAIT();
   extern __shared__ __align__(16) float smem_raw[];
   const LayoutParams& p = q.p;
   const Smem s = carve(smem_raw, p.lcap, p.H, p.W, HAS_MASK);
@@ -570,6 +572,7 @@ __global__ void __launch_bounds__(NTHREADS) layout_bwd_ring_kernel(Params q) {
 
 __global__ void layout_bwd_sum_splits_kernel(const float* __restrict__ partial, float* __restrict__ dvecs,
                                              long long n, int splits) {
+  CSG_PDL_WAIT();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float acc = 0.f;
@@ -917,8 +920,8 @@ CSG_API int csg_layout_bwd_vecs(const float* dout, const float* boxes, const flo
     float* axg = partial + csg_layout_bwd_tc_partial_floats(N, NO, D, H, W, max_objs_per_image);
     float* ayg = axg + (size_t)NO * W;
     int* rng = reinterpret_cast<int*>(ayg + (size_t)NO * H);
-    if (masks) bw::layout_tables_kernel<true><<<NO, 128, 0, stream>>>(tp, NO, axg, ayg, rng);
-    else       bw::layout_tables_kernel<false><<<NO, 128, 0, stream>>>(tp, NO, axg, ayg, rng);
+    if (masks) { CSG_CUDA(csg_launch_pdl(bw::layout_tables_kernel<true>, dim3(NO), dim3(128), 0, stream, tp, NO, axg, ayg, rng)); }
+    else       { CSG_CUDA(csg_launch_pdl(bw::layout_tables_kernel<false>, dim3(NO), dim3(128), 0, stream, tp, NO, axg, ayg, rng)); }
     CSG_CHECK_LAUNCH("csg_layout_bwd_vecs tables");
     return csg_layout_bwd_tc_launch(dout, masks, obj_off, axg, ayg, partial, dvecs, N, NO, D, H, W, M, max_objs_per_image,
                                     stream);
@@ -936,21 +939,21 @@ CSG_API int csg_layout_bwd_vecs(const float* dout, const float* boxes, const flo
     float* ayg = axg + (size_t)NO * W;
     int* rng = reinterpret_cast<int*>(ayg + (size_t)NO * H);
     q.axg = axg; q.ayg = ayg; q.rng = rng;
-    if (masks) bw::layout_tables_kernel<true><<<NO, 128, 0, stream>>>(q.p, NO, axg, ayg, rng);
-    else       bw::layout_tables_kernel<false><<<NO, 128, 0, stream>>>(q.p, NO, axg, ayg, rng);
+    if (masks) { CSG_CUDA(csg_launch_pdl(bw::layout_tables_kernel<true>, dim3(NO), dim3(128), 0, stream, q.p, NO, axg, ayg, rng)); }
+    else       { CSG_CUDA(csg_launch_pdl(bw::layout_tables_kernel<false>, dim3(NO), dim3(128), 0, stream, q.p, NO, axg, ayg, rng)); }
     CSG_CHECK_LAUNCH("csg_layout_bwd_vecs tables");
     const size_t smem = bw::smem_bytes(q.p.lcap, H, W, masks != nullptr);
     const int grid = N * q.cblocks * q.splits;
     if (masks) {
       if (int rc = set_smem(bw::layout_bwd_ring_kernel<true>, smem)) return rc;
-      bw::layout_bwd_ring_kernel<true><<<grid, bw::NTHREADS, smem, stream>>>(q);
+      CSG_CUDA(csg_launch_pdl(bw::layout_bwd_ring_kernel<true>, dim3(grid), dim3(bw::NTHREADS), smem, stream, q));
     } else {
       if (int rc = set_smem(bw::layout_bwd_ring_kernel<false>, smem)) return rc;
-      bw::layout_bwd_ring_kernel<false><<<grid, bw::NTHREADS, smem, stream>>>(q);
+      CSG_CUDA(csg_launch_pdl(bw::layout_bwd_ring_kernel<false>, dim3(grid), dim3(bw::NTHREADS), smem, stream, q));
     }
     CSG_CHECK_LAUNCH("csg_layout_bwd_vecs ring");
     const long long n = (long long)NO * D;
-    bw::layout_bwd_sum_splits_kernel<<<csg_div_up(n, 256), 256, 0, stream>>>(partial, dvecs, n, q.splits);
+    CSG_CUDA(csg_launch_pdl(bw::layout_bwd_sum_splits_kernel, dim3(csg_div_up(n, 256)), dim3(256), 0, stream, partial, dvecs, n, q.splits));
     CSG_CHECK_LAUNCH("csg_layout_bwd_vecs sum");
     return 0;
   }

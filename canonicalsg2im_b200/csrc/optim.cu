@@ -32,6 +32,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 
 __global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(AdamJobs jobs, AdamScalars s) {
+  CSG_PDL_WAIT();
   const int t = blockIdx.y;
   const int n = jobs.n[t];
   const int beg = blockIdx.x * ADAM_CHUNK;
@@ -97,7 +98,7 @@ CSG_API int csg_adam_multi(int count, void* const* params, const void* const* gr
       }
     }
     if (max_n == 0) continue;
-    adam_multi_kernel<<<dim3(csg_div_up(max_n, ADAM_CHUNK), k), ADAM_THREADS, 0, stream>>>(jobs, s);
+    CSG_CUDA(csg_launch_pdl(adam_multi_kernel, dim3(dim3(csg_div_up(max_n, ADAM_CHUNK), k)), dim3(ADAM_THREADS), 0, stream, jobs, s));
     CSG_CHECK_LAUNCH("csg_adam_multi");
   }
   return 0;
