@@ -532,28 +532,45 @@ __global__ void __launch_bounds__(NTHREADS) layout_bwd_ring_kernel(Params q) {
         for (int i = 0; i < SUB_PX / 4; ++i) g[i] = ld_f4(gch + 4 * i);
       }
       mbar_arrive(empty0 + 8 * st);          // the stage is free as soon as the registers hold it
-#pragma unroll 1
-      for (int a = 0; a < na; ++a) {
-        const int c = myact[a];
-        const int2 xr = *reinterpret_cast<const int2*>(s.rng + 4 * c);
-        const float wy = HAS_MASK ? 1.f : __ldg(q.ayg + (size_t)(cbeg + c) * p.H + row);   // used after the dot product
-        const float* wrow = HAS_MASK ? s.wS + c * BAND + sub * SUB_PX : s.ax + c * p.W + col0;
+      // Weights outside an object's column interval are exact zeros, so the dot product over the whole 32-pixel
+      // sub-band needs no per-quarter test (adding 0 * g changes nothing), and two objects are walked per iteration:
+      // their weight loads, FMA chains and accumulator updates are independent and overlap.
+      auto dot = [&](const float* wrow) {
         float sum = 0.f;
 #pragma unroll
         for (int qd = 0; qd < SUB_PX / 16; ++qd) {
-          if (xr.x <= col0 + 16 * qd + 15 && xr.y >= col0 + 16 * qd) {
-            const float4 w0 = ld_f4(wrow + 16 * qd), w1 = ld_f4(wrow + 16 * qd + 4);
-            const float4 w2 = ld_f4(wrow + 16 * qd + 8), w3 = ld_f4(wrow + 16 * qd + 12);
-            const float4 g0 = g[4 * qd], g1 = g[4 * qd + 1], g2 = g[4 * qd + 2], g3 = g[4 * qd + 3];
-            float t0 = g0.x * w0.x, t1 = g1.x * w1.x, t2 = g2.x * w2.x, t3 = g3.x * w3.x;
-            t0 = fmaf(g0.y, w0.y, t0); t1 = fmaf(g1.y, w1.y, t1); t2 = fmaf(g2.y, w2.y, t2); t3 = fmaf(g3.y, w3.y, t3);
-            t0 = fmaf(g0.z, w0.z, t0); t1 = fmaf(g1.z, w1.z, t1); t2 = fmaf(g2.z, w2.z, t2); t3 = fmaf(g3.z, w3.z, t3);
-            t0 = fmaf(g0.w, w0.w, t0); t1 = fmaf(g1.w, w1.w, t1); t2 = fmaf(g2.w, w2.w, t2); t3 = fmaf(g3.w, w3.w, t3);
-            sum += (t0 + t1) + (t2 + t3);
-          }
+          const float4 w0 = ld_f4(wrow + 16 * qd), w1 = ld_f4(wrow + 16 * qd + 4);
+          const float4 w2 = ld_f4(wrow + 16 * qd + 8), w3 = ld_f4(wrow + 16 * qd + 12);
+          const float4 g0 = g[4 * qd], g1 = g[4 * qd + 1], g2 = g[4 * qd + 2], g3 = g[4 * qd + 3];
+          float t0 = g0.x * w0.x, t1 = g1.x * w1.x, t2 = g2.x * w2.x, t3 = g3.x * w3.x;
+          t0 = fmaf(g0.y, w0.y, t0); t1 = fmaf(g1.y, w1.y, t1); t2 = fmaf(g2.y, w2.y, t2); t3 = fmaf(g3.y, w3.y, t3);
+          t0 = fmaf(g0.z, w0.z, t0); t1 = fmaf(g1.z, w1.z, t1); t2 = fmaf(g2.z, w2.z, t2); t3 = fmaf(g3.z, w3.z, t3);
+          t0 = fmaf(g0.w, w0.w, t0); t1 = fmaf(g1.w, w1.w, t1); t2 = fmaf(g2.w, w2.w, t2); t3 = fmaf(g3.w, w3.w, t3);
+          sum += (t0 + t1) + (t2 + t3);
         }
-        if (!HAS_MASK) sum *= wy;
-        s.acc[(c * SUBS + sub) * DC + lane] += sum;
+        return sum;
+      };
+      auto wrow_of = [&](int c) { return HAS_MASK ? s.wS + c * BAND + sub * SUB_PX : s.ax + c * p.W + col0; };
+      int a = 0;
+#pragma unroll 1
+      for (; a + 1 < na; a += 2) {
+        const int c0 = myact[a], c1 = myact[a + 1];                    // distinct objects: the two updates do not alias
+        float wy0 = 1.f, wy1 = 1.f;
+        if (!HAS_MASK) {
+          wy0 = __ldg(q.ayg + (size_t)(cbeg + c0) * p.H + row);
+          wy1 = __ldg(q.ayg + (size_t)(cbeg + c1) * p.H + row);
+        }
+        float* acc0 = s.acc + (c0 * SUBS + sub) * DC + lane;
+        float* acc1 = s.acc + (c1 * SUBS + sub) * DC + lane;
+        const float old0 = *acc0, old1 = *acc1;
+        const float s0 = dot(wrow_of(c0)), s1 = dot(wrow_of(c1));
+        *acc0 = old0 + s0 * wy0;
+        *acc1 = old1 + s1 * wy1;
+      }
+      if (a < na) {
+        const int c = myact[a];
+        const float wy = HAS_MASK ? 1.f : __ldg(q.ayg + (size_t)(cbeg + c) * p.H + row);
+        s.acc[(c * SUBS + sub) * DC + lane] += dot(wrow_of(c)) * wy;
       }
       if (HAS_MASK) consumer_sync();      // wS is rebuilt for the next band
     }
