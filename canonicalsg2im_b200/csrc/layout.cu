@@ -927,7 +927,7 @@ CSG_API int csg_layout_bwd_vecs(const float* dout, const float* boxes, const flo
   // CSG_LAYOUT_BWD = tc | ring | generic forces a path (benchmarks).  Default: the ring kernel.  The tcgen05 3xTF32
   // contraction (layout_bwd_tc.cu) is bit-compatible with the 1e-5 contract and streams the gradient at 4.9 TB/s when
   // its MMAs are switched off, but a kind::tf32 MMA of M = 128 with a narrow N costs ~180 cycles whatever N is, and
-  // the 8 it needs per 32-pixel tile make it MMA-bound at 112 us on the cfg2 canvas (ring kernel: 98 us).
+  // the 8 it needs per 32-pixel tile make it MMA-bound at 112 us on the cfg2 canvas (ring kernel: 81 us).
   static const char* force = getenv("CSG_LAYOUT_BWD");
   const bool want_tc = force && force[0] == 't';
   if (want_tc && csg_layout_bwd_tc_eligible(dout, N, D, H, W, max_objs_per_image)) {
