@@ -168,6 +168,7 @@ __device__ void build_weights(const LayoutParams& p, const Smem& s, int L, int x
 
 template <bool HAS_MASK, int CH>
 __global__ void __launch_bounds__(NTHREADS) layout_fwd_kernel(LayoutParams p, float* __restrict__ out) {
+  CSG_PDL_WAIT();
   extern __shared__ __align__(16) float smem_raw[];
   __shared__ int s_cursor, s_count;
   const Smem s = carve(smem_raw, p.lcap, p.D, p.TW, p.TH, HAS_MASK);
@@ -892,7 +893,7 @@ CSG_API int csg_layout_fwd(const float* vecs, const float* boxes, const float* m
 #define CSG_FWD_LAUNCH(MASK, CH)                                                          \
   do {                                                                                    \
     if (int rc = set_smem(fw::layout_fwd_kernel<MASK, CH>, smem)) return rc;              \
-    fw::layout_fwd_kernel<MASK, CH><<<grid, fw::NTHREADS, smem, stream>>>(p, out);        \
+    CSG_CUDA(csg_launch_pdl(fw::layout_fwd_kernel<MASK, CH>, grid, dim3(fw::NTHREADS), smem, stream, p, out)); \
   } while (0)
   if (masks) { if (wide) CSG_FWD_LAUNCH(true, 16); else CSG_FWD_LAUNCH(true, 4); }
   else       { if (wide) CSG_FWD_LAUNCH(false, 16); else CSG_FWD_LAUNCH(false, 4); }
