@@ -4,11 +4,15 @@
     python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...     # CPU restatement of the reference (oracle port)
 
-Workload (BASELINE.json configs[1], "cfg2"): 128 scene graphs per GPU, 3-30 objects each (+ the
+Headline workload (BASELINE.json configs[1], "cfg2"): 128 scene graphs per GPU, 3-30 objects each (+ the
 __image__ dummy), VG-like vocabulary (50 predicates), WSGC canonicalization with learned converse +
-transitive edges, 5-layer GraphTripleConv stack (embed 128 / hidden 512) + box_net, boxes_to_layout
-64x64x128 canvas on the GT boxes, backward through both, Adam.  Synthetic graphs, random-init weights.
-One JSON line on rank 0; see the prompt's bench contract for the keys.
+transitive edges, 5-layer GraphTripleConv stack (embed 128 / hidden 512) + box_net + box loss, the generator-side
+object embedding composited by boxes_to_layout into a 64x64x128 canvas on the GT boxes, backward through both, Adam.
+Synthetic graphs, random-init weights.  One JSON line on rank 0; see the prompt's bench contract for the keys.
+
+The same line carries `configs`: BASELINE.json's other configurations measured in the same run
+(cfg1 CPU-sized step, cfg3 256x256 mask canvas, cfg4 CLEVR forward-only path, cfg5 ~1M-triple batch sharded over the
+ranks = strong scaling) and the fp32 parity engine on cfg2 -- each with its own roofline fraction and CPU-port number.
 """
 import argparse
 import json
@@ -29,7 +33,11 @@ from canonicalsg2im_b200 import synth   # noqa: E402
 METRIC = "scene_graphs_per_sec_gcn_layout_fwd_bwd"
 UNIT = "graphs/s"
 WORKLOAD = ("cfg2: packed_vg-like SG->layout training step with WSGC canonicalization, batch 128/GPU, 3-30 objects, "
-            "P=50, 5x GraphTripleConv(128/512) + box_net + boxes_to_layout 64x64x128, fwd+bwd+Adam")
+            "P=50, 5x GraphTripleConv(128/512) + box_net + box loss + boxes_to_layout 64x64x128 of the generator "
+            "embedding, fwd+bwd+Adam")
+FLOP_PER_TRIPLE_LAYER = 1572864.0       # forward, D = 128, H = 512
+FLOP_PER_OBJECT_LAYER = 655360.0
+FLOP_PER_OBJECT_BOXNET = 135168.0
 
 
 def parse():
@@ -42,11 +50,16 @@ def parse():
                     help="bf16 = tcgen05 tensor-core engine (north_star: bf16 MLP, fp32 accumulate, 1e-2 rel); "
                          "fp32 = the 1e-5 parity engine")
     ap.add_argument("--batch", type=int, default=128, help="graphs per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=8, help="graphs in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=16,
+                    help="graphs per step of the bounded CPU sample of the cfg2 workload (cfg1's batch size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default=os.environ.get("CSG_BENCH_CONFIGS", "all"),
+                    help="extra BASELINE configs measured beside the cfg2 headline: all | none | comma list of "
+                         "cfg1,cfg3,cfg4,cfg5,fp32,nccl_check")
+    ap.add_argument("--cfg5-graphs", type=int, default=1100, help="graphs of the cfg5 global batch (~1M triples)")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run: cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off), "
-                         "no e2e / CPU legs; the printed numbers are not bench values")
+                         "no e2e / CPU legs / extra configs; the printed numbers are not bench values")
     return ap.parse_args()
 
 
@@ -56,6 +69,16 @@ def peaks():
         d = json.load(open(path))
         return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 class ClockSampler:
@@ -106,48 +129,117 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------ workloads
 def workload_graphs(batch, seed):
     vocab = synth.Vocab(42)
     return vocab, synth.make_graphs(batch, 1000 + seed, 3, 30, vocab, include_dummies=True)
 
 
+def cfg1_graphs(batch=16):
+    vocab = synth.Vocab(0)
+    return vocab, synth.make_graphs(batch, 3100, 3, 8, vocab, include_dummies=True)
+
+
+def cfg4_graphs(batch=10):
+    CFG4_ATTR_SIZES = list(synth.CLEVR_ATTR_SIZES)
+    vocab = synth.Vocab(0, num_attributes=4)
+    graphs = synth.make_graphs(batch, 4400, 32, 64, vocab, include_dummies=True, box_mode="clevr", mask_size=16)
+    for g in graphs:
+        for k, n in enumerate(CFG4_ATTR_SIZES):
+            g.objs[:-1, k] = 1 + (g.objs[:-1, k] - 1) % (n - 1)
+    return vocab, graphs, CFG4_ATTR_SIZES
+
+
+def cfg3_objects(batch=16):
+    vocab = synth.Vocab(0)
+    vecs, boxes, masks, off = [], [], [], [0]
+    for i in range(batch):
+        g = synth.make_graph(3300 + i, 3, 8, vocab, include_dummies=False, mask_size=16)
+        n = len(g.boxes)
+        vecs.append(synth.det_tensor((n, 128), 3400 + i, 1.0))
+        boxes.append(g.boxes); masks.append(g.masks); off.append(off[-1] + n)
+    return np.concatenate(vecs), np.concatenate(boxes), np.concatenate(masks).astype(np.float32), np.array(off, np.int32)
+
+
+def main_config(args, world, n_obj, n_tri):
+    prec = args.precision
+    return {"workload": WORKLOAD, "graphs_per_gpu": args.batch, "objects": n_obj, "triples_after_canon": n_tri,
+            "precision": prec, "parallelism": "graph-sharded dp%d" % world,
+            "l2": "per-step working set (net1 activations %.0f MB + 268 MB canvas + 268 MB canvas grad) exceeds the 126 MB L2"
+                  % (n_tri * (1152 + 512) * (4 if prec == "fp32" else 2) / 1e6)}
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_step_runner(vocab, sample, threads):
+def model_conv_weights(state):
+    """sg2im/model.py:8-15 on the random-init state: the symmetrised converse weights the dataset samples from."""
+    tri = np.triu(state["converse_candidates_weights"])
+    return (tri + tri.T).astype(np.float64)
+
+
+def cpu_step_runner(vocab, graphs, threads, H=64, W=64):
     from oracle.step import CpuStep
     torch.set_num_threads(threads)
-    _, graphs = workload_graphs(sample, 0)
-    W = synth.make_conv_weights(vocab, 0)
-    step = CpuStep(vocab, synth.make_state(vocab, seed=0), W)
+    st = synth.make_state(vocab, seed=0)
+    step = CpuStep(vocab, st, model_conv_weights(st), synth.make_layout_state(vocab, 128, seed=0), H=H, W=W)
     uni = synth.det_uniform(sum(len(g.triplets) for g in graphs), 13)
-    return step, graphs, uni
+    return step, uni
 
 
-def run_cpu_baseline(sample, threads, budget_s=25.0):
-    vocab = synth.Vocab(42)
-    step, graphs, uni = cpu_step_runner(vocab, sample, threads)
-    step.step(graphs, uni)                       # warm-up
+def time_cpu_steps(step, graphs, uni, budget_s, max_steps, warm=True):
+    if warm:
+        step.step(graphs, uni)
     t0 = time.perf_counter()
     n = 0
     while True:
         step.step(graphs, uni)
         n += 1
-        if time.perf_counter() - t0 > budget_s or n >= 5:
+        if time.perf_counter() - t0 > budget_s or n >= max_steps:
             break
-    dt = (time.perf_counter() - t0) / n
-    return {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d graphs of the cfg2 workload per step, %d timed steps, oracle/step.py (torch-CPU + numpy)"
-                      % (sample, n)}
+    return (time.perf_counter() - t0) / n, n
+
+
+CPU_NOTE = ("per-graph CPU cost of the reference grows with the batch (rows padded to the longest graph; the backward of "
+            "its per-sample slicing loop, graph.py:85-107, is O(B^2)): the full cfg2 batch of 128 costs ~290 s/step = "
+            "0.44 graphs/s on 8 cores (measured once, DESIGN.md section 6), so this sample OVER-states its throughput")
+
+
+def run_cpu_baseline(sample, threads, budget_s=25.0):
+    vocab, graphs = workload_graphs(sample, 0)
+    step, uni = cpu_step_runner(vocab, graphs, threads)
+    dt, n = time_cpu_steps(step, graphs, uni, budget_s, 3, warm=False)
+    return {"value": sample / dt, "unit": UNIT, "cores": threads, "cpu": cpu_model(), "kind": "port",
+            "ms_per_step": 1e3 * dt,
+            "sample": "%d graphs of the cfg2 workload per step, %d timed steps, oracle/step.py (torch-CPU + numpy); %s"
+                      % (sample, n, CPU_NOTE)}
+
+
+def canon_count_cpu(vocab, graphs, seed):
+    """Canonicalized triple count of the full workload with the draws the GPU arm uses (oracle, ~1 s)."""
+    from oracle import canon as ocanon
+    Wc = model_conv_weights(synth.make_state(vocab, seed=0))
+    tri_off = np.concatenate([[0], np.cumsum([len(g.triplets) for g in graphs])])
+    uni = synth.det_uniform(int(tri_off[-1]), seed * 7919 + 13)
+    total = 0
+    for i, g in enumerate(graphs):
+        tr, _, _, _ = ocanon.add_learnt_triplets(g.triplets, vocab.num_preds, vocab.meta_ids, Wc, True, True, uni[tri_off[i]:])
+        total += len(tr)
+    return total
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port: the reference is Python and cannot travel to the
+    box) on the host cores, `config` = the GPU arm's; each step a bounded sample of it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    vocab = synth.Vocab(42)
-    sample = max(1, args.cpu_sample // 2)         # bounded so that K steps end within a few minutes
-    step, graphs, uni = cpu_step_runner(vocab, sample, threads)
-    step.step(graphs, uni)                       # one bounded warm-up step (each CPU step costs seconds)
+    sample = max(1, args.cpu_sample)
+    vocab, full = workload_graphs(args.batch, 0)
+    n_obj = sum(len(g.objs) for g in full)
+    graphs = full[:sample]
+    step, uni = cpu_step_runner(vocab, graphs, threads)
+    for _ in range(min(args.warmup, 1)):          # one bounded warm-up step (each CPU step costs seconds, nothing to JIT)
+        step.step(graphs, uni)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step.step(graphs, uni)
@@ -157,64 +249,362 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_graphs_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d graphs of the cfg2 workload per step (oracle/step.py, torch-CPU + numpy)" % sample},
+        "config": main_config(args, args.gpus, n_obj, canon_count_cpu(vocab, full, 0)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "cpu": cpu_model(), "kind": "port",
+                         "sample": "%d graphs (the first %d of the %d-graph cfg2 batch) per step, oracle/step.py "
+                                   "(torch-CPU + numpy), 1 warm-up step; %s" % (sample, sample, args.batch, CPU_NOTE)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------ GPU arm
-def layout_roofline(d, G, pk, iters=20):
-    """The layout compositor pair of this workload timed alone (CUDA events on the launching stream; the 268 MB
-    canvas and its gradient exceed the 126 MB L2, so every launch streams from / to HBM).  Algorithmic bytes:
-    forward = one write of N*D*H*W*4, backward = one read of the same."""
+# ------------------------------------------------------------------------------------------ GPU helpers
+class L2Flusher:
+    """Writes a 256 MB buffer (2x the 126 MB L2) between timed iterations of workloads whose inputs fit in L2."""
+
+    def __init__(self, dev):
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def __call__(self):
+        self.buf.fill_(1)
+
+
+def time_each(fn, steps, warmup, flush=None):
+    """Per-iteration CUDA-event timing on the current stream with an (untimed) L2 flush between iterations."""
+    for _ in range(max(warmup, 3)):
+        fn()
+    evs = []
+    torch.cuda.synchronize()
+    for _ in range(steps):
+        if flush is not None:
+            flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) * 1e-3 / steps
+
+
+def layout_roofline(boxes, off, max_objs, N, D, H, W, pk, masks=None, iters=20, flush=None):
+    """The layout compositor pair timed alone through the C ABI (CUDA events on the launching stream).  Algorithmic
+    bytes: forward = one write of N*D*H*W*4, backward = one read of the same."""
     from canonicalsg2im_b200 import _lib
     from canonicalsg2im_b200.layout import _linspace
     from canonicalsg2im_b200.ops import lib, ptr, workspace, _stream
     L = lib()
-    dev = G.device
-    N, D, H, W = G.shape
-    boxes, off = d["boxes"].float().contiguous(), d["obj_off"]
+    dev = boxes.device
     NO = boxes.shape[0]
-    vecs = torch.randn((NO, D), device=dev)
+    M = masks.shape[1] if masks is not None else 0
+    gen = torch.Generator(device=dev).manual_seed(7)
+    vecs = torch.randn((NO, D), device=dev, generator=gen)
+    G = torch.randn((N, D, H, W), device=dev, generator=gen)
     out = torch.empty_like(G)
     dv = torch.empty((NO, D), device=dev)
     lx, ly = _linspace(W, dev), _linspace(H, dev)
     ws = workspace(L.csg_layout_bwd_vecs_workspace(N, NO, D, H, W), dev)
-    mo = int(d["max_objs"])
 
     def fwd():
-        _lib.check(L.csg_layout_fwd(ptr(vecs), ptr(boxes), 0, ptr(off), ptr(lx), ptr(ly), ptr(out), N, D, H, W, 0, 0, mo,
-                                    _stream()), "csg_layout_fwd")
+        _lib.check(L.csg_layout_fwd(ptr(vecs), ptr(boxes), ptr(masks), ptr(off), ptr(lx), ptr(ly), ptr(out), N, D, H, W, M,
+                                    0, max_objs, _stream()), "csg_layout_fwd")
 
     def bwd():
-        _lib.check(L.csg_layout_bwd_vecs(ptr(G), ptr(boxes), 0, ptr(off), ptr(lx), ptr(ly), ptr(dv), N, NO, D, H, W, 0, 0,
-                                         mo, ptr(ws), ws.numel(), _stream()), "csg_layout_bwd_vecs")
+        _lib.check(L.csg_layout_bwd_vecs(ptr(G), ptr(boxes), ptr(masks), ptr(off), ptr(lx), ptr(ly), ptr(dv), N, NO, D, H,
+                                         W, M, 0, max_objs, ptr(ws), ws.numel(), _stream()), "csg_layout_bwd_vecs")
     res = {}
     nbytes = N * D * H * W * 4
     for name, fn in (("fwd", fwd), ("bwd", bwd)):
-        for _ in range(3):
-            fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        sec = e0.elapsed_time(e1) * 1e-3 / iters
+        sec = time_each(fn, iters, 3, flush)
         res[name] = {"us": sec * 1e6, "achieved": nbytes / sec / 1e9, "frac": nbytes / sec / 1e9 / pk["hbm"]}
-    return {"kernel": "layout_fwd_kernel / layout_bwd_ring_kernel (boxes_to_layout %dx%dx%dx%d)" % (N, D, H, W),
+    kind = "masks_to_layout" if masks is not None else "boxes_to_layout"
+    return {"kernel": "layout_fwd_kernel / layout_bwd_ring_kernel (%s %dx%dx%dx%d)" % (kind, N, D, H, W),
             "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"], "peak_source": pk["src"] + " copy bandwidth",
-            "bytes_per_launch": nbytes, "fwd": res["fwd"], "bwd": res["bwd"]}
+            "bytes_per_launch": nbytes, "fwd": res["fwd"], "bwd": res["bwd"],
+            "l2": "canvas of %.0f MB %s the 126 MB L2%s" % (nbytes / 1e6, "exceeds" if nbytes > 126e6 else "fits in",
+                                                           "" if nbytes > 126e6 else "; L2 flushed between iterations")}
 
 
+def mlp_flops(n_tri, n_obj, layers=5, train=True):
+    f = layers * (n_tri * FLOP_PER_TRIPLE_LAYER + n_obj * FLOP_PER_OBJECT_LAYER) + n_obj * FLOP_PER_OBJECT_BOXNET
+    return f * (3.0 if train else 1.0)
+
+
+def train_leg(vocab, graphs, dev, precision, steps, warmup, pk, flush=None, cpu=None, H=64, W=64, seed=0):
+    """K training steps of a small config (cfg1 / fp32 engine): device-timed with resident inputs, per-step events."""
+    from canonicalsg2im_b200.pipeline import SgToLayoutStep, HostBatch
+    hb = HostBatch(graphs, seed=seed)
+    step = SgToLayoutStep(vocab, dev, precision=precision, H=H, W=W, seed=0)
+    G = torch.randn((len(graphs), 128, H, W), device=dev, generator=torch.Generator(device=dev).manual_seed(99)) * 1e-3
+    d = hb.to_device(dev)
+    box = {}
+
+    def one():
+        box["loss"], box["n_tri"] = step.step(d, G, prefetch=d)
+    sec = time_each(one, steps, warmup, flush)
+    n_obj, n_tri = int(hb.obj_off[-1]), box["n_tri"]
+    flops = mlp_flops(n_tri, n_obj)
+    out = {"ms_per_step": 1e3 * sec, "graphs_per_s": len(graphs) / sec, "graphs": len(graphs), "objects": n_obj,
+           "triples_after_canon": n_tri, "precision": precision, "steps": steps,
+           "mlp_tflops_whole_step": flops / sec / 1e12, "loss": float(box["loss"].item())}
+    del step, G, d
+    return out
+
+
+# ------------------------------------------------------------------------------------------ extra configs
+def run_cfg1(dev, pk, args, flush, with_cpu):
+    """BASELINE configs[0]: batch 16, <= 8 objects, P = 8, boxes_to_layout 64x64 -- the reference's CPU-runnable case.
+    The working set (33 MB canvas) fits in L2, so L2 is flushed between the timed steps."""
+    vocab, graphs = cfg1_graphs()
+    out = {"workload": "cfg1: packed_coco-like training step, batch 16, 3-8 objects, P=8, 5x GraphTripleConv(128/512), "
+                       "boxes_to_layout 64x64x128, fwd+bwd+Adam", "l2": "working set fits in L2; flushed between steps"}
+    for prec in ("bf16", "fp32"):
+        out[prec] = train_leg(vocab, graphs, dev, prec, max(args.steps, 10), args.warmup, pk, flush)
+    boxes = torch.from_numpy(np.concatenate([g.boxes for g in graphs])).to(dev)
+    off = torch.from_numpy(np.concatenate([[0], np.cumsum([len(g.objs) for g in graphs])]).astype(np.int32)).to(dev)
+    out["roofline_hbm"] = layout_roofline(boxes, off, max(len(g.objs) for g in graphs), len(graphs), 128, 64, 64, pk,
+                                          flush=flush)
+    if with_cpu:
+        threads = os.cpu_count() or 1
+        step, uni = cpu_step_runner(vocab, graphs, threads)
+        dt, n = time_cpu_steps(step, graphs, uni, 10.0, 5)
+        out["cpu_baseline"] = {"value": len(graphs) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                               "ms_per_step": 1e3 * dt,
+                               "sample": "the whole cfg1 batch (16 graphs), %d timed steps, oracle/step.py" % n}
+    return out
+
+
+def run_fp32(dev, pk, args):
+    """cfg2 on the fp32 (1e-5 parity) engine."""
+    vocab, graphs = workload_graphs(args.batch, 0)
+    out = train_leg(vocab, graphs, dev, "fp32", 5, 3, pk)
+    out["note"] = "cfg2 batch on the fp32 FMA parity engine (csrc/gemm_f32.cu); same step as the headline"
+    return out
+
+
+def run_cfg3(dev, pk, args, with_cpu):
+    """BASELINE configs[2]: masks_to_layout, batch 16, 3-8 objects, 16x16 masks, D = 128, 256x256 (512 MiB canvas)."""
+    from canonicalsg2im_b200.layout import layout_batched
+    vecs, boxes, masks, off = cfg3_objects()
+    tb, tm, to = torch.from_numpy(boxes).to(dev), torch.from_numpy(masks).to(dev), torch.from_numpy(off).to(dev)
+    N = len(off) - 1
+    mo = int(np.diff(off).max())
+    hbm = layout_roofline(tb, to, mo, N, 128, 256, 256, pk, masks=tm, iters=max(args.steps, 10))
+    # the same through the public autograd API: fwd + bwd of masks_to_layout on the flat batch
+    v = torch.from_numpy(vecs).to(dev).requires_grad_(True)
+    G = torch.randn((N, 128, 256, 256), device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+
+    def both():
+        v.grad = None
+        layout_batched(v, tb, to, 256, 256, masks=tm, max_objs_per_image=mo).backward(G)
+    sec = time_each(both, max(args.steps, 10), 3)
+    out = {"workload": "cfg3: masks_to_layout fwd+bwd, batch 16, 3-8 objects, 16x16 masks, D=128, 256x256 (canvas 512 MiB)",
+           "objects": int(off[-1]), "ms_fwd_bwd": 1e3 * sec, "images_per_s": N / sec,
+           "hbm_fwd_bwd": {"achieved": 2 * hbm["bytes_per_launch"] / sec / 1e9, "frac": 2 * hbm["bytes_per_launch"] / sec / 1e9 / pk["hbm"],
+                           "unit": "GB/s", "note": "2 x 512 MiB algorithmic / time of layout_batched(...).backward(G) "
+                                                    "(includes the allocation of the canvas by torch)"},
+           "roofline_hbm": hbm}
+    del G
+    if with_cpu:
+        from oracle import layout as olayout
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        vc = torch.from_numpy(vecs).requires_grad_(True)
+        t0 = time.perf_counter()
+        y = olayout.batched_layout([vc[off[i]:off[i + 1]] for i in range(N)],
+                                   [torch.from_numpy(boxes[off[i]:off[i + 1]]) for i in range(N)],
+                                   [torch.from_numpy(masks[off[i]:off[i + 1]]) for i in range(N)], 256, 256)
+        y.backward(torch.ones_like(y))
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": N / dt, "unit": "images/s", "cores": threads, "kind": "port",
+                               "ms_fwd_bwd": 1e3 * dt, "sample": "the whole cfg3 batch once, oracle/layout.py fwd+bwd"}
+    return out
+
+
+def run_cfg4(dev, pk, args, flush, with_cpu):
+    """BASELINE configs[3]: CLEVR-sized graphs (10 graphs of 32-64 objects, 4 attributes x emb 32), forward only,
+    test_mode: add_location_triplets + dummies -> canonicalization -> GCN -> occlusion canvas 256x256, all on device."""
+    from canonicalsg2im_b200.pipeline import SgToLayoutInference, HostBatch
+    vocab, graphs, sizes = cfg4_graphs()
+    nu = sum(4 * len(g.objs) ** 2 for g in graphs)
+    hb = HostBatch(graphs, seed=4, with_geometry=True, num_uniforms=nu)
+    inf = SgToLayoutInference(vocab, dev, precision="bf16", H=256, W=256, embedding_dim=32, attr_sizes=sizes)
+    d = hb.to_device(dev)
+    box = {}
+
+    def one():
+        canvas, boxes_pred, n = inf.step(d)
+        box["n"], box["canvas"] = n, canvas
+    sec = time_each(one, max(args.steps // 2, 5), 3, flush)
+    n_obj, n_tri = int(hb.obj_off[-1]), box["n"]
+    # end to end: host buffers in, canvas checksum out
+    chk = torch.empty(1, dtype=torch.float32, pin_memory=True)
+    t0 = time.perf_counter()
+    k = 5
+    for _ in range(k):
+        dd = hb.to_device(dev)
+        canvas, _, _ = inf.step(dd)
+        chk.copy_(canvas.sum().reshape(1), non_blocking=False)
+    e2e = (time.perf_counter() - t0) / k
+    canvas_bytes = box["canvas"].numel() * 4
+    flops = mlp_flops(n_tri, n_obj, train=False)
+    out = {"workload": "cfg4: CLEVR forward-only path (generate_clevr), 10 graphs x 32-64 objects, 4 attributes x emb 32, "
+                       "location+dummy triplets -> canonicalization -> 5x GraphTripleConv + box_net -> "
+                       "masks_to_layout(test_mode) 256x256x128 on the predicted boxes",
+           "graphs": len(graphs), "objects": n_obj, "triples_after_canon": n_tri, "ms_per_step": 1e3 * sec,
+           "graphs_per_s": len(graphs) / sec, "e2e_ms_per_step": 1e3 * e2e, "e2e_graphs_per_s": len(graphs) / e2e,
+           "h2d_bytes_per_step": int(hb.nbytes), "mlp_tflops_whole_step": flops / sec / 1e12,
+           "canvas_bytes": canvas_bytes, "l2": "flushed between steps",
+           "note": "latency-bound: 2 host waits (location / canonicalization sizes) and ~60 launches per step"}
+    del box, d
+    if with_cpu:
+        out["cpu_baseline"] = cfg4_cpu(vocab, graphs, sizes, hb)
+    return out
+
+
+def cfg4_cpu(vocab, graphs, sizes, hb):
+    """Oracle port of the same forward path on 2 of the 10 graphs (the per-graph cost does not depend on the batch:
+    every stage is a per-graph Python loop except the padded GCN forward)."""
+    from oracle import canon as ocanon, graph as ograph, layout as olayout
+    from oracle.step import collate
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sub = graphs[:2]
+    st_np = synth.make_state(vocab, embedding_dim=32, seed=0, attr_vocab_sizes=sizes)
+    Wc = model_conv_weights(st_np)
+    st = {k: torch.from_numpy(v) for k, v in st_np.items()}
+    lst = {"generator.attribute_embedding." + k: torch.from_numpy(v)
+           for k, v in synth.make_layout_state(vocab, 32, seed=0, attr_vocab_sizes=sizes).items()}
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        canon = []
+        for g in sub:
+            cen = np.concatenate([g.centers, np.zeros((len(g.boxes) - len(g.centers), 2), np.float32)])
+            trip = list(ocanon.add_location_triplets(g.boxes, cen, g.objs[:, 0], vocab.image_obj_id, vocab.pred_ids))
+            trip += list(ocanon.add_dummy_triplets(g.objs[:, 0], vocab.image_obj_id, vocab.in_image_id, True))
+            trip = np.array(trip, dtype=np.int64).reshape(-1, 3)
+            tr, _, ty, _ = ocanon.add_learnt_triplets(trip, vocab.num_preds, vocab.meta_ids, Wc, True, True,
+                                                      synth.det_uniform(2 * len(trip) + 8, 5))
+            canon.append((tr, ty))
+        objs, boxes, trips, types = collate(vocab, sub, canon)
+        _, boxes_pred = ograph.sg2layout_forward(st, objs, trips, types, vocab.padding_id)
+        lv = ograph.attribute_embeddings(lst, "generator.attribute_embedding.", objs)
+        for b, g in enumerate(sub):
+            keep = (objs[b] != 0)[:, 0]
+            m = torch.from_numpy(g.masks.astype(np.float32))[:int(keep.sum())]
+            olayout.masks_to_layout(lv[b][keep], boxes_pred[b][keep], m, 256, 256, test_mode=True)
+    dt = time.perf_counter() - t0
+    return {"value": len(sub) / dt, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": 1e3 * dt,
+            "sample": "2 of the 10 cfg4 graphs once: oracle add_location_triplets + add_learnt_triplets + "
+                      "sg2layout_forward + masks_to_layout(test_mode)"}
+
+
+def run_cfg5(dev, pk, args, world, rank, want_check):
+    """BASELINE configs[4]: one GLOBAL ragged batch of ~1M canonicalized triples, cut on graph boundaries into
+    `world` contiguous shards balanced by canonicalized triple count (parallel.shard_by_cost); weight gradients are
+    summed over ranks by the bucketed NCCL all-reduce.  Total work is fixed: strong scaling."""
+    import torch.distributed as dist
+    from canonicalsg2im_b200.pipeline import SgToLayoutStep, HostBatch
+    from canonicalsg2im_b200.parallel import shard_by_cost
+    vocab = synth.Vocab(42)
+    graphs = synth.make_graphs(args.cfg5_graphs, 4242, 3, 30, vocab, include_dummies=True)
+    NG = len(graphs)
+    hb_all = HostBatch(graphs, seed=3, pin=False)
+    probe = SgToLayoutStep(vocab, dev, precision=args.precision, seed=0)
+    d_all = hb_all.to_device(dev)
+    res = probe.canonicalize(d_all)                      # per-graph canonicalized triple counts = the shard costs
+    costs = (res.tri_off[1:] - res.tri_off[:-1]).cpu().tolist()
+    total_tri = int(res.triplets.shape[0])
+    del res
+    a, b = shard_by_cost(costs, world)[rank]
+    local = graphs[a:b]
+    hb = HostBatch(local, seed=3, pin=True)
+    u0 = int(hb_all.tri_off[a])
+    hb.t["uniforms"] = hb_all.t["uniforms"][u0:u0 + int(hb.tri_off[-1])].clone()     # the global batch's draws
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    G_all = torch.randn((NG, 128, 64, 64), device=dev, generator=gen) * 1e-3         # identical on every rank
+    G = G_all[a:b]
+    step = SgToLayoutStep(vocab, dev, precision=args.precision, distributed=world > 1, seed=0, global_batch=NG)
+    d = hb.to_device(dev)
+    check = None
+    if want_check and world > 1:
+        # NCCL equivalence: the all-reduced gradients of the sharded batch vs rank 0 running the whole batch alone
+        step.backward(d, G)
+        mine = {k: v.clone() for k, v in step.named_grads().items()}
+        step.reducer.zero()
+        if rank == 0:
+            solo = SgToLayoutStep(vocab, dev, precision=args.precision, distributed=False, seed=0, global_batch=NG)
+            solo.backward(d_all, G_all)
+            ref = solo.named_grads()
+            worst, worst_name = 0.0, ""
+            for k, g in ref.items():
+                e = ((mine[k].double() - g.double()).norm() / g.double().norm().clamp_min(1e-30)).item()
+                if e > worst:
+                    worst, worst_name = e, k
+            check = {"max_rel_l2_grad_error_vs_single_gpu": worst, "tensor": worst_name, "tensors": len(ref),
+                     "note": "rank-0 all-reduced gradients of the %d-way sharded batch vs the same global batch run on "
+                             "rank 0 alone (differences: split-K / all-reduce summation order of bf16-engine "
+                             "gradients)" % world}
+            del solo, ref
+        del mine
+    del probe, d_all
+    if not (want_check and world > 1):
+        pass
+    steps5 = max(3, min(args.steps, 8))
+    step.tail_events = [] if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(3):
+        step.step(d, G, prefetch=d)
+    if step.tail_events is not None:
+        step.tail_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    n_tri = 0
+    for _ in range(steps5):
+        _, n_tri = step.step(d, G, prefetch=d)
+    e1.record()
+    barrier()
+    sec = e0.elapsed_time(e1) * 1e-3
+    tail = 0.0
+    if step.tail_events:
+        tail = sum(x.elapsed_time(y) for x, y in step.tail_events) / len(step.tail_events)
+    stats = torch.tensor([sec, float(n_tri), float(b - a), tail], device=dev, dtype=torch.float64)
+    if world > 1:
+        allst = [torch.empty_like(stats) for _ in range(world)]
+        dist.all_gather(allst, stats)
+    else:
+        allst = [stats]
+    allst = torch.stack(allst).cpu().numpy()
+    sec = float(allst[:, 0].max())
+    tri = allst[:, 1]
+    n_obj_total = int(hb_all.obj_off[-1])
+    flops = mlp_flops(total_tri, n_obj_total)
+    out = {"workload": "cfg5: one global ragged batch of %d graphs (3-30 objects, P=50), ~1M canonicalized triples, "
+                       "cut by parallel.shard_by_cost on canonicalized triple counts; training step as cfg2; weight "
+                       "gradients summed by bucketed NCCL all-reduce" % NG,
+           "scaling": "strong", "n_gpus": world, "graphs_total": NG, "triples_total": total_tri, "steps": steps5,
+           "ms_per_step": 1e3 * sec / steps5, "graphs_per_s": NG * steps5 / sec,
+           "per_rank_triples": [int(x) for x in tri], "per_rank_graphs": [int(x) for x in allst[:, 2]],
+           "imbalance_max_over_mean": float(tri.max() / tri.mean()),
+           "mlp_tflops_whole_step_all_gpus": flops / (sec / steps5) / 1e12,
+           "allreduce_tail_ms": float(allst[:, 3].max()),
+           "allreduce_tail_note": "time from the end of this rank's backward launches to the completion of the last "
+                                  "gradient bucket (reducer.finish), CUDA events, max over ranks",
+           "nccl_check": check}
+    del step, d, G, G_all
+    return out
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch.distributed as dist
-    from canonicalsg2im_b200 import _lib, ops
+    from canonicalsg2im_b200 import _lib
     from canonicalsg2im_b200.pipeline import SgToLayoutStep, HostBatch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -228,6 +618,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.load()
     pk = peaks()
+    want = set() if (args.profile or args.configs == "none") else (
+        {"cfg1", "cfg3", "cfg4", "cfg5", "fp32", "nccl_check"} if args.configs == "all" else set(args.configs.split(",")))
 
     vocab, graphs = workload_graphs(args.batch, rank)
     hb = HostBatch(graphs, seed=rank)
@@ -329,14 +721,43 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e = {"value": world * args.batch * args.steps / max(e2e_sec, 1e-9), "unit": UNIT,
            "h2d_bytes_per_step": int(hb.nbytes), "d2h_bytes_per_step": 4 + 8,   # loss scalar + the two canonicalization size words
-           "ms_per_step": 1e3 * e2e_sec / args.steps}
+           "ms_per_step": 1e3 * e2e_sec / max(args.steps, 1)}
 
+    hbm = None
+    if rank == 0 and not args.profile:
+        hbm = layout_roofline(d["boxes"].float().contiguous(), d["obj_off"], int(d["max_objs"]), args.batch, 128, 64, 64, pk)
+    n_obj = int(hb.obj_off[-1])
+    # free the headline state before the other configs (cfg5 holds ~25 GB of activations)
+    del step, G, d, dd
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, in the same run
+    configs = {}
+    flush = L2Flusher(dev) if want else None
+
+    def leg(name, fn):
+        try:
+            configs[name] = fn()
+        except Exception as ex:      # an extra config never costs the headline line
+            configs[name] = {"error": repr(ex)[:300]}
+        torch.cuda.empty_cache()
+    with_cpu = not args.no_cpu_baseline
+    if "cfg5" in want:               # every rank takes part (strong scaling over the world)
+        leg("cfg5", lambda: run_cfg5(dev, pk, args, world, rank, "nccl_check" in want))
+    if rank == 0 and world == 1:
+        if "cfg1" in want:
+            leg("cfg1", lambda: run_cfg1(dev, pk, args, flush, with_cpu))
+        if "cfg3" in want:
+            leg("cfg3", lambda: run_cfg3(dev, pk, args, with_cpu))
+        if "cfg4" in want:
+            leg("cfg4", lambda: run_cfg4(dev, pk, args, flush, with_cpu))
+        if "fp32" in want:
+            leg("cfg2_fp32_engine", lambda: run_fp32(dev, pk, args))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    hbm = None if args.profile else layout_roofline(d, G, pk)
-    n_obj = int(hb.obj_off[-1])
+
     peak_tf = pk["tf_sustained"]
     ach_tf = gemm_flops / gemm_sec / 1e12 if gemm_sec > 0 else 0.0
     traffic = None
@@ -348,12 +769,9 @@ def run_ours(args):
             traffic = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * sec / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "graphs_per_gpu": args.batch, "objects": n_obj, "triples_after_canon": n_tri,
-                   "precision": args.precision, "parallelism": "graph-sharded dp%d" % world,
-                   "l2": "per-step working set (net1 activations %.0f MB + 268 MB canvas + 268 MB canvas grad) exceeds the 126 MB L2"
-                         % (n_tri * (1152 + 512) * (4 if args.precision == "fp32" else 2) / 1e6)},
+        "config": main_config(args, world, n_obj, n_tri),      # objects / triples of rank 0's batch
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
@@ -361,12 +779,15 @@ def run_ours(args):
                      "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": ach_tf / peak_tf, "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
                      "launches_timed": gemm_n, "share_of_step": gemm_sec / prof_sec if prof_sec > 0 else None,
+                     "whole_step_tflops": mlp_flops(n_tri, n_obj) / (sec / max(args.steps, 1)) / 1e12,
                      "note": "measured in a separate instrumented pass of the same %d steps (%.3f ms/step)"
-                             % (args.steps, 1e3 * prof_sec / args.steps)},
+                             % (args.steps, 1e3 * prof_sec / max(args.steps, 1))},
         "roofline_hbm": hbm,
         "loss": lv,
+        "triples_after_canon_rank0": n_tri,
+        "configs": configs,
     }
-    if not args.no_cpu_baseline and not args.profile and world == 1:
+    if with_cpu and not args.profile and world == 1:
         try:
             line["cpu_baseline"] = run_cpu_baseline(args.cpu_sample, os.cpu_count() or 1)
         except Exception as ex:   # the baseline is a reported number, never a reason to lose the GPU line

@@ -128,7 +128,28 @@ class CsgError(RuntimeError):
     pass
 
 
+_ASYNC_WHAT = {1: "triple subject/object id", 2: "triple predicate id", 3: "embedding id", 4: "canonicalization triplet"}
+_async_rec = (ctypes.c_int * 4)()
+
+
+def poll_async_errors(synchronize=False):
+    """Raise ``IndexError`` if a kernel met an out-of-range index (include/csg2im.h, csg_async_error_poll).
+
+    The reference raises IndexError synchronously on such inputs (graph.py:63-64,73,98-103, model.py:108-109);
+    kernels cannot, so they neutralise the row and leave a record that the next library call (every ``check``)
+    or an explicit ``poll_async_errors(synchronize=True)`` turns into the exception."""
+    if synchronize:
+        import torch
+        torch.cuda.synchronize()
+    code = load().csg_async_error_poll(_async_rec)
+    if code:
+        _, row, value, limit = list(_async_rec)
+        raise IndexError("csg2im: %s out of range: value %d at row %d is not in [0, %d)"
+                         % (_ASYNC_WHAT.get(code, "index (code %d)" % code), value, row, limit))
+
+
 def check(rc, what=""):
     if rc != 0:
         msg = load().csg_last_error()
         raise CsgError("%s failed (rc=%d): %s" % (what or "csg call", rc, msg.decode() if msg else "?"))
+    poll_async_errors()

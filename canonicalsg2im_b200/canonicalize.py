@@ -142,8 +142,12 @@ def add_learnt_triplets_batched(triplets, tri_off, obj_off, num_rel, meta_ids, c
 AUGMENTED_RELATIONS = ("__below__", "__above__", "__left of__", "__right of__", "__inside__", "__surrounding__")
 
 
-def add_location_triplets_batched(boxes, obj_centers, objs, obj_off, image_obj_id, pred_ids, max_objs_per_graph=None):
-    """``BaseDataset.add_location_triplets`` (base_dataset.py:35-87) for a whole flat batch on the device.
+def add_location_triplets_batched(boxes, obj_centers, objs, obj_off, image_obj_id, pred_ids, max_objs_per_graph=None,
+                                  in_image_pred=None):
+    """``BaseDataset.add_location_triplets`` (base_dataset.py:35-87) for a whole flat batch on the device; with
+    ``in_image_pred`` (the id of ``__in_image__``) also ``add_dummy_triplets`` (base_dataset.py:141-150): every graph's
+    rows are its location triplets followed by ``[i, __in_image__, image]`` for its objects, i.e. the ``triplets`` list
+    the reference datasets hand to ``add_learnt_triplets`` (packed_coco.py:355-357).
 
     boxes [NO, 4] xywh float32, obj_centers [NO, 2] float32, objs [NO] or [NO, A] int64 class ids (column 0 is used),
     obj_off [B+1] int32 (all CUDA); ``pred_ids`` maps the six augmented relation names to predicate ids.  Returns
@@ -167,6 +171,9 @@ def add_location_triplets_batched(boxes, obj_centers, objs, obj_off, image_obj_i
     args = (ptr(bx), ptr(cen), ptr(ob), ob.stride(0) if ob.numel() else 1, ptr(off), B, int(image_obj_id), pid,
             int(max(max_objs_per_graph, 1)))
     _lib.check(L.csg_location_count(*args, ptr(cnt[0]), _stream()), "csg_location_count")
+    if in_image_pred is not None:
+        _lib.check(L.csg_dummy_triplets_count(ptr(ob), ob.stride(0) if ob.numel() else 1, ptr(off), B, int(image_obj_id),
+                                              ptr(cnt[1]), _stream()), "csg_dummy_triplets_count")
     out_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
     summary = torch.empty(2, dtype=torch.int32, device=dev)
     _lib.check(L.csg_canon_offsets(ptr(cnt[0]), ptr(cnt[1]), B, ptr(out_off), ptr(summary), _stream()), "csg_canon_offsets")
@@ -175,6 +182,10 @@ def add_location_triplets_batched(boxes, obj_centers, objs, obj_off, image_obj_i
         raise _lib.CsgError("location triplets: a graph has more objects than max_objs_per_graph=%d" % max_objs_per_graph)
     out = torch.empty((max(total, 1), 3), dtype=torch.int64, device=dev)
     _lib.check(L.csg_location_emit(*args, ptr(out_off), ptr(out), _stream()), "csg_location_emit")
+    if in_image_pred is not None:
+        _lib.check(L.csg_dummy_triplets_emit(ptr(ob), ob.stride(0) if ob.numel() else 1, ptr(off), B, int(image_obj_id),
+                                             int(in_image_pred), ptr(out_off), ptr(cnt[0]), ptr(out), _stream()),
+                   "csg_dummy_triplets_emit")
     return out[:total], out_off
 
 

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <mutex>
 
 static thread_local char g_err[512] = "";
 
@@ -28,6 +29,38 @@ static unsigned long long g_launches = 0;
 void csg_count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 // number of kernel-launch sites passed since load (a launch site may issue 1-2 kernels); bench.py reports it
 CSG_API long long csg_launch_count(void) { return (long long)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+// ------------------------------------------------------------------------------------------------
+// Asynchronous index errors.  Kernels that use caller-supplied integers as offsets (triple subject / object /
+// predicate ids, embedding ids, canonicalization triplets) cannot raise; they neutralise the offending row and
+// report it through one pinned, device-mapped host record {code, row, value, limit}.  The host reads the record
+// without synchronising (csg_async_error_poll): the reference raises IndexError at the same inputs, here the error
+// surfaces at the first library call after the kernel has run (like a CUDA device-side assert, but recoverable).
+// ------------------------------------------------------------------------------------------------
+static int* g_async_rec = nullptr;
+int* csg_async_err_ptr() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int* p = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&p), 8 * sizeof(int), cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess) {
+      for (int i = 0; i < 8; ++i) p[i] = 0;
+      g_async_rec = p;
+    } else {
+      cudaGetLastError();
+    }
+  });
+  return g_async_rec;   // unified addressing: the host pointer is valid on every device
+}
+// out4 (HOST, may be NULL) <- {code, row, value, limit}; returns code (0 = none) and clears the record.
+CSG_API int csg_async_error_poll(int* out4) {
+  int* p = csg_async_err_ptr();
+  if (!p) return 0;
+  volatile int* v = p;
+  const int code = v[0];
+  if (out4) for (int i = 0; i < 4; ++i) out4[i] = v[i];
+  if (code) for (int i = 0; i < 4; ++i) v[i] = 0;
+  return code;
+}
 
 CSG_API const char* csg_last_error(void) { return g_err; }
 CSG_API void csg_clear_error(void) { g_err[0] = 0; }

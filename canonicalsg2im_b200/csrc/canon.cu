@@ -48,6 +48,7 @@ struct CanonParams {
   const int* out_off;          // [B+1]
   long long* out_triplets;     // [NTout, 3]
   long long* out_type;         // [NTout]
+  int* err;                    // asynchronous index-error record (common.cuh), may be NULL
 };
 
 __device__ __forceinline__ int block_exclusive_scan(int v, int* scratch, int* total) {
@@ -89,8 +90,13 @@ __global__ void __launch_bounds__(CTHREADS) canon_kernel(CanonParams p) {
   __syncthreads();
   // ---- unique input edges
   for (int t = tbeg + tid; t < tend; t += CTHREADS) {
-    int s = (int)p.triplets[3 * (size_t)t], r = (int)p.triplets[3 * (size_t)t + 1], o = (int)p.triplets[3 * (size_t)t + 2];
-    if (s < n && o < n && r < P) atomicOr(&A[(size_t)r * rowsz + s * W + (o >> 6)], 1ull << (o & 63));
+    const long long s = p.triplets[3 * (size_t)t], r = p.triplets[3 * (size_t)t + 1], o = p.triplets[3 * (size_t)t + 2];
+    if (s >= 0 && s < n && o >= 0 && o < n && r >= 0 && r < P) {
+      atomicOr(&A[(size_t)r * rowsz + (int)s * W + ((int)o >> 6)], 1ull << ((int)o & 63));
+    } else if (!EMIT) {     // dropped and reported (the reference indexes its adjacency lists with these ids)
+      const bool bad_r = r < 0 || r >= P;
+      csg_report_index(p.err, CSG_ERR_CANON_TRIPLET, t, bad_r ? r : ((s < 0 || s >= n) ? s : o), bad_r ? P : n);
+    }
   }
   __syncthreads();
 
@@ -278,6 +284,7 @@ int fill(CanonParams& p, const long long* triplets, const int* tri_off, const in
   p.ncand = ncand; p.P = P; p.meta0 = meta0; p.meta1 = meta1;
   p.learned_converse = learned_converse; p.learned_transitivity = learned_transitivity;
   p.W = (max_objs + 63) / 64; p.nmax = max_objs;
+  p.err = csg_async_err_ptr();
   *smem = (size_t)2 * P * p.nmax * p.W * sizeof(u64);
   CSG_REQUIRE(*smem <= 220 * 1024, "canon: P=%d with %d objects per graph needs %zu bytes of shared memory", P, max_objs, *smem);
   return 0;

@@ -72,6 +72,17 @@ static inline cudaError_t csg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, di
 
 int csg_num_sms();   // SM count of the current device (cached per device)
 
+// Asynchronous index-error record (api.cu): pinned, device-mapped {code, row, value, limit}; NULL if unavailable.
+int* csg_async_err_ptr();
+enum { CSG_ERR_TRIPLE_OBJECT = 1, CSG_ERR_TRIPLE_PREDICATE = 2, CSG_ERR_EMBED_ID = 3, CSG_ERR_CANON_TRIPLET = 4 };
+__device__ __forceinline__ void csg_report_index(int* rec, int code, long long row, long long value, long long limit) {
+  if (!rec) return;
+  volatile int* v = rec;       // plain stores: concurrent offenders race, any one of them is a valid report
+  v[1] = (int)row; v[2] = (int)value; v[3] = (int)limit;
+  __threadfence_system();
+  v[0] = code;
+}
+
 __device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 // streaming (evict-first) 128-bit store: canvas tiles are written once and not re-read by the writer

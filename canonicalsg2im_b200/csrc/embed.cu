@@ -7,7 +7,7 @@
 //                   contiguous range of rows in order, accumulating into a private [V, E] table in shared memory;
 //                   the per-block tables are then summed in block order (torch's embedding backward sorts the
 //                   indices with a radix sort per call and accumulates with atomics);
-//   csg_box_loss    mean smooth-L1 over the coordinates of real boxes (gt >= 0) and its gradient, one block.
+//   csg_box_loss    per-image masked smooth-L1 box loss of the generator (bbox_pred_all / bbox_pred) and its gradient.
 #include "common.cuh"
 #include <cuda_bf16.h>
 
@@ -27,13 +27,16 @@ __device__ __forceinline__ float4 load_row4(const void* base, size_t elem, bool 
 // one warp per row, 4 columns per lane per step
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict__ table, const long long* __restrict__ idx,
                                                         long long idx_stride, int n, int V, int E,
-                                                        void* __restrict__ out, int ld_out, int out_bf16) {
+                                                        void* __restrict__ out, int ld_out, int out_bf16, int* err) {
   CSG_PDL_WAIT();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= n) return;
   const int lane = threadIdx.x & 31;
   long long v = idx[(size_t)r * idx_stride];
-  if (v < 0 || v >= V) v = 0;                        // caller validates; never read out of bounds
+  if (v < 0 || v >= V) {                             // nn.Embedding raises IndexError here: report, read row 0
+    if (lane == 0) csg_report_index(err, CSG_ERR_EMBED_ID, r, v, V);
+    v = 0;
+  }
   const float* src = table + (size_t)v * E;
   for (int c = lane * 4; c < E; c += 128) {
     const float4 x = ld_f4(src + c);
@@ -159,39 +162,57 @@ __device__ __forceinline__ float block_sum_1024(float v, float* red) {
   return red[32];
 }
 
-__global__ void __launch_bounds__(1024) box_loss_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int n,
-                                                        float* __restrict__ loss, float* __restrict__ dpred) {
+// pix2pix_model.py:72-85 on a flat batch.  One warp per image: count the real objects (objs != 0, or the sum of the
+// attribute ids != 0 for multi-attribute objects), then loss_all[b] = weight * sum smooth_l1 / n_real and the gradient
+// rows.  Lanes own rows b0 + lane, b0 + lane + 32, ...; the warp sums are xor trees, i.e. a fixed order.
+constexpr int BL_WARPS = 8;
+__global__ void __launch_bounds__(32 * BL_WARPS) box_loss_image_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                                     const long long* __restrict__ objs, int A,
+                                                                     const int* __restrict__ obj_off, int B, float weight,
+                                                                     float* __restrict__ loss_all, float* __restrict__ dpred) {
   CSG_PDL_WAIT();
-  __shared__ float red[33];
-  float cnt = 0.f, sum = 0.f;
-  for (int r = threadIdx.x; r < n; r += 1024) {
-    const float4 g = ld_f4(gt + 4 * (size_t)r), p = ld_f4(pred + 4 * (size_t)r);
-    if (g.x >= 0.f && g.y >= 0.f && g.z >= 0.f && g.w >= 0.f) {
-      cnt += 1.f;
+  const int b = blockIdx.x * BL_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int r0 = obj_off[b], r1 = obj_off[b + 1];
+  auto is_real = [&](int r) {
+    long long sum = 0;
+    for (int k = 0; k < A; ++k) sum += objs[(size_t)r * A + k];
+    return sum != 0;
+  };
+  float cnt = 0.f;
+  for (int r = r0 + lane; r < r1; r += 32) cnt += is_real(r) ? 1.f : 0.f;
+  cnt = warp_sum(cnt);
+  const float inv = 1.f / cnt;                       // 0 real objects: 0 * inf = NaN below, as 0 / 0 in the reference
+  const float gscale = weight * inv / (float)B;
+  float sum = 0.f;
+  for (int r = r0 + lane; r < r1; r += 32) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (is_real(r)) {
+      const float4 g = ld_f4(gt + 4 * (size_t)r), p = ld_f4(pred + 4 * (size_t)r);
       const float d[4] = {p.x - g.x, p.y - g.y, p.z - g.z, p.w - g.w};
+      float q[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float a = fabsf(d[k]);
         sum += a < 1.f ? 0.5f * d[k] * d[k] : a - 0.5f;
+        q[k] = (a < 1.f ? d[k] : (d[k] > 0.f ? 1.f : -1.f)) * gscale;
       }
-    }
-  }
-  const float total_cnt = block_sum_1024(cnt, red);
-  const float total = block_sum_1024(sum, red);
-  const float scale = total_cnt > 0.f ? 1.f / (4.f * total_cnt) : 0.f;
-  if (threadIdx.x == 0) loss[0] = total * scale;
-  for (int r = threadIdx.x; r < n; r += 1024) {
-    const float4 g = ld_f4(gt + 4 * (size_t)r), p = ld_f4(pred + 4 * (size_t)r);
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g.x >= 0.f && g.y >= 0.f && g.z >= 0.f && g.w >= 0.f) {
-      const float d[4] = {p.x - g.x, p.y - g.y, p.z - g.z, p.w - g.w};
-      float q[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) q[k] = (fabsf(d[k]) < 1.f ? d[k] : (d[k] > 0.f ? 1.f : -1.f)) * scale;
       o = make_float4(q[0], q[1], q[2], q[3]);
     }
     st_f4(dpred + 4 * (size_t)r, o);
   }
+  sum = warp_sum(sum);
+  if (lane == 0) loss_all[b] = weight * sum * inv;
+}
+
+// loss[0] = mean_b loss_all[b], summed in a fixed order (thread-strided partial sums, then a fixed tree)
+__global__ void __launch_bounds__(1024) box_loss_mean_kernel(const float* __restrict__ loss_all, int B, float* __restrict__ loss) {
+  CSG_PDL_WAIT();
+  __shared__ float red[33];
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += 1024) s += loss_all[b];
+  const float total = block_sum_1024(s, red);
+  if (threadIdx.x == 0) loss[0] = total / (float)B;
 }
 
 }  // namespace
@@ -201,7 +222,7 @@ CSG_API int csg_embed_fwd(const float* table, const long long* idx, long long id
   if (n == 0) return 0;
   CSG_REQUIRE(V > 0 && E > 0 && (E & 3) == 0 && (ld_out & 3) == 0, "embed_fwd: E=%d / ld=%d must be multiples of 4", E, ld_out);
   CSG_CUDA(csg_launch_pdl(embed_fwd_kernel, dim3(csg_div_up((long long)n * 32, 256)), dim3(256), 0, stream, table, idx, idx_stride, n, V, E, out, ld_out,
-                                                                          out_bf16));
+                                                                          out_bf16, csg_async_err_ptr()));
   CSG_CHECK_LAUNCH("csg_embed_fwd");
   return 0;
 }
@@ -247,9 +268,17 @@ CSG_API int csg_onehot_bf16(const long long* idx, long long idx_stride, int n, i
   return 0;
 }
 
-// loss[0] = mean over the 4 coordinates of the rows with gt >= 0 of smooth_l1(pred - gt); dpred = d loss / d pred.
-CSG_API int csg_box_loss(const float* pred, const float* gt, int n, float* loss, float* dpred, cudaStream_t stream) {
-  CSG_CUDA(csg_launch_pdl(box_loss_kernel, dim3(1), dim3(1024), 0, stream, pred, gt, n, loss, dpred));
-  CSG_CHECK_LAUNCH("csg_box_loss");
+// Box regression term of the generator loss (pix2pix_model.py:72-85): loss_all[b] (G_losses["bbox_pred_all"]) =
+// weight * sum over the real objects of image b of smooth_l1(pred - gt) / n_real(b); loss[0] (G_losses["bbox_pred"]) =
+// mean_b loss_all[b]; dpred [NO, 4] = d loss[0] / d pred.  objs [NO, A] int64 class / attribute ids; a row is real iff
+// its id (A == 1) or the sum of its ids (A > 1) is non-zero (the __image__ dummy and collate padding are 0).
+CSG_API int csg_box_loss(const float* pred, const float* gt, const long long* objs, int A, const int* obj_off, int B,
+                         double weight, float* loss, float* loss_all, float* dpred, cudaStream_t stream) {
+  CSG_REQUIRE(B > 0 && A > 0, "box_loss: B=%d A=%d", B, A);
+  CSG_CUDA(csg_launch_pdl(box_loss_image_kernel, dim3(csg_div_up(B, BL_WARPS)), dim3(32 * BL_WARPS), 0, stream, pred, gt, objs, A,
+                          obj_off, B, (float)weight, loss_all, dpred));
+  CSG_CHECK_LAUNCH("csg_box_loss image");
+  CSG_CUDA(csg_launch_pdl(box_loss_mean_kernel, dim3(1), dim3(1024), 0, stream, (const float*)loss_all, B, loss));
+  CSG_CHECK_LAUNCH("csg_box_loss mean");
   return 0;
 }

@@ -26,23 +26,43 @@ __device__ __forceinline__ int find_graph(const int* __restrict__ off, int B, in
   return lo;
 }
 
-__global__ void triple_prep_kernel(const long long* __restrict__ triplets, const long long* __restrict__ ttype,
-                                   const int* __restrict__ tri_off, const int* __restrict__ obj_off, int B,
-                                   int NT, int T_pad, int O_pad, int padding_id,
-                                   int* __restrict__ s_idx, int* __restrict__ o_idx, int* __restrict__ pred,
-                                   int* __restrict__ type32, int* __restrict__ valid) {
-  CSG_PDL_WAIT();
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= NT) return;
-  int base;
-  if (T_pad > 0) base = (t / T_pad) * O_pad;
-  else base = obj_off[find_graph(tri_off, B, t)];
-  long long s = triplets[3 * (size_t)t], p = triplets[3 * (size_t)t + 1], o = triplets[3 * (size_t)t + 2];
+// Subject / object ids are graph-local and become raw row offsets of every later kernel (gathers, CSR counters in
+// shared memory): an id outside [0, n_g) or a predicate id outside [0, num_preds) -- the inputs at which the
+// reference raises IndexError (graph.py:63-64,73,98-103) -- is reported through the asynchronous error record
+// and the row is neutralised (ids 0, valid 0, type 2 = zero confidence) so that nothing reads out of bounds.
+__device__ __forceinline__ void triple_prep_store(int t, int base, int n_g, long long s, long long p, long long o,
+                                                  int ty, int ok_valid, int num_preds, int* __restrict__ s_idx,
+                                                  int* __restrict__ o_idx, int* __restrict__ pred, int* __restrict__ type32,
+                                                  int* __restrict__ valid, int* err) {
+  const bool bad_obj = s < 0 || s >= n_g || o < 0 || o >= n_g;
+  const bool bad_pred = num_preds > 0 && (p < 0 || p >= num_preds);
+  if (bad_obj || bad_pred) {
+    if (bad_obj) csg_report_index(err, CSG_ERR_TRIPLE_OBJECT, t, (s < 0 || s >= n_g) ? s : o, n_g);
+    else csg_report_index(err, CSG_ERR_TRIPLE_PREDICATE, t, p, num_preds);
+    s_idx[t] = base; o_idx[t] = base; pred[t] = 0; type32[t] = 2; valid[t] = 0;
+    return;
+  }
   s_idx[t] = base + (int)s;
   o_idx[t] = base + (int)o;
   pred[t] = (int)p;
-  type32[t] = ttype ? (int)ttype[t] : 0;
-  valid[t] = (p != padding_id) ? 1 : 0;
+  type32[t] = ty;
+  valid[t] = ok_valid;
+}
+
+__global__ void triple_prep_kernel(const long long* __restrict__ triplets, const long long* __restrict__ ttype,
+                                   const int* __restrict__ tri_off, const int* __restrict__ obj_off, int B,
+                                   int NT, int T_pad, int O_pad, int padding_id, int num_preds,
+                                   int* __restrict__ s_idx, int* __restrict__ o_idx, int* __restrict__ pred,
+                                   int* __restrict__ type32, int* __restrict__ valid, int* err) {
+  CSG_PDL_WAIT();
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= NT) return;
+  int base, n_g;
+  if (T_pad > 0) { base = (t / T_pad) * O_pad; n_g = O_pad; }
+  else { const int g = find_graph(tri_off, B, t); base = obj_off[g]; n_g = obj_off[g + 1] - base; }
+  long long s = triplets[3 * (size_t)t], p = triplets[3 * (size_t)t + 1], o = triplets[3 * (size_t)t + 2];
+  triple_prep_store(t, base, n_g, s, p, o, ttype ? (int)ttype[t] : 0, (p != padding_id) ? 1 : 0, num_preds,
+                    s_idx, o_idx, pred, type32, valid, err);
 }
 
 // GraphTripleConv.forward's own argument layout (graph.py:44): edges [NT, 2], predicate ids, indicators
@@ -50,18 +70,17 @@ __global__ void triple_prep_edges_kernel(const long long* __restrict__ edges, co
                                          const unsigned char* __restrict__ indicators,
                                          const long long* __restrict__ ttype, const int* __restrict__ tri_off,
                                          const int* __restrict__ obj_off, int B, int NT, int T_pad, int O_pad,
-                                         int* __restrict__ s_idx, int* __restrict__ o_idx, int* __restrict__ pred,
-                                         int* __restrict__ type32, int* __restrict__ valid) {
+                                         int num_preds, int* __restrict__ s_idx, int* __restrict__ o_idx,
+                                         int* __restrict__ pred, int* __restrict__ type32, int* __restrict__ valid,
+                                         int* err) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= NT) return;
-  int base;
-  if (T_pad > 0) base = (t / T_pad) * O_pad;
-  else base = obj_off[find_graph(tri_off, B, t)];
-  s_idx[t] = base + (int)edges[2 * (size_t)t];
-  o_idx[t] = base + (int)edges[2 * (size_t)t + 1];
-  pred[t] = (int)pred_ids[t];
-  type32[t] = ttype ? (int)ttype[t] : 0;
-  valid[t] = indicators ? (indicators[t] ? 1 : 0) : 1;
+  int base, n_g;
+  if (T_pad > 0) { base = (t / T_pad) * O_pad; n_g = O_pad; }
+  else { const int g = find_graph(tri_off, B, t); base = obj_off[g]; n_g = obj_off[g + 1] - base; }
+  triple_prep_store(t, base, n_g, edges[2 * (size_t)t], pred_ids[t], edges[2 * (size_t)t + 1],
+                    ttype ? (int)ttype[t] : 0, indicators ? (indicators[t] ? 1 : 0) : 1, num_preds,
+                    s_idx, o_idx, pred, type32, valid, err);
 }
 
 __global__ void offsets_uniform_kernel(int* __restrict__ off, int B, int stride) {
@@ -345,25 +364,26 @@ CSG_API int csg_offsets_uniform(int* off, int B, int stride, cudaStream_t stream
 }
 
 CSG_API int csg_triple_prep(const long long* triplets, const long long* triplet_type, const int* tri_off,
-                            const int* obj_off, int B, int NT, int T_pad, int O_pad, int padding_id,
+                            const int* obj_off, int B, int NT, int T_pad, int O_pad, int padding_id, int num_preds,
                             int* s_idx, int* o_idx, int* pred, int* type32, int* valid, cudaStream_t stream) {
   if (NT == 0) return 0;
   CSG_REQUIRE(T_pad > 0 || (tri_off && obj_off), "triple_prep: ragged mode needs offsets");
   CSG_CUDA(csg_launch_pdl(triple_prep_kernel, dim3(csg_div_up(NT, 256)), dim3(256), 0, stream, triplets, triplet_type, tri_off, obj_off, B, NT, T_pad,
-                                                              O_pad, padding_id, s_idx, o_idx, pred, type32, valid));
+                                                              O_pad, padding_id, num_preds, s_idx, o_idx, pred, type32, valid,
+                                                              csg_async_err_ptr()));
   CSG_CHECK_LAUNCH("csg_triple_prep");
   return 0;
 }
 
 CSG_API int csg_triple_prep_edges(const long long* edges, const long long* pred_ids, const unsigned char* indicators,
                                   const long long* triplet_type, const int* tri_off, const int* obj_off, int B,
-                                  int NT, int T_pad, int O_pad, int* s_idx, int* o_idx, int* pred, int* type32,
-                                  int* valid, cudaStream_t stream) {
+                                  int NT, int T_pad, int O_pad, int num_preds, int* s_idx, int* o_idx, int* pred,
+                                  int* type32, int* valid, cudaStream_t stream) {
   if (NT == 0) return 0;
   CSG_REQUIRE(T_pad > 0 || (tri_off && obj_off), "triple_prep_edges: ragged mode needs offsets");
   triple_prep_edges_kernel<<<csg_div_up(NT, 256), 256, 0, stream>>>(edges, pred_ids, indicators, triplet_type, tri_off,
-                                                                    obj_off, B, NT, T_pad, O_pad, s_idx, o_idx, pred,
-                                                                    type32, valid);
+                                                                    obj_off, B, NT, T_pad, O_pad, num_preds, s_idx, o_idx,
+                                                                    pred, type32, valid, csg_async_err_ptr());
   CSG_CHECK_LAUNCH("csg_triple_prep_edges");
   return 0;
 }

@@ -159,6 +159,38 @@ __global__ void __launch_bounds__(LOC_THREADS) location_kernel(LocParams p) {
   }
 }
 
+// add_dummy_triplets (base_dataset.py:141-150): [i, __in_image__, image] for every object i != image, in ascending i,
+// appended behind the graph's location triplets.  One warp per graph.  COUNT: cnt[g] = n_g - 1 (0 when the graph holds
+// no __image__ object); EMIT: rows at out_off[g] + skip[g].  With several __image__ objects the last one is used
+// (the reference's int(nonzero().squeeze()) raises there).
+template <bool EMIT>
+__global__ void __launch_bounds__(128) dummy_triplets_kernel(const long long* __restrict__ objs, long long objs_stride,
+                                                             const int* __restrict__ obj_off, int B, long long image_id,
+                                                             int in_image_pred, int* __restrict__ cnt,
+                                                             const int* __restrict__ out_off, const int* __restrict__ skip,
+                                                             long long* __restrict__ out) {
+  CSG_PDL_WAIT();
+  const int g = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= B) return;
+  const int obeg = obj_off[g], n = obj_off[g + 1] - obeg;
+  int img = -1;
+  for (int i = lane; i < n; i += 32)
+    if (objs[(size_t)(obeg + i) * objs_stride] == image_id) img = i;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) img = max(img, __shfl_xor_sync(0xffffffffu, img, off));
+  if (!EMIT) {
+    if (lane == 0) cnt[g] = img >= 0 ? n - 1 : 0;
+    return;
+  }
+  if (img < 0) return;
+  const size_t base = (size_t)out_off[g] + (skip ? skip[g] : 0);
+  for (int i = lane; i < n; i += 32) {
+    if (i == img) continue;
+    long long* dst = out + 3 * (base + (i < img ? i : i - 1));
+    dst[0] = i; dst[1] = in_image_pred; dst[2] = img;
+  }
+}
+
 int loc_fill(LocParams& p, const float* boxes, const float* centers, const long long* objs, long long objs_stride,
              const int* obj_off, long long image_id, const int* pred_ids, int max_objs, size_t* smem) {
   CSG_REQUIRE(max_objs > 0 && pred_ids, "location_triplets: bad max_objs=%d", max_objs);
@@ -200,5 +232,25 @@ CSG_API int csg_location_emit(const float* boxes, const float* centers, const lo
   CSG_CUDA(cudaFuncSetAttribute(location_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   location_kernel<true><<<B, LOC_THREADS, smem, stream>>>(p);
   CSG_CHECK_LAUNCH("csg_location_emit");
+  return 0;
+}
+
+// add_dummy_triplets (sg2im/data/base_dataset.py:141-150) for a flat batch; see dummy_triplets_kernel above.
+CSG_API int csg_dummy_triplets_count(const long long* objs, long long objs_stride, const int* obj_off, int B,
+                                     long long image_id, int* cnt, cudaStream_t stream) {
+  if (B == 0) return 0;
+  CSG_CUDA(csg_launch_pdl(dummy_triplets_kernel<false>, dim3(csg_div_up(B, 4)), dim3(128), 0, stream, objs, objs_stride, obj_off, B,
+                          image_id, 0, cnt, (const int*)nullptr, (const int*)nullptr, (long long*)nullptr));
+  CSG_CHECK_LAUNCH("csg_dummy_triplets_count");
+  return 0;
+}
+
+CSG_API int csg_dummy_triplets_emit(const long long* objs, long long objs_stride, const int* obj_off, int B,
+                                    long long image_id, int in_image_pred, const int* out_off, const int* skip,
+                                    long long* out_triplets, cudaStream_t stream) {
+  if (B == 0) return 0;
+  CSG_CUDA(csg_launch_pdl(dummy_triplets_kernel<true>, dim3(csg_div_up(B, 4)), dim3(128), 0, stream, objs, objs_stride, obj_off, B,
+                          image_id, in_image_pred, (int*)nullptr, out_off, skip, out_triplets));
+  CSG_CHECK_LAUNCH("csg_dummy_triplets_emit");
   return 0;
 }

@@ -17,6 +17,8 @@ struct AdamJobs {
   float* m[ADAM_MAX];
   float* v[ADAM_MAX];
   int n[ADAM_MAX];
+  float lr_over_bc1[ADAM_MAX];     // per tensor: torch.optim.Adam keeps one step count per parameter
+  float inv_bc2_sqrt[ADAM_MAX];
 };
 
 struct AdamScalars {
@@ -34,6 +36,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(AdamJobs jobs, AdamScalars s) {
   CSG_PDL_WAIT();
   const int t = blockIdx.y;
+  s.lr_over_bc1 = jobs.lr_over_bc1[t];
+  s.inv_bc2_sqrt = jobs.inv_bc2_sqrt[t];
   const int n = jobs.n[t];
   const int beg = blockIdx.x * ADAM_CHUNK;
   if (beg >= n) return;
@@ -70,15 +74,13 @@ __global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(AdamJobs jobs,
 
 }  // namespace
 
-// count tensors (HOST arrays of device pointers / element counts); step >= 1 is the update index t.
+// count tensors (HOST arrays of device pointers / element counts / per-tensor update indices t >= 1).
 CSG_API int csg_adam_multi(int count, void* const* params, const void* const* grads, void* const* exp_avg,
                            void* const* exp_avg_sq, const int* numel, double lr, double beta1, double beta2, double eps,
-                           double weight_decay, int step, cudaStream_t stream) {
-  CSG_REQUIRE(count >= 0 && step >= 1, "adam_multi: bad count=%d / step=%d", count, step);
+                           double weight_decay, const int* steps, cudaStream_t stream) {
+  CSG_REQUIRE(count >= 0 && steps, "adam_multi: bad count=%d / steps", count);
   AdamScalars s;
-  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
-  s.lr_over_bc1 = (float)(lr / bc1);
-  s.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  s.lr_over_bc1 = 0.f; s.inv_bc2_sqrt = 0.f;
   s.b1 = (float)beta1; s.b2 = (float)beta2; s.eps = (float)eps; s.wd = (float)weight_decay;
   for (int base = 0; base < count; base += ADAM_MAX) {
     const int k = count - base < ADAM_MAX ? count - base : ADAM_MAX;
@@ -91,7 +93,13 @@ CSG_API int csg_adam_multi(int count, void* const* params, const void* const* gr
       jobs.m[i] = on ? reinterpret_cast<float*>(exp_avg[base + i]) : nullptr;
       jobs.v[i] = on ? reinterpret_cast<float*>(exp_avg_sq[base + i]) : nullptr;
       jobs.n[i] = on ? numel[base + i] : 0;
+      jobs.lr_over_bc1[i] = 0.f; jobs.inv_bc2_sqrt[i] = 0.f;
       if (on) {
+        const int step = steps[base + i];
+        CSG_REQUIRE(step >= 1, "adam_multi: tensor %d has step %d < 1", base + i, step);
+        const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+        jobs.lr_over_bc1[i] = (float)(lr / bc1);
+        jobs.inv_bc2_sqrt[i] = (float)(1.0 / sqrt(bc2));
         CSG_REQUIRE(numel[base + i] >= 0 && (numel[base + i] == 0 || (jobs.p[i] && jobs.g[i] && jobs.m[i] && jobs.v[i])),
                     "adam_multi: tensor %d has a null pointer", base + i);
         if (jobs.n[i] > max_n) max_n = jobs.n[i];

@@ -72,9 +72,10 @@ class TripleBatch:
         return off
 
     @classmethod
-    def from_padded_edges(cls, edges, pred_indicators, triplet_type, predicate_ids, O):
+    def from_padded_edges(cls, edges, pred_indicators, triplet_type, predicate_ids, O, num_preds=0):
         """The argument layout of ``GraphTripleConv.forward`` (graph.py:44): edges [B,T,2] i64,
-        pred_indicators [B,T] bool, triplet_type [B,T] i64, predicate_ids [B,T] i64."""
+        pred_indicators [B,T] bool, triplet_type [B,T] i64, predicate_ids [B,T] i64.  ``num_preds`` > 0 also
+        range-checks the predicate ids (they index the transitive weights, graph.py:73)."""
         need_cuda(edges, pred_indicators, triplet_type, predicate_ids)
         B, T = edges.shape[0], edges.shape[1]
         dev = edges.device
@@ -84,14 +85,14 @@ class TripleBatch:
         pid = predicate_ids.contiguous().to(torch.int64)
         ind = pred_indicators.contiguous().to(torch.uint8) if pred_indicators is not None else None
         tt = triplet_type.contiguous().to(torch.int64) if triplet_type is not None else None
-        rc = lib().csg_triple_prep_edges(ptr(e), ptr(pid), ptr(ind), ptr(tt), 0, 0, B, NT, T, O,
+        rc = lib().csg_triple_prep_edges(ptr(e), ptr(pid), ptr(ind), ptr(tt), 0, 0, B, NT, T, O, int(num_preds),
                                          ptr(s_idx), ptr(o_idx), ptr(pred), ptr(type32), ptr(valid), _stream())
         _lib.check(rc, "csg_triple_prep_edges")
         return cls(s_idx[:NT], o_idx[:NT], pred[:NT], type32[:NT], valid[:NT],
                    cls._uniform_off(B, T, dev), cls._uniform_off(B, O, dev), B * O)
 
     @classmethod
-    def from_padded_triplets(cls, triplets, triplet_type, padding_id, O):
+    def from_padded_triplets(cls, triplets, triplet_type, padding_id, O, num_preds=0):
         """``Sg2LayoutModel.forward``'s layout (model.py:104-107): triplets [B,T,3] i64."""
         need_cuda(triplets, triplet_type)
         B, T = triplets.shape[0], triplets.shape[1]
@@ -100,14 +101,14 @@ class TripleBatch:
         s_idx, o_idx, pred, type32, valid = cls._alloc(NT, dev)
         tr = triplets.contiguous().to(torch.int64)
         tt = triplet_type.contiguous().to(torch.int64) if triplet_type is not None else None
-        rc = lib().csg_triple_prep(ptr(tr), ptr(tt), 0, 0, B, NT, T, O, int(padding_id),
+        rc = lib().csg_triple_prep(ptr(tr), ptr(tt), 0, 0, B, NT, T, O, int(padding_id), int(num_preds),
                                    ptr(s_idx), ptr(o_idx), ptr(pred), ptr(type32), ptr(valid), _stream())
         _lib.check(rc, "csg_triple_prep")
         return cls(s_idx[:NT], o_idx[:NT], pred[:NT], type32[:NT], valid[:NT],
                    cls._uniform_off(B, T, dev), cls._uniform_off(B, O, dev), B * O)
 
     @classmethod
-    def from_ragged(cls, triplets, triplet_type, tri_off, obj_off, NO, padding_id=-1):
+    def from_ragged(cls, triplets, triplet_type, tri_off, obj_off, NO, padding_id=-1, num_preds=0):
         """Flat batch: triplets [NT,3] i64 with per-graph LOCAL object ids, tri_off/obj_off [B+1] i32."""
         need_cuda(triplets, triplet_type, tri_off, obj_off)
         NT = triplets.shape[0]
@@ -118,7 +119,7 @@ class TripleBatch:
         tt = triplet_type.contiguous().to(torch.int64) if triplet_type is not None else None
         tri_off = tri_off.to(torch.int32).contiguous()
         obj_off = obj_off.to(torch.int32).contiguous()
-        rc = lib().csg_triple_prep(ptr(tr), ptr(tt), ptr(tri_off), ptr(obj_off), B, NT, 0, 0, int(padding_id),
+        rc = lib().csg_triple_prep(ptr(tr), ptr(tt), ptr(tri_off), ptr(obj_off), B, NT, 0, 0, int(padding_id), int(num_preds),
                                    ptr(s_idx), ptr(o_idx), ptr(pred), ptr(type32), ptr(valid), _stream())
         _lib.check(rc, "csg_triple_prep")
         return cls(s_idx[:NT], o_idx[:NT], pred[:NT], type32[:NT], valid[:NT], tri_off, obj_off, NO)
@@ -263,6 +264,41 @@ class _DenseMLP2F32(torch.autograd.Function):
         return dx, dw0, db0, dw1, db1, None
 
 
+class _LinearF32(torch.autograd.Function):
+    """y = x W^T + b on the fp32 engine (``attribute_fc_gen``, attribute_embed.py:24-25,46-47)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w = f32c(x), f32c(w)
+        y = ops.gemm_f32(A_ROW, B_NK, x.shape[0], w.shape[0], w.shape[1], x, w, bias=f32c(b))
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = f32c(dy)
+        M, (N, K) = x.shape[0], w.shape
+        dw = ops.gemm_f32(A_COL, B_KN, N, K, M, dy, x)
+        db = ops.colsum_f32(dy)
+        dx = ops.gemm_f32(A_ROW, B_KN, M, K, N, dy, w) if ctx.needs_input_grad[0] else None
+        return dx, dw, db
+
+
+def linear(x, w, b, precision="fp32"):
+    """``F.linear`` on the csg2im GEMMs (2-D ``x``).  fp32: feature widths must be multiples of 4;
+    bf16 (tcgen05, bf16 output) needs multiples of 64 and falls back to the fp32 engine otherwise."""
+    need_cuda(x, w, b)
+    if x.dim() != 2:
+        raise ValueError("linear expects a 2-D input (got %s)" % (tuple(x.shape),))
+    if precision == "bf16" and w.shape[0] % 64 == 0 and w.shape[1] % 64 == 0:
+        from . import graph_tc
+        return graph_tc._LinearBF16.apply(x, w, b)
+    if w.shape[0] % 4 or w.shape[1] % 4:
+        raise _lib.CsgError("linear: feature widths must be multiples of 4 (got %s)" % (tuple(w.shape),))
+    return _LinearF32.apply(x, w, b)
+
+
 def dense_mlp2(x, w0, b0, w1, b1, final_relu, precision="fp32"):
     need_cuda(x, w0, w1)
     if precision == "bf16":
@@ -301,21 +337,40 @@ def build_mlp(dim_list, final_nonlinearity="relu"):
     return nn.Sequential(*layers)
 
 
-_BATCH_CACHE = {}
+def _tensor_key(x):
+    return None if x is None else (x.data_ptr(), x._version, tuple(x.shape), tuple(x.stride()), x.dtype)
 
 
-def _cached_batch(edges, pred_indicators, triplet_type, predicate_ids, O):
-    """All five layers of a forward pass receive the same index tensors (model.py:111-112); build the
-    CSR once.  Keyed on storage + version so in-place edits invalidate the entry."""
-    key = (edges.data_ptr(), edges._version, tuple(edges.shape), pred_indicators.data_ptr(), pred_indicators._version,
-           triplet_type.data_ptr(), triplet_type._version, predicate_ids.data_ptr(), predicate_ids._version, O)
-    hit = _BATCH_CACHE.get("k")
-    if hit is not None and hit[0] == key:
-        return hit[1]
-    b = TripleBatch.from_padded_edges(edges, pred_indicators, triplet_type, predicate_ids, O)
-    # keep the keyed tensors alive so that a data_ptr cannot be recycled while the entry exists
-    _BATCH_CACHE["k"] = (key, b, (edges, pred_indicators, triplet_type, predicate_ids))
-    return b
+class _BatchCache:
+    """All layers of a forward pass receive the same index tensors (model.py:111-112): the CSR is built once.
+    One entry per (device, stream), keyed on storage + version so in-place edits invalidate it; the entry keeps
+    the keyed tensors alive, so a data_ptr cannot be recycled while it exists, and is dropped when a different
+    batch arrives on that stream (``clear()`` releases everything)."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def get(self, edges, pred_indicators, triplet_type, predicate_ids, O, num_preds):
+        need_cuda(edges, pred_indicators, triplet_type, predicate_ids)
+        slot = (edges.device, torch.cuda.current_stream(edges.device).cuda_stream)
+        key = (_tensor_key(edges), _tensor_key(pred_indicators), _tensor_key(triplet_type), _tensor_key(predicate_ids),
+               O, num_preds)
+        hit = self.entries.get(slot)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        b = TripleBatch.from_padded_edges(edges, pred_indicators, triplet_type, predicate_ids, O, num_preds)
+        self.entries[slot] = (key, b, (edges, pred_indicators, triplet_type, predicate_ids))
+        return b
+
+    def clear(self):
+        self.entries.clear()
+
+
+_BATCH_CACHE = _BatchCache()
+
+
+def _cached_batch(edges, pred_indicators, triplet_type, predicate_ids, O, num_preds=0):
+    return _BATCH_CACHE.get(edges, pred_indicators, triplet_type, predicate_ids, O, num_preds)
 
 
 class GraphTripleConv(nn.Module):
@@ -356,7 +411,8 @@ class GraphTripleConv(nn.Module):
         obj_vecs [B,O,Din], pred_vecs [B,T,Dp], edges [B,T,2] i64, pred_indicators [B,T] bool,
         triplet_type [B,T] i64, predicate_ids [B,T] i64 -> (new_obj [B,O,Dout], new_p [B,T,Dp_out])."""
         B, O, T = obj_vecs.size(0), obj_vecs.size(1), pred_vecs.size(1)
-        batch = _cached_batch(edges, pred_indicators, triplet_type, predicate_ids, O)
+        w = self.predicates_transitive_weights
+        batch = _cached_batch(edges, pred_indicators, triplet_type, predicate_ids, O, w.numel() if w is not None else 0)
         new_obj, new_p = self.forward_flat(batch, obj_vecs.reshape(B * O, -1), pred_vecs.reshape(B * T, -1))
         return new_obj.view(B, O, -1), new_p.reshape(B, T, -1)
 

@@ -321,6 +321,38 @@ class _DenseMLP2BF16(torch.autograd.Function):
         return dx, dw0, db0, dw1, db1
 
 
+class _LinearBF16(torch.autograd.Function):
+    """y = x W^T + b on tcgen05 (bf16 operands, fp32 accumulate, bf16 output): ``attribute_fc_gen`` of the
+    multi-attribute object embedding (attribute_embed.py:24-25,46-47) in front of the bf16 GCN."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        xb = as_bf16_rows(x)
+        need_bwd = any(ctx.needs_input_grad)
+        casts = cast_bf16_multi([(w, False)] + ([(w, True)] if need_bwd else []))
+        N, K = w.shape
+        y = ops.gemm_bf16(xb.shape[0], N, K, xb, casts[0], bias=f32c(b))
+        ctx.save_for_backward(xb)
+        ctx.wt = casts[1] if need_bwd else None
+        ctx.x_dtype, ctx.shape = x.dtype, (N, K)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xb,) = ctx.saved_tensors
+        N, K = ctx.shape
+        M = xb.shape[0]
+        dyb = as_bf16_rows(dy)
+        dw = ops.gemm_bf16(N, K, M, dyb, xb, mn_major=True)
+        db = colsum_bf16(dyb)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm_bf16(M, K, N, dyb, ctx.wt)
+            if ctx.x_dtype != BF:
+                dx = dx.to(ctx.x_dtype)
+        return dx, dw, db
+
+
 def dense_mlp2(x, w0, b0, w1, b1, final_relu):
     """box_net (model.py:58-60).  Feature widths that fit the tensor-core tiles and a head of <= 8 outputs run on
     ``_DenseMLP2BF16``; anything else on the fp32 engine."""

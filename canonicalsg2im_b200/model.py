@@ -12,7 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .graph import GraphTripleConv, TripleBatch, build_mlp, dense_mlp2, get_predicates_weights
+from .graph import GraphTripleConv, TripleBatch, build_mlp, dense_mlp2, get_predicates_weights, linear
 from .ops import lib, ptr, need_cuda, workspace, _stream
 
 
@@ -73,25 +73,43 @@ def embedding_lookup(weight, idx, out_dtype=torch.float32):
 
 class _BoxLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, gt):
-        need_cuda(pred, gt)
+    def forward(ctx, pred, gt, objs, obj_off, weight):
+        need_cuda(pred, gt, objs, obj_off)
         p, g = pred.detach().float().contiguous(), gt.float().contiguous()
+        objs = objs.to(torch.int64).contiguous()
+        B, A = obj_off.numel() - 1, objs.shape[1]
         loss = torch.empty(1, dtype=torch.float32, device=p.device)
+        loss_all = torch.empty(B, dtype=torch.float32, device=p.device)
         dpred = torch.empty_like(p)
-        _lib.check(lib().csg_box_loss(ptr(p), ptr(g), p.shape[0], ptr(loss), ptr(dpred), _stream()), "csg_box_loss")
+        _lib.check(lib().csg_box_loss(ptr(p), ptr(g), ptr(objs), A, ptr(obj_off), B, float(weight), ptr(loss),
+                                      ptr(loss_all), ptr(dpred), _stream()), "csg_box_loss")
         ctx.save_for_backward(dpred)
-        return loss[0]
+        ctx.mark_non_differentiable(loss_all)
+        return loss[0], loss_all
 
     @staticmethod
-    def backward(ctx, dloss):
+    def backward(ctx, dloss, _dall):
         (dpred,) = ctx.saved_tensors
-        return dpred * dloss, None
+        return dpred * dloss, None, None, None, None
 
 
-def masked_box_loss(boxes_pred, boxes_gt):
-    """Mean smooth-L1 between predicted and ground-truth boxes over the REAL objects (gt >= 0; the ``__image__``
-    dummy has box -1), the regression term of pix2pix_model.py:72-85 on a flat batch.  One launch, no host sync."""
-    return _BoxLossFn.apply(boxes_pred.reshape(-1, 4), boxes_gt.reshape(-1, 4))
+def bbox_pred_loss_ragged(boxes_pred, boxes_gt, objs, obj_off, weight=10.0):
+    """Box term of ``Pix2PixModel.compute_generator_loss`` (sg2im/pix2pix_model.py:72-85) on a flat batch:
+    per image, the smooth-L1 of the real objects (``objs != 0``; ``objs.sum(1) != 0`` for multi-attribute objects)
+    summed over boxes and coordinates, times ``bbox_pred_loss_weight`` (args.py:172, default 10), divided by the
+    image's real-object count.  Returns ``(G_losses["bbox_pred"], G_losses["bbox_pred_all"])`` = (mean over images,
+    per-image values).  One pass, no host sync; an image without real objects gives NaN as the reference's 0/0."""
+    objs = objs if objs.dim() == 2 else objs.reshape(-1, 1)
+    off = obj_off if obj_off.dtype == torch.int32 else obj_off.to(torch.int32)
+    return _BoxLossFn.apply(boxes_pred.reshape(-1, 4), boxes_gt.reshape(-1, 4), objs, off.contiguous(), weight)
+
+
+def bbox_pred_loss(boxes_pred, boxes, objs, weight=10.0):
+    """Padded form, the reference's own tensors: boxes_pred / boxes [B, O, 4], objs [B, O, A]."""
+    from .graph import TripleBatch
+    B, O = boxes.shape[0], boxes.shape[1]
+    off = TripleBatch._uniform_off(B, O, boxes.device)
+    return bbox_pred_loss_ragged(boxes_pred, boxes, objs.reshape(B * O, -1), off, weight)
 
 
 def get_conv_converse(model):
@@ -106,29 +124,86 @@ def get_conv_converse(model):
     return triu + triu.t()
 
 
-class AttributeEmbeddings(nn.Module):
-    """sg2im/attribute_embed.py:18-48 (lookup tables feeding the GCN; plain torch gathers)."""
+class _MultiEmbedFn(torch.autograd.Function):
+    """``torch.cat([att_emb_k(x[:, k]) for k], -1)`` (attribute_embed.py:38-45) without the concat pass: every
+    lookup writes its column slice of the ``[n, A*E]`` result (``csg_embed_fwd`` with ``ld_out = A*E``); the backward
+    reads the slices of the incoming gradient in place."""
 
-    def __init__(self, attributes, embedding_dim, use_attr_fc_gen=False):
+    @staticmethod
+    def forward(ctx, idx, out_dtype, *tables):
+        need_cuda(idx, *tables)
+        idx = idx.to(torch.int64).contiguous()
+        n, A = idx.shape
+        tabs = [t.detach() if (t.dtype == torch.float32 and t.is_contiguous()) else t.detach().float().contiguous()
+                for t in tables]
+        widths = [t.shape[1] for t in tabs]
+        W = sum(widths)
+        out = torch.empty((n, W), dtype=out_dtype, device=idx.device)
+        esz, col = out.element_size(), 0
+        for k, tab in enumerate(tabs):
+            V, E = tab.shape
+            rc = lib().csg_embed_fwd(ptr(tab), idx.data_ptr() + 8 * k, A, n, V, E, out.data_ptr() + col * esz, W,
+                                     int(out_dtype == torch.bfloat16), _stream())
+            _lib.check(rc, "csg_embed_fwd")
+            col += E
+        ctx.save_for_backward(idx)
+        ctx.shapes = [tuple(t.shape) for t in tabs]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        n, A = idx.shape
+        if dout.dtype not in (torch.float32, torch.bfloat16):
+            dout = dout.float()
+        if dout.stride(-1) != 1 or dout.stride(0) % 4 != 0 or dout.data_ptr() % 16 != 0:
+            dout = dout.contiguous()
+        L = lib()
+        esz, col, grads = dout.element_size(), 0, []
+        for k, (V, E) in enumerate(ctx.shapes):
+            dtable = torch.empty((V, E), dtype=torch.float32, device=dout.device)
+            ws = workspace(L.csg_embed_bwd_workspace(n, V, E), dout.device)
+            rc = L.csg_embed_bwd(dout.data_ptr() + col * esz, dout.stride(0) if n else E,
+                                 int(dout.dtype == torch.bfloat16), idx.data_ptr() + 8 * k, A, n, V, E, ptr(dtable),
+                                 ptr(ws), ws.numel(), _stream())
+            _lib.check(rc, "csg_embed_bwd")
+            grads.append(dtable)
+            col += E
+        return (None, None) + tuple(grads)
+
+
+class AttributeEmbeddings(nn.Module):
+    """sg2im/attribute_embed.py:18-48: one lookup table per attribute, the rows concatenated and (for more than
+    one attribute, or ``use_attr_fc_gen``) mixed by ``attribute_fc_gen``.  Lookups are ``csg_embed_fwd``, the
+    Linear runs on the csg2im GEMMs (``graph.linear``); parameter names equal the reference's."""
+
+    def __init__(self, attributes, embedding_dim, use_attr_fc_gen=False, precision="fp32"):
         super().__init__()
         num_attr = len(attributes)
         if num_attr > 1 or use_attr_fc_gen:
+            # parameter container only (weight / bias under the reference's names); never called as a module
             self.attribute_fc_gen = nn.Linear(num_attr * embedding_dim, num_attr * embedding_dim)
         for i, name in enumerate(list(attributes)):
             self.add_module("att_emb_%d" % i, nn.Embedding(max(attributes[name].values()) + 1, embedding_dim))
         self.num_attr = num_attr
+        self.precision = precision
 
     def forward(self, x, out_dtype=torch.float32):
         lead = x.shape[:-1]
         flat = x.reshape(-1, x.size(-1))
-        if not hasattr(self, "attribute_fc_gen") and flat.size(-1) == 1:
+        fc = getattr(self, "attribute_fc_gen", None)
+        if fc is None and flat.size(-1) == 1:
             # single attribute (COCO / VG): the rows go straight out in the GCN's operand type
             v = embedding_lookup(self._modules["att_emb_0"].weight, flat[:, 0], out_dtype)
             return v.view(*lead, -1)
-        vecs = [embedding_lookup(self._modules["att_emb_%d" % k].weight, flat[:, k]) for k in range(flat.size(-1))]
-        v = torch.cat(vecs, dim=-1)
-        if hasattr(self, "attribute_fc_gen"):
-            v = self.attribute_fc_gen(v)
+        tables = [self._modules["att_emb_%d" % k].weight for k in range(flat.size(-1))]
+        if fc is None:
+            return _MultiEmbedFn.apply(flat, out_dtype, *tables).view(*lead, -1)
+        bf16 = out_dtype == torch.bfloat16 and fc.weight.shape[0] % 64 == 0
+        v = _MultiEmbedFn.apply(flat, torch.bfloat16 if bf16 else torch.float32, *tables)
+        v = linear(v, fc.weight, fc.bias, "bf16" if bf16 else "fp32")
+        if v.dtype != out_dtype:
+            v = v.to(out_dtype)
         return v.view(*lead, -1)
 
 
@@ -141,7 +216,7 @@ class Sg2LayoutModel(nn.Module):
         self.precision = precision
         emb = args["embedding_dim"]
         self.attribute_embedding = AttributeEmbeddings(self.vocab["attributes"], emb)
-        num_preds = len(self.vocab["pred_idx_to_name"])
+        num_preds = self.num_preds = len(self.vocab["pred_idx_to_name"])
         self.pred_embeddings = nn.Embedding(num_preds, emb)
         num_attributes = len(self.vocab["attributes"].keys())
         init = args.get("learned_init", "uniform")
@@ -177,7 +252,7 @@ class Sg2LayoutModel(nn.Module):
         """Padded interface (model.py:90-124): objs [B,O,A] i64, triplets [B,T,3] i64, triplet_type [B,T] i64
         -> (obj_vecs [B,O,D], boxes_pred [B,O,4], None)."""
         B, O, T = objs.size(0), objs.size(1), triplets.size(1)
-        batch = TripleBatch.from_padded_triplets(triplets, triplet_type, self.padding_id, O)
+        batch = TripleBatch.from_padded_triplets(triplets, triplet_type, self.padding_id, O, self.num_preds)
         obj_vecs = self.attribute_embedding(objs, self._act_dtype()).reshape(B * O, -1)
         pred_vecs = embedding_lookup(self.pred_embeddings.weight, triplets.reshape(B * T, 3)[:, 1], self._act_dtype())
         obj_vecs, boxes = self._run(batch, obj_vecs, pred_vecs)
@@ -186,7 +261,8 @@ class Sg2LayoutModel(nn.Module):
     def forward_ragged(self, objs, triplets, triplet_type, tri_off, obj_off):
         """Flat interface: objs [NO,A], triplets [NT,3] (graph-local ids), triplet_type [NT], offsets [B+1] i32
         -> (obj_vecs [NO,D], boxes_pred [NO,4])."""
-        batch = TripleBatch.from_ragged(triplets, triplet_type, tri_off, obj_off, objs.size(0), self.padding_id)
+        batch = TripleBatch.from_ragged(triplets, triplet_type, tri_off, obj_off, objs.size(0), self.padding_id,
+                                        self.num_preds)
         obj_vecs = self.attribute_embedding(objs, self._act_dtype())
         pred_vecs = embedding_lookup(self.pred_embeddings.weight, triplets[:, 1], self._act_dtype())
         return self._run(batch, obj_vecs, pred_vecs)

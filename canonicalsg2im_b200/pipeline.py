@@ -1,10 +1,14 @@
 """One scene-graph -> layout training step on one GPU (the unit ``bench.py`` times):
 
     canonicalization (base_dataset.py:89-139)  ->  Sg2LayoutModel GCN stack + box_net (model.py:90-124)
-    ->  boxes_to_layout canvas (layout.py:12-45, generator.py:81-96)  ->  backward  ->  [grad all-reduce]  ->  Adam
+    ->  box loss (pix2pix_model.py:72-85)
+    generator-side attribute embedding of the objects + GT boxes  ->  boxes_to_layout canvas
+    (generator.py:16,80-96, layout.py:12-45)
+    ->  backward of both  ->  [grad all-reduce]  ->  Adam
 
-All heavy stages are csg2im kernels; torch provides memory, autograd bookkeeping, the tiny box loss and
-the optimizer update.
+As in the reference's training graph the canvas is composited from the GENERATOR's own ``AttributeEmbeddings``
+table (generator.py:16,80), not from the GCN output, so the canvas gradient reaches that table only; the GCN is
+trained by the box loss.  All stages are csg2im kernels; torch provides memory and autograd bookkeeping.
 """
 import numpy as np
 import torch
@@ -13,7 +17,7 @@ import torch.nn.functional as F
 from . import synth
 from .canonicalize import canon_count_async, canon_emit, converse_tables
 from .layout import layout_batched
-from .model import Sg2LayoutModel, get_conv_converse, masked_box_loss
+from .model import AttributeEmbeddings, Sg2LayoutModel, bbox_pred_loss_ragged, get_conv_converse
 from .optim import FusedAdam
 from .parallel import BucketedGradAllReduce
 
@@ -31,7 +35,7 @@ def build_opt(vocab: synth.Vocab, embedding_dim=128, gconv_dim=128, hidden_dim=5
 class HostBatch:
     """Flat host-side batch (pinned when CUDA is available): what a collate function would emit."""
 
-    def __init__(self, graphs, seed=0, pin=True):
+    def __init__(self, graphs, seed=0, pin=True, with_geometry=False, num_uniforms=None):
         self.B = len(graphs)
         self.tri_off = np.concatenate([[0], np.cumsum([len(g.triplets) for g in graphs])]).astype(np.int32)
         self.obj_off = np.concatenate([[0], np.cumsum([len(g.objs) for g in graphs])]).astype(np.int32)
@@ -41,8 +45,13 @@ class HostBatch:
             tri_off=self.tri_off, obj_off=self.obj_off,
             objs=np.concatenate([g.objs for g in graphs]).astype(np.int64),
             boxes=np.concatenate([g.boxes for g in graphs]).astype(np.float32),
-            uniforms=synth.det_uniform(int(self.tri_off[-1]), seed * 7919 + 13),
+            uniforms=synth.det_uniform(int(num_uniforms or self.tri_off[-1]), seed * 7919 + 13),
         )
+        if with_geometry:      # inputs of the on-device graph construction / mask compositor (cfg4)
+            arrs["centers"] = np.concatenate([np.concatenate([g.centers, np.zeros((len(g.boxes) - len(g.centers), 2),
+                                                                                  np.float32)]) for g in graphs])
+            if graphs[0].masks is not None:
+                arrs["masks"] = np.concatenate([g.masks for g in graphs]).astype(np.float32)
         self.t = {}
         for k, v in arrs.items():
             x = torch.from_numpy(np.ascontiguousarray(v))
@@ -60,7 +69,13 @@ class HostBatch:
 
 class SgToLayoutStep:
     def __init__(self, vocab, device, precision="fp32", H=64, W=64, learned_converse=True,
-                 learned_transitivity=True, lr=1e-4, seed=0, distributed=False):
+                 learned_transitivity=True, lr=1e-4, seed=0, distributed=False, bbox_pred_loss_weight=10.0,
+                 global_batch=None):
+        """``global_batch``: number of graphs of the GLOBAL batch this rank holds a shard of.  The box loss is a mean
+        over images (pix2pix_model.py:85), so with shards of unequal graph counts (cost-balanced sharding) every rank
+        scales its loss by B_local / B_global and the gradients are SUMMED over ranks: the result equals the
+        single-GPU gradient of the concatenated batch.  ``None``: every rank has the same number of graphs and the
+        gradients are averaged (the reference's DataParallel behaviour, meta_models.py:17)."""
         self.vocab, self.device, self.H, self.W = vocab, device, H, W
         self.flags = (learned_converse, learned_transitivity)
         self.model = Sg2LayoutModel(build_opt(vocab), precision=precision).to(device)
@@ -68,6 +83,13 @@ class SgToLayoutStep:
         for i in range(len(self.model.gconvs)):
             st["gconvs.%d.predicates_transitive_weights" % i] = st["trans_candidates_weights"]
         self.model.load_state_dict(st, strict=True)
+        # the generator's own object embedding (generator.py:16), the source of the canvas vectors (generator.py:80)
+        opt = build_opt(vocab)
+        self.layout_embedding = AttributeEmbeddings(opt.vocab["attributes"], opt.embedding_dim).to(device)
+        self.layout_embedding.load_state_dict(
+            {k: torch.from_numpy(v) for k, v in synth.make_layout_state(vocab, opt.embedding_dim, seed=seed).items()},
+            strict=True)
+        self.bbox_pred_loss_weight = bbox_pred_loss_weight
         self.refresh_tables()
         # gradient buckets in the order they complete: box_net, gconvs 4..0, then embeddings + shared weights
         layers = list(self.model.gconvs)
@@ -75,9 +97,12 @@ class SgToLayoutStep:
         for layer in reversed(layers):
             buckets.append([p for n, p in layer.named_parameters() if "predicates_transitive_weights" not in n])
         buckets.append(list(self.model.attribute_embedding.parameters()) + list(self.model.pred_embeddings.parameters())
-                       + [self.model.trans_candidates_weights])
-        self.reducer = BucketedGradAllReduce(buckets) if distributed else None
+                       + [self.model.trans_candidates_weights] + list(self.layout_embedding.parameters()))
+        self.global_batch = global_batch
+        self.reducer = BucketedGradAllReduce(buckets, average=global_batch is None) if distributed else None
+        self.tail_events = None      # set to [] to time the part of the all-reduce that trails the backward pass
         params = [p for p in self.model.parameters() if p is not self.model.converse_candidates_weights]
+        params += list(self.layout_embedding.parameters())
         self.opt = FusedAdam(params, lr=lr)                      # torch.optim.Adam arithmetic, one multi-tensor launch
 
     def refresh_tables(self):
@@ -103,25 +128,112 @@ class SgToLayoutStep:
     def forward(self, d, res):
         obj_vecs, boxes_pred = self.model.forward_ragged(d["objs"], res.triplets, res.triplet_type, res.tri_off,
                                                          d["obj_off"])
-        # canvas from GT boxes, as training does (train.py:358, generator.py:81-96); the __image__ dummy
-        # has box -1 and contributes exact zeros, so no object filtering pass is needed
-        canvas = layout_batched(obj_vecs, d["boxes"], d["obj_off"], self.H, self.W, max_objs_per_image=d["max_objs"])
-        loss = masked_box_loss(boxes_pred, d["boxes"])                   # pix2pix_model.py:72-85
+        # canvas: the generator's own embedding of the objects on the GT boxes (train.py:358, generator.py:80-96).
+        # remove_dummy_objects (utils.py:56-63) needs no filtering pass: the __image__ dummy has box -1 and
+        # contributes exact zeros to the canvas and receives an exactly zero gradient
+        layout_vecs = self.layout_embedding(d["objs"])
+        canvas = layout_batched(layout_vecs, d["boxes"], d["obj_off"], self.H, self.W,
+                                max_objs_per_image=d["max_objs"])
+        weight = self.bbox_pred_loss_weight
+        if self.global_batch is not None:
+            weight = weight * d["B"] / float(self.global_batch)
+        loss, _ = bbox_pred_loss_ragged(boxes_pred, d["boxes"], d["objs"], d["obj_off"], weight)   # pix2pix_model.py:72-85
         return canvas, loss
 
-    def step(self, d, canvas_grad, prefetch=None):
-        """One training step on batch ``d``.  ``prefetch``: the batch of the NEXT step (may be ``d`` itself); its
-        canonicalization counting pass is enqueued right behind this step's emit pass."""
+    def backward(self, d, canvas_grad, prefetch=None):
+        """Canonicalization + forward + backward (+ the gradient all-reduce): leaves the final gradients in ``.grad``."""
         res = self.canonicalize(d)
         if prefetch is not None:
             self.prefetch(prefetch)
         canvas, loss = self.forward(d, res)
         torch.autograd.backward([canvas, loss], [canvas_grad, None])
         if self.reducer is not None:
-            self.reducer.finish()
+            if self.tail_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self.reducer.finish()
+                e1.record()
+                self.tail_events.append((e0, e1))
+            else:
+                self.reducer.finish()
+        return loss, int(res.triplets.shape[0])
+
+    def step(self, d, canvas_grad, prefetch=None):
+        """One training step on batch ``d``.  ``prefetch``: the batch of the NEXT step (may be ``d`` itself); its
+        canonicalization counting pass is enqueued right behind this step's emit pass."""
+        loss, n_tri = self.backward(d, canvas_grad, prefetch)
         self.opt.step()
         if self.reducer is not None:
             self.reducer.zero()
         else:
             self.opt.zero_grad(set_to_none=True)
-        return loss.detach(), int(res.triplets.shape[0])
+        return loss.detach(), n_tri
+
+    def named_grads(self):
+        out = {"model." + n: p.grad for n, p in self.model.named_parameters() if p.grad is not None}
+        out.update({"layout_embedding." + n: p.grad for n, p in self.layout_embedding.named_parameters() if p.grad is not None})
+        return out
+
+
+class SgToLayoutInference:
+    """Forward-only scene graph -> layout canvas, the call path of ``scripts/generate_clevr.py:249-301``
+    (``model(objs, triplets, triplet_type, test_mode=True)``) with graph construction on the device:
+
+        add_location_triplets + add_dummy_triplets (base_dataset.py:35-87,141-150)  ->  add_learnt_triplets (:89-139)
+        ->  Sg2LayoutModel (model.py:90-124; 4 attributes -> attribute_fc_gen)  ->  generator-side embedding
+        (generator.py:16,80)  ->  masks_to_layout(test_mode=True) occlusion compositor on the PREDICTED boxes
+        (layout.py:48-77,135-147), dummy objects removed (utils.py:56-63)
+
+    ``step(d)`` expects the device tensors of :class:`HostBatch` plus ``centers [NO, 2]`` and ``masks [NO, M, M]``."""
+
+    def __init__(self, vocab, device, precision="bf16", H=256, W=256, embedding_dim=32, attr_sizes=None,
+                 learned_converse=True, learned_transitivity=True, seed=0):
+        import argparse
+        self.vocab, self.device, self.H, self.W = vocab, device, H, W
+        self.flags = (learned_converse, learned_transitivity)
+        A = vocab.num_attributes
+        sizes = attr_sizes or [vocab.num_obj_classes if A == 1 else 8] * A
+        attrs = {"a%d" % i: {str(j): j for j in range(sizes[i])} for i in range(A)}
+        opt = argparse.Namespace(
+            vocab={"attributes": attrs, "pred_idx_to_name": vocab.pred_names, "pred_name_to_idx": vocab.pred_ids},
+            embedding_dim=embedding_dim, gconv_dim=128, gconv_hidden_dim=512, gconv_pooling="avg", gconv_num_layers=5,
+            mlp_normalization="none", mask_size=0, learned_init="uniform")
+        self.model = Sg2LayoutModel(opt, precision=precision).to(device)
+        st = {k: torch.from_numpy(v) for k, v in
+              synth.make_state(vocab, embedding_dim=embedding_dim, seed=seed, attr_vocab_sizes=sizes).items()}
+        for i in range(len(self.model.gconvs)):
+            st["gconvs.%d.predicates_transitive_weights" % i] = st["trans_candidates_weights"]
+        self.model.load_state_dict(st, strict=True)
+        self.layout_embedding = AttributeEmbeddings(attrs, embedding_dim).to(device)
+        self.layout_embedding.load_state_dict(
+            {k: torch.from_numpy(v) for k, v in
+             synth.make_layout_state(vocab, embedding_dim, seed=seed, attr_vocab_sizes=sizes).items()}, strict=True)
+        Wc = get_conv_converse(self.model).detach().double().cpu().numpy()
+        cdf, vals = converse_tables(Wc, vocab.num_preds, vocab.meta_ids)
+        self.tables = (torch.from_numpy(cdf).to(device), torch.from_numpy(vals).to(device))
+
+    @torch.no_grad()
+    def build_graph(self, d):
+        """Location + dummy triplets on the device, then the WSGC completion."""
+        from .canonicalize import add_location_triplets_batched, add_learnt_triplets_batched
+        v = self.vocab
+        trip, tri_off = add_location_triplets_batched(d["boxes"], d["centers"], d["objs"], d["obj_off"], v.image_obj_id,
+                                                      v.pred_ids, max_objs_per_graph=d["max_objs"],
+                                                      in_image_pred=v.in_image_id)
+        if d["uniforms"].numel() < trip.shape[0]:
+            raise ValueError("need one converse draw per input triple (%d > %d)" % (trip.shape[0], d["uniforms"].numel()))
+        return add_learnt_triplets_batched(trip, tri_off, d["obj_off"], v.num_preds, v.meta_ids, None, self.flags[0],
+                                           self.flags[1], d["uniforms"], max_objs_per_graph=d["max_objs"],
+                                           tables=self.tables)
+
+    @torch.no_grad()
+    def step(self, d):
+        res = self.build_graph(d)
+        obj_vecs, boxes_pred = self.model.forward_ragged(d["objs"], res.triplets, res.triplet_type, res.tri_off,
+                                                         d["obj_off"])
+        # the __image__ dummy is removed from the canvas (utils.py:56-63): a box of -1 samples nothing
+        dummy = (d["objs"][:, :1] == 0)
+        boxes = torch.where(dummy, torch.full_like(boxes_pred, -1.0), boxes_pred.float())
+        canvas = layout_batched(self.layout_embedding(d["objs"]), boxes, d["obj_off"], self.H, self.W, masks=d["masks"],
+                                test_mode=True)
+        return canvas, boxes_pred, int(res.triplets.shape[0])

@@ -25,6 +25,8 @@ META_RELATIONS = ("__padding__", "__in_image__")
 AUGMENTED_RELATIONS = ("__below__", "__above__", "__left of__", "__right of__",
                        "__inside__", "__surrounding__")
 
+CLEVR_ATTR_SIZES = (4, 9, 3, 3)     # vocabulary sizes of CLEVR's shape / color / material / size (+ 0 = none)
+
 _M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
@@ -262,4 +264,21 @@ def make_state(vocab: Vocab, embedding_dim=128, gconv_dim=128, hidden_dim=512, n
         d_obj, d_pred = gconv_dim, gconv_dim
     lin("box_net.0", hidden_dim, gconv_dim)
     lin("box_net.2", 4, hidden_dim)
+    return st
+
+
+def make_layout_state(vocab: Vocab, embedding_dim=128, seed=0, attr_vocab_sizes=None):
+    """Random-init weights of the generator-side ``AttributeEmbeddings`` (``spade/models/networks/generator.py:16``),
+    the table the training canvas is composited from (``generator.py:80``), keyed like that module's state dict."""
+    st = {}
+    A = vocab.num_attributes
+    sizes = attr_vocab_sizes or [vocab.num_obj_classes if A == 1 else 8] * A
+    k = seed * 2003 + 501
+    for a in range(A):
+        k += 1
+        st["att_emb_%d.weight" % a] = det_tensor((sizes[a], embedding_dim), k, 1.0)
+    if A > 1:
+        n = A * embedding_dim
+        st["attribute_fc_gen.weight"] = det_tensor((n, n), k + 1, float(np.sqrt(6.0 / n)))
+        st["attribute_fc_gen.bias"] = det_tensor((n,), k + 2, float(1.0 / np.sqrt(n)))
     return st

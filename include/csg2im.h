@@ -36,6 +36,13 @@ void csg_clear_error(void);
 int csg_version(void);
 int csg_device_sms(void);
 long long csg_launch_count(void);   /* kernel-launch sites passed since the library was loaded */
+/* Asynchronous index errors: kernels that use caller-supplied integers as offsets (triple subject / object /
+ * predicate ids, embedding ids, canonicalization triplets) neutralise an out-of-range row and report it in a
+ * pinned host record instead of reading out of bounds; the reference raises IndexError on the same inputs
+ * (sg2im/graph.py:63-64,73,98-103, sg2im/model.py:108-109).  out4 (HOST, may be NULL) <- {code, row, value, limit};
+ * returns the code (0 none, 1 triple subject/object, 2 triple predicate, 3 embedding id, 4 canonicalization
+ * triplet) and clears the record.  Never synchronises: an error is visible once its kernel has run. */
+int csg_async_error_poll(int* out4);
 /* Live timing of kernel classes (measurement aid, off by default): while enabled, the instrumented entry points
  * record CUDA events on their stream.  csg_prof_collect fills a HOST array [8][3] = {work, seconds, calls} per
  * class (0 bf16 GEMMs: FLOP, 1 fp32 GEMMs: FLOP, 2 layout fwd: bytes, 3 layout bwd: bytes, 4 pooling: bytes,
@@ -90,16 +97,18 @@ int csg_crop_bbox_bwd(const float* dcrops, const float* bbox, const int* crop_of
 
 /* ---- triple graph convolution: sg2im/graph.py:44-113 ---------------------------------------- */
 int csg_offsets_uniform(int* off, int B, int stride, csg_stream_t stream);
-/* model.py:104-107 + graph.py:60-61: split int64 triplets, globalise indices, valid = (p != padding) */
+/* model.py:104-107 + graph.py:60-61: split int64 triplets, globalise indices, valid = (p != padding).
+ * Subject / object ids outside [0, n_g) and (when num_preds > 0) predicate ids outside [0, num_preds) -- where the
+ * reference raises IndexError -- neutralise the row and are reported through csg_async_error_poll. */
 int csg_triple_prep(const long long* triplets, const long long* triplet_type, const int* tri_off,
-                    const int* obj_off, int B, int NT, int T_pad, int O_pad, int padding_id,
+                    const int* obj_off, int B, int NT, int T_pad, int O_pad, int padding_id, int num_preds,
                     int* s_idx, int* o_idx, int* pred, int* type32, int* valid, csg_stream_t stream);
 /* same, from GraphTripleConv.forward's argument layout (graph.py:44): edges [NT,2], predicate ids,
  * pred_indicators (uint8/bool, may be NULL = all valid) */
 int csg_triple_prep_edges(const long long* edges, const long long* pred_ids, const unsigned char* indicators,
                           const long long* triplet_type, const int* tri_off, const int* obj_off, int B,
-                          int NT, int T_pad, int O_pad, int* s_idx, int* o_idx, int* pred, int* type32,
-                          int* valid, csg_stream_t stream);
+                          int NT, int T_pad, int O_pad, int num_preds, int* s_idx, int* o_idx, int* pred,
+                          int* type32, int* valid, csg_stream_t stream);
 /* stable CSR orderings by subject and by object (replace scatter_add, graph.py:98-103) */
 size_t csg_csr_workspace(int NO);
 int csg_csr_build(const int* keys_s, const int* keys_o, const int* tri_off, const int* obj_off, int B, int NT, int NO,
@@ -229,6 +238,16 @@ int csg_location_emit(const float* boxes, const float* centers, const long long*
                       const int* obj_off, int B, long long image_id, const int* pred_ids, int max_objs,
                       const int* out_off, long long* out_triplets, csg_stream_t stream);
 
+/* add_dummy_triplets (sg2im/data/base_dataset.py:141-150) on a flat batch: [i, __in_image__, image] for every object
+ * i != image of a graph that holds an __image__ object, in ascending i.  count: cnt[g] = n_g - 1 (or 0); pass it as
+ * cnt1 of csg_canon_offsets next to csg_location_count's cnt0, so that every graph's output range holds its location
+ * triplets followed by its dummy triplets; emit: rows written at out_off[g] + skip[g] (skip = the location counts). */
+int csg_dummy_triplets_count(const long long* objs, long long objs_stride, const int* obj_off, int B,
+                             long long image_id, int* cnt, csg_stream_t stream);
+int csg_dummy_triplets_emit(const long long* objs, long long objs_stride, const int* obj_off, int B,
+                            long long image_id, int in_image_pred, const int* out_off, const int* skip,
+                            long long* out_triplets, csg_stream_t stream);
+
 /* Narrow output head (box_net's Linear(H, 4), model.py:58-60) of the bf16 engine: y = h w^T + b forward; backward
  * writes dh = (h > 0) * (dy w) as bf16 (the first layer's ReLU folded in), dw = dy^T h and db = colsum(dy) in fp32,
  * deterministically.  h / dh bf16 with pitches ldh / lddh, nout <= 8. */
@@ -240,14 +259,19 @@ int csg_head_bwd(const float* dy, const void* h, int ldh, const float* w, int M,
 
 /* Multi-tensor Adam (torch.optim.Adam arithmetic, amsgrad off): updates `count` fp32 tensors in place in
  * ceil(count / 48) launches.  params / grads / exp_avg / exp_avg_sq / numel are HOST arrays (device pointers, element
- * counts); step >= 1 is the update index used for the bias corrections.  The reference's training loop
- * (scripts/train.py) calls torch.optim.Adam.step() at this point. */
+ * counts); steps[i] >= 1 (HOST) is tensor i's own update index used for its bias corrections (torch.optim.Adam keeps
+ * one step count per parameter).  The reference's training loop (scripts/train.py) calls torch.optim.Adam.step()
+ * at this point. */
 int csg_adam_multi(int count, void* const* params, const void* const* grads, void* const* exp_avg,
                    void* const* exp_avg_sq, const int* numel, double lr, double beta1, double beta2, double eps,
-                   double weight_decay, int step, csg_stream_t stream);
+                   double weight_decay, const int* steps, csg_stream_t stream);
 
-/* loss[0] = mean smooth-L1 over the coordinates of rows with gt >= 0; dpred [n, 4] = d loss / d pred */
-int csg_box_loss(const float* pred, const float* gt, int n, float* loss, float* dpred, csg_stream_t stream);
+/* Box term of the generator loss, sg2im/pix2pix_model.py:72-85, on a flat batch: loss_all[b] ("bbox_pred_all") =
+ * weight * sum over the real objects of image b of smooth_l1(pred - gt) / n_real(b); loss[0] ("bbox_pred") = mean_b;
+ * dpred [NO, 4] = d loss[0] / d pred.  objs [NO, A] int64: a row is real iff its id (A == 1) / the sum of its ids
+ * (A > 1) is non-zero.  An image without real objects yields NaN, as the reference's 0 / 0. */
+int csg_box_loss(const float* pred, const float* gt, const long long* objs, int A, const int* obj_off, int B,
+                 double weight, float* loss, float* loss_all, float* dpred, csg_stream_t stream);
 
 /* ---- canonicalization: sg2im/data/base_dataset.py:89-139, scripts/graphs_utils.py:15-155 ------ */
 /* pass 1: per-graph output sizes (cnt0 = type-0 edges, cnt1 = transitive edges; cnt0 = -1 flags a

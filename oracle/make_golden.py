@@ -47,6 +47,7 @@ sys.path.insert(0, ROOT)
 from canonicalsg2im_b200 import synth  # noqa: E402
 from oracle import canon as ocanon, graph as ograph, layout as olayout  # noqa: E402
 from tests import golden_inputs as gi  # noqa: E402
+from tests import baseline_cases as bc  # noqa: E402
 
 
 def t(x):
@@ -434,15 +435,180 @@ def gen_collate():
     np.savez_compressed(os.path.join(OUT, "collate.npz"), **out)
 
 
+def reference_canonicalize(bd, vocab, g, W, seed, conv=True, trans=True, dummies=True):
+    """The unmodified ``BaseDataset.add_learnt_triplets`` on one synthetic graph, with numpy's global RNG seeded the way
+    the oracle's explicit draws are (RandomState(seed).random_sample)."""
+    ds = bd.BaseDataset()
+    ds.vocab = {"pred_name_to_idx": dict(vocab.pred_ids), "pred_idx_to_name": list(vocab.pred_names),
+                "object_name_to_idx": {"__image__": vocab.image_obj_id},
+                "attributes": {"objects": {"__image__": vocab.image_obj_id}}}
+    ds.include_dummies = dummies
+    ds.learned_converse, ds.learned_transitivity = bool(conv), bool(trans)
+    ds.converse_candidates_weights = W
+    np.random.seed(seed)
+    r_trip, r_counts, r_type = ds.add_learnt_triplets([list(x) for x in g.triplets], len(g.objs))
+    uniforms = np.random.RandomState(seed).random_sample(len(g.triplets) * 2 + 8)
+    o_trip, o_counts, o_type, used = ocanon.add_learnt_triplets(g.triplets, vocab.num_preds, vocab.meta_ids, W,
+                                                                bool(conv), bool(trans), uniforms)
+    assert (o_trip == np.asarray(r_trip).astype(np.int64)).all() and (o_type == np.asarray(r_type)).all()
+    return np.asarray(r_trip).astype(np.int64), np.asarray(r_type).astype(np.int64), uniforms[:max(used, 1)]
+
+
+def reference_bbox_loss(boxes_pred, boxes, objs, weight=10.0):
+    """``Pix2PixModel.compute_generator_loss`` (pix2pix_model.py:65-143) of the unmodified reference with generation
+    switched off: only the box term runs."""
+    import sg2im.pix2pix_model as pm
+    me = types.SimpleNamespace(opt=argparse.Namespace(skip_graph_model=False, skip_generation=True,
+                                                      bbox_pred_loss_weight=weight))
+    batch = (None, objs, boxes, None, None, None, None, None)
+    out = pm.Pix2PixModel.compute_generator_loss(me, batch, (None, boxes_pred, None))
+    return out["bbox_pred"], out["bbox_pred_all"]
+
+
+def gen_box_loss():
+    """Box term of the generator loss on padded batches: single-attribute (VG / COCO) and 4-attribute (CLEVR) objects,
+    errors on both sides of the smooth-L1 knee."""
+    from oracle import step as ostep
+    out = {}
+    for ci, (A, B, O, seed) in enumerate([(1, 5, 9, 1), (4, 3, 12, 2), (1, 64, 31, 3)]):
+        objs = synth.det_int(B * O * A, seed * 11 + 1, 0 if A > 1 else 1, 7).reshape(B, O, A)
+        n_real = synth.det_int(B, seed * 11 + 2, 1, O - 1)
+        boxes = synth.det_tensor((B, O, 4), seed * 11 + 3, 0.5) + np.float32(0.5)
+        for b in range(B):
+            objs[b, n_real[b]:] = 0                      # __image__ dummy + collate padding are all-zero rows
+            boxes[b, n_real[b]:] = -1.0
+            if A > 1:
+                objs[b, :n_real[b], 0] = np.maximum(objs[b, :n_real[b], 0], 1)
+        pred = boxes + synth.det_tensor((B, O, 4), seed * 11 + 4, 2.0)
+        bp = t(pred).clone().requires_grad_(True)
+        loss, loss_all = reference_bbox_loss(bp, t(boxes), t(objs))
+        (3.0 * loss).backward()
+        o_loss, o_all = ostep.bbox_pred_loss(t(pred), t(boxes), t(objs))
+        assert torch.allclose(o_loss, loss.detach(), rtol=1e-6, atol=0) and torch.allclose(o_all, loss_all.detach(), rtol=1e-6, atol=0)
+        out["c%d_spec" % ci] = np.array([A, B, O, seed])
+        out["c%d_loss" % ci] = np.array(loss.item(), np.float64)
+        out["c%d_loss_all" % ci] = loss_all.detach().numpy()
+        out["c%d_dpred" % ci] = bp.grad.numpy()
+    out["num_cases"] = np.array(3)
+    np.savez_compressed(os.path.join(OUT, "box_loss.npz"), **out)
+    print("box loss fixtures:", len(out), "arrays")
+
+
+def _store_model_run(out, model, obj_vecs, boxes_pred, loss):
+    out.update(obj_vecs=obj_vecs.detach().numpy(), boxes_pred=boxes_pred.detach().numpy(), loss=np.array(loss.item()))
+    for name, prm in model.named_parameters():
+        if "predicates_transitive_weights" in name or prm.grad is None:
+            continue
+        gflat = prm.grad.numpy().reshape(-1)
+        if gflat.size <= 4096:
+            out["d_" + name] = prm.grad.numpy().copy()
+        else:
+            out["dsub_" + name] = gflat[::GRAD_STRIDE].copy()
+        out["dnorm_" + name] = np.array(np.linalg.norm(gflat.astype(np.float64)))
+
+
+def _gen_shape_model(bd, rmodel, case, fname):
+    vocab, graphs, W, seeds, st, opt = case
+    canon = []
+    for g, seed in zip(graphs, seeds):
+        tr, ty, _ = reference_canonicalize(bd, vocab, g, W, seed)
+        canon.append((tr, ty))
+    objs, boxes, trips, types_ = bc.pad_batch(vocab, graphs, canon)
+    model = rmodel.Sg2LayoutModel(opt)
+    missing = model.load_state_dict({k: t(v) for k, v in st.items()}, strict=False)
+    assert all("predicates_transitive_weights" in k for k in missing.missing_keys), missing
+    obj_vecs, boxes_pred, _ = model(t(objs), t(trips), t(types_))
+    bl, _ = reference_bbox_loss(boxes_pred, t(boxes), t(objs))
+    loss = bl + (obj_vecs * t(bc.obj_grad(obj_vecs.shape))).sum() * 1e-2
+    loss.backward()
+    out = dict(n_canon=np.array([len(tr) for tr, _ in canon]), types_sum=np.array(int(types_.sum())),
+               trip_hash=np.array(int((trips.astype(np.int64) * np.arange(1, trips.size + 1).reshape(trips.shape)).sum()
+                                      % (2 ** 61 - 1))))
+    _store_model_run(out, model, obj_vecs, boxes_pred, loss)
+    st_t = {k: t(v).clone() for k, v in st.items()}
+    o_vecs, o_boxes = ograph.sg2layout_forward(st_t, t(objs), t(trips), t(types_), vocab.padding_id)
+    assert torch.allclose(o_vecs, obj_vecs, rtol=1e-5, atol=1e-6) and torch.allclose(o_boxes, boxes_pred, rtol=1e-5, atol=1e-6)
+    np.savez_compressed(os.path.join(OUT, fname), **out)
+    print("%s: B=%d O=%d T=%d (real triples %s) loss=%.6f" % (fname, objs.shape[0], objs.shape[1], trips.shape[1],
+                                                               [len(tr) for tr, _ in canon], loss.item()))
+
+
+def gen_cfg2_model(bd, rmodel):
+    """BASELINE config 2 shapes through the UNMODIFIED reference: 8 VG-like graphs (3-30 objects, P = 50), canonicalized
+    by the reference's add_learnt_triplets (learned converse + transitive), padded by the reference's collate rule,
+    Sg2LayoutModel forward, box loss of compute_generator_loss + a seeded linear functional of obj_vecs, backward.
+    Inputs: tests/baseline_cases.py."""
+    _gen_shape_model(bd, rmodel, bc.cfg2_case(), "cfg2_model.npz")
+
+
+def gen_cfg4_model(bd, rmodel):
+    """BASELINE config 4 shapes through the UNMODIFIED reference: 2 CLEVR-like graphs of 32-64 objects with 4
+    attributes x embedding 32 (attribute_fc_gen in front of the GCN), closure-dense canonicalized triples."""
+    _gen_shape_model(bd, rmodel, bc.cfg4_case(), "cfg4_model.npz")
+
+
+def gen_cfg3_layout(rlayout):
+    """BASELINE config 3 / 4 canvas shapes through the UNMODIFIED reference: one 256 x 256 image, D = 128, 16 x 16 masks
+    (train path with gradient wrt vecs; test_mode occlusion path).  The 32 MiB canvases are stored subsampled
+    (every 8th row and column, which are also rows / columns of the SPADE pyramid levels)."""
+    vocab = synth.Vocab(0)
+    out = {}
+    g = synth.make_graph(777, 8, 8, vocab, include_dummies=False, mask_size=16)
+    vecs = synth.det_tensor((8, 128), 12, 1.0)
+    gsub = synth.det_tensor((1, 128, 32, 32), 13, 1.0)
+    v = t(vecs).clone().requires_grad_(True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        y = rlayout.masks_to_layout(v, t(g.boxes), t(g.masks), 256, 256)
+        yt = rlayout.masks_to_layout(t(vecs), t(g.boxes), t(g.masks), 256, 256, test_mode=True)
+        oy = olayout.masks_to_layout(t(vecs), t(g.boxes), t(g.masks), 256, 256)
+        oyt = olayout.masks_to_layout(t(vecs), t(g.boxes), t(g.masks), 256, 256, test_mode=True)
+    assert torch.equal(oy, y.detach()) and torch.equal(oyt, yt)
+    # upstream gradient: non-zero on the 8-strided lattice only, so the fixture stays small and regenerable
+    G = torch.zeros_like(y)
+    G[:, :, ::8, ::8] = t(gsub)
+    (y * G).sum().backward()
+    out.update(train_sub=y.detach()[:, :, ::8, ::8].numpy(), test_sub=yt[:, :, ::8, ::8].numpy(),
+               train_sum=np.array(y.detach().double().sum().item()), test_sum=np.array(yt.double().sum().item()),
+               train_abs=np.array(y.detach().double().abs().sum().item()), dvecs=v.grad.numpy())
+    np.savez_compressed(os.path.join(OUT, "cfg3_layout.npz"), **out)
+    print("cfg3 layout: canvas", tuple(y.shape))
+
+
+def gen_pyramid(rlayout):
+    """SPADE-side consumers of the canvas (spade/models/networks/generator.py:99, normalization.py:102): the nearest
+    resizes every SPADE block applies to the full-resolution canvas, for a 64 x 64 canvas of 3 images."""
+    import torch.nn.functional as F
+    vocab = synth.Vocab(0)
+    graphs = synth.make_graphs(3, 31, 2, 6, vocab, include_dummies=False)
+    canv = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i, g in enumerate(graphs):
+            canv.append(rlayout.boxes_to_layout(t(synth.det_tensor((len(g.boxes), 16), 50 + i, 1.0)), t(g.boxes), 64, 64))
+    seg = torch.cat(canv, 0)
+    out = {"seg": seg.numpy()}
+    out["head"] = F.interpolate(seg, size=(2, 2)).numpy()                              # generator.py:99 (sh, sw)
+    for s_ in (4, 8, 16, 32):
+        out["l%d" % s_] = F.interpolate(seg, size=(s_, s_), mode="nearest").numpy()    # normalization.py:102
+    np.savez_compressed(os.path.join(OUT, "pyramid.npz"), **out)
+
+
 def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="", help="comma-separated fixture names (default: all)")
+    only = [x for x in ap.parse_args().only.split(",") if x]
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
     gu, bd, rgraph, rmodel, rlayout, rbil = import_reference()
-    gen_canon(gu, bd)
-    gen_gconv(rgraph)
-    gen_model(rmodel)
-    gen_layout(rlayout, rbil)
-    gen_collate()
+    jobs = [("canon", lambda: gen_canon(gu, bd)), ("gconv_layer", lambda: gen_gconv(rgraph)),
+            ("sg2layout_model", lambda: gen_model(rmodel)), ("layout", lambda: gen_layout(rlayout, rbil)),
+            ("collate", gen_collate), ("box_loss", gen_box_loss), ("cfg2_model", lambda: gen_cfg2_model(bd, rmodel)),
+            ("cfg4_model", lambda: gen_cfg4_model(bd, rmodel)), ("cfg3_layout", lambda: gen_cfg3_layout(rlayout)),
+            ("pyramid", lambda: gen_pyramid(rlayout))]
+    for name, fn in jobs:
+        if not only or name in only:
+            fn()
     for f in sorted(os.listdir(OUT)):
         print("%-28s %8.1f KB" % (f, os.path.getsize(os.path.join(OUT, f)) / 1024))
 

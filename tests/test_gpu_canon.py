@@ -104,14 +104,15 @@ def _centers(g):
     return np.concatenate([g.centers, np.zeros((len(g.boxes) - n_real, 2), np.float32)]).astype(np.float32)
 
 
-def _gpu_location(graphs, vocab, max_objs=None):
+def _gpu_location(graphs, vocab, max_objs=None, dummies=False):
     from canonicalsg2im_b200 import canonicalize as C
     boxes = np.concatenate([g.boxes for g in graphs]).astype(np.float32)
     cen = np.concatenate([_centers(g) for g in graphs])
     objs = np.concatenate([g.objs for g in graphs]).astype(np.int64)
     off = np.concatenate([[0], np.cumsum([len(g.boxes) for g in graphs])]).astype(np.int32)
     trip, tri_off = C.add_location_triplets_batched(t(boxes), t(cen), t(objs), t(off), vocab.image_obj_id, vocab.pred_ids,
-                                                    max_objs_per_graph=max_objs)
+                                                    max_objs_per_graph=max_objs,
+                                                    in_image_pred=vocab.in_image_id if dummies else None)
     trip, tri_off = trip.cpu().numpy(), tri_off.cpu().numpy()
     return [trip[tri_off[i]:tri_off[i + 1]] for i in range(len(graphs))]
 
@@ -130,6 +131,25 @@ def test_location_triplets_golden(golden):
                                           include_dummies=len(g.boxes) > len(g.centers))
         got = np.concatenate([loc, np.array(dummy, dtype=np.int64).reshape(-1, 3)])
         assert (got == gd["c%d_base" % c]).all()
+        # add_dummy_triplets on the device as well (csg_dummy_triplets_*): the whole reference list in one call
+        both = _gpu_location([g], vocab, dummies=True)[0]
+        assert both.shape == gd["c%d_base" % c].shape and (both == gd["c%d_base" % c]).all()
+
+
+def test_location_and_dummy_triplets_batched():
+    """Ragged batch, graphs with and without the __image__ object: location triplets followed by the
+    [i, __in_image__, image] rows (base_dataset.py:141-150), graph by graph, against the oracle."""
+    from oracle import canon as ocanon
+    vocab = synth.Vocab(0)
+    graphs = [synth.make_graph(9100 + i, 1, 40, vocab, include_dummies=(i % 4 != 1), box_mode="clevr" if i % 2 else "coco")
+              for i in range(40)]
+    got = _gpu_location(graphs, vocab, dummies=True)
+    for g, trip in zip(graphs, got):
+        has_img = len(g.boxes) > len(g.centers)
+        ref = ocanon.add_location_triplets(g.boxes, _centers(g), g.objs[:, 0], vocab.image_obj_id, vocab.pred_ids)
+        ref = list(ref) + list(ocanon.add_dummy_triplets(g.objs[:, 0], vocab.image_obj_id, vocab.in_image_id, has_img))
+        ref = np.array(ref, dtype=np.int64).reshape(-1, 3)
+        assert trip.shape == ref.shape and (trip == ref).all()
 
 
 @pytest.mark.parametrize("n_min,n_max,mode", [(1, 4, "coco"), (3, 30, "coco"), (32, 64, "clevr"), (60, 100, "coco")])

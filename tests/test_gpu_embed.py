@@ -74,37 +74,51 @@ def test_embedding_bwd_large_bf16_tensor_core_path():
 
 
 def test_model_embeddings_match_torch_modules():
-    """AttributeEmbeddings with several attributes + attribute_fc_gen (CLEVR layout, attribute_embed.py:18-48)."""
+    """AttributeEmbeddings with several attributes + attribute_fc_gen (CLEVR layout, attribute_embed.py:18-48): lookups
+    (csg_embed_fwd writing column slices) and the Linear (csg_gemm_f32 / csg_gemm_bf16, no cuBLAS) against plain torch
+    ops on the CPU, forward and every gradient."""
     from canonicalsg2im_b200.model import AttributeEmbeddings
     attrs = {"shape": {"a": 0, "b": 1, "c": 2, "d": 3}, "color": {str(i): i for i in range(9)},
-             "size": {"s": 0, "l": 1, "x": 2}}
+             "size": {"s": 0, "l": 1, "x": 2}, "material": {"r": 0, "m": 1, "q": 2}}
     torch.manual_seed(0)
-    m = AttributeEmbeddings(attrs, 32).cuda()
-    x = torch.stack([torch.randint(0, 4, (6, 5)), torch.randint(0, 9, (6, 5)), torch.randint(0, 3, (6, 5))], -1).cuda()
-    y = m(x)
-    ref = torch.cat([F.embedding(x[..., k], m._modules["att_emb_%d" % k].weight) for k in range(3)], -1)
-    ref = m.attribute_fc_gen(ref)
-    assert y.shape == (6, 5, 96)
-    assert_close(y, ref, 1e-6, "attribute embeddings")
+    for emb, out_dtype, tol in ((32, torch.float32, 1e-5), (24, torch.float32, 1e-5), (32, torch.bfloat16, 1e-2)):
+        m = AttributeEmbeddings(attrs, emb).cuda()
+        x = torch.stack([torch.randint(0, 4, (6, 50)), torch.randint(0, 9, (6, 50)), torch.randint(0, 3, (6, 50)),
+                         torch.randint(0, 3, (6, 50))], -1).cuda()
+        y = m(x, out_dtype)
+        assert y.shape == (6, 50, 4 * emb) and y.dtype == out_dtype
+        gy = torch.randn(y.shape, device="cuda")
+        (y.float() * gy).sum().backward()
+        cpu = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.named_parameters()}
+        ref = torch.cat([F.embedding(x[..., k].cpu(), cpu["att_emb_%d.weight" % k]) for k in range(4)], -1)
+        ref = F.linear(ref, cpu["attribute_fc_gen.weight"], cpu["attribute_fc_gen.bias"])
+        (ref * gy.cpu()).sum().backward()
+        assert_close(y.float(), ref, tol, "attribute embeddings")
+        for k, v in m.named_parameters():
+            a, b_ = v.grad.double().cpu(), cpu[k].grad.double()
+            assert ((a - b_).norm() / b_.norm()).item() <= tol, k
 
 
-@pytest.mark.parametrize("n", [1, 9, 2349])
-def test_masked_box_loss(n):
-    from canonicalsg2im_b200.model import masked_box_loss
-    rng = np.random.RandomState(n)
-    gt = rng.rand(n, 4).astype(np.float32)
-    gt[::7] = -1.0                                     # __image__ dummies
-    pred = (gt + rng.randn(n, 4).astype(np.float32) * 1.5).astype(np.float32)
+@pytest.mark.parametrize("B,O", [(1, 3), (7, 9), (128, 31)])
+def test_bbox_pred_loss_vs_torch(B, O):
+    """csg_box_loss vs the reference formula (pix2pix_model.py:72-85) written with torch ops on the CPU."""
+    from canonicalsg2im_b200.model import bbox_pred_loss
+    rng = np.random.RandomState(B)
+    objs = rng.randint(1, 100, size=(B, O, 1))
+    gt = rng.rand(B, O, 4).astype(np.float32)
+    for b in range(B):
+        n = rng.randint(1, O)
+        objs[b, n:] = 0
+        gt[b, n:] = -1.0
+    pred = (gt + rng.randn(B, O, 4).astype(np.float32) * 1.5).astype(np.float32)
     p = t(pred).requires_grad_(True)
-    loss = masked_box_loss(p, t(gt))
+    loss, loss_all = bbox_pred_loss(p, t(gt), t(objs), weight=10.0)
     (3.0 * loss).backward()
     pc = torch.from_numpy(pred).requires_grad_(True)
-    g = torch.from_numpy(gt)
-    real = (g >= 0).all(-1)
-    if real.any():
-        ref = F.smooth_l1_loss(pc[real], g[real])
-        (3.0 * ref).backward()
-        assert_close(loss, ref, 1e-5, "loss")
-        assert_close(p.grad, pc.grad, 1e-5, "dpred")
-    else:
-        assert loss.item() == 0.0 and (p.grad == 0).all()
+    flat = F.smooth_l1_loss(pc.view(-1, 4), torch.from_numpy(gt).view(-1, 4), reduction="none") * 10.0
+    real = (torch.from_numpy(objs).view(-1, 1) != 0).float()
+    ref_all = (flat * real).view(B, O, 4).sum(dim=[1, 2]) / real.view(B, O).sum(dim=1)
+    (3.0 * ref_all.mean()).backward()
+    assert_close(loss, ref_all.mean(), 1e-5, "loss")
+    assert_close(loss_all, ref_all, 1e-5, "loss_all")
+    assert_close(p.grad, pc.grad, 1e-5, "dpred")

@@ -74,3 +74,47 @@ def test_crop_bbox(golden):
     assert torch.equal(c.detach(), t(g["crop_out"]))
     (c * t(gi.crop_out_grad(c.shape))).sum().backward()
     assert torch.allclose(im.grad, t(g["crop_dimgs"]), rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE-shaped fixtures (round 2): the oracle against outputs of the unmodified reference at cfg2 / cfg4 / cfg3 shapes
+# ------------------------------------------------------------------------------------------------
+def test_oracle_model_at_cfg2_and_cfg4_shapes(golden):
+    from tests import baseline_cases as bc, parity
+    for name, case in (("cfg2_model", bc.cfg2_case()), ("cfg4_model", bc.cfg4_case())):
+        out = parity.check_oracle_against_golden(parity.oracle_run(case), golden(name), gi.GRAD_STRIDE)
+        bad = {k: v for k, v in out.items() if v > 2e-5}
+        assert not bad and len(out) >= 47, (name, bad)
+
+
+def test_oracle_bbox_pred_loss(golden):
+    from canonicalsg2im_b200 import synth
+    from oracle import step as ostep
+    g = golden("box_loss")
+    for ci in range(int(g["num_cases"])):
+        A, B, O, seed = [int(x) for x in g["c%d_spec" % ci]]
+        objs = synth.det_int(B * O * A, seed * 11 + 1, 0 if A > 1 else 1, 7).reshape(B, O, A)
+        n_real = synth.det_int(B, seed * 11 + 2, 1, O - 1)
+        boxes = synth.det_tensor((B, O, 4), seed * 11 + 3, 0.5) + np.float32(0.5)
+        for b in range(B):
+            objs[b, n_real[b]:] = 0
+            boxes[b, n_real[b]:] = -1.0
+            if A > 1:
+                objs[b, :n_real[b], 0] = np.maximum(objs[b, :n_real[b], 0], 1)
+        pred = t(boxes + synth.det_tensor((B, O, 4), seed * 11 + 4, 2.0)).requires_grad_(True)
+        loss, loss_all = ostep.bbox_pred_loss(pred, t(boxes), t(objs))
+        (3.0 * loss).backward()
+        assert abs(loss.item() - float(g["c%d_loss" % ci])) <= 1e-6 * float(g["c%d_loss" % ci])
+        assert torch.allclose(loss_all, t(g["c%d_loss_all" % ci]), rtol=1e-6, atol=0)
+        assert torch.allclose(pred.grad, t(g["c%d_dpred" % ci]), rtol=1e-6, atol=1e-9)
+
+
+def test_oracle_layout_at_cfg3_shape(golden):
+    from canonicalsg2im_b200 import synth
+    g = golden("cfg3_layout")
+    gr = synth.make_graph(777, 8, 8, synth.Vocab(0), include_dummies=False, mask_size=16)
+    vecs = t(synth.det_tensor((8, 128), 12, 1.0))
+    y = olayout.masks_to_layout(vecs, t(gr.boxes), t(gr.masks), 256, 256)
+    yt = olayout.masks_to_layout(vecs, t(gr.boxes), t(gr.masks), 256, 256, test_mode=True)
+    assert torch.equal(y[:, :, ::8, ::8], t(g["train_sub"])) and torch.equal(yt[:, :, ::8, ::8], t(g["test_sub"]))
+    assert abs(y.double().sum().item() - float(g["train_sum"])) <= 1e-9 * float(g["train_abs"])   # summation order only
