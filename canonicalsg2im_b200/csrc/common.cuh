@@ -106,6 +106,49 @@ __device__ __forceinline__ float ordered_sum(const float* __restrict__ p, size_t
   return s;
 }
 
+// ---- 16-bit activation formats of the tensor-core engine: bf16 or fp16, chosen per tensor (fp16 carries the forward
+// activations / weights: 11 significant bits instead of 8 at the same tcgen05 kind::f16 rate; bf16 carries the
+// gradients, whose range fp16 cannot hold).  Eight packed values <-> floats.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+__device__ __forceinline__ void unpack8_16(const uint4& u, float (&f)[8], bool fp16) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  if (fp16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = x.x; f[2 * i + 1] = x.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+}
+__device__ __forceinline__ uint32_t pack2_16(float a, float b, bool fp16) {
+  if (fp16) {      // saturating: an activation beyond +-65504 must not become inf
+    __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 pack8_16(const float (&f)[8], bool fp16) {
+  uint4 u;
+  u.x = pack2_16(f[0], f[1], fp16); u.y = pack2_16(f[2], f[3], fp16);
+  u.z = pack2_16(f[4], f[5], fp16); u.w = pack2_16(f[6], f[7], fp16);
+  return u;
+}
+__device__ __forceinline__ unsigned short cvt16(float a, bool fp16) {
+  if (fp16) { __half h = __float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f)); return *reinterpret_cast<unsigned short*>(&h); }
+  __nv_bfloat16 h = __float2bfloat16_rn(a);
+  return *reinterpret_cast<unsigned short*>(&h);
+}
+// x > 0 for either format: sign bit clear and magnitude non-zero
+__device__ __forceinline__ bool pos16(uint32_t h) { return h != 0 && h < 0x8000u; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -40,11 +40,10 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
   const float* src = table + (size_t)v * E;
   for (int c = lane * 4; c < E; c += 128) {
     const float4 x = ld_f4(src + c);
-    if (out_bf16) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(x.x, x.y), b = __floats2bfloat162_rn(x.z, x.w);
+    if (out_bf16) {      // 1 = bf16, 2 = fp16
       uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&a);
-      u.y = *reinterpret_cast<uint32_t*>(&b);
+      u.x = pack2_16(x.x, x.y, out_bf16 == 2);
+      u.y = pack2_16(x.z, x.w, out_bf16 == 2);
       *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)r * ld_out + c) = u;
     } else {
       st_f4(reinterpret_cast<float*>(out) + (size_t)r * ld_out + c, x);

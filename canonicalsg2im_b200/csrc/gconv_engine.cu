@@ -22,11 +22,12 @@ namespace {
 
 struct Dims {
   int NT, NO, Din, Dp, H, Dout, Dpo, P;
+  int f16;     // 1: forward tensors (inputs, weights, hidden, net1 output, pooled, net2 hidden, output) are fp16; gradients stay bf16
   int K1() const { return 2 * Din + Dp; }
   int Wd() const { return 2 * H + Dpo; }
 };
 
-inline Dims read_dims(const int* d) { return Dims{d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7]}; }
+inline Dims read_dims(const int* d) { return Dims{d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8] ? 1 : 0}; }
 
 inline size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -110,7 +111,7 @@ __global__ void relu_mask_out_kernel(const void* __restrict__ dy, const __nv_bfl
   if (i >= n) return;
   const float v = DY_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[i])
                           : reinterpret_cast<const float*>(dy)[i];
-  out[i] = __float2bfloat16_rn(__bfloat162float(y[i]) > 0.f ? v : 0.f);
+  out[i] = __float2bfloat16_rn(pos16(reinterpret_cast<const unsigned short*>(y)[i]) ? v : 0.f);
 }
 
 #define CSG_TRY(call)            \
@@ -128,7 +129,7 @@ CSG_API size_t csg_gconv_bf16_out_offset(const int* dims, int need_bwd) {
 }
 CSG_API size_t csg_gconv_bf16_workspace(const int* dims) { return plan_work(read_dims(dims)).total; }
 
-// dims (HOST): {NT, NO, Din, Dp, H, Dout, Dpo, P}.  params (HOST array of 9 device pointers, fp32): w1 [H, 2Din+Dp],
+// dims (HOST int[9]): {NT, NO, Din, Dp, H, Dout, Dpo, P, fwd_fp16}.  params (HOST array of 9 device pointers, fp32): w1 [H, 2Din+Dp],
 // b1, w2 [2H+Dpo, H], b2, w3 [H, H], b3, w4 [Dout, H], b4, w_trans [P].  index (HOST array of 9 device pointers,
 // int32): s_idx, o_idx, pred_id, type32, valid [NT]; rowptr_s [NO+1], perm_s [NT], rowptr_o, perm_o.
 // obj [NO, Din] bf16 contiguous; pred [NT, Dp] bf16 with row pitch ldp; new_obj [NO, Dout] bf16 (written);
@@ -153,31 +154,32 @@ CSG_API int csg_gconv_bf16_fwd(const int* dims, const void* obj, const void* pre
   const int *rowptr_s = (const int*)index[5], *perm_s = (const int*)index[6], *rowptr_o = (const int*)index[7],
             *perm_o = (const int*)index[8];
   const int K1 = d.K1(), Wd = d.Wd();
-  // ---- bf16 copies of the weights (+ transposes for the dX-type GEMMs of backward), one launch
+  const int fmt = d.f16 ? 7 : 0;      // csg_gemm_bf16 formats: A, B and C of every forward GEMM are forward tensors
+  // ---- 16-bit copies of the weights (+ transposes for the dX-type GEMMs of backward), one launch
   {
     const void* src[8] = {w[0], w[1], w[2], w[3], w[0], w[1], w[2], w[3]};
     void* dst[8] = {sv + s.w1b, sv + s.w2b, sv + s.w3b, sv + s.w4b, sv + s.w1t, sv + s.w2t, sv + s.w3t, sv + s.w4t};
     const int rows[8] = {d.H, Wd, d.H, d.Dout, d.H, Wd, d.H, d.Dout};
     const int cols[8] = {K1, d.H, d.H, d.H, K1, d.H, d.H, d.H};
     const int tr[8] = {0, 0, 0, 0, 1, 1, 1, 1};
-    CSG_TRY(csg_cast_bf16_multi(need_bwd ? 8 : 4, src, dst, rows, cols, tr, stream));
+    CSG_TRY(csg_cast_bf16_multi(need_bwd ? 8 : 4, src, dst, rows, cols, tr, d.f16, stream));
   }
   float* conf = reinterpret_cast<float*>(sv + s.conf);
   CSG_TRY(csg_triple_conf(type32, pred_id, w_trans, d.NT, conf, stream));
   // ---- net1 on the gathered triple rows
   CSG_TRY(csg_gemm_bf16(0, 1, d.NT, d.H, K1, nullptr, 0, sv + s.w1b, K1, sv + s.hidden, d.H, 0, b[0], 1, nullptr, nullptr, 0,
-                        obj, pred, s_idx, o_idx, d.Din, d.Dp, ldp, d.NO, nullptr, 0, stream));
+                        obj, pred, s_idx, o_idx, d.Din, d.Dp, ldp, d.NO, fmt, nullptr, 0, stream));
   CSG_TRY(csg_gemm_bf16(0, 0, d.NT, Wd, d.H, sv + s.hidden, d.H, sv + s.w2b, d.H, sv + s.out, Wd, 0, b[1], 1, conf, nullptr, 0,
-                        nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, stream));
+                        nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, fmt, nullptr, 0, stream));
   // ---- confidence-weighted average onto objects
   CSG_TRY(csg_segpool_bf16(sv + s.out, Wd, 0, d.H + d.Dpo, d.H, rowptr_s, perm_s, rowptr_o, perm_o, valid, conf, d.NO,
                            reinterpret_cast<float*>(sv + s.pooled32), sv + s.pooled16, d.H,
-                           reinterpret_cast<float*>(sv + s.cnt), 1, stream));
+                           reinterpret_cast<float*>(sv + s.cnt), 1, d.f16, stream));
   // ---- net2
   CSG_TRY(csg_gemm_bf16(0, 0, d.NO, d.H, d.H, sv + s.pooled16, d.H, sv + s.w3b, d.H, sv + s.h2, d.H, 0, b[2], 1, nullptr,
-                        nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, stream));
+                        nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, fmt, nullptr, 0, stream));
   CSG_TRY(csg_gemm_bf16(0, 0, d.NO, d.Dout, d.H, sv + s.h2, d.H, sv + s.w4b, d.H, new_obj, d.Dout, 0, b[3], 1, nullptr,
-                        nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, stream));
+                        nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, fmt, nullptr, 0, stream));
   return 0;
 }
 
@@ -236,11 +238,14 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
   const void* pooled16 = sv + s.pooled16;
   const float* conf = reinterpret_cast<const float*>(sv + s.conf);
 
+  // every backward GEMM multiplies a gradient (A, bf16) with a forward tensor (B: activations, weights or the gathered
+  // triple input, fp16 when d.f16) and writes a gradient (bf16 / fp32)
+  const int bfmt = d.f16 ? 2 : 0;
 #define GEMM(mn, gather, M, N, K, A, lda, B, ldb, C, ldc, f32, mask, ldm)                                            \
   CSG_TRY(csg_gemm_bf16(mn, gather, M, N, K, A, lda, B, ldb, C, ldc, f32, nullptr, 0, nullptr, mask, ldm,            \
                         (gather) ? obj : nullptr, (gather) ? pred : nullptr, (gather) ? s_idx : nullptr,             \
                         (gather) ? o_idx : nullptr, (gather) ? d.Din : 0, (gather) ? d.Dp : 0, (gather) ? ldp : 0,   \
-                        (gather) ? NO : 0, splitk, w.splitk_bytes, stream))
+                        (gather) ? NO : 0, bfmt, splitk, w.splitk_bytes, stream))
 
   // ---- net2 backward (graph.py:110)
   const long long n4 = (long long)NO * Dout;
@@ -267,7 +272,7 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
   CSG_TRY(csg_pool_bwd_obj(dpooled, reinterpret_cast<const float*>(sv + s.pooled32),
                            reinterpret_cast<const float*>(sv + s.cnt), NO, H, dS, dcnt, stream));
   CSG_TRY(csg_triple_bwd_assemble_bf16(out, dS, d_new_p, d_new_p ? ld_dnewp : 0, dcnt, s_idx, o_idx, valid, type32, conf,
-                                       NT, H, d.Dpo, g, dconf, db2, small, w.small_bytes, stream));
+                                       NT, H, d.Dpo, g, dconf, db2, d.f16, small, w.small_bytes, stream));
   // ---- net1 backward (graph.py:63-67)
   GEMM(1, 0, Wd, H, NT, g, Wd, hidden, H, dw2, H, 1, nullptr, 0);
   GEMM(0, 0, NT, H, Wd, g, Wd, sv + s.w2t, Wd, dhid, H, 0, hidden, H);
@@ -278,7 +283,7 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
   // ---- gather backward: segmented sums of dX over ALL triples onto their subject / object rows
   CSG_TRY(csg_segpool_bf16(dX, K1, 0, d.Din + d.Dp, d.Din, rowptr_s, perm_s, rowptr_o, perm_o, nullptr, nullptr, NO,
                            dobj_bf16 ? nullptr : reinterpret_cast<float*>(dobj), dobj_bf16 ? dobj : nullptr, d.Din, nullptr,
-                           0, stream));
+                           0, 0, stream));
   // ---- confidence backward (graph.py:69-74)
   CSG_TRY(csg_conf_bwd(dconf, type32, pred_id, w_trans, NT, d.P, dwt, small, w.small_bytes, stream));
   return 0;

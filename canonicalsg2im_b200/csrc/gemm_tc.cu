@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -57,6 +58,7 @@ struct TcParams {
   const int* g_oidx;
   int g_din, g_dp, g_rows;
   int debug;                   // scratch/bench_gemm.py only: 1 = no operand loads, 2 = no MMAs, 4 = no epilogue work
+  int a_f16, b_f16, c_f16;     // operand / 16-bit output element formats: 0 = bf16, 1 = fp16 (kind::f16 takes both, per operand)
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -213,11 +215,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;
   return d;
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
-// a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A format [7,10), B format [10,13) (kind::f16:
+// 0 = fp16, 1 = bf16, chosen per operand), a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23),
+// M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn, bool a_f16 = false, bool b_f16 = false) {
+  return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((a_mn ? 1u : 0u) << 15) |
+         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 struct __align__(8) Barriers {
@@ -246,6 +249,12 @@ __host__ __device__ inline SmemPlan smem_plan(int BN, int b_rows, int stages, bo
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// 16-bit output pair in the requested format; fp16 saturates at +-65504 instead of producing inf
+__device__ __forceinline__ uint32_t pack16(float a, float b, bool f16) {
+  if (!f16) return pack_bf16(a, b);
+  __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
   return *reinterpret_cast<uint32_t*>(&h);
 }
 // bf16 > 0  <=>  sign bit clear and magnitude non-zero
@@ -481,7 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // the last n-tile may be narrower than BN: issue MMAs of its real width (N % 32 == 0 is required by the host
         // side; an MMA of N = 192 costs as much as N = 256, which is why BN is 256 with a narrow tail and not 192)
         const int mma_n = (!MN && CG == 1) ? min(BN, p.N - nt * BN) : BN;
-        const uint32_t idesc = make_idesc(BLOCK_M * CG, mma_n, MN, MN);
+        const uint32_t idesc = make_idesc(BLOCK_M * CG, mma_n, MN, MN, p.a_f16 != 0, p.b_f16 != 0);
         mbar_wait(smem_u32(&bars->tmem_empty[as]), aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
@@ -538,6 +547,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t row_off = (uint32_t)lane * 128;
       const int crow = lane >> 3, cpiece = lane & 7;           // coalesced layout: rows i*4 + crow, 16-byte piece cpiece
       __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
+      const bool cf16 = p.c_f16 != 0;
       auto load_mask = [&](uint4 (&ax)[8], int row0, int col) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -615,8 +625,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 const uint32_t off = row_off + ((((uint32_t)(h * 4 + j4)) << 4) ^ sw);
-                const uint32_t u0 = pack_bf16(v[j4 * 8], v[j4 * 8 + 1]), u1 = pack_bf16(v[j4 * 8 + 2], v[j4 * 8 + 3]);
-                const uint32_t u2 = pack_bf16(v[j4 * 8 + 4], v[j4 * 8 + 5]), u3 = pack_bf16(v[j4 * 8 + 6], v[j4 * 8 + 7]);
+                const uint32_t u0 = pack16(v[j4 * 8], v[j4 * 8 + 1], cf16), u1 = pack16(v[j4 * 8 + 2], v[j4 * 8 + 3], cf16);
+                const uint32_t u2 = pack16(v[j4 * 8 + 4], v[j4 * 8 + 5], cf16), u3 = pack16(v[j4 * 8 + 6], v[j4 * 8 + 7], cf16);
                 asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sC + off), "r"(u0), "r"(u1), "r"(u2), "r"(u3) : "memory");
               }
             }
@@ -706,8 +716,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 uint4 u;
-                u.x = pack_bf16(v[j], v[j + 1]); u.y = pack_bf16(v[j + 2], v[j + 3]);
-                u.z = pack_bf16(v[j + 4], v[j + 5]); u.w = pack_bf16(v[j + 6], v[j + 7]);
+                const bool cf16 = p.c_f16 != 0;
+                u.x = pack16(v[j], v[j + 1], cf16); u.y = pack16(v[j + 2], v[j + 3], cf16);
+                u.z = pack16(v[j + 4], v[j + 5], cf16); u.w = pack16(v[j + 6], v[j + 7], cf16);
                 *reinterpret_cast<uint4*>(dst + j) = u;
               }
             }
@@ -899,12 +910,14 @@ CSG_API size_t csg_gemm_bf16_workspace(int M, int N, int K, int mn_major) {
 // mn_major = 1:  C[M,N] = A[K,M]^T * B[K,N]             A, B row-major with M / N contiguous; fp32 output,
 //                K split over the persistent CTAs (workspace: csg_gemm_bf16_workspace bytes)
 //                gather = 2: B rows are the gathered triple input (N = 2*Din + Dp), B / ldb ignored
-// out_f32 selects fp32 or bf16 C.  bias [N] fp32, rowscale [M] fp32, mask_aux [M, ld_aux] bf16 may be null.
+// out_f32 selects fp32 or 16-bit C.  bias [N] fp32, rowscale [M] fp32, mask_aux [M, ld_aux] (16-bit, only its sign is
+// used) may be null.  formats: bit 0 = A (or the gathered rows of gather = 1) is fp16, bit 1 = B (or the gathered rows
+// of gather = 2) is fp16, bit 2 = the 16-bit C is written as fp16 (saturating); clear bits mean bf16.
 CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
                           const void* A, int lda, const void* B, int ldb, void* C, int ldc, int out_f32,
                           const float* bias, int relu, const float* rowscale, const void* mask_aux, int ld_aux,
                           const void* g_obj, const void* g_pred, const int* g_sidx, const int* g_oidx,
-                          int g_din, int g_dp, int g_ldp, int g_nobj,
+                          int g_din, int g_dp, int g_ldp, int g_nobj, int formats,
                           void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (M == 0 || N == 0) return 0;
   if (K == 0 && mn_major && out_f32 && M > 0 && N > 0) {      // empty reduction (no triples): the gradient is zero
@@ -923,6 +936,7 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
   p.mask_aux = reinterpret_cast<const __nv_bfloat16*>(mask_aux); p.ld_aux = ld_aux;
   p.g_sidx = g_sidx; p.g_oidx = g_oidx; p.g_din = g_din; p.g_dp = g_dp;
   p.g_rows = mn_major ? K : M;
+  p.a_f16 = formats & 1; p.b_f16 = (formats >> 1) & 1; p.c_f16 = (formats >> 2) & 1;
   { const char* dbg = getenv("CSG_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   if (gather) {
     CSG_REQUIRE(g_obj && g_pred && g_sidx && g_oidx && g_nobj > 0, "gemm_bf16: gather sources missing");

@@ -26,7 +26,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // dst[r, c] (or dst[c, r] when transpose) = bf16(src[r, c])
 __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, int ld_src,
-                                 __nv_bfloat16* __restrict__ dst, int ld_dst, int transpose) {
+                                 __nv_bfloat16* __restrict__ dst, int ld_dst, int transpose, bool fp16) {
   __shared__ float tile[32][33];
   int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -37,10 +37,10 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int co
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     if (!transpose) {
       int r = r0 + i, c = c0 + threadIdx.x;
-      if (r < rows && c < cols) dst[(size_t)r * ld_dst + c] = __float2bfloat16_rn(tile[i][threadIdx.x]);
+      if (r < rows && c < cols) reinterpret_cast<unsigned short*>(dst)[(size_t)r * ld_dst + c] = cvt16(tile[i][threadIdx.x], fp16);
     } else {
       int c = c0 + i, r = r0 + threadIdx.x;
-      if (r < rows && c < cols) dst[(size_t)c * ld_dst + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+      if (r < rows && c < cols) reinterpret_cast<unsigned short*>(dst)[(size_t)c * ld_dst + r] = cvt16(tile[threadIdx.x][i], fp16);
     }
   }
 }
@@ -55,7 +55,7 @@ struct CastJobs {
   int tile_end[CAST_MAX];      // exclusive prefix of 32x32 tiles
   int n;
 };
-__global__ void cast_bf16_multi_kernel(const CastJobs jobs) {
+__global__ void cast_bf16_multi_kernel(const CastJobs jobs, bool fp16) {
   CSG_PDL_WAIT();
   __shared__ float tile[32][33];
   int j = 0;
@@ -74,10 +74,10 @@ __global__ void cast_bf16_multi_kernel(const CastJobs jobs) {
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     if (!jobs.transpose[j]) {
       int r = r0 + i, c = c0 + threadIdx.x;
-      if (r < rows && c < cols) dst[(size_t)r * cols + c] = __float2bfloat16_rn(tile[i][threadIdx.x]);
+      if (r < rows && c < cols) reinterpret_cast<unsigned short*>(dst)[(size_t)r * cols + c] = cvt16(tile[i][threadIdx.x], fp16);
     } else {
       int c = c0 + i, r = r0 + threadIdx.x;
-      if (r < rows && c < cols) dst[(size_t)c * rows + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+      if (r < rows && c < cols) reinterpret_cast<unsigned short*>(dst)[(size_t)c * rows + r] = cvt16(tile[threadIdx.x][i], fp16);
     }
   }
 }
@@ -94,7 +94,7 @@ segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int
                     const int* __restrict__ rp_o, const int* __restrict__ perm_o,
                     const int* __restrict__ valid, const float* __restrict__ conf,
                     float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int ldo,
-                    float* __restrict__ cnt_out) {
+                    float* __restrict__ cnt_out, bool fp16) {
   CSG_PDL_WAIT();
   __shared__ float red[SP_MAX_THREADS * 8];
   __shared__ float red_cnt[SP_MAX_THREADS];
@@ -132,7 +132,7 @@ segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int
     for (int k = 0; k < 4; ++k) {
       if (v[k]) {
         float f[8];
-        unpack8(r[k], f);
+        unpack8_16(r[k], f, fp16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += f[i];
         cnt += w[k];
@@ -163,7 +163,7 @@ segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int
       st_f4(out_f32 + (size_t)o * ldo + c, make_float4(acc[0], acc[1], acc[2], acc[3]));
       st_f4(out_f32 + (size_t)o * ldo + c + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
     }
-    if (out_bf16) *reinterpret_cast<uint4*>(out_bf16 + (size_t)o * ldo + c) = pack8(acc);
+    if (out_bf16) *reinterpret_cast<uint4*>(out_bf16 + (size_t)o * ldo + c) = pack8_16(acc, fp16);
   }
   if (AVG && tx == 0) cnt_out[o] = cnt;
 }
@@ -171,7 +171,7 @@ segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int
 __global__ void relu_mask_bf16_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                       __nv_bfloat16* __restrict__ out, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __float2bfloat16_rn(__bfloat162float(y[i]) > 0.f ? dy[i] : 0.f);
+  if (i < n) out[i] = __float2bfloat16_rn(pos16(reinterpret_cast<const unsigned short*>(y)[i]) ? dy[i] : 0.f);
 }
 
 // column sums of a bf16 matrix (bias gradients), fp32 accumulation, ordered two-stage reduction.
@@ -263,7 +263,7 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
                                 const int* __restrict__ o_idx, const int* __restrict__ valid,
                                 const int* __restrict__ type32, const float* __restrict__ conf,
                                 int NT, int H, int Dp, __nv_bfloat16* __restrict__ g,
-                                float* __restrict__ dconf, float* __restrict__ cs_partial) {
+                                float* __restrict__ dconf, float* __restrict__ cs_partial, bool out_fp16) {
   CSG_PDL_WAIT();
   __shared__ __align__(16) float cs_red[CS ? (ASM_WARPS / 2) * ASM_MAXI * 256 : 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -316,7 +316,7 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
           for (int i = 0; i < 8; ++i) raw[i] = 0.f;
         }
         float y[8], r[8];
-        unpack8(__ldcs(reinterpret_cast<const uint4*>(orow + j)), y);
+        unpack8_16(__ldcs(reinterpret_cast<const uint4*>(orow + j)), y, out_fp16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           dot += raw[i] * y[i];
@@ -386,12 +386,12 @@ int asm_blocks(int NT) {
 
 }  // namespace
 
-CSG_API int csg_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, int transpose,
+CSG_API int csg_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, int transpose, int fp16,
                           cudaStream_t stream) {
   if (rows == 0 || cols == 0) return 0;
   dim3 grid(csg_div_up(cols, 32), csg_div_up(rows, 32));
   cast_bf16_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, rows, cols, ld_src, reinterpret_cast<__nv_bfloat16*>(dst),
-                                                     ld_dst, transpose);
+                                                     ld_dst, transpose, fp16 != 0);
   CSG_CHECK_LAUNCH("csg_cast_bf16");
   return 0;
 }
@@ -399,7 +399,7 @@ CSG_API int csg_cast_bf16(const float* src, int rows, int cols, int ld_src, void
 // n contiguous fp32 matrices src[i] [rows[i], cols[i]] -> contiguous bf16 dst[i] ([cols, rows] when transpose[i]).
 // The pointer / size arrays are HOST arrays of length n <= 16.
 CSG_API int csg_cast_bf16_multi(int n, const void* const* src, void* const* dst, const int* rows, const int* cols,
-                                const int* transpose, cudaStream_t stream) {
+                                const int* transpose, int fp16, cudaStream_t stream) {
   if (n == 0) return 0;
   CSG_REQUIRE(n > 0 && n <= CAST_MAX, "cast_bf16_multi: n=%d out of range", n);
   CastJobs jobs;
@@ -413,7 +413,7 @@ CSG_API int csg_cast_bf16_multi(int n, const void* const* src, void* const* dst,
     jobs.tile_end[i] = total;
   }
   if (total == 0) return 0;
-  CSG_CUDA(csg_launch_pdl(cast_bf16_multi_kernel, dim3(total), dim3(dim3(32, 8)), 0, stream, jobs));
+  CSG_CUDA(csg_launch_pdl(cast_bf16_multi_kernel, dim3(total), dim3(dim3(32, 8)), 0, stream, jobs, fp16 != 0));
   CSG_CHECK_LAUNCH("csg_cast_bf16_multi");
   return 0;
 }
@@ -421,7 +421,7 @@ CSG_API int csg_cast_bf16_multi(int n, const void* const* src, void* const* dst,
 CSG_API int csg_segpool_bf16(const void* X, int ldx, int col_s, int col_o, int W,
                              const int* rowptr_s, const int* perm_s, const int* rowptr_o, const int* perm_o,
                              const int* valid, const float* conf, int NO, float* out_f32, void* out_bf16, int ldo,
-                             float* cnt_out, int avg, cudaStream_t stream) {
+                             float* cnt_out, int avg, int fp16, cudaStream_t stream) {
   if (NO == 0) return 0;
   CSG_REQUIRE((W & 7) == 0 && (ldx & 7) == 0 && (col_s & 7) == 0 && (col_o & 7) == 0 && (ldo & 7) == 0,
               "segpool_bf16: widths/offsets must be multiples of 8");
@@ -436,10 +436,10 @@ CSG_API int csg_segpool_bf16(const void* X, int ldx, int col_s, int col_o, int W
   if (avg) {
     CSG_REQUIRE(valid && conf && cnt_out, "segpool_bf16(avg): valid/conf/cnt required");
     CSG_CUDA(csg_launch_pdl(segpool_bf16_kernel<true>, dim3(NO), dim3(threads), 0, stream, x, ldx, col_s, col_o, W, TX, TY, rowptr_s, perm_s, rowptr_o,
-                                                          perm_o, valid, conf, out_f32, ob, ldo, cnt_out));
+                                                          perm_o, valid, conf, out_f32, ob, ldo, cnt_out, fp16 != 0));
   } else {
     CSG_CUDA(csg_launch_pdl(segpool_bf16_kernel<false>, dim3(NO), dim3(threads), 0, stream, x, ldx, col_s, col_o, W, TX, TY, rowptr_s, perm_s, rowptr_o,
-                                                           perm_o, nullptr, nullptr, out_f32, ob, ldo, nullptr));
+                                                           perm_o, nullptr, nullptr, out_f32, ob, ldo, nullptr, fp16 != 0));
   }
   CSG_CHECK_LAUNCH("csg_segpool_bf16");
   return 0;
@@ -485,8 +485,8 @@ CSG_API size_t csg_triple_bwd_assemble_bf16_workspace(int NT, int H, int Dp) {
 CSG_API int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const void* d_newp, int ld_newp,
                                          const float* dcnt, const int* s_idx, const int* o_idx, const int* valid,
                                          const int* type32, const float* conf, int NT, int H, int Dp, void* g,
-                                         float* dconf, float* colsum_g, void* workspace, size_t workspace_bytes,
-                                         cudaStream_t stream) {
+                                         float* dconf, float* colsum_g, int out_fp16, void* workspace,
+                                         size_t workspace_bytes, cudaStream_t stream) {
   const int Wd = 2 * H + Dp;
   if (NT == 0) {
     if (colsum_g) CSG_CUDA(cudaMemsetAsync(colsum_g, 0, (size_t)Wd * sizeof(float), stream));
@@ -503,13 +503,13 @@ CSG_API int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const
                 "bwd_assemble_bf16: workspace too small");
     float* partial = reinterpret_cast<float*>(workspace);
     CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream, 
-        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, partial));
+        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, partial, out_fp16 != 0));
     CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16");
     CSG_CUDA(csg_launch_pdl(colsum_bf16_final_kernel, dim3(csg_div_up(Wd, 32)), dim3(256), 0, stream, partial, blocks, Wd, colsum_g));
     CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16 colsum");
   } else {
     CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<false>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream, 
-        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, nullptr));
+        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, (float*)nullptr, out_fp16 != 0));
     CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16");
   }
   return 0;

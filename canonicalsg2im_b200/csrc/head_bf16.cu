@@ -15,7 +15,7 @@ constexpr int HB_ROWS = 32;            // rows per block of the backward kernel
 
 __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ h, int ldh, const float* __restrict__ w,
                                                        const float* __restrict__ b, int M, int K, int NOUT,
-                                                       float* __restrict__ y) {
+                                                       float* __restrict__ y, bool h_fp16) {
   CSG_PDL_WAIT();
   extern __shared__ __align__(16) float ws[];          // [NOUT][K]
   for (int i = threadIdx.x; i < NOUT * K; i += blockDim.x) ws[i] = w[i];
@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
 #pragma unroll
     for (int j = 0; j < HEAD_MAX_OUT; ++j) acc[j] = 0.f;
     for (int k = lane * 2; k < K; k += 64) {
-      const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(h + (size_t)r * ldh + k));
+      const float2 x = h_fp16 ? __half22float2(*reinterpret_cast<const __half2*>(h + (size_t)r * ldh + k))
+                              : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(h + (size_t)r * ldh + k));
 #pragma unroll
       for (int j = 0; j < HEAD_MAX_OUT; ++j)
         if (j < NOUT) acc[j] = fmaf(x.y, ws[j * K + k + 1], fmaf(x.x, ws[j * K + k], acc[j]));
@@ -43,7 +44,8 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
 // thread = column k; a block walks HB_ROWS rows
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ h, int ldh,
                                                        const float* __restrict__ w, int M, int K, int NOUT,
-                                                       __nv_bfloat16* __restrict__ dh, int lddh, float* __restrict__ partial) {
+                                                       __nv_bfloat16* __restrict__ dh, int lddh, float* __restrict__ partial,
+                                                       bool h_fp16) {
   CSG_PDL_WAIT();
   __shared__ float sdy[HB_ROWS][HEAD_MAX_OUT];
   const int r0 = blockIdx.x * HB_ROWS, nr = min(HB_ROWS, M - r0);
@@ -61,7 +63,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       acc[j] = 0.f;
     }
     for (int r = 0; r < nr; ++r) {
-      const float hv = __bfloat162float(h[(size_t)(r0 + r) * ldh + k]);
+      const float hv = h_fp16 ? __half2float(reinterpret_cast<const __half*>(h)[(size_t)(r0 + r) * ldh + k])
+                              : __bfloat162float(h[(size_t)(r0 + r) * ldh + k]);
       float g = 0.f;
 #pragma unroll
       for (int j = 0; j < HEAD_MAX_OUT; ++j) {
@@ -95,7 +98,7 @@ __global__ void head_bwd_final_kernel(const float* __restrict__ partial, int blo
 }  // namespace
 
 CSG_API int csg_head_fwd(const void* h, int ldh, const float* w, const float* b, int M, int K, int nout, float* y,
-                         cudaStream_t stream) {
+                         int h_fp16, cudaStream_t stream) {
   if (M == 0) return 0;
   CSG_REQUIRE(nout >= 1 && nout <= HEAD_MAX_OUT && K > 0 && (K & 1) == 0 && (ldh & 1) == 0,
               "head_fwd: nout=%d must be in [1, 8], K=%d and ldh=%d even", nout, K, ldh);
@@ -103,7 +106,7 @@ CSG_API int csg_head_fwd(const void* h, int ldh, const float* w, const float* b,
   CSG_REQUIRE(smem <= 48 * 1024, "head_fwd: weight [%d, %d] does not fit shared memory", nout, K);
   int blocks = csg_div_up(M, 8);
   if (blocks > 4 * csg_num_sms()) blocks = 4 * csg_num_sms();
-  CSG_CUDA(csg_launch_pdl(head_fwd_kernel, dim3(blocks), dim3(256), smem, stream, reinterpret_cast<const __nv_bfloat16*>(h), ldh, w, b, M, K, nout, y));
+  CSG_CUDA(csg_launch_pdl(head_fwd_kernel, dim3(blocks), dim3(256), smem, stream, reinterpret_cast<const __nv_bfloat16*>(h), ldh, w, b, M, K, nout, y, h_fp16 != 0));
   CSG_CHECK_LAUNCH("csg_head_fwd");
   return 0;
 }
@@ -114,7 +117,7 @@ CSG_API size_t csg_head_bwd_workspace(int M, int K, int nout) {
 
 // dh [M, K] bf16 (pitch lddh), dw [nout, K] fp32, db [nout] fp32 are fully written.
 CSG_API int csg_head_bwd(const float* dy, const void* h, int ldh, const float* w, int M, int K, int nout, void* dh, int lddh,
-                         float* dw, float* db, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                         float* dw, float* db, int h_fp16, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   CSG_REQUIRE(nout >= 1 && nout <= HEAD_MAX_OUT && K > 0, "head_bwd: nout=%d must be in [1, 8]", nout);
   if (M == 0) {
     CSG_CUDA(cudaMemsetAsync(dw, 0, (size_t)nout * K * sizeof(float), stream));
@@ -125,7 +128,7 @@ CSG_API int csg_head_bwd(const float* dy, const void* h, int ldh, const float* w
   const int blocks = csg_div_up(M, HB_ROWS);
   float* partial = reinterpret_cast<float*>(workspace);
   CSG_CUDA(csg_launch_pdl(head_bwd_kernel, dim3(blocks), dim3(256), 0, stream, dy, reinterpret_cast<const __nv_bfloat16*>(h), ldh, w, M, K, nout,
-                                              reinterpret_cast<__nv_bfloat16*>(dh), lddh, partial));
+                                              reinterpret_cast<__nv_bfloat16*>(dh), lddh, partial, h_fp16 != 0));
   CSG_CHECK_LAUNCH("csg_head_bwd");
   const int cells = nout * K + HEAD_MAX_OUT;
   CSG_CUDA(csg_launch_pdl(head_bwd_final_kernel, dim3(csg_div_up(cells, 256)), dim3(256), 0, stream, partial, blocks, K, nout, dw, db));

@@ -26,7 +26,7 @@ def cast_bf16(w, transpose=False):
     w = f32c(w)
     rows, cols = w.shape
     out = torch.empty((cols, rows) if transpose else (rows, cols), dtype=BF, device=w.device)
-    _lib.check(lib().csg_cast_bf16(ptr(w), rows, cols, w.stride(0), ptr(out), out.stride(0), int(transpose), _stream()),
+    _lib.check(lib().csg_cast_bf16(ptr(w), rows, cols, w.stride(0), ptr(out), out.stride(0), int(transpose), 0, _stream()),
                "csg_cast_bf16")
     return out
 
@@ -41,7 +41,7 @@ def cast_bf16_multi(jobs):
     VP, IA = ctypes.c_void_p * n, ctypes.c_int * n
     rc = lib().csg_cast_bf16_multi(n, VP(*[w.data_ptr() for w in srcs]), VP(*[o.data_ptr() for o in outs]),
                                    IA(*[w.shape[0] for w in srcs]), IA(*[w.shape[1] for w in srcs]),
-                                   IA(*[int(tr) for _, tr in jobs]), _stream())
+                                   IA(*[int(tr) for _, tr in jobs]), 0, _stream())
     _lib.check(rc, "csg_cast_bf16_multi")
     return outs
 
@@ -64,7 +64,7 @@ def segpool_bf16(X, col_s, col_o, W, batch, conf=None, avg=True, want_f32=True, 
     cnt = torch.empty(batch.NO, dtype=torch.float32, device=dev) if avg else None
     rc = lib().csg_segpool_bf16(ptr(X), X.stride(0), col_s, col_o, W, ptr(batch.rowptr_s), ptr(batch.perm_s),
                                 ptr(batch.rowptr_o), ptr(batch.perm_o), ptr(batch.valid) if avg else 0,
-                                ptr(conf) if avg else 0, batch.NO, ptr(out32), ptr(out16), W, ptr(cnt), int(avg), _stream())
+                                ptr(conf) if avg else 0, batch.NO, ptr(out32), ptr(out16), W, ptr(cnt), int(avg), 0, _stream())
     _lib.check(rc, "csg_segpool_bf16")
     return out32, out16, cnt
 
@@ -149,7 +149,7 @@ class _TripleConvBF16(torch.autograd.Function):
         ws = workspace(L.csg_triple_bwd_assemble_bf16_workspace(NT, H, Dpo), dev)
         rc = L.csg_triple_bwd_assemble_bf16(ptr(out), ptr(dS), ptr(dnp), dnp.stride(0) if dnp is not None else 0,
                                             ptr(dcnt), ptr(batch.s_idx), ptr(batch.o_idx), ptr(batch.valid),
-                                            ptr(batch.type32), ptr(conf), NT, H, Dpo, ptr(g), ptr(dconf), ptr(db2),
+                                            ptr(batch.type32), ptr(conf), NT, H, Dpo, ptr(g), ptr(dconf), ptr(db2), 0,
                                             ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "csg_triple_bwd_assemble_bf16")
         # ---- net1 backward
@@ -206,7 +206,7 @@ class _TripleConvEngine(torch.autograd.Function):
             obj_b = obj_b.contiguous()
         params = [f32c(p.detach()) for p in (w1, b1, w2, b2, w3, b3, w4, b4, w_trans)]
         Dout, P = w4.shape[0], w_trans.numel()
-        dims = (ctypes.c_int * 8)(batch.NT, batch.NO, obj_b.shape[1], pred_b.shape[1], H, Dout, Dpo, P)
+        dims = (ctypes.c_int * 9)(batch.NT, batch.NO, obj_b.shape[1], pred_b.shape[1], H, Dout, Dpo, P, 0)
         need_bwd = int(any(ctx.needs_input_grad))
         nsaved = L.csg_gconv_bf16_saved_bytes(dims, need_bwd)
         saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
@@ -228,7 +228,7 @@ class _TripleConvEngine(torch.autograd.Function):
     def backward(ctx, d_obj_out, d_newp):
         obj, pred, saved, new_obj = ctx.saved_tensors
         batch, dims, params = ctx.batch, ctx.dims, ctx.params
-        NT, NO, Din, Dp, H, Dout, Dpo, P = list(dims)
+        NT, NO, Din, Dp, H, Dout, Dpo, P, _ = list(dims)
         K1, Wd = 2 * Din + Dp, 2 * H + Dpo
         dev = obj.device
         L = lib()
@@ -268,6 +268,17 @@ USE_ENGINE = os.environ.get("CSG_STAGED", "0") != "1"     # CSG_STAGED=1: one ct
 def triple_conv(batch, obj, pred, params, w_trans, hidden_dim, pred_out_dim, staged=None):
     din, dp = obj.shape[1], pred.shape[1]
     dout = params[6].shape[0]
+    if dp % 64 and not (din % 64 or hidden_dim % 64 or pred_out_dim % 64 or dout % 64):
+        # predicate rows narrower than one 128-byte operand chunk (CLEVR: embedding_dim 32, model.py:109 -> layer 0
+        # only): zero-pad them and the matching columns of net1.0.weight to the next multiple of 64 -- the products
+        # with the zero columns vanish, and autograd slices the gradients back (two tiny torch ops on [NT, 64] /
+        # [H, 2 Din + 64] outside the kernels' hot loop)
+        pad = (-dp) % 64
+        w1 = params[0]
+        pred = torch.nn.functional.pad(pred, (0, pad))
+        w1 = torch.cat([w1[:, :din + dp], w1.new_zeros((w1.shape[0], pad)), w1[:, din + dp:]], dim=1)
+        params = (w1,) + tuple(params[1:])
+        dp += pad
     if din % 64 or dp % 64 or hidden_dim % 64 or pred_out_dim % 64 or dout % 64:
         raise _lib.CsgError("precision='bf16' needs feature widths that are multiples of 64 "
                             "(got Din=%d Dp=%d H=%d Dout=%d Dp_out=%d); use precision='fp32'"
@@ -292,7 +303,7 @@ class _DenseMLP2BF16(torch.autograd.Function):
         h = ops.gemm_bf16(M, H, D, xb, casts[0], bias=f32c(b0), relu=True)
         y = torch.empty((M, nout), dtype=torch.float32, device=xb.device)
         w1c = f32c(w1.detach())
-        _lib.check(L.csg_head_fwd(ptr(h), h.stride(0), ptr(w1c), ptr(f32c(b1.detach())), M, H, nout, ptr(y), _stream()),
+        _lib.check(L.csg_head_fwd(ptr(h), h.stride(0), ptr(w1c), ptr(f32c(b1.detach())), M, H, nout, ptr(y), 0, _stream()),
                    "csg_head_fwd")
         ctx.save_for_backward(xb, h, w1c)
         ctx.w0t = casts[1] if need_bwd else None
@@ -312,7 +323,7 @@ class _DenseMLP2BF16(torch.autograd.Function):
         db1 = torch.empty(nout, dtype=torch.float32, device=dev)
         ws = workspace(L.csg_head_bwd_workspace(M, H, nout), dev)
         _lib.check(L.csg_head_bwd(ptr(dy), ptr(h), h.stride(0), ptr(w1c), M, H, nout, ptr(dh), dh.stride(0), ptr(dw1),
-                                  ptr(db1), ptr(ws), ws.numel(), _stream()), "csg_head_bwd")
+                                  ptr(db1), 0, ptr(ws), ws.numel(), _stream()), "csg_head_bwd")
         dw0 = ops.gemm_bf16(H, D, M, dh, xb, mn_major=True)
         db0 = colsum_bf16(dh)
         dx = ops.gemm_bf16(M, D, H, dh, ctx.w0t)

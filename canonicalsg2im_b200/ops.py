@@ -134,22 +134,32 @@ def relu_mask_f32(dy, y):
 
 
 # ---------------------------------------------------------------------------- GEMM family (bf16 tensor cores)
+F16, BF16 = torch.float16, torch.bfloat16
+
+
 def gemm_bf16(M, N, K, A, B, mn_major=False, out=None, out_f32=False, bias=None, relu=False, rowscale=None,
-              mask_aux=None, gather=None, gather_mode=0):
-    """tcgen05 GEMM.  mn_major=False: C = epi(A[M,K] @ B[N,K]^T); mn_major=True: C = A[K,M]^T @ B[K,N] (fp32 out)."""
+              mask_aux=None, gather=None, gather_mode=0, out_dtype=None):
+    """tcgen05 GEMM.  mn_major=False: C = epi(A[M,K] @ B[N,K]^T); mn_major=True: C = A[K,M]^T @ B[K,N] (fp32 out).
+    A and B (or the gathered operand) may independently be fp16 or bf16; a 16-bit C is bf16 unless ``out_dtype`` /
+    ``out`` says fp16."""
     dev = (A if A is not None else B).device
     if mn_major:
         out_f32 = True
     if out is None:
-        out = torch.empty((M, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=dev)
+        out = torch.empty((M, N), dtype=torch.float32 if out_f32 else (out_dtype or BF16), device=dev)
     need_cuda(A, B, out, bias, rowscale, mask_aux)
     for x in (A, B, mask_aux):
-        assert x is None or (x.dtype == torch.bfloat16 and x.stride(-1) == 1)
+        assert x is None or (x.dtype in (BF16, F16) and x.stride(-1) == 1)
+    g = gather
+    a_t = g.obj.dtype if (g is not None and gather_mode == 1) else A.dtype
+    b_t = g.obj.dtype if (g is not None and gather_mode == 2) else B.dtype
+    if g is not None:
+        assert g.obj.dtype == g.pred.dtype
+    formats = int(a_t == F16) | (int(b_t == F16) << 1) | (int(out.dtype == F16) << 2)
     L = lib()
     ws = None
     if mn_major:
         ws = workspace(L.csg_gemm_bf16_workspace(M, N, K, 1), dev)
-    g = gather
     timer = TIMERS.get("gemm")
     if timer is not None:
         e0, e1 = timer.events()
@@ -160,7 +170,7 @@ def gemm_bf16(M, N, K, A, B, mn_major=False, out=None, out_f32=False, bias=None,
         ptr(out), out.stride(0), int(out_f32),
         ptr(bias), int(relu), ptr(rowscale), ptr(mask_aux), (mask_aux.stride(0) if mask_aux is not None else 0),
         ptr(g.obj) if g else 0, ptr(g.pred) if g else 0, ptr(g.s_idx) if g else 0, ptr(g.o_idx) if g else 0,
-        g.din if g else 0, g.dp if g else 0, g.ldp if g else 0, g.obj.shape[0] if g else 0,
+        g.din if g else 0, g.dp if g else 0, g.ldp if g else 0, g.obj.shape[0] if g else 0, formats,
         ptr(ws), (ws.numel() if ws is not None else 0), _stream())
     _lib.check(rc, "csg_gemm_bf16")
     if timer is not None:

@@ -153,13 +153,18 @@ int csg_colsum_f32(const float* X, int M, int N, int ld, float* out, void* works
  * mn_major = 1: C[M,N] = A[K,M]^T B[K,N] (weight gradients, fp32 out, split-K); gather = 2 gathers B's rows.
  * The gathered operand is the virtual row [g_obj[g_sidx[t]] | g_pred[t] | g_obj[g_oidx[t]]] (graph.py:63-66);
  * g_obj is [g_nobj, g_din] contiguous, g_pred has row pitch g_ldp.  Object rows arrive by TMA tile::gather4.
- * A, B, mask_aux, g_obj, g_pred are bf16; bias, rowscale fp32; C is bf16 or (out_f32) fp32. */
+ * A, B, mask_aux, g_obj, g_pred are 16-bit floats; bias, rowscale fp32; C is 16-bit or (out_f32) fp32.
+ * formats selects the 16-bit element formats per operand (tcgen05 kind::f16 takes fp16 and bf16, independently for A
+ * and B): bit 0 = A (or the gathered rows when gather = 1) is fp16, bit 1 = B (or the gathered rows when gather = 2)
+ * is fp16, bit 2 = a 16-bit C is written as fp16 (saturating at +-65504); a clear bit means bf16.  The engine keeps
+ * FORWARD tensors (activations, weights) in fp16 -- 11 significant bits instead of bf16's 8 at the same tensor-pipe
+ * rate -- and GRADIENT tensors in bf16 (fp16 cannot hold their range).  mask_aux is only tested for > 0. */
 size_t csg_gemm_bf16_workspace(int M, int N, int K, int mn_major);
 int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
                   const void* A, int lda, const void* B, int ldb, void* C, int ldc, int out_f32,
                   const float* bias, int relu, const float* rowscale, const void* mask_aux, int ld_aux,
                   const void* g_obj, const void* g_pred, const int* g_sidx, const int* g_oidx,
-                  int g_din, int g_dp, int g_ldp, int g_nobj,
+                  int g_din, int g_dp, int g_ldp, int g_nobj, int formats,
                   void* workspace, size_t workspace_bytes, csg_stream_t stream);
 /* CTA-pair policy of the K-major GEMMs (tcgen05.mma.cta_group::2, 256 x N pair tiles, each CTA stages half of B):
  * -1 automatic (default: pairs once M >= 2 * 128 * #SMs and K >= 1024), 0 never, 1 whenever the shape allows.
@@ -167,15 +172,16 @@ int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
 void csg_gemm_bf16_set_pair_mode(int mode);
 
 /* bf16-activation twins of the pooling / assembly kernels (fp32 accumulation) + weight cast */
-int csg_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, int transpose,
+int csg_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, int transpose, int fp16,
                   csg_stream_t stream);
-/* n <= 16 contiguous fp32 matrices -> contiguous bf16 copies (transposed when transpose[i]); HOST arrays */
+/* n <= 16 contiguous fp32 matrices -> contiguous 16-bit copies (transposed when transpose[i]; fp16 when fp16, else
+ * bf16); HOST arrays */
 int csg_cast_bf16_multi(int n, const void* const* src, void* const* dst, const int* rows, const int* cols,
-                        const int* transpose, csg_stream_t stream);
+                        const int* transpose, int fp16, csg_stream_t stream);
 int csg_segpool_bf16(const void* X, int ldx, int col_s, int col_o, int W,
                      const int* rowptr_s, const int* perm_s, const int* rowptr_o, const int* perm_o,
                      const int* valid, const float* conf, int NO, float* out_f32, void* out_bf16, int ldo,
-                     float* cnt_out, int avg, csg_stream_t stream);
+                     float* cnt_out, int avg, int fp16, csg_stream_t stream);   /* fp16: X and out_bf16 hold fp16 */
 int csg_relu_mask_bf16(const float* dy, const void* y, void* out, long long n, csg_stream_t stream);
 size_t csg_colsum_bf16_workspace(int M, int N);
 int csg_colsum_bf16(const void* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
@@ -185,12 +191,14 @@ size_t csg_triple_bwd_assemble_bf16_workspace(int NT, int H, int Dp);
 int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const void* d_newp, int ld_newp,
                                  const float* dcnt, const int* s_idx, const int* o_idx, const int* valid,
                                  const int* type32, const float* conf, int NT, int H, int Dp, void* g,
-                                 float* dconf, float* colsum_g, void* workspace, size_t workspace_bytes,
-                                 csg_stream_t stream);
+                                 float* dconf, float* colsum_g, int out_fp16, void* workspace, size_t workspace_bytes,
+                                 csg_stream_t stream);   /* out_fp16: `out` holds fp16; d_newp and g are bf16 */
 
 /* ---- one GraphTripleConv layer (sg2im/graph.py:44-113) per call on the bf16 engine: the launch sequence of the
  *      stages above issued natively, out of caller-owned `saved` (activations kept for backward + bf16 weights)
- *      and `workspace` (scratch).  dims (HOST int[8]) = {NT, NO, Din, Dp, H, Dout, Dpo, P}; all widths % 64 == 0.
+ *      and `workspace` (scratch).  dims (HOST int[9]) = {NT, NO, Din, Dp, H, Dout, Dpo, P, fwd_fp16}; all widths % 64
+ *      == 0; fwd_fp16 = 1 keeps the forward tensors (obj, pred, weights, hidden, net1 output, pooled, net2 hidden,
+ *      new_obj) in fp16 instead of bf16 -- gradient tensors (d_new_obj, d_new_p, dX, dobj) are bf16 either way.
  *      params (HOST array of 9 device pointers, fp32): net1.0.weight [H, 2Din+Dp], net1.0.bias, net1.2.weight
  *      [2H+Dpo, H], net1.2.bias, net2.0.weight [H, H], net2.0.bias, net2.2.weight [Dout, H], net2.2.bias,
  *      predicates_transitive_weights [P].  index (HOST array of 9 device pointers, int32): s_idx, o_idx, pred_id,
@@ -215,7 +223,7 @@ int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pred, int l
 
 /* ---- embeddings + box loss around the GCN: sg2im/model.py:108-109, sg2im/attribute_embed.py:38-48,
  *      sg2im/pix2pix_model.py:72-85 --------------------------------------------------------------- */
-/* out[r, 0:E] = table[idx[r * idx_stride], :]  (out fp32 or bf16 rows with leading dimension ld_out) */
+/* out[r, 0:E] = table[idx[r * idx_stride], :]  (rows with leading dimension ld_out; out_bf16: 0 fp32, 1 bf16, 2 fp16) */
 int csg_embed_fwd(const float* table, const long long* idx, long long idx_stride, int n, int V, int E,
                   void* out, int ld_out, int out_bf16, csg_stream_t stream);
 size_t csg_embed_bwd_workspace(int n, int V, int E);
@@ -252,10 +260,10 @@ int csg_dummy_triplets_emit(const long long* objs, long long objs_stride, const 
  * writes dh = (h > 0) * (dy w) as bf16 (the first layer's ReLU folded in), dw = dy^T h and db = colsum(dy) in fp32,
  * deterministically.  h / dh bf16 with pitches ldh / lddh, nout <= 8. */
 int csg_head_fwd(const void* h, int ldh, const float* w, const float* b, int M, int K, int nout, float* y,
-                 csg_stream_t stream);
+                 int h_fp16, csg_stream_t stream);
 size_t csg_head_bwd_workspace(int M, int K, int nout);
 int csg_head_bwd(const float* dy, const void* h, int ldh, const float* w, int M, int K, int nout, void* dh, int lddh,
-                 float* dw, float* db, void* workspace, size_t workspace_bytes, csg_stream_t stream);
+                 float* dw, float* db, int h_fp16, void* workspace, size_t workspace_bytes, csg_stream_t stream);
 
 /* Multi-tensor Adam (torch.optim.Adam arithmetic, amsgrad off): updates `count` fp32 tensors in place in
  * ceil(count / 48) launches.  params / grads / exp_avg / exp_avg_sq / numel are HOST arrays (device pointers, element

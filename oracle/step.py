@@ -36,7 +36,7 @@ def bbox_pred_loss(boxes_pred, boxes, objs, weight=10.0):
     flat = F.smooth_l1_loss(boxes_pred.view(-1, 4), boxes.view(-1, 4), reduction='none') * weight
     fo = objs.view(-1, objs.size(-1))
     mask = (fo.sum(1, keepdim=True) != 0) if objs.size(-1) > 1 else (fo != 0)
-    real = mask.to(torch.float32)
+    real = mask.to(boxes_pred.dtype)
     per_image = (flat * real).view(boxes.shape).sum(dim=[1, 2]) / real.view(boxes.shape[0], boxes.shape[1]).sum(dim=1)
     return per_image.mean(), per_image
 

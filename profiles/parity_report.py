@@ -89,8 +89,15 @@ def main():
     rep = {"layer_fixture": layer_report(), "model_fixture": model_fixture_report()}
     for name, case in (("cfg2", bc.cfg2_case()), ("cfg4", bc.cfg4_case())):
         ref = parity.oracle_run(case)
+        ref64 = parity.oracle_run(case, torch.float64)
+        rep["%s_reference_fp32_vs_f64" % name] = parity.compare(ref64, ref)
         for prec in ("fp32", "bf16"):
-            rep["%s_%s" % (name, prec)] = parity.compare(ref, parity.cuda_run(case, ref, prec))
+            try:
+                got = parity.cuda_run(case, ref, prec)
+                rep["%s_%s" % (name, prec)] = parity.compare(ref, got)
+                rep["%s_%s_vs_f64" % (name, prec)] = parity.compare(ref64, got)
+            except Exception as ex:
+                print("FAILED", name, prec, repr(ex)[:300])
     for k, tab in rep.items():
         if k in ("layer_fixture", "model_fixture"):
             for prec, tb in tab.items():

@@ -19,9 +19,11 @@ def errs(a, b):
             "l2": d.norm().item() / max(b.norm().item(), 1e-30)}
 
 
-def oracle_run(case):
+def oracle_run(case, dtype=torch.float32):
     """Canonicalize with the oracle (pinned to the reference's add_learnt_triplets by make_golden), pad like the
-    reference collate, run the oracle model fwd + (box loss + linear functional) bwd.  Returns inputs and results."""
+    reference collate, run the oracle model fwd + (box loss + linear functional) bwd.  Returns inputs and results.
+    ``dtype=torch.float64`` evaluates the same graph in double precision: the yardstick that separates kernel error
+    from the fp32 rounding noise of the reference itself (see tests/test_gpu_baseline_shapes.py)."""
     from oracle import canon as ocanon, graph as ograph, step as ostep
     vocab, graphs, W, seeds, st, opt = case
     canon = []
@@ -30,11 +32,12 @@ def oracle_run(case):
                                                   bc.canon_uniforms(g, seed))
         canon.append((tr, ty))
     objs, boxes, trips, types = bc.pad_batch(vocab, graphs, canon)
-    state = {k: torch.from_numpy(v).clone().requires_grad_(k != "converse_candidates_weights") for k, v in st.items()}
+    state = {k: torch.from_numpy(v).to(dtype).clone().requires_grad_(k != "converse_candidates_weights")
+             for k, v in st.items()}
     T = lambda x: torch.from_numpy(np.ascontiguousarray(x))
     obj_vecs, boxes_pred = ograph.sg2layout_forward(state, T(objs), T(trips), T(types), vocab.padding_id)
-    bl, _ = ostep.bbox_pred_loss(boxes_pred, T(boxes), T(objs))
-    loss = bl + (obj_vecs * T(bc.obj_grad(obj_vecs.shape))).sum() * 1e-2
+    bl, _ = ostep.bbox_pred_loss(boxes_pred, T(boxes).to(dtype), T(objs))
+    loss = bl + (obj_vecs * T(bc.obj_grad(obj_vecs.shape)).to(dtype)).sum() * 1e-2
     loss.backward()
     grads = {k: v.grad for k, v in state.items() if v.grad is not None}
     return dict(objs=objs, boxes=boxes, trips=trips, types=types, canon=canon, obj_vecs=obj_vecs.detach(),
