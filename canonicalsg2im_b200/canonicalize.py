@@ -113,16 +113,28 @@ def canon_count_async(triplets, tri_off, obj_off, num_rel, meta_ids, conv_weight
     return CanonPlan(args, keep, B, out_off, conv_counts, summary_host, event, max_objs_per_graph)
 
 
-def canon_emit(plan):
-    """Second half: waits (on the host) for the sizes of ``plan`` -- already there when the plan was launched a step
-    ahead --, allocates the output and launches ``csg_canon_emit``.  Returns a :class:`CanonResult`."""
+def canon_total(plan):
+    """Number of output triples of ``plan`` (waits on the host for the counting pass)."""
     plan.event.synchronize()                   # sizes the output allocation (the one host wait per batch)
     total, min_cnt0 = plan.summary_host.tolist()
     if plan.B and min_cnt0 < 0:
         raise _lib.CsgError("canonicalize: a graph has more objects than max_objs_per_graph=%d" % plan.max_objs)
+    return total
+
+
+def canon_emit(plan, out=None):
+    """Second half: waits (on the host) for the sizes of ``plan`` -- already there when the plan was launched a step
+    ahead --, allocates the output (or uses ``out = (triplets [>= total, 3], types [>= total])`` int64 buffers) and
+    launches ``csg_canon_emit``.  Returns a :class:`CanonResult`."""
+    total = canon_total(plan)
     dev = plan.out_off.device
-    out_t = torch.empty((max(total, 1), 3), dtype=torch.int64, device=dev)
-    out_ty = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+    if out is not None:
+        out_t, out_ty = out
+        if out_t.shape[0] < total or out_ty.shape[0] < total or out_t.dtype != torch.int64 or not out_t.is_contiguous():
+            raise ValueError("canon_emit: `out` buffers must be contiguous int64 with at least %d rows" % total)
+    else:
+        out_t = torch.empty((max(total, 1), 3), dtype=torch.int64, device=dev)
+        out_ty = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
     _lib.check(lib().csg_canon_emit(*plan.args, ptr(plan.out_off), ptr(out_t), ptr(out_ty), _stream()), "csg_canon_emit")
     return CanonResult(out_t[:total], out_ty[:total], plan.out_off, plan.conv_counts[:plan.B])
 

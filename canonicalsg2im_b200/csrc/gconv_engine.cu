@@ -15,6 +15,7 @@
 //   backward  net2 dW/db/dX -> pooling backward -> assemble d(net1 pre-activation) (+ db2, dconf) -> dW2, dhidden,
 //             dW1 (re-gathers its operand), db1, dX -> segmented sums of dX onto objects -> d w_trans
 #include "common.cuh"
+#include "internal.h"
 #include "csg2im.h"
 #include <cuda_bf16.h>
 
@@ -56,8 +57,13 @@ Saved plan_saved(const Dims& d, bool need_bwd) {
 }
 
 // ---- layout of the backward workspace
+// Every producer of partial sums owns its region: the final passes of a layer run together in ONE launch at the end
+// of the layer's backward (csg_reduce_multi), so no partial buffer may be reused before that.
 struct Work {
-  size_t g4, dh2, dpooled, dS, dcnt, g, dconf, dhid, splitk, small, splitk_bytes, small_bytes, total;
+  size_t g4, dh2, dpooled, dS, dcnt, g, dhid, total;
+  size_t sk[4], sk_bytes[4];     // split-K partials of dw4, dw3, dw2, dw1
+  size_t cs[3], cs_bytes[3];     // column-sum partials of db4, db3, db1
+  size_t asm_ws, asm_bytes;      // assemble: column sums of g (db2) + per-predicate confidence-gradient bins (d w_trans)
 };
 Work plan_work(const Dims& d) {
   Work w;
@@ -70,21 +76,19 @@ Work plan_work(const Dims& d) {
   w.dS = take((size_t)d.NO * d.H * 4);
   w.dcnt = take((size_t)d.NO * 4);
   w.g = take((size_t)d.NT * d.Wd() * 2);
-  w.dconf = take((size_t)(d.NT > 0 ? d.NT : 1) * 4);
   w.dhid = take((size_t)d.NT * d.H * 2);
-  size_t sk = csg_gemm_bf16_workspace(d.Dout, d.H, d.NO, 1);
-  sk = mx(sk, csg_gemm_bf16_workspace(d.H, d.H, d.NO, 1));
-  sk = mx(sk, csg_gemm_bf16_workspace(d.Wd(), d.H, d.NT, 1));
-  sk = mx(sk, csg_gemm_bf16_workspace(d.H, d.K1(), d.NT, 1));
-  w.splitk_bytes = sk;
-  w.splitk = take(sk);
-  size_t sm = csg_colsum_bf16_workspace(d.NO, d.Dout);
-  sm = mx(sm, csg_colsum_bf16_workspace(d.NO, d.H));
-  sm = mx(sm, csg_colsum_bf16_workspace(d.NT, d.H));
-  sm = mx(sm, csg_triple_bwd_assemble_bf16_workspace(d.NT, d.H, d.Dpo));
-  sm = mx(sm, csg_conf_bwd_workspace(d.P));
-  w.small_bytes = sm;
-  w.small = take(sm);
+  (void)mx;
+  w.sk_bytes[0] = csg_gemm_bf16_workspace(d.Dout, d.H, d.NO, 1);
+  w.sk_bytes[1] = csg_gemm_bf16_workspace(d.H, d.H, d.NO, 1);
+  w.sk_bytes[2] = csg_gemm_bf16_workspace(d.Wd(), d.H, d.NT, 1);
+  w.sk_bytes[3] = csg_gemm_bf16_workspace(d.H, d.K1(), d.NT, 1);
+  for (int i = 0; i < 4; ++i) w.sk[i] = take(w.sk_bytes[i]);
+  w.cs_bytes[0] = csg_colsum_bf16_workspace(d.NO, d.Dout);
+  w.cs_bytes[1] = csg_colsum_bf16_workspace(d.NO, d.H);
+  w.cs_bytes[2] = csg_colsum_bf16_workspace(d.NT, d.H);
+  for (int i = 0; i < 3; ++i) w.cs[i] = take(w.cs_bytes[i]);
+  w.asm_bytes = csg_triple_bwd_assemble_bf16_deferred_workspace(d.NT, d.H, d.Dpo, d.P);
+  w.asm_ws = take(w.asm_bytes);
   w.total = o + 256;
   return w;
 }
@@ -194,6 +198,10 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
                                float* dparams, void* workspace, size_t workspace_bytes, csg_stream_t stream) {
   const Dims d = read_dims(dims);
   CSG_TRY(check_dims(d));
+  // tcgen05.mma kind::f16 takes ONE 16-bit format for both operands (a mixed fp16 x bf16 instruction descriptor raises
+  // "illegal instruction" on sm_100a: scratch/probe_mixed_mma.py), gradients need bf16's range, and every backward GEMM
+  // multiplies a gradient with a forward tensor: fp16 forward tensors are therefore inference-only
+  CSG_REQUIRE(!d.f16, "gconv_bf16_bwd: fp16 forward tensors (dims[8] = 1) are inference-only");
   const Saved s = plan_saved(d, true);
   const Work w = plan_work(d);
   CSG_REQUIRE(saved && (reinterpret_cast<uintptr_t>(saved) & 255) == 0, "gconv_bf16_bwd: `saved` must be 256-byte aligned");
@@ -228,24 +236,25 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
   float* dS = reinterpret_cast<float*>(ws + w.dS);
   float* dcnt = reinterpret_cast<float*>(ws + w.dcnt);
   void* g = ws + w.g;
-  float* dconf = reinterpret_cast<float*>(ws + w.dconf);
   void* dhid = ws + w.dhid;
-  void* splitk = ws + w.splitk;
-  void* small = ws + w.small;
   const void* hidden = sv + s.hidden;
   const void* out = sv + s.out;
   const void* h2 = sv + s.h2;
   const void* pooled16 = sv + s.pooled16;
   const float* conf = reinterpret_cast<const float*>(sv + s.conf);
+  CsgReduceJob jobs[CSG_REDUCE_MAX_JOBS];
+  int njobs = 0;
 
   // every backward GEMM multiplies a gradient (A, bf16) with a forward tensor (B: activations, weights or the gathered
-  // triple input, fp16 when d.f16) and writes a gradient (bf16 / fp32)
-  const int bfmt = d.f16 ? 2 : 0;
-#define GEMM(mn, gather, M, N, K, A, lda, B, ldb, C, ldc, f32, mask, ldm)                                            \
-  CSG_TRY(csg_gemm_bf16(mn, gather, M, N, K, A, lda, B, ldb, C, ldc, f32, nullptr, 0, nullptr, mask, ldm,            \
-                        (gather) ? obj : nullptr, (gather) ? pred : nullptr, (gather) ? s_idx : nullptr,             \
-                        (gather) ? o_idx : nullptr, (gather) ? d.Din : 0, (gather) ? d.Dp : 0, (gather) ? ldp : 0,   \
-                        (gather) ? NO : 0, bfmt, splitk, w.splitk_bytes, stream))
+  // triple input) and writes a gradient (bf16 / fp32); split-K final passes are deferred to the end of the layer
+  const int bfmt = 0;
+#define GEMM(mn, gather, M, N, K, A, lda, B, ldb, C, ldc, f32, mask, ldm, SK)                                         \
+  CSG_TRY(csg_gemm_bf16_deferred(mn, gather, M, N, K, A, lda, B, ldb, C, ldc, f32, nullptr, 0, nullptr, mask, ldm,     \
+                                 (gather) ? obj : nullptr, (gather) ? pred : nullptr, (gather) ? s_idx : nullptr,      \
+                                 (gather) ? o_idx : nullptr, (gather) ? d.Din : 0, (gather) ? d.Dp : 0,                \
+                                 (gather) ? ldp : 0, (gather) ? NO : 0, bfmt, (SK) >= 0 ? ws + w.sk[(SK) >= 0 ? (SK) : 0] : nullptr, \
+                                 (SK) >= 0 ? w.sk_bytes[(SK) >= 0 ? (SK) : 0] : 0, st, &jobs[njobs]));             \
+  if (jobs[njobs].parts > 0) ++njobs
 
   // ---- net2 backward (graph.py:110)
   const long long n4 = (long long)NO * Dout;
@@ -262,29 +271,35 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
       CSG_CHECK_LAUNCH("csg_gconv_bf16_bwd relu mask");
     }
   }
-  GEMM(1, 0, Dout, H, NO, g4, Dout, h2, H, dw4, H, 1, nullptr, 0);
-  CSG_TRY(csg_colsum_bf16(g4, NO, Dout, Dout, db4, small, w.small_bytes, stream));
-  GEMM(0, 0, NO, H, Dout, g4, Dout, sv + s.w4t, Dout, dh2, H, 0, h2, H);
-  GEMM(1, 0, H, H, NO, dh2, H, pooled16, H, dw3, H, 1, nullptr, 0);
-  CSG_TRY(csg_colsum_bf16(dh2, NO, H, H, db3, small, w.small_bytes, stream));
-  GEMM(0, 0, NO, H, H, dh2, H, sv + s.w3t, H, dpooled, H, 1, nullptr, 0);
+  GEMM(1, 0, Dout, H, NO, g4, Dout, h2, H, dw4, H, 1, nullptr, 0, 0);
+  CSG_TRY(csg_colsum_bf16_deferred(g4, NO, Dout, Dout, db4, ws + w.cs[0], w.cs_bytes[0], st, &jobs[njobs]));
+  if (jobs[njobs].parts > 0) ++njobs;
+  GEMM(0, 0, NO, H, Dout, g4, Dout, sv + s.w4t, Dout, dh2, H, 0, h2, H, -1);
+  GEMM(1, 0, H, H, NO, dh2, H, pooled16, H, dw3, H, 1, nullptr, 0, 1);
+  CSG_TRY(csg_colsum_bf16_deferred(dh2, NO, H, H, db3, ws + w.cs[1], w.cs_bytes[1], st, &jobs[njobs]));
+  if (jobs[njobs].parts > 0) ++njobs;
+  GEMM(0, 0, NO, H, H, dh2, H, sv + s.w3t, H, dpooled, H, 1, nullptr, 0, -1);
   // ---- pooling backward (graph.py:83-107)
   CSG_TRY(csg_pool_bwd_obj(dpooled, reinterpret_cast<const float*>(sv + s.pooled32),
                            reinterpret_cast<const float*>(sv + s.cnt), NO, H, dS, dcnt, stream));
-  CSG_TRY(csg_triple_bwd_assemble_bf16(out, dS, d_new_p, d_new_p ? ld_dnewp : 0, dcnt, s_idx, o_idx, valid, type32, conf,
-                                       NT, H, d.Dpo, g, dconf, db2, d.f16, small, w.small_bytes, stream));
+  // gradient wrt net1's pre-activation (+ partial column sums = db2, + per-predicate bins of d conf = d w_trans)
+  CSG_TRY(csg_triple_bwd_assemble_bf16_deferred(out, dS, d_new_p, d_new_p ? ld_dnewp : 0, dcnt, s_idx, o_idx, valid, type32,
+                                                pred_id, conf, w_trans, NT, H, d.Dpo, d.P, g, db2, dwt, d.f16,
+                                                ws + w.asm_ws, w.asm_bytes, st, &jobs[njobs], &jobs[njobs + 1]));
+  if (jobs[njobs].parts > 0) { if (jobs[njobs + 1].parts > 0) { njobs += 2; } else { ++njobs; } }
   // ---- net1 backward (graph.py:63-67)
-  GEMM(1, 0, Wd, H, NT, g, Wd, hidden, H, dw2, H, 1, nullptr, 0);
-  GEMM(0, 0, NT, H, Wd, g, Wd, sv + s.w2t, Wd, dhid, H, 0, hidden, H);
-  GEMM(1, 2, H, K1, NT, dhid, H, nullptr, 0, dw1, K1, 1, nullptr, 0);
-  CSG_TRY(csg_colsum_bf16(dhid, NT, H, H, db1, small, w.small_bytes, stream));
-  GEMM(0, 0, NT, K1, H, dhid, H, sv + s.w1t, H, dX, K1, 0, nullptr, 0);
+  GEMM(1, 0, Wd, H, NT, g, Wd, hidden, H, dw2, H, 1, nullptr, 0, 2);
+  GEMM(0, 0, NT, H, Wd, g, Wd, sv + s.w2t, Wd, dhid, H, 0, hidden, H, -1);
+  GEMM(1, 2, H, K1, NT, dhid, H, nullptr, 0, dw1, K1, 1, nullptr, 0, 3);
+  CSG_TRY(csg_colsum_bf16_deferred(dhid, NT, H, H, db1, ws + w.cs[2], w.cs_bytes[2], st, &jobs[njobs]));
+  if (jobs[njobs].parts > 0) ++njobs;
+  GEMM(0, 0, NT, K1, H, dhid, H, sv + s.w1t, H, dX, K1, 0, nullptr, 0, -1);
 #undef GEMM
   // ---- gather backward: segmented sums of dX over ALL triples onto their subject / object rows
   CSG_TRY(csg_segpool_bf16(dX, K1, 0, d.Din + d.Dp, d.Din, rowptr_s, perm_s, rowptr_o, perm_o, nullptr, nullptr, NO,
                            dobj_bf16 ? nullptr : reinterpret_cast<float*>(dobj), dobj_bf16 ? dobj : nullptr, d.Din, nullptr,
                            0, 0, stream));
-  // ---- confidence backward (graph.py:69-74)
-  CSG_TRY(csg_conf_bwd(dconf, type32, pred_id, w_trans, NT, d.P, dwt, small, w.small_bytes, stream));
+  // ---- all deferred final passes of the layer: dw1..dw4 (split-K), db1..db4 (column sums), d w_trans
+  CSG_TRY(csg_reduce_multi(jobs, njobs, st));
   return 0;
 }

@@ -18,6 +18,7 @@
 //               is prefetched by TMA into smem as well, so the epilogue issues no strided global accesses
 // TMEM: 512 columns = 2 accumulator stages x 256, so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
+#include "internal.h"
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -736,13 +737,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) { if (CG == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
-__global__ void splitk_reduce_tc_kernel(const float* __restrict__ partial, float* __restrict__ C, long long MN, int splits) {
-  CSG_PDL_WAIT();
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= MN) return;
-  C[i] = ordered_sum<8>(partial + i, (size_t)MN, splits);
-}
-
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -919,6 +913,21 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
                           const void* g_obj, const void* g_pred, const int* g_sidx, const int* g_oidx,
                           int g_din, int g_dp, int g_ldp, int g_nobj, int formats,
                           void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  CsgReduceJob job;
+  if (int rc = csg_gemm_bf16_deferred(mn_major, gather, M, N, K, A, lda, B, ldb, C, ldc, out_f32, bias, relu, rowscale,
+                                      mask_aux, ld_aux, g_obj, g_pred, g_sidx, g_oidx, g_din, g_dp, g_ldp, g_nobj, formats,
+                                      workspace, workspace_bytes, stream, &job)) return rc;
+  return job.parts > 0 ? csg_reduce_multi(&job, 1, stream) : 0;     // split-K final pass (fixed order: split 0, 1, ...)
+}
+
+int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K,
+                           const void* A, int lda, const void* B, int ldb, void* C, int ldc, int out_f32,
+                           const float* bias, int relu, const float* rowscale, const void* mask_aux, int ld_aux,
+                           const void* g_obj, const void* g_pred, const int* g_sidx, const int* g_oidx,
+                           int g_din, int g_dp, int g_ldp, int g_nobj, int formats,
+                           void* workspace, size_t workspace_bytes, cudaStream_t stream, CsgReduceJob* job) {
+  job->parts = 0; job->n = 0; job->partial = nullptr; job->out = nullptr; job->stride = 0; job->lanes = 1;
+  job->op = CSG_RED_SUM; job->aux = nullptr;
   if (M == 0 || N == 0) return 0;
   if (K == 0 && mn_major && out_f32 && M > 0 && N > 0) {      // empty reduction (no triples): the gradient is zero
     CSG_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, stream));
@@ -1009,10 +1018,10 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
   else rc = gather == 2 ? launch_bn<true, G_B, 1>(BN, maps, p, stream) : launch_bn<true, G_NONE, 1>(BN, maps, p, stream);
   if (rc) return rc;
   if (p.splits > 1) {
-    long long MN = (long long)M * N;
-    CSG_CUDA(csg_launch_pdl(splitk_reduce_tc_kernel, dim3(csg_div_up(MN, 256)), dim3(256), 0, stream, reinterpret_cast<const float*>(p.C),
-                                                                     reinterpret_cast<float*>(out), MN, p.splits));
-    CSG_CHECK_LAUNCH("csg_gemm_bf16 split-K reduce");
+    CSG_REQUIRE((long long)M * N < (1ll << 31), "gemm_bf16: split-K output too large");
+    job->partial = reinterpret_cast<const float*>(p.C);
+    job->out = reinterpret_cast<float*>(out);
+    job->n = M * N; job->parts = p.splits; job->stride = (long long)M * N;
   }
   return 0;
 }

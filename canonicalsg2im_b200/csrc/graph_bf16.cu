@@ -2,6 +2,7 @@
 // the fp32 -> bf16 weight cast (with the transposed copy the dX-type GEMMs consume).
 // Semantics are those of graph.cu (sg2im/graph.py:69-107); accumulation stays fp32.
 #include "common.cuh"
+#include "internal.h"
 #include <cuda_bf16.h>
 
 namespace {
@@ -222,24 +223,7 @@ __global__ void __launch_bounds__(CS_TX * CS_TY) colsum_bf16_partial_kernel(cons
     }
   }
 }
-// final pass: 32 columns x 8 chunk lanes per block, lanes combined in lane order
-__global__ void __launch_bounds__(256) colsum_bf16_final_kernel(const float* __restrict__ partial, int chunks, int N,
-                                                                float* __restrict__ out) {
-  CSG_PDL_WAIT();
-  __shared__ float red[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + tx;
-  float acc = 0.f;
-  if (n < N && ty < chunks) acc = ordered_sum<8>(partial + (size_t)ty * N + n, (size_t)8 * N, (chunks - ty + 7) / 8);
-  red[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0 && n < N) {
-    float s = 0.f;
-#pragma unroll
-    for (int y = 0; y < 8; ++y) s += red[y][tx];
-    out[n] = s;
-  }
-}
+// final pass: csg_reduce_multi (reduce.cu) with lanes = 8: 32 columns x 8 chunk lanes per block, combined in lane order
 int colsum_bf16_chunks(int M, int N) {
   int col_blocks = csg_div_up(N, CS_TX * CS_VEC);
   int want = csg_div_up(4 * 148, col_blocks);
@@ -263,28 +247,41 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
                                 const int* __restrict__ o_idx, const int* __restrict__ valid,
                                 const int* __restrict__ type32, const float* __restrict__ conf,
                                 int NT, int H, int Dp, __nv_bfloat16* __restrict__ g,
-                                float* __restrict__ dconf, float* __restrict__ cs_partial, bool out_fp16) {
+                                float* __restrict__ dconf, float* __restrict__ cs_partial, bool out_fp16,
+                                const int* __restrict__ pred, int P, float* __restrict__ wt_partial) {
   CSG_PDL_WAIT();
   __shared__ __align__(16) float cs_red[CS ? (ASM_WARPS / 2) * ASM_MAXI * 256 : 4];
+  // per-warp bins of the confidence gradient by predicate (d w_trans, graph.py:69-74): each warp adds its triples in
+  // the order it visits them, the warps are combined in warp order below -> one partial row per block
+  extern __shared__ float wt_bins[];       // [ASM_WARPS][P] when wt_partial
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (wt_partial) {
+    for (int i = threadIdx.x; i < ASM_WARPS * P; i += blockDim.x) wt_bins[i] = 0.f;
+    __syncthreads();
+  }
   const int Wd = 2 * H + Dp;
   float cs[ASM_MAXI][8];
 #pragma unroll
   for (int u = 0; u < ASM_MAXI; ++u)
 #pragma unroll
     for (int i = 0; i < 8; ++i) cs[u][i] = 0.f;
-  const int stride = gridDim.x * ASM_WARPS;
-  int t = blockIdx.x * ASM_WARPS + warp;
+  // a block owns a CONTIGUOUS chunk of triples (its warps interleave inside it): consecutive triples belong to the same
+  // graph, so the <= ~30 dS rows the chunk gathers (fp32, 2 KB each) stay in this SM's L1 instead of being re-fetched
+  // from L2 for every triple (the gathers were as many bytes as the streamed rows)
+  const int chunk = (NT + gridDim.x - 1) / gridDim.x;
+  const int t_end = min(NT, (int)(blockIdx.x + 1) * chunk);
+  const int stride = ASM_WARPS;
+  int t = blockIdx.x * chunk + warp;
   // scalars of the next triple are fetched one iteration ahead: the row addresses depend on them
-  int s = 0, o = 0, vi = 0, ty = 0;
+  int s = 0, o = 0, vi = 0, ty = 0, pr = 0;
   float cf = 0.f;
-  if (t < NT) { s = s_idx[t]; o = o_idx[t]; vi = valid[t]; ty = type32[t]; cf = conf[t]; }
-  for (; t < NT; t += stride) {
+  if (t < t_end) { s = s_idx[t]; o = o_idx[t]; vi = valid[t]; ty = type32[t]; cf = conf[t]; pr = wt_partial ? pred[t] : 0; }
+  for (; t < t_end; t += stride) {
     const int tn = t + stride;
-    int s2 = 0, o2 = 0, vi2 = 0, ty2 = 0;
+    int s2 = 0, o2 = 0, vi2 = 0, ty2 = 0, pr2 = 0;
     float cf2 = 0.f;
-    if (tn < NT) {
-      s2 = s_idx[tn]; o2 = o_idx[tn]; vi2 = valid[tn]; ty2 = type32[tn]; cf2 = conf[tn];
+    if (tn < t_end) {
+      s2 = s_idx[tn]; o2 = o_idx[tn]; vi2 = valid[tn]; ty2 = type32[tn]; cf2 = conf[tn]; pr2 = wt_partial ? pred[tn] : 0;
       // pull the next row of `out` (the only DRAM-resident operand) into L2 while this one is processed
       const __nv_bfloat16* nrow = out + (size_t)tn * Wd;
 #pragma unroll
@@ -337,9 +334,19 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
       float dc = 0.f;
       if (ty == 1 && cf > 0.f) dc = dot / cf;
       if (v) dc += dcnt[s] + dcnt[o];
-      dconf[t] = dc;
+      if (dconf) dconf[t] = dc;
+      if (wt_partial && ty == 1) wt_bins[warp * P + pr] += dc;
     }
-    s = s2; o = o2; vi = vi2; ty = ty2; cf = cf2;
+    s = s2; o = o2; vi = vi2; ty = ty2; cf = cf2; pr = pr2;
+  }
+  if (wt_partial) {
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < ASM_WARPS; ++w) a += wt_bins[w * P + p];
+      wt_partial[(size_t)blockIdx.x * P + p] = a;
+    }
   }
   if (CS) {
     // ordered tree over the 8 warps: (w, w+4), then (w, w+2), then (w, w+1); lane owns columns lane*8 + u*256 + i
@@ -459,6 +466,15 @@ CSG_API size_t csg_colsum_bf16_workspace(int M, int N) {
 
 CSG_API int csg_colsum_bf16(const void* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
                             cudaStream_t stream) {
+  CsgReduceJob job;
+  if (int rc = csg_colsum_bf16_deferred(X, M, N, ld, out, workspace, workspace_bytes, stream, &job)) return rc;
+  return csg_reduce_multi(&job, 1, stream);
+}
+
+int csg_colsum_bf16_deferred(const void* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
+                             cudaStream_t stream, CsgReduceJob* job) {
+  job->parts = 0; job->n = 0; job->partial = nullptr; job->out = out; job->stride = N; job->lanes = 8;
+  job->op = CSG_RED_SUM; job->aux = nullptr;
   if (N == 0) return 0;
   CSG_REQUIRE((N & 7) == 0 && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
               "colsum_bf16: N and ld must be multiples of 8 and X 16-byte aligned");
@@ -466,11 +482,10 @@ CSG_API int csg_colsum_bf16(const void* X, int M, int N, int ld, float* out, voi
   const int chunks = colsum_bf16_chunks(M, N);
   const int rows_per_chunk = csg_div_up(M > 0 ? M : 1, chunks);
   float* partial = reinterpret_cast<float*>(workspace);
-  CSG_CUDA(csg_launch_pdl(colsum_bf16_partial_kernel, dim3(dim3(csg_div_up(N, CS_TX * CS_VEC), chunks)), dim3(CS_TX * CS_TY), 0, stream, 
+  CSG_CUDA(csg_launch_pdl(colsum_bf16_partial_kernel, dim3(dim3(csg_div_up(N, CS_TX * CS_VEC), chunks)), dim3(CS_TX * CS_TY), 0, stream,
       reinterpret_cast<const __nv_bfloat16*>(X), M, N, ld, rows_per_chunk, partial));
   CSG_CHECK_LAUNCH("csg_colsum_bf16 partial");
-  CSG_CUDA(csg_launch_pdl(colsum_bf16_final_kernel, dim3(csg_div_up(N, 32)), dim3(256), 0, stream, partial, chunks, N, out));
-  CSG_CHECK_LAUNCH("csg_colsum_bf16 final");
+  job->partial = partial; job->n = N; job->parts = chunks;
   return 0;
 }
 
@@ -503,14 +518,52 @@ CSG_API int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const
                 "bwd_assemble_bf16: workspace too small");
     float* partial = reinterpret_cast<float*>(workspace);
     CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream, 
-        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, partial, out_fp16 != 0));
+        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, partial, out_fp16 != 0,
+        (const int*)nullptr, 0, (float*)nullptr));
     CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16");
-    CSG_CUDA(csg_launch_pdl(colsum_bf16_final_kernel, dim3(csg_div_up(Wd, 32)), dim3(256), 0, stream, partial, blocks, Wd, colsum_g));
-    CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16 colsum");
+    CsgReduceJob job = {partial, colsum_g, Wd, blocks, (long long)Wd, 8, CSG_RED_SUM, nullptr};
+    if (int rc = csg_reduce_multi(&job, 1, stream)) return rc;
   } else {
     CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<false>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream, 
-        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, (float*)nullptr, out_fp16 != 0));
+        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, (float*)nullptr, out_fp16 != 0,
+        (const int*)nullptr, 0, (float*)nullptr));
     CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16");
   }
+  return 0;
+}
+
+size_t csg_triple_bwd_assemble_bf16_deferred_workspace(int NT, int H, int Dp, int P) {
+  return (size_t)asm_blocks(NT) * (2 * H + Dp + P) * sizeof(float) + 64;
+}
+
+int csg_triple_bwd_assemble_bf16_deferred(const void* out, const float* dS, const void* d_newp, int ld_newp,
+                                          const float* dcnt, const int* s_idx, const int* o_idx, const int* valid,
+                                          const int* type32, const int* pred, const float* conf, const float* w_trans,
+                                          int NT, int H, int Dp, int P, void* g, float* db2, float* dwt, int out_fp16,
+                                          void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                                          CsgReduceJob* job_db2, CsgReduceJob* job_dwt) {
+  const int Wd = 2 * H + Dp;
+  *job_db2 = CsgReduceJob{nullptr, db2, 0, 0, (long long)Wd, 8, CSG_RED_SUM, nullptr};
+  *job_dwt = CsgReduceJob{nullptr, dwt, 0, 0, (long long)P, 8, CSG_RED_SIGMOID_GRAD, w_trans};
+  if (NT == 0) {
+    CSG_CUDA(cudaMemsetAsync(db2, 0, (size_t)Wd * sizeof(float), stream));
+    CSG_CUDA(cudaMemsetAsync(dwt, 0, (size_t)P * sizeof(float), stream));
+    return 0;
+  }
+  CSG_REQUIRE((H & 7) == 0 && (Dp & 7) == 0 && (ld_newp & 7) == 0, "bwd_assemble_bf16: H, Dp, ld must be multiples of 8");
+  CSG_REQUIRE(Wd <= ASM_MAXI * 256, "bwd_assemble_bf16: 2H+Dp=%d exceeds %d", Wd, ASM_MAXI * 256);
+  CSG_REQUIRE(P > 0 && (size_t)ASM_WARPS * P * sizeof(float) <= 24 * 1024, "bwd_assemble_bf16: P=%d predicates do not fit the per-warp bins", P);
+  CSG_REQUIRE(workspace && workspace_bytes >= csg_triple_bwd_assemble_bf16_deferred_workspace(NT, H, Dp, P),
+              "bwd_assemble_bf16: workspace too small");
+  const int blocks = asm_blocks(NT);
+  float* cs_partial = reinterpret_cast<float*>(workspace);
+  float* wt_partial = cs_partial + (size_t)blocks * Wd;
+  CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true>, dim3(blocks), dim3(ASM_WARPS * 32), (size_t)ASM_WARPS * P * sizeof(float),
+                          stream, reinterpret_cast<const __nv_bfloat16*>(out), dS, reinterpret_cast<const __nv_bfloat16*>(d_newp),
+                          ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, reinterpret_cast<__nv_bfloat16*>(g),
+                          (float*)nullptr, cs_partial, out_fp16 != 0, pred, P, wt_partial));
+  CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16 (deferred)");
+  job_db2->partial = cs_partial; job_db2->n = Wd; job_db2->parts = blocks;
+  job_dwt->partial = wt_partial; job_dwt->n = P; job_dwt->parts = blocks;
   return 0;
 }

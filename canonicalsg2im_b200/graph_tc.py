@@ -1,10 +1,12 @@
 """Tensor-core (bf16 operands, fp32 accumulation) engine of the triple graph convolution.
 
-Same dataflow as ``graph._TripleConvF32`` with every GEMM on tcgen05 (csrc/gemm_tc.cu):
+Same dataflow as ``graph._TripleConvF32`` with every GEMM on tcgen05 (csrc/gemm_tc.cu), one native call per layer
+and direction (csrc/gconv_engine.cu):
 
     forward   F1 (gather fused into A)  ->  F2 (+bias, ReLU, x confidence)  ->  CSR pooling  ->  net2
     backward  dW-type GEMMs are MN-major split-K GEMMs over the triples (dW1 re-gathers its B operand),
-              dX-type GEMMs use per-call transposed bf16 copies of the weights so both operands are K-major
+              dX-type GEMMs use per-call transposed bf16 copies of the weights so both operands are K-major;
+              all final passes of a layer's ordered reductions (split-K, bias column sums, d w_trans) run in one launch
 
 Activations between layers stay bf16; weight gradients, pooling sums and confidences are fp32.
 Tolerance vs the fp32 reference: 1e-2 relative (north_star).
@@ -85,98 +87,8 @@ def relu_mask_bf16(dy, y):
     return out
 
 
-class _TripleConvBF16(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, batch, H, Dpo, obj, pred, w1, b1, w2, b2, w3, b3, w4, b4, w_trans):
-        from .graph import triple_confidence
-        NT, NO = batch.NT, batch.NO
-        ctx.in_dtypes = (obj.dtype, pred.dtype)
-        obj_b, pred_b = as_bf16_rows(obj), as_bf16_rows(pred)
-        need_bwd = any(ctx.needs_input_grad)
-        casts = cast_bf16_multi([(w1, False), (w2, False), (w3, False), (w4, False)] +
-                                ([(w1, True), (w2, True), (w3, True), (w4, True)] if need_bwd else []))
-        w1b, w2b, w3b, w4b = casts[:4]
-        ctx.wt = tuple(casts[4:]) if need_bwd else None
-        g = Gather(obj_b, pred_b, batch.s_idx, batch.o_idx)
-        conf = triple_confidence(batch, w_trans)
-        Wd = 2 * H + Dpo
-        hidden = ops.gemm_bf16(NT, H, g.width, None, w1b, bias=f32c(b1), relu=True, gather=g, gather_mode=1)
-        out = ops.gemm_bf16(NT, Wd, H, hidden, w2b, bias=f32c(b2), relu=True, rowscale=conf)
-        pooled32, pooled16, cnt = segpool_bf16(out, 0, H + Dpo, H, batch, conf, avg=True)
-        h2 = ops.gemm_bf16(NO, H, H, pooled16, w3b, bias=f32c(b3), relu=True)
-        new_obj = ops.gemm_bf16(NO, w4.shape[0], H, h2, w4b, bias=f32c(b4), relu=True)
-        new_p = out[:, H:H + Dpo]
-        ctx.batch, ctx.H, ctx.Dpo = batch, H, Dpo
-        ctx.save_for_backward(obj_b, pred_b, w1, w2, w3, w4, f32c(w_trans), conf, hidden, out, pooled32, pooled16, cnt,
-                              h2, new_obj)
-        ctx.set_materialize_grads(False)
-        return new_obj, new_p
-
-    @staticmethod
-    def backward(ctx, d_obj_out, d_newp):
-        batch, H, Dpo = ctx.batch, ctx.H, ctx.Dpo
-        (obj, pred, w1, w2, w3, w4, w_trans, conf, hidden, out, pooled32, pooled16, cnt, h2, new_obj) = ctx.saved_tensors
-        NT, NO = batch.NT, batch.NO
-        dev = obj.device
-        L = lib()
-        Dout = w4.shape[0]
-        Din, Dp = obj.shape[1], pred.shape[1]
-        Wd = 2 * H + Dpo
-        if d_obj_out is None:
-            d_obj_out = torch.zeros((NO, Dout), dtype=torch.float32, device=dev)
-        # transposed bf16 weights: dy @ W needs W^T stored [in, out] so that K (= out features) is contiguous
-        w1t, w2t, w3t, w4t = ctx.wt
-        # ---- net2 backward
-        g4 = relu_mask_bf16(d_obj_out, new_obj)
-        dw4 = ops.gemm_bf16(Dout, H, NO, g4, h2, mn_major=True)
-        db4 = colsum_bf16(g4)
-        dh2 = ops.gemm_bf16(NO, H, Dout, g4, w4t, mask_aux=h2)
-        dw3 = ops.gemm_bf16(H, H, NO, dh2, pooled16, mn_major=True)
-        db3 = colsum_bf16(dh2)
-        dpooled = ops.gemm_bf16(NO, H, H, dh2, w3t, out_f32=True)
-        # ---- pooling backward
-        dS = torch.empty_like(dpooled)
-        dcnt = torch.empty(NO, dtype=torch.float32, device=dev)
-        _lib.check(L.csg_pool_bwd_obj(ptr(dpooled), ptr(pooled32), ptr(cnt), NO, H, ptr(dS), ptr(dcnt), _stream()),
-                   "csg_pool_bwd_obj")
-        dnp = None
-        if d_newp is not None:
-            dnp = d_newp if (d_newp.dtype == BF and d_newp.stride(-1) == 1 and d_newp.stride(0) % 8 == 0
-                             and d_newp.data_ptr() % 16 == 0) else d_newp.to(BF).contiguous()
-        g = torch.empty((NT, Wd), dtype=BF, device=dev)
-        dconf = torch.empty(max(NT, 1), dtype=torch.float32, device=dev)
-        db2 = torch.empty(Wd, dtype=torch.float32, device=dev)
-        ws = workspace(L.csg_triple_bwd_assemble_bf16_workspace(NT, H, Dpo), dev)
-        rc = L.csg_triple_bwd_assemble_bf16(ptr(out), ptr(dS), ptr(dnp), dnp.stride(0) if dnp is not None else 0,
-                                            ptr(dcnt), ptr(batch.s_idx), ptr(batch.o_idx), ptr(batch.valid),
-                                            ptr(batch.type32), ptr(conf), NT, H, Dpo, ptr(g), ptr(dconf), ptr(db2), 0,
-                                            ptr(ws), ws.numel(), _stream())
-        _lib.check(rc, "csg_triple_bwd_assemble_bf16")
-        # ---- net1 backward
-        dw2 = ops.gemm_bf16(Wd, H, NT, g, hidden, mn_major=True)
-        dhid = ops.gemm_bf16(NT, H, Wd, g, w2t, mask_aux=hidden)
-        gat = Gather(obj, pred, batch.s_idx, batch.o_idx)
-        dw1 = ops.gemm_bf16(H, gat.width, NT, dhid, None, mn_major=True, gather=gat, gather_mode=2)
-        db1 = colsum_bf16(dhid)
-        dX = ops.gemm_bf16(NT, gat.width, H, dhid, w1t)
-        # ---- gather backward
-        dobj32, _, _ = segpool_bf16(dX, 0, Din + Dp, Din, batch, avg=False, want_f32=True, want_bf16=False)
-        dobj = dobj32 if ctx.in_dtypes[0] == torch.float32 else dobj32.to(ctx.in_dtypes[0])
-        dpred = dX[:, Din:Din + Dp]
-        if ctx.in_dtypes[1] != BF:
-            dpred = dpred.to(ctx.in_dtypes[1])
-        # ---- confidence backward
-        P = w_trans.numel()
-        dwt = torch.empty(P, dtype=torch.float32, device=dev)
-        ws = workspace(L.csg_conf_bwd_workspace(P), dev)
-        rc = L.csg_conf_bwd(ptr(dconf), ptr(batch.type32), ptr(batch.pred), ptr(w_trans), NT, P, ptr(dwt),
-                            ptr(ws), ws.numel(), _stream())
-        _lib.check(rc, "csg_conf_bwd")
-        return None, None, None, dobj, dpred, dw1, db1, dw2, db2, dw3, db3, dw4, db4, dwt
-
-
 # --------------------------------------------------------------------------------------------
-# native layer executor (csrc/gconv_engine.cu): the same launch sequence, issued by ONE call per direction
+# native layer executor (csrc/gconv_engine.cu): the launch sequence of a layer issued by ONE call per direction
 # --------------------------------------------------------------------------------------------
 _WS = {}      # device -> reusable scratch (dead once the call has returned on the stream)
 
@@ -262,10 +174,7 @@ class _TripleConvEngine(torch.autograd.Function):
                 dw4.view(Dout, H), db4, dwt)
 
 
-USE_ENGINE = os.environ.get("CSG_STAGED", "0") != "1"     # CSG_STAGED=1: one ctypes call per stage (debugging)
-
-
-def triple_conv(batch, obj, pred, params, w_trans, hidden_dim, pred_out_dim, staged=None):
+def triple_conv(batch, obj, pred, params, w_trans, hidden_dim, pred_out_dim):
     din, dp = obj.shape[1], pred.shape[1]
     dout = params[6].shape[0]
     if dp % 64 and not (din % 64 or hidden_dim % 64 or pred_out_dim % 64 or dout % 64):
@@ -283,10 +192,7 @@ def triple_conv(batch, obj, pred, params, w_trans, hidden_dim, pred_out_dim, sta
         raise _lib.CsgError("precision='bf16' needs feature widths that are multiples of 64 "
                             "(got Din=%d Dp=%d H=%d Dout=%d Dp_out=%d); use precision='fp32'"
                             % (din, dp, hidden_dim, dout, pred_out_dim))
-    if staged is None:
-        staged = not USE_ENGINE
-    fn = _TripleConvBF16 if staged else _TripleConvEngine
-    return fn.apply(batch, hidden_dim, pred_out_dim, obj, pred, *params, w_trans)
+    return _TripleConvEngine.apply(batch, hidden_dim, pred_out_dim, obj, pred, *params, w_trans)
 
 
 class _DenseMLP2BF16(torch.autograd.Function):

@@ -15,7 +15,7 @@ import torch
 import torch.nn.functional as F
 
 from . import synth
-from .canonicalize import canon_count_async, canon_emit, converse_tables
+from .canonicalize import canon_count_async, canon_emit, canon_total, converse_tables
 from .layout import layout_batched
 from .model import AttributeEmbeddings, Sg2LayoutModel, bbox_pred_loss_ragged, get_conv_converse
 from .optim import FusedAdam
@@ -60,8 +60,19 @@ class HostBatch:
             self.t[k] = x
         self.nbytes = sum(x.numel() * x.element_size() for x in self.t.values())
 
-    def to_device(self, device):
-        d = {k: v.to(device, non_blocking=True) for k, v in self.t.items()}
+    def to_device(self, device, out=None):
+        """Upload (asynchronously, from pinned memory).  ``out``: a dict returned by an earlier ``to_device`` of a batch
+        with the same shapes: its tensors are overwritten in place, so the device addresses stay the same (a data
+        pipeline cycling through a fixed set of batch buffers; what the CUDA-graph replay of the step keys on)."""
+        if out is not None:
+            if any(out[k].shape != v.shape for k, v in self.t.items()):
+                raise ValueError("to_device(out=...): shapes differ from the buffers' batch")
+            for k, v in self.t.items():
+                out[k].copy_(v, non_blocking=True)
+            out.pop("_canon_plan", None)
+            d = out
+        else:
+            d = {k: v.to(device, non_blocking=True) for k, v in self.t.items()}
         d["max_objs"] = self.max_objs
         d["B"] = self.B
         return d
@@ -70,7 +81,7 @@ class HostBatch:
 class SgToLayoutStep:
     def __init__(self, vocab, device, precision="fp32", H=64, W=64, learned_converse=True,
                  learned_transitivity=True, lr=1e-4, seed=0, distributed=False, bbox_pred_loss_weight=10.0,
-                 global_batch=None):
+                 global_batch=None, use_graph=False):
         """``global_batch``: number of graphs of the GLOBAL batch this rank holds a shard of.  The box loss is a mean
         over images (pix2pix_model.py:85), so with shards of unequal graph counts (cost-balanced sharding) every rank
         scales its loss by B_local / B_global and the gradients are SUMMED over ranks: the result equals the
@@ -101,6 +112,12 @@ class SgToLayoutStep:
         self.global_batch = global_batch
         self.reducer = BucketedGradAllReduce(buckets, average=global_batch is None) if distributed else None
         self.tail_events = None      # set to [] to time the part of the all-reduce that trails the backward pass
+        # CUDA-graph replay of forward + backward (see _step_graphed): one captured graph per (batch buffers, sizes)
+        self.use_graph = use_graph
+        self._graphs = {}
+        self.graph_replays = 0
+        self.graph_launches = 0
+        self._eager_steps = 0
         params = [p for p in self.model.parameters() if p is not self.model.converse_candidates_weights]
         params += list(self.layout_embedding.parameters())
         self.opt = FusedAdam(params, lr=lr)                      # torch.optim.Adam arithmetic, one multi-tensor launch
@@ -158,10 +175,86 @@ class SgToLayoutStep:
                 self.reducer.finish()
         return loss, int(res.triplets.shape[0])
 
+    # ------------------------------------------------------------------------------------------ CUDA-graph replay
+    # Everything after the canonicalization emit pass has static shapes once the canonicalized triple count is known
+    # (the one host read of a step).  The ~150 launches of forward + backward then cost more HOST time (Python, ctypes,
+    # cudaLaunchKernelEx: ~5 us each) than the device needs to run them, so the device idles ~10 % of a step.  A step
+    # whose (input buffers, object / triple counts) were seen before replays a captured graph instead: one
+    # cudaGraphLaunch for the whole forward + backward (+ gradient all-reduce).  The graph reads the batch from the
+    # buffers it was captured on (a data pipeline cycles through a fixed set of device batch buffers, two in bench.py's
+    # end-to-end leg) and the canonicalized triples from buffers owned by the cache entry, which the eager emit pass
+    # fills right before the replay.  A step with a new key is captured (and replayed once); a triple count never seen
+    # on these buffers simply captures another graph, up to `max_graphs`, then falls back to eager launches.
+    max_graphs = 8
+
+    def _graph_key(self, d, G, total):
+        return (int(total), int(d["objs"].shape[0]), int(d["B"]), int(d["max_objs"]), d["objs"].data_ptr(),
+                d["boxes"].data_ptr(), d["obj_off"].data_ptr(), G.data_ptr(), tuple(G.shape))
+
+    def _capture(self, key, d, G, plan, total):
+        dev = self.device
+        ent = {"triplets": torch.empty((max(total, 1), 3), dtype=torch.int64, device=dev),
+               "types": torch.empty(max(total, 1), dtype=torch.int64, device=dev),
+               "tri_off": torch.empty(d["B"] + 1, dtype=torch.int32, device=dev),
+               "keep": (d["objs"], d["boxes"], d["obj_off"], G)}
+        res = canon_emit(plan, out=(ent["triplets"], ent["types"]))
+        ent["tri_off"].copy_(res.tri_off)
+        from .canonicalize import CanonResult
+        static = CanonResult(ent["triplets"][:total], ent["types"][:total], ent["tri_off"], res.conv_counts)
+        params = list(self.opt.params)
+        for p in params:
+            p.grad = None
+        torch.cuda.synchronize()
+        from .ops import lib
+        launches0 = lib().csg_launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            canvas, loss = self.forward(d, static)
+            torch.autograd.backward([canvas, loss], [G, None])
+            if self.reducer is not None:
+                self.reducer.finish()
+        ent.update(graph=graph, canvas=canvas, loss=loss.detach(), grads=[p.grad for p in params], total=total,
+                   launches=int(lib().csg_launch_count() - launches0))
+        return ent
+
+    def _step_graphed(self, d, canvas_grad, prefetch):
+        if self._eager_steps == 0:         # the first step runs eagerly: it fills the host-side caches (linspace tables,
+            return None                    # scratch buffers, function attributes) that must not be created under capture
+        if d.get("_canon_plan") is None:
+            self.prefetch(d)
+        plan = d.pop("_canon_plan")
+        total = canon_total(plan)
+        key = self._graph_key(d, canvas_grad, total)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= self.max_graphs:
+                d["_canon_plan"] = plan
+                return None
+            ent = self._graphs[key] = self._capture(key, d, canvas_grad, plan, total)
+        else:
+            res = canon_emit(plan, out=(ent["triplets"], ent["types"]))
+            ent["tri_off"].copy_(res.tri_off)
+        if prefetch is not None:
+            self.prefetch(prefetch)
+        ent["graph"].replay()
+        self.graph_replays += 1
+        self.graph_launches += ent["launches"]      # kernel-launch sites executed by the replay (counted at capture)
+        for p, g in zip(self.opt.params, ent["grads"]):
+            p.grad = g
+        self.opt.step()
+        for p in self.opt.params:          # the entry keeps its gradient buffers; an eager step must not accumulate into them
+            p.grad = None
+        return ent["loss"], total
+
     def step(self, d, canvas_grad, prefetch=None):
         """One training step on batch ``d``.  ``prefetch``: the batch of the NEXT step (may be ``d`` itself); its
         canonicalization counting pass is enqueued right behind this step's emit pass."""
+        if self.use_graph:
+            out = self._step_graphed(d, canvas_grad, prefetch)
+            if out is not None:
+                return out
         loss, n_tri = self.backward(d, canvas_grad, prefetch)
+        self._eager_steps += 1
         self.opt.step()
         if self.reducer is not None:
             self.reducer.zero()

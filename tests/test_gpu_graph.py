@@ -264,44 +264,6 @@ def test_bf16_large_batch_matches_fp32_engine():
         assert ((a - b).norm() / b.norm()).item() <= 6.5e-2, what
 
 
-def test_native_layer_executor_is_bitwise_the_staged_path():
-    """csg_gconv_bf16_fwd/bwd issue exactly the launch sequence of the staged (one ctypes call per stage) layer:
-    outputs and every gradient must be bit-identical, on padded golden inputs and on a ragged batch with a
-    strided predicate operand (the previous layer's net1 output)."""
-    from canonicalsg2im_b200 import graph_tc
-    from canonicalsg2im_b200.graph import TripleBatch
-    obj, pred, s, o, p, ty = gi.layer_inputs()
-    B, O, T = obj.shape[0], obj.shape[1], pred.shape[1]
-    layer = _layer("bf16")
-    batch = TripleBatch.from_padded_edges(t(np.stack([s, o], -1)), t(p) != 0, t(ty), t(p), O)
-    gen = torch.Generator(device="cuda").manual_seed(5)
-    wide = torch.randn((B * T, 1152), device="cuda", generator=gen).bfloat16()
-    cases = [(t(obj).reshape(B * O, -1), t(pred).reshape(B * T, -1)),                 # fp32 inputs (layer 0 style)
-             (t(obj).reshape(B * O, -1).bfloat16(), wide[:, 512:640])]               # bf16 inputs, strided pred view
-    for oi, pi in cases:
-        res = []
-        for staged in (True, False):
-            layer.zero_grad()
-            ov = oi.clone().requires_grad_(True)
-            pv = pi.detach().clone() if pi.is_contiguous() else pi
-            wide.grad = None
-            if not pi.is_contiguous():
-                base = wide.clone().requires_grad_(True)
-                pv = base[:, 512:640]
-            else:
-                pv = pv.requires_grad_(True)
-                base = pv
-            a, b = graph_tc.triple_conv(batch, ov, pv, layer.layer_params(), layer.predicates_transitive_weights,
-                                        512, 128, staged=staged)
-            ga = torch.randn(a.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9)).to(a.dtype)
-            gb = torch.randn(b.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(10)).to(b.dtype)
-            torch.autograd.backward([a, b], [ga, gb])
-            grads = [q.grad.clone() for q in layer.parameters()]
-            res.append([a.detach().clone(), b.detach().clone(), ov.grad.clone(), base.grad.clone()] + grads)
-        for x, y in zip(*res):
-            assert x.dtype == y.dtype and torch.equal(x, y)
-
-
 def test_box_net_bf16_head_vs_fp32_reference():
     """box_net (model.py:58-60) on the bf16 engine: tcgen05 first layer + the 4-wide row-dot head (csrc/head_bf16.cu),
     forward and all five gradients against torch fp32 on the same bf16-rounded operands: 1e-2 relative (north_star's
@@ -388,3 +350,27 @@ def test_ragged_collate_batch_runs_the_model_like_the_padded_batch():
     sel_b = torch.cat([boxes_p[b, :off[b + 1] - off[b]] for b in range(rb["B"])])
     assert_close(vecs_r, sel_v, 1e-6, "ragged collate vs padded collate: obj_vecs")
     assert_close(boxes_r, sel_b, 1e-6, "ragged collate vs padded collate: boxes")
+
+
+def test_cuda_graph_replay_equals_eager_steps():
+    """SgToLayoutStep(use_graph=True) replays forward + backward from a captured CUDA graph (one per batch buffer and
+    triple count); the kernels are deterministic, so losses and weights after several optimizer steps must equal the
+    eagerly launched steps bit for bit -- also when two batches with different sizes alternate."""
+    from canonicalsg2im_b200.pipeline import SgToLayoutStep, HostBatch
+    vocab = synth.Vocab(42)
+    hbs = [HostBatch(synth.make_graphs(12, 500 + i, 3, 20, vocab, include_dummies=True), seed=i) for i in range(2)]
+    results = []
+    for use_graph in (False, True):
+        step = SgToLayoutStep(vocab, torch.device("cuda"), precision="bf16", seed=0, use_graph=use_graph)
+        ds = [hb.to_device("cuda") for hb in hbs]
+        G = torch.randn((12, 128, 64, 64), device="cuda", generator=torch.Generator("cuda").manual_seed(3)) * 1e-3
+        losses = []
+        for it in range(7):
+            l, n = step.step(ds[it & 1], G, prefetch=ds[(it + 1) & 1])
+            losses.append((float(l), n))
+        if use_graph:
+            assert step.graph_replays >= 5 and len(step._graphs) == 2
+        results.append((losses, step.model.gconvs[0].net1[0].weight.detach().clone(),
+                        step.layout_embedding.att_emb_0.weight.detach().clone()))
+    assert results[0][0] == results[1][0]
+    assert torch.equal(results[0][1], results[1][1]) and torch.equal(results[0][2], results[1][2])
