@@ -12,14 +12,14 @@ the operators without the built library, or calling them on CPU tensors, raises.
 from . import synth  # noqa: F401  (host-side synthetic inputs; no kernels)
 
 __all__ = ["synth", "GraphTripleConv", "GraphTripleConvNet", "TripleBatch", "Sg2LayoutModel", "get_conv_converse",
-           "boxes_to_layout", "masks_to_layout", "layout_batched", "add_learnt_triplets",
+           "boxes_to_layout", "masks_to_layout", "layout_batched", "layout_pyramid", "add_learnt_triplets",
            "add_learnt_triplets_batched", "add_location_triplets_batched", "canon_count_async", "canon_emit",
            "converse_tables", "closure", "crop_bbox", "crop_bbox_batch", "crop_bbox_ragged", "FusedAdam"]
 
 _LAZY = {
     "GraphTripleConv": "graph", "GraphTripleConvNet": "graph", "TripleBatch": "graph",
     "Sg2LayoutModel": "model", "get_conv_converse": "model",
-    "boxes_to_layout": "layout", "masks_to_layout": "layout", "layout_batched": "layout",
+    "boxes_to_layout": "layout", "masks_to_layout": "layout", "layout_batched": "layout", "layout_pyramid": "layout",
     "add_learnt_triplets": "canonicalize", "add_learnt_triplets_batched": "canonicalize",
     "add_location_triplets_batched": "canonicalize", "canon_count_async": "canonicalize", "canon_emit": "canonicalize",
     "converse_tables": "canonicalize", "closure": "canonicalize", "FusedAdam": "optim",

@@ -81,9 +81,9 @@ def crop_bbox(feats, bbox, HH, WW=None, backend="cudnn", align_corners=False):
     assert bbox.size(1) == 4
     if backend not in ("cudnn", "jj"):
         raise ValueError('Invalid backend "%s"' % backend)
-    if backend == "jj":
-        raise NotImplementedError("crop_bbox: only the grid_sample ('cudnn') formulation is provided")
     off = torch.arange(N + 1, dtype=torch.int32, device=feats.device)
+    if backend == "jj":          # bilinear_sample (bilinear.py:97-152): the kernels' third coordinate mode
+        return _CropFn.apply(feats, bbox, off, int(HH), int(HH if WW is None else WW), 2)
     return crop_bbox_ragged(feats, bbox, off, HH, WW, align_corners)
 
 

@@ -31,6 +31,21 @@ __device__ __forceinline__ float crop_coord(float sw, float ew, float start, flo
   return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)size), 1.f), 0.5f);
 }
 
+// backend 'jj' (bilinear.py:97-152, selected with align = 2): coordinates stay in [0, 1] (no 2x - 1), are scaled by the
+// image size, and the four taps are floor / floor + 1 CLAMPED into the image with the weights (x1 - X), (X - x0)
+// taken against the clamped taps (so a sample beyond the last pixel gets a zero or negative weight, as there)
+struct JJAxis { int a, b; float wa, wb; };
+__device__ __forceinline__ JJAxis jj_axis(float sw, float ew, float start, float extent, int size) {
+  const float X = __fmul_rn(__fadd_rn(__fmul_rn(sw, start), __fmul_rn(ew, __fadd_rn(start, extent))), (float)size);
+  const float hi = (float)(size - 1);
+  const float a = fminf(fmaxf(floorf(X), 0.f), hi);
+  const float b = fminf(fmaxf(__fadd_rn(a, 1.f), 0.f), hi);
+  JJAxis r;
+  r.a = (int)a; r.b = (int)b;
+  r.wa = __fsub_rn(b, X); r.wb = __fsub_rn(X, a);
+  return r;
+}
+
 __global__ void crop_img_kernel(const int* __restrict__ crop_off, int N, int* __restrict__ crop_img) {
   const int n = blockIdx.x;
   for (int i = crop_off[n] + threadIdx.x; i < crop_off[n + 1]; i += blockDim.x) crop_img[i] = n;
@@ -45,6 +60,18 @@ __global__ void __launch_bounds__(256) crop_fwd_kernel(CropParams p, const int* 
   const float* img = p.feats + (size_t)n * p.C * plane;
   for (int px = threadIdx.x + blockIdx.y * blockDim.x; px < p.HH * p.WW; px += blockDim.x * gridDim.y) {
     const int yy = px / p.WW, xx = px % p.WW;
+    if (p.align == 2) {
+      const JJAxis ax = jj_axis(p.swx[xx], p.ewx[xx], b.x, b.z, p.W), ay = jj_axis(p.swy[yy], p.ewy[yy], b.y, b.w, p.H);
+      const float w1 = __fmul_rn(ax.wa, ay.wa), w2 = __fmul_rn(ax.wa, ay.wb), w3 = __fmul_rn(ax.wb, ay.wa), w4 = __fmul_rn(ax.wb, ay.wb);
+      for (int c = 0; c < p.C; ++c) {
+        const float* src = img + (size_t)c * plane;
+        const float v1 = __ldg(src + (size_t)ay.a * p.W + ax.a), v2 = __ldg(src + (size_t)ay.b * p.W + ax.a);
+        const float v3 = __ldg(src + (size_t)ay.a * p.W + ax.b), v4 = __ldg(src + (size_t)ay.b * p.W + ax.b);
+        out[(((size_t)i * p.C + c) * p.HH + yy) * p.WW + xx] =
+            __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, v1), __fmul_rn(w2, v2)), __fmul_rn(w3, v3)), __fmul_rn(w4, v4));
+      }
+      continue;
+    }
     const float ix = crop_coord(p.swx[xx], p.ewx[xx], b.x, b.z, p.W, p.align);
     const float iy = crop_coord(p.swy[yy], p.ewy[yy], b.y, b.w, p.H, p.align);
     const float fx = floorf(ix), fy = floorf(iy);
@@ -93,6 +120,24 @@ __global__ void __launch_bounds__(BW_THREADS) crop_bwd_kernel(CropParams p, cons
       }
       __syncthreads();
       if (!live) continue;
+      if (p.align == 2) {
+        // 'jj' taps: weight of image pixel (y, x) in crop pixel (yy, xx) = wy * wx with both clamped taps counted
+        for (int yy = 0; yy < p.HH; ++yy) {
+          const JJAxis ay = jj_axis(p.swy[yy], p.ewy[yy], b.y, b.w, p.H);
+          const float wy = (ay.a == y ? ay.wa : 0.f) + (ay.b == y ? ay.wb : 0.f);
+          if (ay.a != y && ay.b != y) continue;
+          for (int xx = 0; xx < p.WW; ++xx) {
+            const JJAxis ax = jj_axis(p.swx[xx], p.ewx[xx], b.x, b.z, p.W);
+            if (ax.a != x && ax.b != x) continue;
+            const float w = ((ax.a == x ? ax.wa : 0.f) + (ax.b == x ? ax.wb : 0.f)) * wy;
+#pragma unroll
+            for (int j = 0; j < BW_CH; ++j)
+              if (c0 + j < p.C)
+                acc[j] = fmaf(__ldg(dcrops + (((size_t)i * p.C + c0 + j) * p.HH + yy) * p.WW + xx), w, acc[j]);
+          }
+        }
+        continue;
+      }
       for (int yy = 0; yy < p.HH; ++yy) {
         const float iy = sy[yy];
         const float fy = floorf(iy);

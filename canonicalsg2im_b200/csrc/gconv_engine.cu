@@ -143,6 +143,7 @@ CSG_API int csg_gconv_bf16_fwd(const int* dims, const void* obj, const void* pre
                                size_t saved_bytes, void* new_obj, csg_stream_t stream) {
   const Dims d = read_dims(dims);
   CSG_TRY(check_dims(d));
+  CSG_REQUIRE(!(d.f16 && need_bwd), "gconv_bf16_fwd: fp16 forward tensors (dims[8] = 1) are inference-only");
   const Saved s = plan_saved(d, need_bwd != 0);
   CSG_REQUIRE(saved && saved_bytes >= s.total && (reinterpret_cast<uintptr_t>(saved) & 255) == 0,
               "gconv_bf16_fwd: `saved` must be 256-byte aligned and hold %zu bytes", s.total);

@@ -239,7 +239,7 @@ int colsum_bf16_chunks(int M, int N) {
 // one partial row per block is written for the ordered final pass (deterministic for a given grid).
 constexpr int ASM_WARPS = 8, ASM_MAXI = 5;      // ASM_MAXI * 256 >= Wd
 constexpr int ASM_CTAS_PER_SM = 3;
-template <bool CS>
+template <bool CS, bool OUT_FP16>
 __global__ void __launch_bounds__(ASM_WARPS * 32, ASM_CTAS_PER_SM)
 triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const float* __restrict__ dS,
                                 const __nv_bfloat16* __restrict__ d_newp, int ld_newp,
@@ -247,7 +247,7 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
                                 const int* __restrict__ o_idx, const int* __restrict__ valid,
                                 const int* __restrict__ type32, const float* __restrict__ conf,
                                 int NT, int H, int Dp, __nv_bfloat16* __restrict__ g,
-                                float* __restrict__ dconf, float* __restrict__ cs_partial, bool out_fp16,
+                                float* __restrict__ dconf, float* __restrict__ cs_partial,
                                 const int* __restrict__ pred, int P, float* __restrict__ wt_partial) {
   CSG_PDL_WAIT();
   __shared__ __align__(16) float cs_red[CS ? (ASM_WARPS / 2) * ASM_MAXI * 256 : 4];
@@ -313,13 +313,17 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
           for (int i = 0; i < 8; ++i) raw[i] = 0.f;
         }
         float y[8], r[8];
-        unpack8_16(__ldcs(reinterpret_cast<const uint4*>(orow + j)), y, out_fp16);
+        const uint4 yw = __ldcs(reinterpret_cast<const uint4*>(orow + j));
+        unpack8_16(yw, y, OUT_FP16);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           dot += raw[i] * y[i];
-          r[i] = y[i] > 0.f ? raw[i] * cf : 0.f;
+          r[i] = raw[i] * cf;
         }
-        const uint4 packed = pack8(r);
+        // ReLU mask on the packed words: a 16-bit float (bf16 or fp16) is > 0 iff its bits, read as int16, are > 0
+        uint4 packed = pack8(r);
+        packed.x &= __vcmpgts2(yw.x, 0u); packed.y &= __vcmpgts2(yw.y, 0u);
+        packed.z &= __vcmpgts2(yw.z, 0u); packed.w &= __vcmpgts2(yw.w, 0u);
         *reinterpret_cast<uint4*>(grow + j) = packed;
         if (CS) {
           float rb[8];
@@ -517,16 +521,28 @@ CSG_API int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const
     CSG_REQUIRE(workspace && workspace_bytes >= csg_triple_bwd_assemble_bf16_workspace(NT, H, Dp),
                 "bwd_assemble_bf16: workspace too small");
     float* partial = reinterpret_cast<float*>(workspace);
-    CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream, 
-        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, partial, out_fp16 != 0,
-        (const int*)nullptr, 0, (float*)nullptr));
+    if (out_fp16) {
+      CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true, true>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream,
+          o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, partial,
+          (const int*)nullptr, 0, (float*)nullptr));
+    } else {
+      CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true, false>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream,
+          o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, partial,
+          (const int*)nullptr, 0, (float*)nullptr));
+    }
     CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16");
     CsgReduceJob job = {partial, colsum_g, Wd, blocks, (long long)Wd, 8, CSG_RED_SUM, nullptr};
     if (int rc = csg_reduce_multi(&job, 1, stream)) return rc;
   } else {
-    CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<false>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream, 
-        o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, (float*)nullptr, out_fp16 != 0,
-        (const int*)nullptr, 0, (float*)nullptr));
+    if (out_fp16) {
+      CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<false, true>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream,
+          o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, (float*)nullptr,
+          (const int*)nullptr, 0, (float*)nullptr));
+    } else {
+      CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<false, false>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream,
+          o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, (float*)nullptr,
+          (const int*)nullptr, 0, (float*)nullptr));
+    }
     CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16");
   }
   return 0;
@@ -558,10 +574,11 @@ int csg_triple_bwd_assemble_bf16_deferred(const void* out, const float* dS, cons
   const int blocks = asm_blocks(NT);
   float* cs_partial = reinterpret_cast<float*>(workspace);
   float* wt_partial = cs_partial + (size_t)blocks * Wd;
-  CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true>, dim3(blocks), dim3(ASM_WARPS * 32), (size_t)ASM_WARPS * P * sizeof(float),
+  CSG_REQUIRE(!out_fp16, "bwd_assemble_bf16 (deferred): fp16 forward tensors are inference-only");
+  CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true, false>, dim3(blocks), dim3(ASM_WARPS * 32), (size_t)ASM_WARPS * P * sizeof(float),
                           stream, reinterpret_cast<const __nv_bfloat16*>(out), dS, reinterpret_cast<const __nv_bfloat16*>(d_newp),
                           ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, reinterpret_cast<__nv_bfloat16*>(g),
-                          (float*)nullptr, cs_partial, out_fp16 != 0, pred, P, wt_partial));
+                          (float*)nullptr, cs_partial, pred, P, wt_partial));
   CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16 (deferred)");
   job_db2->partial = cs_partial; job_db2->n = Wd; job_db2->parts = blocks;
   job_dwt->partial = wt_partial; job_dwt->n = P; job_dwt->parts = blocks;

@@ -14,7 +14,8 @@ flat (ragged) tensors: no padded rows are computed at all.
 
 ``precision``: ``"fp32"`` = fp32 FMA GEMMs (1e-5 parity with the reference);
 ``"bf16"`` = tcgen05 tensor-core GEMMs with bf16 operands / fp32 accumulation
-(1e-2 tolerance, the throughput path).
+(1e-2 tolerance, the throughput path); ``"fp16"`` = the same engine with fp16
+forward tensors (8x finer rounding at the same tensor-pipe rate), inference only.
 """
 import torch
 import torch.nn as nn
@@ -291,7 +292,7 @@ def linear(x, w, b, precision="fp32"):
     need_cuda(x, w, b)
     if x.dim() != 2:
         raise ValueError("linear expects a 2-D input (got %s)" % (tuple(x.shape),))
-    if precision == "bf16" and w.shape[0] % 64 == 0 and w.shape[1] % 64 == 0:
+    if precision in ("bf16", "fp16") and w.shape[0] % 64 == 0 and w.shape[1] % 64 == 0:
         from . import graph_tc
         return graph_tc._LinearBF16.apply(x, w, b)
     if w.shape[0] % 4 or w.shape[1] % 4:
@@ -301,7 +302,7 @@ def linear(x, w, b, precision="fp32"):
 
 def dense_mlp2(x, w0, b0, w1, b1, final_relu, precision="fp32"):
     need_cuda(x, w0, w1)
-    if precision == "bf16":
+    if precision in ("bf16", "fp16"):
         from . import graph_tc
         return graph_tc.dense_mlp2(x, w0, b0, w1, b1, final_relu)
     return _DenseMLP2F32.apply(x, w0, b0, w1, b1, final_relu)
@@ -310,7 +311,9 @@ def dense_mlp2(x, w0, b0, w1, b1, final_relu, precision="fp32"):
 def triple_conv(batch, obj, pred, params, w_trans, hidden_dim, pred_out_dim, precision="fp32"):
     """One layer on flat tensors.  params = (w1, b1, w2, b2, w3, b3, w4, b4)."""
     need_cuda(obj, pred, w_trans)
-    if precision == "bf16":
+    if precision in ("bf16", "fp16"):
+        if precision == "fp16" and obj.dtype != torch.float16:      # the layer called on its own (GraphTripleConv.forward)
+            obj, pred = obj.to(torch.float16), pred.to(torch.float16)
         from . import graph_tc
         return graph_tc.triple_conv(batch, obj, pred, params, w_trans, hidden_dim, pred_out_dim)
     return _TripleConvF32.apply(batch, hidden_dim, pred_out_dim, obj, pred, *params, w_trans)

@@ -21,6 +21,15 @@ from . import ops
 from .ops import lib, ptr, f32c, workspace, _stream, Gather
 
 BF = torch.bfloat16
+F16 = torch.float16
+INFERENCE_ONLY = ("precision='fp16' keeps the forward tensors in fp16 (11 significant bits instead of bf16's 8, same "
+                  "tensor-core rate) and is inference-only: gradients need bf16's range and tcgen05.mma cannot mix an "
+                  "fp16 operand with a bf16 one (scratch/probe_mixed_mma.py); run under torch.no_grad() or use 'bf16'")
+
+
+def _fmt(dtype):
+    """csg_embed_fwd's output selector: 0 fp32, 1 bf16, 2 fp16."""
+    return {torch.float32: 0, BF: 1, F16: 2}[dtype]
 
 
 def cast_bf16(w, transpose=False):
@@ -33,27 +42,28 @@ def cast_bf16(w, transpose=False):
     return out
 
 
-def cast_bf16_multi(jobs):
-    """jobs: list of (fp32 matrix, transpose) -> list of bf16 copies, one launch."""
+def cast_bf16_multi(jobs, dtype=BF):
+    """jobs: list of (fp32 matrix, transpose) -> list of bf16 (or fp16) copies, one launch."""
     import ctypes
     srcs = [f32c(w) for w, _ in jobs]
-    outs = [torch.empty((w.shape[1], w.shape[0]) if tr else tuple(w.shape), dtype=BF, device=w.device)
+    outs = [torch.empty((w.shape[1], w.shape[0]) if tr else tuple(w.shape), dtype=dtype, device=w.device)
             for w, (_, tr) in zip(srcs, jobs)]
     n = len(jobs)
     VP, IA = ctypes.c_void_p * n, ctypes.c_int * n
     rc = lib().csg_cast_bf16_multi(n, VP(*[w.data_ptr() for w in srcs]), VP(*[o.data_ptr() for o in outs]),
                                    IA(*[w.shape[0] for w in srcs]), IA(*[w.shape[1] for w in srcs]),
-                                   IA(*[int(tr) for _, tr in jobs]), 0, _stream())
+                                   IA(*[int(tr) for _, tr in jobs]), int(dtype == F16), _stream())
     _lib.check(rc, "csg_cast_bf16_multi")
     return outs
 
 
-def as_bf16_rows(x):
-    """bf16 2-D tensor with unit inner stride and 16-byte aligned rows (views are kept)."""
-    if x.dtype != BF:
-        if x.dtype == torch.float32 and x.is_contiguous():
+def as_bf16_rows(x, dtype=BF):
+    """16-bit (bf16, or fp16 for the inference-only precision) 2-D tensor with unit inner stride and 16-byte aligned
+    rows (views are kept)."""
+    if x.dtype != dtype:
+        if x.dtype == torch.float32 and x.is_contiguous() and dtype == BF:
             return cast_bf16(x)
-        x = x.to(BF)
+        x = x.to(dtype)
     if x.stride(-1) != 1 or x.stride(0) % 8 != 0 or x.data_ptr() % 16 != 0:
         x = x.contiguous()
     return x
@@ -113,23 +123,26 @@ class _TripleConvEngine(torch.autograd.Function):
         L = lib()
         dev = obj.device
         ctx.in_dtypes = (obj.dtype, pred.dtype)
-        obj_b, pred_b = as_bf16_rows(obj), as_bf16_rows(pred)
+        act = F16 if obj.dtype == F16 else BF       # fp16 inputs select the inference-only fp16 forward format
+        need_bwd = int(any(ctx.needs_input_grad))
+        if act == F16 and need_bwd:
+            raise _lib.CsgError(INFERENCE_ONLY)
+        obj_b, pred_b = as_bf16_rows(obj, act), as_bf16_rows(pred, act)
         if not obj_b.is_contiguous():
             obj_b = obj_b.contiguous()
         params = [f32c(p.detach()) for p in (w1, b1, w2, b2, w3, b3, w4, b4, w_trans)]
         Dout, P = w4.shape[0], w_trans.numel()
-        dims = (ctypes.c_int * 9)(batch.NT, batch.NO, obj_b.shape[1], pred_b.shape[1], H, Dout, Dpo, P, 0)
-        need_bwd = int(any(ctx.needs_input_grad))
+        dims = (ctypes.c_int * 9)(batch.NT, batch.NO, obj_b.shape[1], pred_b.shape[1], H, Dout, Dpo, P, int(act == F16))
         nsaved = L.csg_gconv_bf16_saved_bytes(dims, need_bwd)
         saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
-        new_obj = torch.empty((batch.NO, Dout), dtype=BF, device=dev)
+        new_obj = torch.empty((batch.NO, Dout), dtype=act, device=dev)
         index = batch.index_array()
         rc = L.csg_gconv_bf16_fwd(dims, ptr(obj_b), ptr(pred_b), pred_b.stride(0), _ptr_array(params), index, need_bwd,
                                   ptr(saved), nsaved, ptr(new_obj), _stream())
         _lib.check(rc, "csg_gconv_bf16_fwd")
         Wd = 2 * H + Dpo
         off = L.csg_gconv_bf16_out_offset(dims, need_bwd)
-        out = saved[off:off + batch.NT * Wd * 2].view(BF).view(batch.NT, Wd)
+        out = saved[off:off + batch.NT * Wd * 2].view(act).view(batch.NT, Wd)
         new_p = out[:, H:H + Dpo]
         ctx.batch, ctx.dims, ctx.params = batch, dims, params
         ctx.save_for_backward(obj_b, pred_b, saved, new_obj)
@@ -202,14 +215,17 @@ class _DenseMLP2BF16(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w0, b0, w1, b1):
         L = lib()
-        xb = as_bf16_rows(x)
-        M, (H, D), nout = xb.shape[0], w0.shape, w1.shape[0]
+        act = F16 if x.dtype == F16 else BF
         need_bwd = any(ctx.needs_input_grad)
-        casts = cast_bf16_multi([(w0, False)] + ([(w0, True)] if need_bwd else []))
-        h = ops.gemm_bf16(M, H, D, xb, casts[0], bias=f32c(b0), relu=True)
+        if act == F16 and need_bwd:
+            raise _lib.CsgError(INFERENCE_ONLY)
+        xb = as_bf16_rows(x, act)
+        M, (H, D), nout = xb.shape[0], w0.shape, w1.shape[0]
+        casts = cast_bf16_multi([(w0, False)] + ([(w0, True)] if need_bwd else []), act)
+        h = ops.gemm_bf16(M, H, D, xb, casts[0], bias=f32c(b0), relu=True, out_dtype=act)
         y = torch.empty((M, nout), dtype=torch.float32, device=xb.device)
         w1c = f32c(w1.detach())
-        _lib.check(L.csg_head_fwd(ptr(h), h.stride(0), ptr(w1c), ptr(f32c(b1.detach())), M, H, nout, ptr(y), 0, _stream()),
+        _lib.check(L.csg_head_fwd(ptr(h), h.stride(0), ptr(w1c), ptr(f32c(b1.detach())), M, H, nout, ptr(y), int(act == F16), _stream()),
                    "csg_head_fwd")
         ctx.save_for_backward(xb, h, w1c)
         ctx.w0t = casts[1] if need_bwd else None
@@ -244,11 +260,14 @@ class _LinearBF16(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b):
-        xb = as_bf16_rows(x)
+        act = F16 if x.dtype == F16 else BF
         need_bwd = any(ctx.needs_input_grad)
-        casts = cast_bf16_multi([(w, False)] + ([(w, True)] if need_bwd else []))
+        if act == F16 and need_bwd:
+            raise _lib.CsgError(INFERENCE_ONLY)
+        xb = as_bf16_rows(x, act)
+        casts = cast_bf16_multi([(w, False)] + ([(w, True)] if need_bwd else []), act)
         N, K = w.shape
-        y = ops.gemm_bf16(xb.shape[0], N, K, xb, casts[0], bias=f32c(b))
+        y = ops.gemm_bf16(xb.shape[0], N, K, xb, casts[0], bias=f32c(b), out_dtype=act)
         ctx.save_for_backward(xb)
         ctx.wt = casts[1] if need_bwd else None
         ctx.x_dtype, ctx.shape = x.dtype, (N, K)

@@ -38,14 +38,18 @@ def _offsets(obj_offsets, device):
 
 class _LayoutFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, vecs, boxes, masks, obj_off, H, W, align_corners, max_objs):
+    def forward(ctx, vecs, boxes, masks, obj_off, H, W, align_corners, max_objs, lin_x=None, lin_y=None):
         need_cuda(vecs, boxes, masks, obj_off)
         vecs_c, boxes_c = f32c(vecs), f32c(boxes)
         masks_c = f32c(masks) if masks is not None else None
         NO, D = vecs_c.shape
         N = obj_off.numel() - 1
         M = masks_c.shape[1] if masks_c is not None else 0
-        lin_x, lin_y = _linspace(W, vecs.device), _linspace(H, vecs.device)
+        # the canvas coordinates of the pixel columns / rows: torch.linspace(0, 1, W) / (0, 1, H) unless the caller
+        # samples a sub-lattice of a finer canvas (layout_pyramid)
+        lin_x = _linspace(W, vecs.device) if lin_x is None else lin_x
+        lin_y = _linspace(H, vecs.device) if lin_y is None else lin_y
+        ctx.lin = (lin_x, lin_y)
         out = torch.empty((N, D, H, W), dtype=torch.float32, device=vecs.device)
         rc = lib().csg_layout_fwd(ptr(vecs_c), ptr(boxes_c), ptr(masks_c), ptr(obj_off), ptr(lin_x), ptr(lin_y),
                                   ptr(out), N, D, H, W, M, int(align_corners), int(max_objs), _stream())
@@ -62,7 +66,7 @@ class _LayoutFn(torch.autograd.Function):
         dout = f32c(dout)
         dvecs = dboxes = dmasks = None
         L = lib()
-        lin_x, lin_y = _linspace(W, dout.device), _linspace(H, dout.device)
+        lin_x, lin_y = ctx.lin
         if ctx.needs_input_grad[0]:
             dvecs = torch.empty((NO, D), dtype=torch.float32, device=dout.device)
             ws = workspace(L.csg_layout_bwd_vecs_workspace(N, NO, D, H, W), dout.device)
@@ -81,7 +85,42 @@ class _LayoutFn(torch.autograd.Function):
             _lib.check(rc, "csg_layout_bwd_geom")
             if not ctx.needs_input_grad[1]:
                 dboxes = None
-        return dvecs, dboxes, dmasks, None, None, None, None, None
+        return dvecs, dboxes, dmasks, None, None, None, None, None, None, None
+
+
+def nearest_source_index(out_size, in_size, device):
+    """Source index of every output index of ``F.interpolate(mode='nearest')`` (ATen nearest_neighbor_compute_source_index:
+    ``min(floor(dst * in / out), in - 1)`` with the scale evaluated in float32)."""
+    scale = torch.tensor(float(in_size) / float(out_size), dtype=torch.float32)
+    idx = torch.floor(torch.arange(out_size, dtype=torch.float32) * scale).to(torch.int64).clamp_(max=in_size - 1)
+    return idx.to(device)
+
+
+def layout_pyramid(vecs, boxes, obj_offsets, H, W=None, sizes=(), masks=None, align_corners=False,
+                   max_objs_per_image=0):
+    """The canvas together with the nearest-neighbour resizes of it that the SPADE consumers compute from it:
+    ``F.interpolate(seg, size=(sh, sw))`` of the generator head (spade/models/networks/generator.py:99) and
+    ``F.interpolate(segmap, size=x.size()[2:], mode='nearest')`` of every SPADE block (normalization.py:102), which
+    re-read the 268-512 MiB canvas about seven times per forward.
+
+    A nearest resize only selects pixels, and a canvas pixel depends on nothing but its own coordinates
+    (layout.py:98-101), so level (h, w) IS the compositor evaluated on the sub-lattice ``lin_y[src_y], lin_x[src_x]``:
+    every level is written directly by the compositor kernels (bit-identical to slicing the full canvas), the big
+    canvas is never re-read, and the backward pass adds the levels' gradients into d vecs / d boxes with the same
+    kernels on the same sub-lattices.  Returns ``(canvas [N, D, H, W], [level [N, D, h, w] for (h, w) in sizes])``."""
+    W = H if W is None else W
+    need_cuda(vecs, boxes, masks)
+    off = _offsets(obj_offsets, vecs.device)
+    canvas = _LayoutFn.apply(vecs, boxes, masks, off, int(H), int(W), bool(align_corners), int(max_objs_per_image))
+    lin_x, lin_y = _linspace(W, vecs.device), _linspace(H, vecs.device)
+    levels = []
+    for size in sizes:
+        h, w = (size, size) if isinstance(size, int) else size
+        ly = lin_y[nearest_source_index(h, H, vecs.device)].contiguous()
+        lx = lin_x[nearest_source_index(w, W, vecs.device)].contiguous()
+        levels.append(_LayoutFn.apply(vecs, boxes, masks, off, int(h), int(w), bool(align_corners),
+                                      int(max_objs_per_image), lx, ly))
+    return canvas, levels
 
 
 def layout_batched(vecs, boxes, obj_offsets, H, W=None, masks=None, pooling="sum", test_mode=False,

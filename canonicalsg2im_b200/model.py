@@ -35,7 +35,7 @@ class _EmbedFn(torch.autograd.Function):
         n, (V, E) = idx.numel(), tab.shape
         out = torch.empty((n, E), dtype=out_dtype, device=tab.device)
         rc = lib().csg_embed_fwd(ptr(tab), ptr(idx), idx.stride(0) if n else 1, n, V, E, ptr(out), E,
-                                 int(out_dtype == torch.bfloat16), _stream())
+                                 {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[out_dtype], _stream())
         _lib.check(rc, "csg_embed_fwd")
         ctx.save_for_backward(idx)
         ctx.dims = (n, V, E)
@@ -143,7 +143,7 @@ class _MultiEmbedFn(torch.autograd.Function):
         for k, tab in enumerate(tabs):
             V, E = tab.shape
             rc = lib().csg_embed_fwd(ptr(tab), idx.data_ptr() + 8 * k, A, n, V, E, out.data_ptr() + col * esz, W,
-                                     int(out_dtype == torch.bfloat16), _stream())
+                                     {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[out_dtype], _stream())
             _lib.check(rc, "csg_embed_fwd")
             col += E
         ctx.save_for_backward(idx)
@@ -199,9 +199,9 @@ class AttributeEmbeddings(nn.Module):
         tables = [self._modules["att_emb_%d" % k].weight for k in range(flat.size(-1))]
         if fc is None:
             return _MultiEmbedFn.apply(flat, out_dtype, *tables).view(*lead, -1)
-        bf16 = out_dtype == torch.bfloat16 and fc.weight.shape[0] % 64 == 0
-        v = _MultiEmbedFn.apply(flat, torch.bfloat16 if bf16 else torch.float32, *tables)
-        v = linear(v, fc.weight, fc.bias, "bf16" if bf16 else "fp32")
+        tc = out_dtype in (torch.bfloat16, torch.float16) and fc.weight.shape[0] % 64 == 0
+        v = _MultiEmbedFn.apply(flat, out_dtype if tc else torch.float32, *tables)
+        v = linear(v, fc.weight, fc.bias, "bf16" if tc else "fp32")
         if v.dtype != out_dtype:
             v = v.to(out_dtype)
         return v.view(*lead, -1)
@@ -239,7 +239,7 @@ class Sg2LayoutModel(nn.Module):
         self.padding_id = self.vocab["pred_name_to_idx"]["__padding__"]
 
     def _act_dtype(self):
-        return torch.bfloat16 if self.precision == "bf16" else torch.float32
+        return {"bf16": torch.bfloat16, "fp16": torch.float16}.get(self.precision, torch.float32)
 
     def _run(self, batch, obj_vecs, pred_vecs):
         for layer in self.gconvs:

@@ -279,7 +279,7 @@ class SgToLayoutInference:
 
     ``step(d)`` expects the device tensors of :class:`HostBatch` plus ``centers [NO, 2]`` and ``masks [NO, M, M]``."""
 
-    def __init__(self, vocab, device, precision="bf16", H=256, W=256, embedding_dim=32, attr_sizes=None,
+    def __init__(self, vocab, device, precision="fp16", H=256, W=256, embedding_dim=32, attr_sizes=None,
                  learned_converse=True, learned_transitivity=True, seed=0):
         import argparse
         self.vocab, self.device, self.H, self.W = vocab, device, H, W

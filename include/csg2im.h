@@ -84,7 +84,9 @@ int csg_layout_bwd_geom(const float* dout, const float* vecs, const float* boxes
 /* ---- box crops: sg2im/bilinear.py:65-94 (crop_bbox, backend 'cudnn'), :44-62 (crop_bbox_batch_cudnn).
  *      Crops crop_off[n]..crop_off[n+1] sample image n of feats [N,C,H,W] in place (the reference expands the
  *      image once per object); bbox [NC,4] xywh; swx/ewx [WW], swy/ewy [HH] = torch.linspace(1,0,.) / (0,1,.)
- *      in fp32 (tensor_linspace, bilinear.py:155-184).  crops [NC,C,HH,WW]. ------------------------------ */
+ *      in fp32 (tensor_linspace, bilinear.py:155-184).  crops [NC,C,HH,WW].  align_corners: 0 / 1 = the two
+ *      F.grid_sample conventions of backend 'cudnn'; 2 = backend 'jj' (bilinear_sample, bilinear.py:97-152: [0, 1]
+ *      coordinates scaled by the image size, taps clamped into the image). ------------------------------------ */
 size_t csg_crop_bbox_workspace(int NC);
 int csg_crop_bbox_fwd(const float* feats, const float* bbox, const int* crop_off, const float* swx,
                       const float* ewx, const float* swy, const float* ewy, float* crops, int N, int NC,

@@ -140,3 +140,39 @@ def crop_bbox_batch(imgs, obj_keep, bbox, HH, WW=None, align_corners=False):
         feats.append(imgs[i].view(1, C, H, W).expand(cur.shape[0], C, H, W).contiguous())
         boxes.append(cur)
     return crop_bbox(torch.cat(feats, 0), torch.cat(boxes, 0), HH, WW, align_corners)
+
+
+def bilinear_sample(feats, X, Y):
+    """sg2im/bilinear.py:97-152: four clamped taps (floor, floor + 1) with weights measured against the clamped taps.
+    feats [N,C,H,W]; X, Y [N,HH,WW] in [0, 1]."""
+    N, C, H, W = feats.shape
+    _, HH, WW = X.shape
+    X = X * W                                                                # :114-115
+    Y = Y * H
+    x0 = X.floor().clamp(min=0, max=W - 1)                                   # :118-121
+    x1 = (x0 + 1).clamp(min=0, max=W - 1)
+    y0 = Y.floor().clamp(min=0, max=H - 1)
+    y1 = (y0 + 1).clamp(min=0, max=H - 1)
+    flat = feats.reshape(N, C, H * W)
+
+    def take(yy, xx):                                                        # :131-143
+        idx = (W * yy + xx).view(N, 1, HH * WW).expand(N, C, HH * WW).long()
+        return flat.gather(2, idx).view(N, C, HH, WW)
+    v1, v2, v3, v4 = take(y0, x0), take(y1, x0), take(y0, x1), take(y1, x1)
+    e = lambda w: w.view(N, 1, HH, WW).expand(N, C, HH, WW)                  # :146-149
+    w1, w2 = e((x1 - X) * (y1 - Y)), e((x1 - X) * (Y - y0))
+    w3, w4 = e((X - x0) * (y1 - Y)), e((X - x0) * (Y - y0))
+    return w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4                             # :152
+
+
+def crop_bbox_jj(feats, bbox, HH, WW=None):
+    """sg2im/bilinear.py:65-94 with backend='jj': the box stays in [0, 1] coordinates and is sampled by
+    ``bilinear_sample``."""
+    WW = HH if WW is None else WW
+    N = feats.shape[0]
+    pts = bbox.clone()
+    pts[:, 2] = bbox[:, 0] + bbox[:, 2]
+    pts[:, 3] = bbox[:, 1] + bbox[:, 3]
+    X = tensor_linspace(pts[:, 0], pts[:, 2], WW).view(N, 1, WW).expand(N, HH, WW)
+    Y = tensor_linspace(pts[:, 1], pts[:, 3], HH).view(N, HH, 1).expand(N, HH, WW)
+    return bilinear_sample(feats, X, Y)

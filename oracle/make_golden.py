@@ -594,6 +594,22 @@ def gen_pyramid(rlayout):
     np.savez_compressed(os.path.join(OUT, "pyramid.npz"), **out)
 
 
+def gen_crop_jj(rbil):
+    """crop_bbox(backend='jj') = bilinear_sample (bilinear.py:97-152) of the unmodified reference, fwd + d/dfeats;
+    boxes inside the image, touching its border and reaching beyond it (clamped taps)."""
+    imgs = synth.det_tensor((4, 3, 24, 20), 31, 1.0)
+    bb = np.array([[0.1, 0.2, 0.5, 0.6], [0.0, 0.0, 1.0, 1.0], [0.6, 0.5, 0.7, 0.8], [0.93, 0.9, 0.05, 0.08]], np.float32)
+    im = t(imgs).clone().requires_grad_(True)
+    crops = rbil.crop_bbox(im, t(bb), 8, 12, backend="jj")
+    gc = t(synth.det_tensor(tuple(crops.shape), 32, 1.0))
+    (crops * gc).sum().backward()
+    oc = olayout.crop_bbox_jj(t(imgs), t(bb), 8, 12)
+    assert torch.allclose(oc, crops.detach(), rtol=0, atol=1e-6), "oracle crop_bbox jj"
+    np.savez_compressed(os.path.join(OUT, "crop_jj.npz"), imgs=imgs, boxes=bb, out=crops.detach().numpy(),
+                        dimgs=im.grad.numpy())
+    print("crop jj:", tuple(crops.shape))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="", help="comma-separated fixture names (default: all)")
@@ -605,7 +621,7 @@ def main():
             ("sg2layout_model", lambda: gen_model(rmodel)), ("layout", lambda: gen_layout(rlayout, rbil)),
             ("collate", gen_collate), ("box_loss", gen_box_loss), ("cfg2_model", lambda: gen_cfg2_model(bd, rmodel)),
             ("cfg4_model", lambda: gen_cfg4_model(bd, rmodel)), ("cfg3_layout", lambda: gen_cfg3_layout(rlayout)),
-            ("pyramid", lambda: gen_pyramid(rlayout))]
+            ("pyramid", lambda: gen_pyramid(rlayout)), ("crop_jj", lambda: gen_crop_jj(rbil))]
     for name, fn in jobs:
         if not only or name in only:
             fn()

@@ -9,7 +9,7 @@ import torch
 class _Round(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
-        return x.to(torch.bfloat16).float()
+        return x.to(torch.bfloat16).to(x.dtype)
 
     @staticmethod
     def backward(ctx, g):
@@ -30,7 +30,7 @@ class _RoundGrad(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return g.to(torch.bfloat16).float()
+        return g.to(torch.bfloat16).to(g.dtype)
 
 
 def rg(x, on=True):
@@ -49,9 +49,9 @@ def layer_bf16_ref(state, obj, pred, s_idx, o_idx, valid, conf_fn, H, Dpo, round
     out = r(torch.relu(rg(hidden @ r(g("net1.2.weight")).T + g("net1.2.bias"), round_grads)) * conf[:, None])
     NO = obj.shape[0]
     v = valid
-    pooled = torch.zeros(NO, H, device=obj.device).index_add(0, s_idx[v], out[v][:, :H])
+    pooled = torch.zeros(NO, H, device=obj.device, dtype=out.dtype).index_add(0, s_idx[v], out[v][:, :H])
     pooled = pooled.index_add(0, o_idx[v], out[v][:, H + Dpo:])
-    cnt = torch.zeros(NO, device=obj.device).index_add(0, s_idx[v], conf[v]).index_add(0, o_idx[v], conf[v])
+    cnt = torch.zeros(NO, device=obj.device, dtype=conf.dtype).index_add(0, s_idx[v], conf[v]).index_add(0, o_idx[v], conf[v])
     pooled = torch.where((cnt > 0)[:, None], pooled / torch.where(cnt > 0, cnt, torch.ones_like(cnt))[:, None], pooled)
     h2 = r(torch.relu(rg(r(pooled) @ r(g("net2.0.weight")).T + g("net2.0.bias"), round_grads)))  # dh2
     new_obj = r(torch.relu(rg(h2 @ r(g("net2.2.weight")).T + g("net2.2.bias"), round_grads)))     # g4
@@ -71,7 +71,7 @@ def model_bf16_ref(state, objs, triplets, types, padding_id, num_layers=5, H=512
     obj = state["attribute_embedding.att_emb_0.weight"][objs.reshape(-1)]
     pred = state["pred_embeddings.weight"][pf]
     w_trans = state["trans_candidates_weights"]
-    conf_fn = lambda: (tyf == 0).float() + (tyf == 1).float() * torch.sigmoid(w_trans)[pf]
+    conf_fn = lambda: (tyf == 0).to(w_trans.dtype) + (tyf == 1).to(w_trans.dtype) * torch.sigmoid(w_trans)[pf]
     for i in range(num_layers):
         st = {k[len("gconvs.%d." % i):]: v for k, v in state.items() if k.startswith("gconvs.%d." % i)}
         obj, pred = layer_bf16_ref(st, obj, pred, sg, og, pf != padding_id, conf_fn, H, D, round_grads=True,

@@ -44,6 +44,21 @@ def oracle_run(case, dtype=torch.float32):
                 boxes_pred=boxes_pred.detach(), loss=loss.item(), grads=grads)
 
 
+def cuda_forward(case, ref, precision):
+    """Forward only, under torch.no_grad() (what the inference-only fp16 precision allows)."""
+    from canonicalsg2im_b200.model import Sg2LayoutModel
+    vocab, graphs, W, seeds, st, opt = case
+    model = Sg2LayoutModel(opt, precision=precision).cuda()
+    sd = {k: torch.from_numpy(v) for k, v in st.items()}
+    for i in range(len(model.gconvs)):
+        sd["gconvs.%d.predicates_transitive_weights" % i] = sd["trans_candidates_weights"]
+    model.load_state_dict(sd, strict=True)
+    T = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    with torch.no_grad():
+        obj_vecs, boxes_pred, _ = model(T(ref["objs"]), T(ref["trips"]), T(ref["types"]))
+    return dict(obj_vecs=obj_vecs.float(), boxes_pred=boxes_pred.float())
+
+
 def cuda_run(case, ref, precision):
     """The same padded batch through canonicalsg2im_b200.Sg2LayoutModel on cuda (reference state-dict keys)."""
     from canonicalsg2im_b200.model import Sg2LayoutModel, bbox_pred_loss

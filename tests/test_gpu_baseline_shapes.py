@@ -23,7 +23,10 @@ bf16 engine (the benched path; north_star: 1e-2).  OUTPUTS (obj_vecs, boxes_pred
 max-norm <= 2.5e-2 (measured 1.0e-2 / 2.0e-2 at cfg2 / cfg4: five stacked layers of four bf16-operand GEMMs each; one
 layer is within 4e-3, tests/test_gpu_graph.py).  GRADIENTS, in two parts:
   (1) kernels vs plain PyTorch running the SAME arithmetic (tests/bf16_ref.py: fp32 torch ops with every stored tensor
-      rounded to bf16): relative L2 <= 1e-2 per tensor -- this pins the kernels;
+      rounded to bf16): relative L2 <= 1e-2 per tensor for ONE layer (tests/test_gpu_graph.py) -- this pins the
+      kernels; through five layers that arithmetic is not reproducible below 1e-2..6e-2 even between two plain-torch
+      evaluations (float32 vs float64 accumulation), so at model level the kernels must sit within twice that
+      self-noise;
   (2) that arithmetic vs the fp32 reference: the mask-flip law above with bf16's unit roundoff u = 2^-8 instead of
       fp32's 2^-24 predicts sqrt(2^16) = 256 x the reference's own 2e-4..4e-4, i.e. 5e-2..1e-1, and that is what ANY
       bf16-operand evaluation of this ReLU network gives (measured: 1e-2..5.6e-2 on the weight matrices, up to 7.8e-2 on
@@ -97,34 +100,63 @@ def test_bf16_engine_at_baseline_shapes(name):
     assert not bad, bad
 
 
-def test_bf16_kernels_match_the_same_arithmetic_in_plain_pytorch():
-    """Part (1) of the bf16 gradient contract at cfg2 shapes: the CUDA engine against torch ops that round the same
-    tensors to bf16 (tests/bf16_ref.py), outputs and every gradient at 1e-2 in relative L2."""
-    from canonicalsg2im_b200.model import bbox_pred_loss
-    from tests.bf16_ref import model_bf16_ref
-    case = bc.cfg2_case()
+@pytest.mark.parametrize("name", ["cfg2", "cfg4"])
+def test_fp16_inference_precision_at_baseline_shapes(name):
+    """precision='fp16' (forward tensors in fp16: 11 significant bits at the tensor-pipe rate of bf16; inference only,
+    what the cfg4 generate_clevr path runs): outputs within north_star's 1e-2 of the oracle in MAX-norm, with margin
+    (measured 1e-3 .. 3e-3), where five stacked bf16 layers sit at 1e-2 .. 2e-2; asking for gradients raises."""
+    from canonicalsg2im_b200 import _lib
+    case = bc.cfg2_case() if name == "cfg2" else bc.cfg4_case()
+    ref = _ref(name)
+    got = parity.cuda_forward(case, ref, "fp16")
+    e_v, e_b = parity.errs(got["obj_vecs"], ref["obj_vecs"]), parity.errs(got["boxes_pred"], ref["boxes_pred"])
+    assert e_v["max"] <= 5e-3 and e_b["max"] <= 5e-3, (e_v, e_b)
+    bf = parity.cuda_forward(case, ref, "bf16")
+    assert e_v["l2"] < 0.5 * parity.errs(bf["obj_vecs"], ref["obj_vecs"])["l2"]
+    with pytest.raises(_lib.CsgError, match="inference-only"):
+        parity.cuda_run(case, ref, "fp16")
+
+
+def _torch_bf16_model_run(case, ref, dtype):
+    """tests/bf16_ref.py (plain torch ops, every stored tensor rounded to bf16) on cuda with `dtype` accumulation."""
+    from tests import bf16_ref
     vocab, graphs, W, seeds, st, opt = case
+    state = {k: t(v).to(dtype).clone().requires_grad_(k != "converse_candidates_weights") for k, v in st.items()}
+    objs, trips, types = t(ref["objs"]), t(ref["trips"]), t(ref["types"])
+    obj_vecs, boxes = bf16_ref.model_bf16_ref(state, objs[:, :, 0], trips, types, vocab.padding_id)
+    B, O = objs.shape[0], objs.shape[1]
+    flat = torch.nn.functional.smooth_l1_loss(boxes, t(ref["boxes"]).to(dtype).view(-1, 4), reduction="none") * 10.0
+    real = (objs.view(-1, 1) != 0).to(dtype)
+    bl = ((flat * real).view(B, O, 4).sum(dim=[1, 2]) / real.view(B, O).sum(dim=1)).mean()
+    loss = bl + (obj_vecs.view(B, O, -1) * t(bc.obj_grad((B, O, obj_vecs.shape[-1]))).to(dtype)).sum() * 1e-2
+    loss.backward()
+    return dict(obj_vecs=obj_vecs.detach().view(B, O, -1), boxes_pred=boxes.detach().view(B, O, 4), loss=loss.item(),
+                grads={k: v.grad for k, v in state.items() if v.grad is not None})
+
+
+def test_bf16_kernels_are_as_close_to_the_bf16_arithmetic_as_that_arithmetic_is_to_itself():
+    """Part (1) of the bf16 gradient contract at cfg2 shapes.  The engine's arithmetic written with plain torch ops
+    (tests/bf16_ref.py: fp32 torch with every tensor the kernels store as bf16 rounded to bf16, gradients included) is
+    itself not reproducible below a few 1e-2 through five layers: evaluating it with float32 or with float64
+    accumulation changes ~1e-4 of the bf16 roundings by one ulp, those flip ReLU masks downstream, and the gradients
+    of the two evaluations differ by 1e-2 .. 6e-2 in relative L2 (measured on the CPU and on the GPU; one LAYER is
+    reproducible to 1e-2, tests/test_gpu_graph.py::test_layer_bf16_vs_golden).  So the kernels are required to sit
+    within that self-noise: err(kernels, model_f64acc) <= 2 x err(model_f32acc, model_f64acc), as max and as rms over
+    the tensors, and their outputs within 1e-2 of the model's."""
+    case = bc.cfg2_case()
     ref = _ref("cfg2")
     got = parity.cuda_run(case, ref, "bf16")
-    state = {k: t(v).clone().requires_grad_(k != "converse_candidates_weights") for k, v in st.items()}
-    objs, trips, types = t(ref["objs"]), t(ref["trips"]), t(ref["types"])
-    obj_vecs, boxes = model_bf16_ref(state, objs[:, :, 0], trips, types, vocab.padding_id)
-    B, O = objs.shape[0], objs.shape[1]
-    # the same loss as parity.cuda_run, with the box term written in torch (pix2pix_model.py:72-85)
-    flat = torch.nn.functional.smooth_l1_loss(boxes, t(ref["boxes"]).view(-1, 4), reduction="none") * 10.0
-    real = (objs.view(-1, 1) != 0).float()
-    bl = ((flat * real).view(B, O, 4).sum(dim=[1, 2]) / real.view(B, O).sum(dim=1)).mean()
-    loss = bl + (obj_vecs.view(B, O, -1) * t(bc.obj_grad((B, O, obj_vecs.shape[-1])))).sum() * 1e-2
-    loss.backward()
-    assert parity.errs(got["obj_vecs"].reshape(B * O, -1), obj_vecs)["l2"] <= 1e-2
-    assert parity.errs(got["boxes_pred"].reshape(B * O, 4), boxes)["l2"] <= 1e-2
-    bad = {}
-    for k, g in got["grads"].items():
-        e = parity.errs(g, state[k].grad)["l2"]
-        if e > 1e-2:
-            bad[k] = e
-    assert not bad, bad
-    assert len(got["grads"]) >= 44
+    m32 = _torch_bf16_model_run(case, ref, torch.float32)
+    m64 = _torch_bf16_model_run(case, ref, torch.float64)
+    mine, theirs = parity.compare(m64, got), parity.compare(m64, m32)
+    for k in ("obj_vecs", "boxes_pred", "loss"):
+        assert mine[k]["l2"] <= 1e-2, (k, mine[k])
+    grads = [k for k in mine if k.startswith("d ")]
+    assert len(grads) >= 44
+    worst = lambda tab: max(tab[k]["l2"] for k in grads)
+    rms = lambda tab: float(np.sqrt(np.mean([tab[k]["l2"] ** 2 for k in grads])))
+    assert worst(mine) <= 2.0 * worst(theirs) + 1e-3, (worst(mine), worst(theirs))
+    assert rms(mine) <= 2.0 * rms(theirs) + 1e-3, (rms(mine), rms(theirs))
 
 
 def test_bf16_engine_vs_reference_golden_directly(golden):

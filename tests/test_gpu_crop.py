@@ -60,3 +60,14 @@ def test_crop_identity_and_errors():
         crop_bbox(x.cpu(), full.cpu(), 8)
     with pytest.raises(AssertionError):
         crop_bbox(x, full[:1], 8)
+
+
+def test_crop_bbox_jj_backend_golden(golden):
+    """backend='jj' (bilinear_sample, bilinear.py:97-152) against the unmodified reference: forward and d/dfeats."""
+    from canonicalsg2im_b200.bilinear import crop_bbox
+    g = golden("crop_jj")
+    im = t(g["imgs"]).requires_grad_(True)
+    crops = crop_bbox(im, t(g["boxes"]), 8, 12, backend="jj")
+    assert_close(crops, g["out"], 1e-5, "crop jj")
+    (crops * t(gi.crop_out_grad(crops.shape))).sum().backward()
+    assert_close(im.grad, g["dimgs"], 1e-5, "crop jj d/dfeats")

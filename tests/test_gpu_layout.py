@@ -288,3 +288,45 @@ def test_tensor_core_backward_path_matches_ring_path():
         a, b = res["tc"][k], res["ring"][k]
         assert np.isfinite(a).all()
         assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max(), k
+
+
+# ------------------------------------------------------------------------------------------------------
+# SPADE-side pyramid: generator.py:99 + normalization.py:102
+# ------------------------------------------------------------------------------------------------------
+def test_layout_pyramid_vs_reference_interpolate(golden, L):
+    """layout_pyramid's levels against the reference's own F.interpolate(mode='nearest') of the reference canvas
+    (tests/golden/pyramid.npz, unmodified reference), 1e-5; and bit-identical to slicing our own canvas."""
+    g = golden("pyramid")
+    vocab = synth.Vocab(0)
+    graphs = synth.make_graphs(3, 31, 2, 6, vocab, include_dummies=False)
+    vecs = np.concatenate([synth.det_tensor((len(gr.boxes), 16), 50 + i, 1.0) for i, gr in enumerate(graphs)])
+    boxes = np.concatenate([gr.boxes for gr in graphs])
+    off = np.concatenate([[0], np.cumsum([len(gr.boxes) for gr in graphs])]).astype(np.int32)
+    canvas, levels = L.layout_pyramid(t(vecs), t(boxes), t(off), 64, 64, sizes=[(2, 2), 4, 8, 16, 32])
+    assert_close(canvas, g["seg"], TOL, "canvas")
+    for lev, name, r in zip(levels, ["head", "l4", "l8", "l16", "l32"], [32, 16, 8, 4, 2]):
+        assert_close(lev, g[name], TOL, "pyramid " + name)
+        assert torch.equal(lev, canvas[:, :, ::r, ::r])
+    # a non-integer ratio follows ATen's source-index rule as well
+    _, (l24,) = L.layout_pyramid(t(vecs), t(boxes), t(off), 64, 64, sizes=[24])
+    ref24 = torch.nn.functional.interpolate(canvas, size=(24, 24), mode="nearest")
+    assert torch.equal(l24, ref24)
+
+
+def test_layout_pyramid_gradients_vs_oracle(L):
+    """d vecs / d boxes through canvas + levels == autograd of the oracle canvas followed by F.interpolate."""
+    from oracle import layout as olayout
+    import torch.nn.functional as F
+    vecs, boxes, masks, off = _rand_objs(17, 3, 2, 7, 16, 8)
+    sizes = [4, 16, 32]
+    v, b = t(vecs).requires_grad_(True), t(boxes).requires_grad_(True)
+    canvas, levels = L.layout_pyramid(v, b, t(off), 64, 64, sizes=sizes, masks=t(masks), max_objs_per_image=7)
+    gs = [synth.det_tensor(tuple(x.shape), 200 + i, 1.0) for i, x in enumerate([canvas] + levels)]
+    sum((x * t(gg)).sum() for x, gg in zip([canvas] + levels, gs)).backward()
+    vc, bcx = torch.from_numpy(vecs).requires_grad_(True), torch.from_numpy(boxes).requires_grad_(True)
+    ref = olayout.batched_layout([vc[off[i]:off[i + 1]] for i in range(3)], [bcx[off[i]:off[i + 1]] for i in range(3)],
+                                 [torch.from_numpy(masks[off[i]:off[i + 1]]) for i in range(3)], 64, 64)
+    rl = [F.interpolate(ref, size=(s_, s_), mode="nearest") for s_ in sizes]
+    sum((x * torch.from_numpy(gg)).sum() for x, gg in zip([ref] + rl, gs)).backward()
+    assert_close(v.grad, vc.grad, TOL, "pyramid dvecs")
+    assert_close(b.grad, bcx.grad, TOL, "pyramid dboxes")
