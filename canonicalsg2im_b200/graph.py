@@ -294,7 +294,7 @@ def linear(x, w, b, precision="fp32"):
         raise ValueError("linear expects a 2-D input (got %s)" % (tuple(x.shape),))
     if precision in ("bf16", "fp16") and w.shape[0] % 64 == 0 and w.shape[1] % 64 == 0:
         from . import graph_tc
-        return graph_tc._LinearBF16.apply(x, w, b)
+        return graph_tc._LinearBF16.apply(torch.is_grad_enabled(), x, w, b)
     if w.shape[0] % 4 or w.shape[1] % 4:
         raise _lib.CsgError("linear: feature widths must be multiples of 4 (got %s)" % (tuple(w.shape),))
     return _LinearF32.apply(x, w, b)

@@ -119,12 +119,13 @@ class _TripleConvEngine(torch.autograd.Function):
     """One GraphTripleConv layer through csg_gconv_bf16_fwd / csg_gconv_bf16_bwd."""
 
     @staticmethod
-    def forward(ctx, batch, H, Dpo, obj, pred, w1, b1, w2, b2, w3, b3, w4, b4, w_trans):
+    def forward(ctx, grad_on, batch, H, Dpo, obj, pred, w1, b1, w2, b2, w3, b3, w4, b4, w_trans):
+        # grad_on: torch.is_grad_enabled() at call time (inside forward() autograd has it switched off)
         L = lib()
         dev = obj.device
         ctx.in_dtypes = (obj.dtype, pred.dtype)
         act = F16 if obj.dtype == F16 else BF       # fp16 inputs select the inference-only fp16 forward format
-        need_bwd = int(any(ctx.needs_input_grad))
+        need_bwd = int(grad_on and any(ctx.needs_input_grad))
         if act == F16 and need_bwd:
             raise _lib.CsgError(INFERENCE_ONLY)
         obj_b, pred_b = as_bf16_rows(obj, act), as_bf16_rows(pred, act)
@@ -183,7 +184,7 @@ class _TripleConvEngine(torch.autograd.Function):
         dpred = dX[:, Din:Din + Dp]
         if ctx.in_dtypes[1] != BF:
             dpred = dpred.to(ctx.in_dtypes[1])
-        return (None, None, None, dobj, dpred, dw1.view(H, K1), db1, dw2.view(Wd, H), db2, dw3.view(H, H), db3,
+        return (None, None, None, None, dobj, dpred, dw1.view(H, K1), db1, dw2.view(Wd, H), db2, dw3.view(H, H), db3,
                 dw4.view(Dout, H), db4, dwt)
 
 
@@ -205,7 +206,7 @@ def triple_conv(batch, obj, pred, params, w_trans, hidden_dim, pred_out_dim):
         raise _lib.CsgError("precision='bf16' needs feature widths that are multiples of 64 "
                             "(got Din=%d Dp=%d H=%d Dout=%d Dp_out=%d); use precision='fp32'"
                             % (din, dp, hidden_dim, dout, pred_out_dim))
-    return _TripleConvEngine.apply(batch, hidden_dim, pred_out_dim, obj, pred, *params, w_trans)
+    return _TripleConvEngine.apply(torch.is_grad_enabled(), batch, hidden_dim, pred_out_dim, obj, pred, *params, w_trans)
 
 
 class _DenseMLP2BF16(torch.autograd.Function):
@@ -213,10 +214,10 @@ class _DenseMLP2BF16(torch.autograd.Function):
     row-dot kernel (csrc/head_bf16.cu); the backward head kernel folds the ReLU mask and writes dh in bf16."""
 
     @staticmethod
-    def forward(ctx, x, w0, b0, w1, b1):
+    def forward(ctx, grad_on, x, w0, b0, w1, b1):
         L = lib()
         act = F16 if x.dtype == F16 else BF
-        need_bwd = any(ctx.needs_input_grad)
+        need_bwd = grad_on and any(ctx.needs_input_grad)
         if act == F16 and need_bwd:
             raise _lib.CsgError(INFERENCE_ONLY)
         xb = as_bf16_rows(x, act)
@@ -251,7 +252,7 @@ class _DenseMLP2BF16(torch.autograd.Function):
         dx = ops.gemm_bf16(M, D, H, dh, ctx.w0t)
         if ctx.x_dtype != BF:
             dx = dx.to(ctx.x_dtype)
-        return dx, dw0, db0, dw1, db1
+        return None, dx, dw0, db0, dw1, db1
 
 
 class _LinearBF16(torch.autograd.Function):
@@ -259,9 +260,9 @@ class _LinearBF16(torch.autograd.Function):
     multi-attribute object embedding (attribute_embed.py:24-25,46-47) in front of the bf16 GCN."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, grad_on, x, w, b):
         act = F16 if x.dtype == F16 else BF
-        need_bwd = any(ctx.needs_input_grad)
+        need_bwd = grad_on and any(ctx.needs_input_grad)
         if act == F16 and need_bwd:
             raise _lib.CsgError(INFERENCE_ONLY)
         xb = as_bf16_rows(x, act)
@@ -282,11 +283,11 @@ class _LinearBF16(torch.autograd.Function):
         dw = ops.gemm_bf16(N, K, M, dyb, xb, mn_major=True)
         db = colsum_bf16(dyb)
         dx = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[1]:
             dx = ops.gemm_bf16(M, K, N, dyb, ctx.wt)
             if ctx.x_dtype != BF:
                 dx = dx.to(ctx.x_dtype)
-        return dx, dw, db
+        return None, dx, dw, db
 
 
 def dense_mlp2(x, w0, b0, w1, b1, final_relu):
@@ -294,7 +295,7 @@ def dense_mlp2(x, w0, b0, w1, b1, final_relu):
     ``_DenseMLP2BF16``; anything else on the fp32 engine."""
     if (not final_relu and w1.shape[0] <= 8 and w0.shape[0] % 64 == 0 and w0.shape[1] % 64 == 0
             and w0.shape[0] * w1.shape[0] * 4 <= 48 * 1024):
-        return _DenseMLP2BF16.apply(x, w0, b0, w1, b1)
+        return _DenseMLP2BF16.apply(torch.is_grad_enabled(), x, w0, b0, w1, b1)
     return _dense_mlp2_f32(x, w0, b0, w1, b1, final_relu)
 
 

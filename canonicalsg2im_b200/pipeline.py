@@ -208,6 +208,10 @@ class SgToLayoutStep:
         from .ops import lib
         launches0 = lib().csg_launch_count()
         graph = torch.cuda.CUDAGraph()
+        try:      # the parameters' AccumulateGrad nodes predate the capture stream: expected here, not a bug to warn about
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             canvas, loss = self.forward(d, static)
             torch.autograd.backward([canvas, loss], [G, None])
