@@ -337,7 +337,7 @@ def train_leg(vocab, graphs, dev, precision, steps, warmup, pk, flush=None, cpu=
     """K training steps of a small config (cfg1 / fp32 engine): device-timed with resident inputs, per-step events."""
     from canonicalsg2im_b200.pipeline import SgToLayoutStep, HostBatch
     hb = HostBatch(graphs, seed=seed)
-    step = SgToLayoutStep(vocab, dev, precision=precision, H=H, W=W, seed=0)
+    step = SgToLayoutStep(vocab, dev, precision=precision, H=H, W=W, seed=0, use_graph=True)
     G = torch.randn((len(graphs), 128, H, W), device=dev, generator=torch.Generator(device=dev).manual_seed(99)) * 1e-3
     d = hb.to_device(dev)
     box = {}
@@ -349,7 +349,8 @@ def train_leg(vocab, graphs, dev, precision, steps, warmup, pk, flush=None, cpu=
     flops = mlp_flops(n_tri, n_obj)
     out = {"ms_per_step": 1e3 * sec, "graphs_per_s": len(graphs) / sec, "graphs": len(graphs), "objects": n_obj,
            "triples_after_canon": n_tri, "precision": precision, "steps": steps,
-           "mlp_tflops_whole_step": flops / sec / 1e12, "loss": float(box["loss"].item())}
+           "mlp_tflops_whole_step": flops / sec / 1e12, "loss": float(box["loss"].item()),
+           "cuda_graph_replays": step.graph_replays}
     del step, G, d
     return out
 
