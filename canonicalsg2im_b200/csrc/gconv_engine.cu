@@ -24,11 +24,14 @@ namespace {
 struct Dims {
   int NT, NO, Din, Dp, H, Dout, Dpo, P;
   int f16;     // 1: forward tensors (inputs, weights, hidden, net1 output, pooled, net2 hidden, output) are fp16; gradients stay bf16
+  int n_gather;   // rows of the table the object segments are gathered from (0: `obj` is [NO, Din] and the gather
+                  // indices are s_idx / o_idx); > 0: `obj` is an embedding table, index[9] / index[10] hold class ids
+  int n_pred;     // > 0: `pred` is a table of n_pred rows gathered by index[11] (predicate ids); 0: [NT, Dp] rows
   int K1() const { return 2 * Din + Dp; }
   int Wd() const { return 2 * H + Dpo; }
 };
 
-inline Dims read_dims(const int* d) { return Dims{d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8] ? 1 : 0}; }
+inline Dims read_dims(const int* d) { return Dims{d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8] ? 1 : 0, d[9], d[10]}; }
 
 inline size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -133,7 +136,7 @@ CSG_API size_t csg_gconv_bf16_out_offset(const int* dims, int need_bwd) {
 }
 CSG_API size_t csg_gconv_bf16_workspace(const int* dims) { return plan_work(read_dims(dims)).total; }
 
-// dims (HOST int[9]): {NT, NO, Din, Dp, H, Dout, Dpo, P, fwd_fp16}.  params (HOST array of 9 device pointers, fp32): w1 [H, 2Din+Dp],
+// dims (HOST int[11]): {NT, NO, Din, Dp, H, Dout, Dpo, P, fwd_fp16, n_gather, n_pred}; index (HOST void*[12]).  params (HOST array of 9 device pointers, fp32): w1 [H, 2Din+Dp],
 // b1, w2 [2H+Dpo, H], b2, w3 [H, H], b3, w4 [Dout, H], b4, w_trans [P].  index (HOST array of 9 device pointers,
 // int32): s_idx, o_idx, pred_id, type32, valid [NT]; rowptr_s [NO+1], perm_s [NT], rowptr_o, perm_o.
 // obj [NO, Din] bf16 contiguous; pred [NT, Dp] bf16 with row pitch ldp; new_obj [NO, Dout] bf16 (written);
@@ -173,18 +176,20 @@ CSG_API int csg_gconv_bf16_fwd(const int* dims, const void* obj, const void* pre
   CSG_TRY(csg_triple_conf(type32, pred_id, w_trans, d.NT, conf, stream));
   // ---- net1 on the gathered triple rows
   CSG_TRY(csg_gemm_bf16(0, 1, d.NT, d.H, K1, nullptr, 0, sv + s.w1b, K1, sv + s.hidden, d.H, 0, b[0], 1, nullptr, nullptr, 0,
-                        obj, pred, s_idx, o_idx, d.Din, d.Dp, ldp, d.NO, fmt, nullptr, 0, stream));
+                        obj, pred, d.n_gather ? (const int*)index[9] : s_idx, d.n_gather ? (const int*)index[10] : o_idx,
+                        d.Din, d.Dp, ldp, d.n_gather ? d.n_gather : d.NO, d.n_pred ? (const int*)index[11] : nullptr,
+                        d.n_pred, fmt, nullptr, 0, stream));
   CSG_TRY(csg_gemm_bf16(0, 0, d.NT, Wd, d.H, sv + s.hidden, d.H, sv + s.w2b, d.H, sv + s.out, Wd, 0, b[1], 1, conf, nullptr, 0,
-                        nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, fmt, nullptr, 0, stream));
+                        nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, fmt, nullptr, 0, stream));
   // ---- confidence-weighted average onto objects
   CSG_TRY(csg_segpool_bf16(sv + s.out, Wd, 0, d.H + d.Dpo, d.H, rowptr_s, perm_s, rowptr_o, perm_o, valid, conf, d.NO,
                            reinterpret_cast<float*>(sv + s.pooled32), sv + s.pooled16, d.H,
                            reinterpret_cast<float*>(sv + s.cnt), 1, d.f16, stream));
   // ---- net2
   CSG_TRY(csg_gemm_bf16(0, 0, d.NO, d.H, d.H, sv + s.pooled16, d.H, sv + s.w3b, d.H, sv + s.h2, d.H, 0, b[2], 1, nullptr,
-                        nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, fmt, nullptr, 0, stream));
+                        nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, fmt, nullptr, 0, stream));
   CSG_TRY(csg_gemm_bf16(0, 0, d.NO, d.Dout, d.H, sv + s.h2, d.H, sv + s.w4b, d.H, new_obj, d.Dout, 0, b[3], 1, nullptr,
-                        nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, fmt, nullptr, 0, stream));
+                        nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, fmt, nullptr, 0, stream));
   return 0;
 }
 
@@ -245,15 +250,20 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
   const float* conf = reinterpret_cast<const float*>(sv + s.conf);
   CsgReduceJob jobs[CSG_REDUCE_MAX_JOBS];
   int njobs = 0;
+  // gather indices of the triple input (the embedding tables' class / predicate ids when layer 0 reads them directly)
+  const int* g_s = d.n_gather ? (const int*)index[9] : s_idx;
+  const int* g_o = d.n_gather ? (const int*)index[10] : o_idx;
+  const int* g_p = d.n_pred ? (const int*)index[11] : nullptr;
 
   // every backward GEMM multiplies a gradient (A, bf16) with a forward tensor (B: activations, weights or the gathered
   // triple input) and writes a gradient (bf16 / fp32); split-K final passes are deferred to the end of the layer
   const int bfmt = 0;
 #define GEMM(mn, gather, M, N, K, A, lda, B, ldb, C, ldc, f32, mask, ldm, SK)                                         \
   CSG_TRY(csg_gemm_bf16_deferred(mn, gather, M, N, K, A, lda, B, ldb, C, ldc, f32, nullptr, 0, nullptr, mask, ldm,     \
-                                 (gather) ? obj : nullptr, (gather) ? pred : nullptr, (gather) ? s_idx : nullptr,      \
-                                 (gather) ? o_idx : nullptr, (gather) ? d.Din : 0, (gather) ? d.Dp : 0,                \
-                                 (gather) ? ldp : 0, (gather) ? NO : 0, bfmt, (SK) >= 0 ? ws + w.sk[(SK) >= 0 ? (SK) : 0] : nullptr, \
+                                 (gather) ? obj : nullptr, (gather) ? pred : nullptr, (gather) ? g_s : nullptr,        \
+                                 (gather) ? g_o : nullptr, (gather) ? d.Din : 0, (gather) ? d.Dp : 0,                  \
+                                 (gather) ? ldp : 0, (gather) ? (d.n_gather ? d.n_gather : NO) : 0,                    \
+                                 (gather) ? g_p : nullptr, (gather) ? d.n_pred : 0, bfmt, (SK) >= 0 ? ws + w.sk[(SK) >= 0 ? (SK) : 0] : nullptr, \
                                  (SK) >= 0 ? w.sk_bytes[(SK) >= 0 ? (SK) : 0] : 0, st, &jobs[njobs]));             \
   if (jobs[njobs].parts > 0) ++njobs
 

@@ -57,6 +57,8 @@ struct TcParams {
   // fused gather of [obj[s] | pred | obj[o]] rows
   const int* g_sidx;
   const int* g_oidx;
+  const int* g_pidx;           // non-NULL: the predicate segment is gathered too (tmP = a table, row g_pidx[t]): layer 0
+                               // reads its rows straight from the embedding tables (sg2im/model.py:108-109)
   int g_din, g_dp, g_rows;
   int debug;                   // scratch/bench_gemm.py only: 1 = no operand loads, 2 = no MMAs, 4 = no epilogue work
   int a_f16, b_f16, c_f16;     // operand / 16-bit output element formats: 0 = bf16, 1 = fp16 (kind::f16 takes both, per operand)
@@ -369,7 +371,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (GATHER == G_NONE) tma_load_2d_pair(a_dst, &tmA, fb, kb * BLOCK_K, m0);
             else {
               const int c0 = kb * BLOCK_K;
-              if (c0 >= p.g_din && c0 < p.g_din + p.g_dp) tma_load_2d_pair(a_dst, &tmP, fb, c0 - p.g_din, m0);
+              if (!p.g_pidx && c0 >= p.g_din && c0 < p.g_din + p.g_dp) tma_load_2d_pair(a_dst, &tmP, fb, c0 - p.g_din, m0);
             }
             tma_load_2d_pair(b_dst, &tmB, fb, kb * BLOCK_K, nt * BN + (int)cta_rank * B_ROWS);
           } else if (!MN) {
@@ -377,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (GATHER == G_NONE) tma_load_2d(a_dst, &tmA, fb, kb * BLOCK_K, mt * BLOCK_M);
             else {
               const int c0 = kb * BLOCK_K;     // predicate block of the virtual row [obj[s] | pred | obj[o]]
-              if (c0 >= p.g_din && c0 < p.g_din + p.g_dp) tma_load_2d(a_dst, &tmP, fb, c0 - p.g_din, mt * BLOCK_M);
+              if (!p.g_pidx && c0 >= p.g_din && c0 < p.g_din + p.g_dp) tma_load_2d(a_dst, &tmP, fb, c0 - p.g_din, mt * BLOCK_M);
             }
             tma_load_2d(b_dst, &tmB, fb, kb * BLOCK_K, nt * BN);
           } else {
@@ -386,7 +388,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = 0; c < BN / 64; ++c) {
               const int n0 = nt * BN + c * 64;
               if (GATHER == G_NONE) tma_load_2d(b_dst + c * 8192, &tmB, fb, n0, kb * BLOCK_K);
-              else if (n0 >= p.g_din && n0 < p.g_din + p.g_dp) tma_load_2d(b_dst + c * 8192, &tmP, fb, n0 - p.g_din, kb * BLOCK_K);
+              else if (!p.g_pidx && n0 >= p.g_din && n0 < p.g_din + p.g_dp) tma_load_2d(b_dst + c * 8192, &tmP, fb, n0 - p.g_din, kb * BLOCK_K);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -407,18 +409,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         kb_range(sp, kb0, kb1);
         if (GATHER == G_A) {
           // A tile [128 triples x 64 k]: this lane owns rows 4*gl .. 4*gl+3 (tmA = object table)
-          int si[4], oi[4];
+          int si[4], oi[4], pi[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int t = mt * TILE_M + (int)cta_rank * BLOCK_M + 4 * gl + i;
             const bool ok = t < p.g_rows;
             si[i] = ok ? __ldg(p.g_sidx + t) : 0;
             oi[i] = ok ? __ldg(p.g_oidx + t) : 0;
+            pi[i] = (ok && p.g_pidx) ? __ldg(p.g_pidx + t) : 0;
           }
           for (int kb = kb0; kb < kb1; ++kb) {
             const int c0 = kb * BLOCK_K;
             const bool seg_s = c0 < p.g_din, seg_o = c0 >= p.g_din + p.g_dp;
-            if (seg_s || seg_o) {
+            if (!seg_s && !seg_o && p.g_pidx) {
+              // predicate segment straight from the predicate table (tmP: box {64, 1})
+              mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
+              const uint32_t fb = leader(&bars->full[stage]);
+              const uint32_t dst = sA + stage * A_STAGE + gl * 512;
+              if (CG == 2) tma_gather4_pair(dst, &tmP, fb, c0 - p.g_din, pi[0], pi[1], pi[2], pi[3]);
+              else tma_gather4(dst, &tmP, fb, c0 - p.g_din, pi[0], pi[1], pi[2], pi[3]);
+            } else if (seg_s || seg_o) {
               mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
               const uint32_t fb = leader(&bars->full[stage]);
               const uint32_t dst = sA + stage * A_STAGE + gl * 512;
@@ -444,11 +454,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int j = gl + 32 * u;
               const int n0 = nt * BN + (j >> 4) * 64;
               const bool seg_s = n0 < p.g_din, seg_o = n0 >= p.g_din + p.g_dp;
-              const int* idx = seg_s ? p.g_sidx : p.g_oidx;
+              const bool seg_p = !seg_s && !seg_o && p.g_pidx != nullptr;
+              const int* idx = seg_s ? p.g_sidx : (seg_o ? p.g_oidx : p.g_pidx);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int t = kb * BLOCK_K + 4 * (j & 15) + i;
-                dst[u][i] = (j < JOBS && (seg_s || seg_o) && t < p.g_rows) ? __ldg(idx + t) : 0;
+                dst[u][i] = (j < JOBS && (seg_s || seg_o || seg_p) && t < p.g_rows) ? __ldg(idx + t) : 0;
               }
             }
           };
@@ -472,6 +483,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (n0 < p.g_din) tma_gather4(dst, &tmB, fb, n0, id[u][0], id[u][1], id[u][2], id[u][3]);
                 else if (n0 >= p.g_din + p.g_dp)
                   tma_gather4(dst, &tmB, fb, n0 - p.g_din - p.g_dp, id[u][0], id[u][1], id[u][2], id[u][3]);
+                else if (p.g_pidx)
+                  tma_gather4(dst, &tmP, fb, n0 - p.g_din, id[u][0], id[u][1], id[u][2], id[u][3]);
               }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -911,12 +924,12 @@ CSG_API int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
                           const void* A, int lda, const void* B, int ldb, void* C, int ldc, int out_f32,
                           const float* bias, int relu, const float* rowscale, const void* mask_aux, int ld_aux,
                           const void* g_obj, const void* g_pred, const int* g_sidx, const int* g_oidx,
-                          int g_din, int g_dp, int g_ldp, int g_nobj, int formats,
+                          int g_din, int g_dp, int g_ldp, int g_nobj, const int* g_pidx, int g_npred, int formats,
                           void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   CsgReduceJob job;
   if (int rc = csg_gemm_bf16_deferred(mn_major, gather, M, N, K, A, lda, B, ldb, C, ldc, out_f32, bias, relu, rowscale,
-                                      mask_aux, ld_aux, g_obj, g_pred, g_sidx, g_oidx, g_din, g_dp, g_ldp, g_nobj, formats,
-                                      workspace, workspace_bytes, stream, &job)) return rc;
+                                      mask_aux, ld_aux, g_obj, g_pred, g_sidx, g_oidx, g_din, g_dp, g_ldp, g_nobj, g_pidx, g_npred,
+                                      formats, workspace, workspace_bytes, stream, &job)) return rc;
   return job.parts > 0 ? csg_reduce_multi(&job, 1, stream) : 0;     // split-K final pass (fixed order: split 0, 1, ...)
 }
 
@@ -924,7 +937,7 @@ int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K,
                            const void* A, int lda, const void* B, int ldb, void* C, int ldc, int out_f32,
                            const float* bias, int relu, const float* rowscale, const void* mask_aux, int ld_aux,
                            const void* g_obj, const void* g_pred, const int* g_sidx, const int* g_oidx,
-                           int g_din, int g_dp, int g_ldp, int g_nobj, int formats,
+                           int g_din, int g_dp, int g_ldp, int g_nobj, const int* g_pidx, int g_npred, int formats,
                            void* workspace, size_t workspace_bytes, cudaStream_t stream, CsgReduceJob* job) {
   job->parts = 0; job->n = 0; job->partial = nullptr; job->out = nullptr; job->stride = 0; job->lanes = 1;
   job->op = CSG_RED_SUM; job->aux = nullptr;
@@ -944,6 +957,8 @@ int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K,
   p.bias = bias; p.relu = relu; p.rowscale = rowscale;
   p.mask_aux = reinterpret_cast<const __nv_bfloat16*>(mask_aux); p.ld_aux = ld_aux;
   p.g_sidx = g_sidx; p.g_oidx = g_oidx; p.g_din = g_din; p.g_dp = g_dp;
+  p.g_pidx = gather ? g_pidx : nullptr;
+  CSG_REQUIRE(!p.g_pidx || g_npred > 0, "gemm_bf16: g_pidx needs the row count of the predicate table");
   p.g_rows = mn_major ? K : M;
   p.a_f16 = formats & 1; p.b_f16 = (formats >> 1) & 1; p.c_f16 = (formats >> 2) & 1;
   { const char* dbg = getenv("CSG_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
@@ -977,7 +992,8 @@ int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K,
     if (gather == 1) {
       // A = [obj[s] | pred | obj[o]]: object table rows by tile::gather4 (box {64, 1}), predicate rows by tile loads
       if (int rc = make_map(&maps.a, g_obj, g_din, g_nobj, (uint64_t)g_din * 2, 1)) return rc;
-      if (int rc = make_map(&maps.p, g_pred, g_dp, M, (uint64_t)g_ldp * 2, BLOCK_M)) return rc;
+      if (p.g_pidx) { if (int rc = make_map(&maps.p, g_pred, g_dp, g_npred, (uint64_t)g_ldp * 2, 1)) return rc; }
+      else if (int rc = make_map(&maps.p, g_pred, g_dp, M, (uint64_t)g_ldp * 2, BLOCK_M)) return rc;
     } else {
       if (int rc = make_map(&maps.a, A, K, M, (uint64_t)lda * 2, BLOCK_M)) return rc;
     }
@@ -1002,7 +1018,8 @@ int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K,
     if (int rc = make_map(&maps.a, A, M, K, (uint64_t)lda * 2, 64)) return rc;
     if (gather == 2) {
       if (int rc = make_map(&maps.b, g_obj, g_din, g_nobj, (uint64_t)g_din * 2, 1)) return rc;
-      if (int rc = make_map(&maps.p, g_pred, g_dp, K, (uint64_t)g_ldp * 2, 64)) return rc;
+      if (p.g_pidx) { if (int rc = make_map(&maps.p, g_pred, g_dp, g_npred, (uint64_t)g_ldp * 2, 1)) return rc; }
+      else if (int rc = make_map(&maps.p, g_pred, g_dp, K, (uint64_t)g_ldp * 2, 64)) return rc;
     } else {
       if (int rc = make_map(&maps.b, B, N, K, (uint64_t)ldb * 2, 64)) return rc;
     }

@@ -83,6 +83,18 @@ __global__ void triple_prep_edges_kernel(const long long* __restrict__ edges, co
                     s_idx, o_idx, pred, type32, valid, err);
 }
 
+__global__ void compose_index_kernel(const int* __restrict__ idx, const long long* __restrict__ map, long long map_stride,
+                                     int n, int n_map, int n_values, int* __restrict__ out, int* err) {
+  CSG_PDL_WAIT();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int j = idx[i];
+  if (j < 0 || j >= n_map) { csg_report_index(err, CSG_ERR_TRIPLE_OBJECT, i, j, n_map); out[i] = 0; return; }
+  const long long v = map[(size_t)j * map_stride];
+  if (n_values > 0 && (v < 0 || v >= n_values)) { csg_report_index(err, CSG_ERR_EMBED_ID, j, v, n_values); out[i] = 0; return; }
+  out[i] = (int)v;
+}
+
 __global__ void offsets_uniform_kernel(int* __restrict__ off, int B, int stride) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i <= B) off[i] = i * stride;
@@ -357,6 +369,15 @@ __global__ void conf_bwd_final_kernel(const float* __restrict__ partial, const f
 // ----------------------------------------------------------------------------------------
 // C ABI
 // ----------------------------------------------------------------------------------------
+CSG_API int csg_compose_index(const int* idx, const long long* map, long long map_stride, int n, int n_map, int n_values,
+                              int* out, cudaStream_t stream) {
+  if (n == 0) return 0;
+  CSG_CUDA(csg_launch_pdl(compose_index_kernel, dim3(csg_div_up(n, 256)), dim3(256), 0, stream, idx, map, map_stride, n, n_map,
+                          n_values, out, csg_async_err_ptr()));
+  CSG_CHECK_LAUNCH("csg_compose_index");
+  return 0;
+}
+
 CSG_API int csg_offsets_uniform(int* off, int B, int stride, cudaStream_t stream) {
   offsets_uniform_kernel<<<csg_div_up(B + 1, 256), 256, 0, stream>>>(off, B, stride);
   CSG_CHECK_LAUNCH("csg_offsets_uniform");

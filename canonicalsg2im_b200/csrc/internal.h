@@ -29,8 +29,8 @@ int csg_reduce_multi(const CsgReduceJob* jobs, int njobs, cudaStream_t stream);
 int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                            void* C, int ldc, int out_f32, const float* bias, int relu, const float* rowscale,
                            const void* mask_aux, int ld_aux, const void* g_obj, const void* g_pred, const int* g_sidx,
-                           const int* g_oidx, int g_din, int g_dp, int g_ldp, int g_nobj, int formats, void* workspace,
-                           size_t workspace_bytes, cudaStream_t stream, CsgReduceJob* job);
+                           const int* g_oidx, int g_din, int g_dp, int g_ldp, int g_nobj, const int* g_pidx, int g_npred,
+                           int formats, void* workspace, size_t workspace_bytes, cudaStream_t stream, CsgReduceJob* job);
 // csg_colsum_bf16 without its final pass
 int csg_colsum_bf16_deferred(const void* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
                              cudaStream_t stream, CsgReduceJob* job);

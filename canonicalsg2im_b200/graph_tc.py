@@ -115,29 +115,65 @@ def _ptr_array(tensors):
     return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
+class FusedTables:
+    """Layer 0 reading straight from the embedding tables (sg2im/model.py:108-109 fused into the net1 producer): the
+    layer's `obj` / `pred` arguments are then the fp32 TABLES, gathered per triple by class id / predicate id."""
+
+    def __init__(self, batch, obj_ids, pred_ids, act):
+        # obj_ids [NO] int64 (any stride): class id of every object; per-triple class ids = obj_ids[s_idx], obj_ids[o_idx]
+        # pred_ids [NT] int64 (any stride): predicate id of every triple (the int32 copy batch.pred feeds the gather)
+        self.obj_ids, self.pred_ids, self.act = obj_ids, pred_ids, act
+        self.batch = batch
+
+    def indices(self, n_classes):
+        """(subject class ids, object class ids) [NT] int32, composed once per batch and table size."""
+        cache = getattr(self.batch, "_class_idx", None)
+        if cache is None or cache[0] != (self.obj_ids.data_ptr(), n_classes):
+            b, L = self.batch, lib()
+            out = torch.empty((2, max(b.NT, 1)), dtype=torch.int32, device=b.s_idx.device)
+            for k, idx in enumerate((b.s_idx, b.o_idx)):
+                _lib.check(L.csg_compose_index(ptr(idx), ptr(self.obj_ids), self.obj_ids.stride(0), b.NT, b.NO, n_classes,
+                                               ptr(out[k]), _stream()), "csg_compose_index")
+            cache = self.batch._class_idx = ((self.obj_ids.data_ptr(), n_classes), out, self.obj_ids)
+        return cache[1][0], cache[1][1]
+
+
 class _TripleConvEngine(torch.autograd.Function):
     """One GraphTripleConv layer through csg_gconv_bf16_fwd / csg_gconv_bf16_bwd."""
 
     @staticmethod
-    def forward(ctx, grad_on, batch, H, Dpo, obj, pred, w1, b1, w2, b2, w3, b3, w4, b4, w_trans):
+    def forward(ctx, grad_on, batch, H, Dpo, obj, pred, w1, b1, w2, b2, w3, b3, w4, b4, w_trans, fused=None):
         # grad_on: torch.is_grad_enabled() at call time (inside forward() autograd has it switched off)
         L = lib()
         dev = obj.device
         ctx.in_dtypes = (obj.dtype, pred.dtype)
-        act = F16 if obj.dtype == F16 else BF       # fp16 inputs select the inference-only fp16 forward format
+        ctx.fused = fused
+        act = fused.act if fused is not None else (F16 if obj.dtype == F16 else BF)   # fp16: inference-only format
         need_bwd = int(grad_on and any(ctx.needs_input_grad))
         if act == F16 and need_bwd:
             raise _lib.CsgError(INFERENCE_ONLY)
-        obj_b, pred_b = as_bf16_rows(obj, act), as_bf16_rows(pred, act)
-        if not obj_b.is_contiguous():
-            obj_b = obj_b.contiguous()
+        n_gather = n_pred = 0
+        if fused is not None:
+            # obj [V, Din] / pred [P, Dp]: the fp32 embedding tables, cast once per step (a few hundred rows)
+            obj_b, pred_b = cast_bf16_multi([(obj.detach(), False), (pred.detach(), False)], act)
+            n_gather, n_pred = obj_b.shape[0], pred_b.shape[0]
+            gs, go = fused.indices(n_gather)
+        else:
+            obj_b, pred_b = as_bf16_rows(obj, act), as_bf16_rows(pred, act)
+            if not obj_b.is_contiguous():
+                obj_b = obj_b.contiguous()
         params = [f32c(p.detach()) for p in (w1, b1, w2, b2, w3, b3, w4, b4, w_trans)]
         Dout, P = w4.shape[0], w_trans.numel()
-        dims = (ctypes.c_int * 9)(batch.NT, batch.NO, obj_b.shape[1], pred_b.shape[1], H, Dout, Dpo, P, int(act == F16))
+        dims = (ctypes.c_int * 11)(batch.NT, batch.NO, obj_b.shape[1], pred_b.shape[1], H, Dout, Dpo, P, int(act == F16),
+                                   n_gather, n_pred)
         nsaved = L.csg_gconv_bf16_saved_bytes(dims, need_bwd)
         saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
         new_obj = torch.empty((batch.NO, Dout), dtype=act, device=dev)
         index = batch.index_array()
+        if fused is not None:
+            index = (ctypes.c_void_p * 12)(*(list(index) + [gs.data_ptr(), go.data_ptr(), batch.pred.data_ptr()]))
+            ctx.gather_idx = (gs, go)
+        ctx.index = index
         rc = L.csg_gconv_bf16_fwd(dims, ptr(obj_b), ptr(pred_b), pred_b.stride(0), _ptr_array(params), index, need_bwd,
                                   ptr(saved), nsaved, ptr(new_obj), _stream())
         _lib.check(rc, "csg_gconv_bf16_fwd")
@@ -154,7 +190,8 @@ class _TripleConvEngine(torch.autograd.Function):
     def backward(ctx, d_obj_out, d_newp):
         obj, pred, saved, new_obj = ctx.saved_tensors
         batch, dims, params = ctx.batch, ctx.dims, ctx.params
-        NT, NO, Din, Dp, H, Dout, Dpo, P, _ = list(dims)
+        NT, NO, Din, Dp, H, Dout, Dpo, P = list(dims)[:8]
+        fused = ctx.fused
         K1, Wd = 2 * Din + Dp, 2 * H + Dpo
         dev = obj.device
         L = lib()
@@ -165,27 +202,44 @@ class _TripleConvEngine(torch.autograd.Function):
         if d_newp is not None and not (d_newp.dtype == BF and d_newp.stride(-1) == 1 and d_newp.stride(0) % 8 == 0
                                        and d_newp.data_ptr() % 16 == 0):
             d_newp = d_newp.to(BF).contiguous()
-        obj_bf16 = ctx.in_dtypes[0] == BF
+        obj_bf16 = ctx.in_dtypes[0] == BF and fused is None
         dobj = torch.empty((NO, Din), dtype=BF if obj_bf16 else torch.float32, device=dev)
         dX = torch.empty((NT, K1), dtype=BF, device=dev)
         sizes = (H * K1, H, Wd * H, Wd, H * H, H, Dout * H, Dout, P)
         dparams = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
         nws = L.csg_gconv_bf16_workspace(dims)
         ws = _scratch(nws, dev)
-        rc = L.csg_gconv_bf16_bwd(dims, ptr(obj), ptr(pred), pred.stride(0), _ptr_array(params), batch.index_array(),
+        rc = L.csg_gconv_bf16_bwd(dims, ptr(obj), ptr(pred), pred.stride(0), _ptr_array(params), ctx.index,
                                   ptr(d_obj_out), int(d_obj_out is not None and d_obj_out.dtype == BF),
                                   ptr(d_newp), d_newp.stride(0) if d_newp is not None else 0,
                                   ptr(saved), ptr(new_obj), ptr(dobj), int(obj_bf16), ptr(dX), ptr(dparams),
                                   ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "csg_gconv_bf16_bwd")
         dw1, db1, dw2, db2, dw3, db3, dw4, db4, dwt = torch.split(dparams, sizes)
-        if not obj_bf16 and ctx.in_dtypes[0] != torch.float32:
-            dobj = dobj.to(ctx.in_dtypes[0])
         dpred = dX[:, Din:Din + Dp]
-        if ctx.in_dtypes[1] != BF:
-            dpred = dpred.to(ctx.in_dtypes[1])
+        if fused is not None:
+            # the gradients of the gathered rows folded back onto the embedding tables (attribute_embed.py:38-48,
+            # model.py:109): per-object rows by class id, per-triple predicate rows by predicate id (one-hot GEMM)
+            dobj = ops.embed_table_grad(dobj, fused.obj_ids, obj.shape[0], Din)
+            dpred = ops.embed_table_grad(dpred, fused.pred_ids, pred.shape[0], Dp)
+        else:
+            if not obj_bf16 and ctx.in_dtypes[0] != torch.float32:
+                dobj = dobj.to(ctx.in_dtypes[0])
+            if ctx.in_dtypes[1] != BF:
+                dpred = dpred.to(ctx.in_dtypes[1])
         return (None, None, None, None, dobj, dpred, dw1.view(H, K1), db1, dw2.view(Wd, H), db2, dw3.view(H, H), db3,
-                dw4.view(Dout, H), db4, dwt)
+                dw4.view(Dout, H), db4, dwt, None)
+
+
+def triple_conv_tables(batch, obj_table, obj_ids, pred_table, pred_ids, params, w_trans, hidden_dim, pred_out_dim,
+                       act=BF):
+    """Layer 0 of ``Sg2LayoutModel`` with the embedding lookups (model.py:108-109) fused into the net1 producer: the
+    object rows are gathered from ``obj_table [V, Din]`` by the class ids ``obj_ids [NO]`` of the triples' subjects /
+    objects, the predicate rows from ``pred_table [P, Dp]`` by the triples' predicate ids (``batch.pred``) -- no
+    ``[NO, Din]`` / ``[NT, Dp]`` rows are materialised; the table gradients come back through the same node.
+    Needs Din, Dp multiples of 64 (single-attribute objects: COCO / VG)."""
+    return _TripleConvEngine.apply(torch.is_grad_enabled(), batch, hidden_dim, pred_out_dim, obj_table, pred_table,
+                                   *params, w_trans, FusedTables(batch, obj_ids, pred_ids, act))
 
 
 def triple_conv(batch, obj, pred, params, w_trans, hidden_dim, pred_out_dim):

@@ -45,25 +45,8 @@ class _EmbedFn(torch.autograd.Function):
     def backward(ctx, dout):
         (idx,) = ctx.saved_tensors
         n, V, E = ctx.dims
-        if dout.dtype not in (torch.float32, torch.bfloat16):
-            dout = dout.float()
-        if dout.stride(-1) != 1 or dout.stride(0) % 4 != 0 or dout.data_ptr() % 16 != 0:
-            dout = dout.contiguous()
-        L = lib()
-        if (dout.dtype == torch.bfloat16 and n >= 1024 and E % 32 == 0 and dout.stride(0) % 8 == 0
-                and dout.data_ptr() % 16 == 0):
-            # large bf16 lookups (the predicate rows of the tensor-core engine): dtable = onehot^T dout on tcgen05
-            from .ops import gemm_bf16
-            ld = (V + 63) // 64 * 64
-            onehot = torch.empty((n, ld), dtype=torch.bfloat16, device=dout.device)
-            _lib.check(L.csg_onehot_bf16(ptr(idx), idx.stride(0), n, V, ptr(onehot), ld, _stream()), "csg_onehot_bf16")
-            return gemm_bf16(ld, E, n, onehot, dout, mn_major=True)[:V], None, None
-        dtable = torch.empty((V, E), dtype=torch.float32, device=dout.device)
-        ws = workspace(L.csg_embed_bwd_workspace(n, V, E), dout.device)
-        rc = L.csg_embed_bwd(ptr(dout), dout.stride(0) if n else E, int(dout.dtype == torch.bfloat16), ptr(idx),
-                             idx.stride(0) if n else 1, n, V, E, ptr(dtable), ptr(ws), ws.numel(), _stream())
-        _lib.check(rc, "csg_embed_bwd")
-        return dtable, None, None
+        from .ops import embed_table_grad
+        return embed_table_grad(dout, idx, V, E), None, None
 
 
 def embedding_lookup(weight, idx, out_dtype=torch.float32):
@@ -214,6 +197,7 @@ class Sg2LayoutModel(nn.Module):
         self.args = args
         self.vocab = args["vocab"]
         self.precision = precision
+        self.fuse_embeddings = True       # False: materialise the embedding rows in front of layer 0 (tests compare both)
         emb = args["embedding_dim"]
         self.attribute_embedding = AttributeEmbeddings(self.vocab["attributes"], emb)
         num_preds = self.num_preds = len(self.vocab["pred_idx_to_name"])
@@ -241,8 +225,31 @@ class Sg2LayoutModel(nn.Module):
     def _act_dtype(self):
         return {"bf16": torch.bfloat16, "fp16": torch.float16}.get(self.precision, torch.float32)
 
-    def _run(self, batch, obj_vecs, pred_vecs):
-        for layer in self.gconvs:
+    def _fusable(self, objs_flat):
+        """Layer 0 can gather its rows straight from the embedding tables (model.py:108-109 fused into the net1
+        producer, csrc/gemm_tc.cu) on the tensor-core engine for single-attribute objects (COCO / VG)."""
+        emb = self.pred_embeddings.weight.shape[1]
+        return (self.precision in ("bf16", "fp16") and objs_flat.shape[1] == 1 and emb % 64 == 0
+                and not hasattr(self.attribute_embedding, "attribute_fc_gen") and self.fuse_embeddings)
+
+    def _embed_and_run(self, batch, objs_flat, pred_ids):
+        """objs_flat [NO, A] int64, pred_ids [NT] int64 (any stride) -> (obj_vecs [NO, D], boxes [NO, 4])."""
+        if self._fusable(objs_flat):
+            from . import graph_tc
+            l0 = self.gconvs[0]
+            obj_vecs, pred_vecs = graph_tc.triple_conv_tables(
+                batch, self.attribute_embedding.att_emb_0.weight, objs_flat[:, 0], self.pred_embeddings.weight, pred_ids,
+                l0.layer_params(), l0.predicates_transitive_weights, l0.hidden_dim, l0.predicate_output_dim,
+                self._act_dtype())
+            if not l0.return_new_p_vecs:
+                raise ValueError("fused layer 0 needs return_new_p_vecs")
+            return self._run(batch, obj_vecs, pred_vecs, first=1)
+        obj_vecs = self.attribute_embedding(objs_flat, self._act_dtype())
+        pred_vecs = embedding_lookup(self.pred_embeddings.weight, pred_ids, self._act_dtype())
+        return self._run(batch, obj_vecs, pred_vecs)
+
+    def _run(self, batch, obj_vecs, pred_vecs, first=0):
+        for layer in list(self.gconvs)[first:]:
             obj_vecs, pred_vecs = layer.forward_flat(batch, obj_vecs, pred_vecs)
         boxes = dense_mlp2(obj_vecs, self.box_net[0].weight, self.box_net[0].bias,
                            self.box_net[2].weight, self.box_net[2].bias, False, self.precision)
@@ -253,9 +260,7 @@ class Sg2LayoutModel(nn.Module):
         -> (obj_vecs [B,O,D], boxes_pred [B,O,4], None)."""
         B, O, T = objs.size(0), objs.size(1), triplets.size(1)
         batch = TripleBatch.from_padded_triplets(triplets, triplet_type, self.padding_id, O, self.num_preds)
-        obj_vecs = self.attribute_embedding(objs, self._act_dtype()).reshape(B * O, -1)
-        pred_vecs = embedding_lookup(self.pred_embeddings.weight, triplets.reshape(B * T, 3)[:, 1], self._act_dtype())
-        obj_vecs, boxes = self._run(batch, obj_vecs, pred_vecs)
+        obj_vecs, boxes = self._embed_and_run(batch, objs.reshape(B * O, -1), triplets.reshape(B * T, 3)[:, 1])
         return obj_vecs.view(B, O, -1), boxes.view(B, O, 4), None
 
     def forward_ragged(self, objs, triplets, triplet_type, tri_off, obj_off):
@@ -263,6 +268,4 @@ class Sg2LayoutModel(nn.Module):
         -> (obj_vecs [NO,D], boxes_pred [NO,4])."""
         batch = TripleBatch.from_ragged(triplets, triplet_type, tri_off, obj_off, objs.size(0), self.padding_id,
                                         self.num_preds)
-        obj_vecs = self.attribute_embedding(objs, self._act_dtype())
-        pred_vecs = embedding_lookup(self.pred_embeddings.weight, triplets[:, 1], self._act_dtype())
-        return self._run(batch, obj_vecs, pred_vecs)
+        return self._embed_and_run(batch, objs, triplets[:, 1])

@@ -75,9 +75,11 @@ def workspace(nbytes, device):
 class Gather:
     """Sources of the fused triple-input gather [obj[s] | pred | obj[o]] (graph.py:63-66)."""
 
-    def __init__(self, obj, pred, s_idx, o_idx):
+    def __init__(self, obj, pred, s_idx, o_idx, p_idx=None):
+        """``p_idx`` (int32 [rows]): ``pred`` is a table and the predicate segment is ``pred[p_idx[t]]`` (and ``obj``
+        may then be the object embedding table with ``s_idx`` / ``o_idx`` class ids): model.py:108-109 fused."""
         assert obj.is_contiguous() and pred.stride(-1) == 1
-        self.obj, self.pred, self.s_idx, self.o_idx = obj, pred, s_idx, o_idx
+        self.obj, self.pred, self.s_idx, self.o_idx, self.p_idx = obj, pred, s_idx, o_idx, p_idx
         self.din, self.dp, self.ldp = obj.shape[1], pred.shape[1], pred.stride(0)
 
     @property
@@ -170,10 +172,35 @@ def gemm_bf16(M, N, K, A, B, mn_major=False, out=None, out_f32=False, bias=None,
         ptr(out), out.stride(0), int(out_f32),
         ptr(bias), int(relu), ptr(rowscale), ptr(mask_aux), (mask_aux.stride(0) if mask_aux is not None else 0),
         ptr(g.obj) if g else 0, ptr(g.pred) if g else 0, ptr(g.s_idx) if g else 0, ptr(g.o_idx) if g else 0,
-        g.din if g else 0, g.dp if g else 0, g.ldp if g else 0, g.obj.shape[0] if g else 0, formats,
+        g.din if g else 0, g.dp if g else 0, g.ldp if g else 0, g.obj.shape[0] if g else 0,
+        ptr(g.p_idx) if g else 0, (g.pred.shape[0] if (g and g.p_idx is not None) else 0), formats,
         ptr(ws), (ws.numel() if ws is not None else 0), _stream())
     _lib.check(rc, "csg_gemm_bf16")
     if timer is not None:
         e1.record()
         timer.add(2.0 * M * N * K, e0, e1)
     return out
+
+
+def embed_table_grad(dout, idx, V, E):
+    """dtable [V, E] fp32 = sum over rows r with idx[r] = v of dout[r] (deterministic): the gradient of an embedding
+    lookup (attribute_embed.py:38-48, model.py:109).  Large bf16 inputs (the predicate rows of the tensor-core engine)
+    go through the one-hot tensor-core product onehot^T dout, everything else through csg_embed_bwd."""
+    n = idx.numel()
+    if dout.dtype not in (torch.float32, torch.bfloat16):
+        dout = dout.float()
+    if dout.stride(-1) != 1 or dout.stride(0) % 4 != 0 or dout.data_ptr() % 16 != 0:
+        dout = dout.contiguous()
+    L = lib()
+    if (dout.dtype == torch.bfloat16 and n >= 1024 and E % 32 == 0 and dout.stride(0) % 8 == 0
+            and dout.data_ptr() % 16 == 0):
+        ld = (V + 63) // 64 * 64
+        onehot = torch.empty((n, ld), dtype=torch.bfloat16, device=dout.device)
+        _lib.check(L.csg_onehot_bf16(ptr(idx), idx.stride(0), n, V, ptr(onehot), ld, _stream()), "csg_onehot_bf16")
+        return gemm_bf16(ld, E, n, onehot, dout, mn_major=True)[:V]
+    dtable = torch.empty((V, E), dtype=torch.float32, device=dout.device)
+    ws = workspace(L.csg_embed_bwd_workspace(n, V, E), dout.device)
+    rc = L.csg_embed_bwd(ptr(dout), dout.stride(0) if n else E, int(dout.dtype == torch.bfloat16), ptr(idx),
+                         idx.stride(0) if n else 1, n, V, E, ptr(dtable), ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "csg_embed_bwd")
+    return dtable

@@ -155,6 +155,10 @@ int csg_colsum_f32(const float* X, int M, int N, int ld, float* out, void* works
  * mn_major = 1: C[M,N] = A[K,M]^T B[K,N] (weight gradients, fp32 out, split-K); gather = 2 gathers B's rows.
  * The gathered operand is the virtual row [g_obj[g_sidx[t]] | g_pred[t] | g_obj[g_oidx[t]]] (graph.py:63-66);
  * g_obj is [g_nobj, g_din] contiguous, g_pred has row pitch g_ldp.  Object rows arrive by TMA tile::gather4.
+ * g_pidx (may be NULL) [rows] int32: the predicate segment is gathered as well, g_pred then being a TABLE of g_npred
+ * rows and the virtual row [g_obj[g_sidx[t]] | g_pred[g_pidx[t]] | g_obj[g_oidx[t]]] -- with g_obj the object
+ * embedding table and g_sidx / g_oidx class ids this is layer 0 reading straight from the embedding tables
+ * (sg2im/model.py:108-109), no [NT, Dp] / [NO, Din] rows materialised.
  * A, B, mask_aux, g_obj, g_pred are 16-bit floats; bias, rowscale fp32; C is 16-bit or (out_f32) fp32.
  * formats selects the 16-bit element formats per operand (tcgen05 kind::f16 takes fp16 and bf16, independently for A
  * and B): bit 0 = A (or the gathered rows when gather = 1) is fp16, bit 1 = B (or the gathered rows when gather = 2)
@@ -166,7 +170,7 @@ int csg_gemm_bf16(int mn_major, int gather, int M, int N, int K,
                   const void* A, int lda, const void* B, int ldb, void* C, int ldc, int out_f32,
                   const float* bias, int relu, const float* rowscale, const void* mask_aux, int ld_aux,
                   const void* g_obj, const void* g_pred, const int* g_sidx, const int* g_oidx,
-                  int g_din, int g_dp, int g_ldp, int g_nobj, int formats,
+                  int g_din, int g_dp, int g_ldp, int g_nobj, const int* g_pidx, int g_npred, int formats,
                   void* workspace, size_t workspace_bytes, csg_stream_t stream);
 /* CTA-pair policy of the K-major GEMMs (tcgen05.mma.cta_group::2, 256 x N pair tiles, each CTA stages half of B):
  * -1 automatic (default: pairs once M >= 2 * 128 * #SMs and K >= 1024), 0 never, 1 whenever the shape allows.
@@ -198,13 +202,18 @@ int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const void* d
 
 /* ---- one GraphTripleConv layer (sg2im/graph.py:44-113) per call on the bf16 engine: the launch sequence of the
  *      stages above issued natively, out of caller-owned `saved` (activations kept for backward + bf16 weights)
- *      and `workspace` (scratch).  dims (HOST int[9]) = {NT, NO, Din, Dp, H, Dout, Dpo, P, fwd_fp16}; all widths % 64
- *      == 0; fwd_fp16 = 1 keeps the forward tensors (obj, pred, weights, hidden, net1 output, pooled, net2 hidden,
- *      new_obj) in fp16 instead of bf16 -- gradient tensors (d_new_obj, d_new_p, dX, dobj) are bf16 either way.
+ *      and `workspace` (scratch).  dims (HOST int[11]) = {NT, NO, Din, Dp, H, Dout, Dpo, P, fwd_fp16, n_gather, n_pred};
+ *      all widths % 64 == 0; fwd_fp16 = 1 keeps the forward tensors (obj, pred, weights, hidden, net1 output, pooled,
+ *      net2 hidden, new_obj) in fp16 instead of bf16 (inference only) -- gradient tensors are bf16 either way.
+ *      n_gather > 0 / n_pred > 0 (layer 0 fused with the embedding lookups, sg2im/model.py:108-109): `obj` is the object
+ *      embedding TABLE [n_gather, Din] gathered by the per-triple class ids index[9] (subjects) / index[10] (objects),
+ *      `pred` the predicate embedding TABLE [n_pred, Dp] gathered by index[11]; dobj is still per object [NO, Din] (the
+ *      caller folds it onto the table by class id) and dX's predicate columns per triple.
  *      params (HOST array of 9 device pointers, fp32): net1.0.weight [H, 2Din+Dp], net1.0.bias, net1.2.weight
  *      [2H+Dpo, H], net1.2.bias, net2.0.weight [H, H], net2.0.bias, net2.2.weight [Dout, H], net2.2.bias,
  *      predicates_transitive_weights [P].  index (HOST array of 9 device pointers, int32): s_idx, o_idx, pred_id,
- *      type32, valid [NT] (csg_triple_prep) and rowptr_s, perm_s, rowptr_o, perm_o (csg_csr_build). ---------- */
+ *      type32, valid [NT] (csg_triple_prep) and rowptr_s, perm_s, rowptr_o, perm_o (csg_csr_build); with the fused
+ *      layer 0 three more: subject class ids, object class ids, predicate ids [NT] (index is then void*[12]). ---- */
 size_t csg_gconv_bf16_saved_bytes(const int* dims, int need_bwd);
 size_t csg_gconv_bf16_out_offset(const int* dims, int need_bwd);   /* byte offset in `saved` of net1's output [NT, 2H+Dpo] bf16 */
 size_t csg_gconv_bf16_workspace(const int* dims);
@@ -222,6 +231,12 @@ int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pred, int l
                        const void* d_new_obj, int d_new_obj_bf16, const void* d_new_p, int ld_dnewp,
                        const void* saved, const void* new_obj, void* dobj, int dobj_bf16, void* dX,
                        float* dparams, void* workspace, size_t workspace_bytes, csg_stream_t stream);
+
+/* out[i] = map[idx[i]] (int32): composes the per-triple class ids of the fused layer 0 from the triples' object indices
+ * and the objects' class ids.  idx values outside [0, n_map) and (n_values > 0) map values outside [0, n_values) --
+ * an embedding id nn.Embedding would raise on -- are reported through csg_async_error_poll. */
+int csg_compose_index(const int* idx, const long long* map, long long map_stride, int n, int n_map, int n_values,
+                      int* out, csg_stream_t stream);
 
 /* ---- embeddings + box loss around the GCN: sg2im/model.py:108-109, sg2im/attribute_embed.py:38-48,
  *      sg2im/pix2pix_model.py:72-85 --------------------------------------------------------------- */

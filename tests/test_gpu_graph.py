@@ -374,3 +374,38 @@ def test_cuda_graph_replay_equals_eager_steps():
                         step.layout_embedding.att_emb_0.weight.detach().clone()))
     assert results[0][0] == results[1][0]
     assert torch.equal(results[0][1], results[1][1]) and torch.equal(results[0][2], results[1][2])
+
+
+def test_layer0_fused_with_embedding_tables_equals_materialised_rows(golden):
+    """with single-attribute objects layer 0 gathers its subject / object rows from the object
+    embedding table by class id and its predicate rows from the predicate table by predicate id inside the net1
+    producer (TMA tile::gather4 over the tables), instead of reading materialised [NO, D] / [NT, D] lookups
+    (model.py:108-109).  Same bf16 values in, so outputs and all GCN gradients are bit-identical; the object table's
+    gradient is folded from fp32 per-object rows (bf16 rows in the materialised path): equal to 1e-2."""
+    g = golden("sg2layout_model")
+    res = []
+    for fuse in (True, False):
+        model = _model("bf16")
+        model.fuse_embeddings = fuse
+        obj_vecs, boxes, _ = model(t(g["objs"]), t(g["triplets"]), t(g["types"]))
+        (boxes.float().pow(2).sum() + (obj_vecs.float() * t(gi.model_obj_grad(obj_vecs.shape))).sum()).backward()
+        res.append((obj_vecs.detach(), boxes.detach(), {n: p.grad for n, p in model.named_parameters() if p.grad is not None}))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    for n, gr in res[0][2].items():
+        if n == "attribute_embedding.att_emb_0.weight":
+            assert rel_l2(gr, res[1][2][n]) <= 1e-2
+        else:
+            assert torch.equal(gr, res[1][2][n]), n
+    # the ragged interface takes the same path
+    model = _model("bf16")
+    objs, trips, types = g["objs"], g["triplets"], g["types"]
+    B, O, T = objs.shape[0], objs.shape[1], trips.shape[1]
+    n_obj = [int((g["boxes"][b] >= 0).all(-1).sum()) + 1 for b in range(B)]
+    n_tri = [int((trips[b, :, 1] != 0).sum()) for b in range(B)]
+    fo = np.concatenate([objs[b, :n_obj[b]] for b in range(B)])
+    ft = np.concatenate([trips[b, :n_tri[b]] for b in range(B)])
+    fy = np.concatenate([types[b, :n_tri[b]] for b in range(B)])
+    vecs_r, boxes_r = model.forward_ragged(t(fo), t(ft), t(fy), t(np.concatenate([[0], np.cumsum(n_tri)]).astype(np.int32)),
+                                           t(np.concatenate([[0], np.cumsum(n_obj)]).astype(np.int32)))
+    sel = torch.cat([res[0][0][b, :n_obj[b]] for b in range(B)])
+    assert_close(vecs_r.float(), sel.float(), 1e-2, "ragged fused vs padded fused")
