@@ -7,6 +7,8 @@ State-dict keys equal the reference's (``attribute_embedding.att_emb_{k}.weight`
 ``box_net.{0,2}.*``), so reference checkpoints load with ``strict=True`` when ``mask_size == 0``.
 The optional cuDNN ``mask_net`` conv stack (``model.py:62-75``) is outside the hot path and not built.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -197,7 +199,8 @@ class Sg2LayoutModel(nn.Module):
         self.args = args
         self.vocab = args["vocab"]
         self.precision = precision
-        self.fuse_embeddings = True       # False: materialise the embedding rows in front of layer 0 (tests compare both)
+        # False (or CSG_FUSE_EMB=0): materialise the embedding rows in front of layer 0 (tests compare both)
+        self.fuse_embeddings = os.environ.get("CSG_FUSE_EMB", "1") != "0"
         emb = args["embedding_dim"]
         self.attribute_embedding = AttributeEmbeddings(self.vocab["attributes"], emb)
         num_preds = self.num_preds = len(self.vocab["pred_idx_to_name"])
