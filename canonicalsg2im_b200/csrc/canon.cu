@@ -124,9 +124,16 @@ __global__ void __launch_bounds__(CTHREADS) canon_kernel(CanonParams p) {
           word &= word - 1;
           double u = p.uniforms[tbeg + k];
           ++k;
+          // searchsorted(cdf, u, side='right') clipped to the last candidate: the cumulative sums are non-decreasing,
+          // so the count of leading entries <= u is an upper bound by bisection (log2(ncand) dependent loads
+          // instead of a linear walk)
           const double* cdf = p.cdf + (size_t)rel * p.ncand;
-          int idx = 0;
-          while (idx < p.ncand - 1 && cdf[idx] <= u) ++idx;      // searchsorted(cdf, u, side='right')
+          int lo = 0, hi = p.ncand - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(cdf + mid) <= u) lo = mid + 1; else hi = mid;
+          }
+          const int idx = lo;
           int r = p.vals[(size_t)rel * p.ncand + idx];
           if (!EMIT) atomicAdd(&p.conv_counts[((size_t)g * P + rel) * (P + 1) + r], 1);
           if (r != P) atomicOr(&C[(size_t)r * rowsz + o * W + (s >> 6)], 1ull << (s & 63));   // edge [o, r, s]
@@ -152,19 +159,35 @@ __global__ void __launch_bounds__(CTHREADS) canon_kernel(CanonParams p) {
     for (int rel = warp; rel < P; rel += CTHREADS / 32) {
       if (is_meta(rel)) continue;
       u64* M = C + (size_t)rel * rowsz;
-      for (int i = 0; i < n; ++i) {
-        const int iw = i >> 6;
-        const u64 ib = 1ull << (i & 63);
-        for (int j = lane; j < n; j += 32) {
-          if (j != i && (M[j * W + iw] & ib)) {
-            for (int w = 0; w < W; ++w) M[j * W + w] |= M[i * W + w];
-          }
+      const u64* U = A + (size_t)rel * rowsz;
+      if (n <= 64 && W == 1) {
+        // the whole adjacency matrix lives in registers: lane j holds rows j and j + 32 (one 64-bit word each); the
+        // pivot row travels by shuffle, so a pivot step is a handful of ALU instructions with no shared-memory round
+        // trip and no warp barrier (ncu r02d: the shared-memory form of this loop was 35-40 % of the kernel)
+        u64 r0 = lane < n ? M[lane] : 0ull, r1 = lane + 32 < n ? M[lane + 32] : 0ull;
+        for (int i = 0; i < n; ++i) {
+          const u64 src = i < 32 ? r0 : r1;
+          const u64 pivot = __shfl_sync(0xffffffffu, src, i & 31);
+          if (lane != i && ((r0 >> i) & 1ull)) r0 |= pivot;
+          if (lane + 32 != i && ((r1 >> i) & 1ull)) r1 |= pivot;
         }
+        if (lane < n) M[lane] = r0 & ~U[lane];
+        if (lane + 32 < n) M[lane + 32] = r1 & ~U[lane + 32];
+        __syncwarp();
+      } else {
+        for (int i = 0; i < n; ++i) {
+          const int iw = i >> 6;
+          const u64 ib = 1ull << (i & 63);
+          for (int j = lane; j < n; j += 32) {
+            if (j != i && (M[j * W + iw] & ib)) {
+              for (int w = 0; w < W; ++w) M[j * W + w] |= M[i * W + w];
+            }
+          }
+          __syncwarp();
+        }
+        for (int i = lane; i < n * W; i += 32) M[i] &= ~U[i];
         __syncwarp();
       }
-      const u64* U = A + (size_t)rel * rowsz;
-      for (int i = lane; i < n * W; i += 32) M[i] &= ~U[i];
-      __syncwarp();
     }
     __syncthreads();
   }

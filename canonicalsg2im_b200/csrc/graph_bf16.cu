@@ -88,6 +88,8 @@ __global__ void cast_bf16_multi_kernel(const CastJobs jobs, bool fp16) {
 // CPU scatter_add visits them, graph.py:98-99) is dealt round-robin to the row lanes, every lane keeps four
 // independent row loads in flight, and the lanes are combined in lane order: a fixed, reproducible sum.
 constexpr int SP_MAX_THREADS = 256;
+constexpr int SP_CHUNK = 256;          // incidences staged per pass
+constexpr int SP_UNROLL = 4;           // 16-byte row loads in flight per thread (8 measured slower: 58 vs 53 us)
 template <bool AVG>
 __global__ void __launch_bounds__(SP_MAX_THREADS)
 segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int col_o, int W, int TX, int TY,
@@ -99,6 +101,12 @@ segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int
   CSG_PDL_WAIT();
   __shared__ float red[SP_MAX_THREADS * 8];
   __shared__ float red_cnt[SP_MAX_THREADS];
+  // The incidence list of the object is staged in shared memory SP_CHUNK entries at a time by the whole block (row
+  // offset in 16-byte units, confidence; -1 marks a triple that does not take part), so that the row loop issues one
+  // shared-memory read per 16-byte row load instead of a perm / valid / conf global load each (ncu r02b: the loop
+  // was at 51 % issue-active for 242 MB in 69 us)
+  __shared__ unsigned s_off[SP_CHUNK];
+  __shared__ float s_w[SP_CHUNK];
   // objects are visited last-to-first: X was just written front-to-back by the producing GEMM and is larger than L2, so
   // its tail is what is still cached; walking forwards would evict that tail before reaching it
   const int o = gridDim.x - 1 - blockIdx.x;
@@ -107,36 +115,44 @@ segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int
   const bool colok = c < W;
   const int bs = rp_s[o], ns = rp_s[o + 1] - bs;
   const int bo = rp_o[o], total = ns + rp_o[o + 1] - bo;
+  const uint4* X16 = reinterpret_cast<const uint4*>(X) + tx;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   float cnt = 0.f;
-  for (int e0 = ty; e0 < total; e0 += 4 * TY) {
-    uint4 r[4];
-    float w[4];
-    bool v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int e = e0 + k * TY;
-      v[k] = e < total;
-      r[k] = make_uint4(0, 0, 0, 0);
-      w[k] = 0.f;
-      if (v[k]) {
-        const bool subj = e < ns;
-        const int t = subj ? perm_s[bs + e] : perm_o[bo + e - ns];
-        // the row load does not wait for valid / conf (invalid rows are rare: padded batches only)
-        if (colok) r[k] = *reinterpret_cast<const uint4*>(X + (size_t)t * ldx + (subj ? col_s : col_o) + c);
-        if (AVG) { v[k] = valid[t] != 0; w[k] = conf[t]; }
-      }
+  for (int base = 0; base < total; base += SP_CHUNK) {
+    const int n = min(SP_CHUNK, total - base);
+    if (base) __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int e = base + i;
+      const bool subj = e < ns;
+      const int t = subj ? perm_s[bs + e] : perm_o[bo + e - ns];
+      s_off[i] = (unsigned)(((size_t)t * ldx + (subj ? col_s : col_o)) >> 3);
+      s_w[i] = AVG ? (valid[t] != 0 ? conf[t] : -1.f) : 0.f;
     }
+    __syncthreads();
+    for (int i0 = ty; i0 < n; i0 += SP_UNROLL * TY) {
+      uint4 r[SP_UNROLL];
+      float w[SP_UNROLL];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (v[k]) {
-        float f[8];
-        unpack8_16(r[k], f, fp16);
+      for (int k = 0; k < SP_UNROLL; ++k) {
+        const int i = i0 + k * TY;
+        w[k] = -1.f;
+        r[k] = make_uint4(0, 0, 0, 0);
+        if (i < n) {
+          w[k] = s_w[i];
+          if (colok && !(w[k] < 0.f)) r[k] = X16[s_off[i]];
+        }
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += f[i];
-        cnt += w[k];
+      for (int k = 0; k < SP_UNROLL; ++k) {
+        if (!(w[k] < 0.f)) {
+          float f[8];
+          unpack8_16(r[k], f, fp16);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += f[i];
+          cnt += w[k];
+        }
       }
     }
   }
@@ -239,17 +255,22 @@ int colsum_bf16_chunks(int M, int N) {
 // one partial row per block is written for the ordered final pass (deterministic for a given grid).
 constexpr int ASM_WARPS = 8, ASM_MAXI = 5;      // ASM_MAXI * 256 >= Wd
 constexpr int ASM_CTAS_PER_SM = 3;
-template <bool CS, bool OUT_FP16>
+// HT / DPT: compile-time H and Dp (0 = use the runtime values).  The reference geometry (hidden 512, predicate width
+// 128: every layer of the default stack) is instantiated with constants, which folds the segment tests and the
+// address arithmetic of the column loop (ncu r02b: the generic loop executes 684 warp instructions per row, a third of
+// them index math and branches, and is issue-bound at 49 % issue-active).
+template <bool CS, bool OUT_FP16, int HT, int DPT>
 __global__ void __launch_bounds__(ASM_WARPS * 32, ASM_CTAS_PER_SM)
 triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const float* __restrict__ dS,
                                 const __nv_bfloat16* __restrict__ d_newp, int ld_newp,
                                 const float* __restrict__ dcnt, const int* __restrict__ s_idx,
                                 const int* __restrict__ o_idx, const int* __restrict__ valid,
                                 const int* __restrict__ type32, const float* __restrict__ conf,
-                                int NT, int H, int Dp, __nv_bfloat16* __restrict__ g,
+                                int NT, int H_rt, int Dp_rt, __nv_bfloat16* __restrict__ g,
                                 float* __restrict__ dconf, float* __restrict__ cs_partial,
                                 const int* __restrict__ pred, int P, float* __restrict__ wt_partial) {
   CSG_PDL_WAIT();
+  const int H = HT ? HT : H_rt, Dp = DPT ? DPT : Dp_rt;
   __shared__ __align__(16) float cs_red[CS ? (ASM_WARPS / 2) * ASM_MAXI * 256 : 4];
   // per-warp bins of the confidence gradient by predicate (d w_trans, graph.py:69-74): each warp adds its triples in
   // the order it visits them, the warps are combined in warp order below -> one partial row per block
@@ -282,7 +303,8 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
     float cf2 = 0.f;
     if (tn < t_end) {
       s2 = s_idx[tn]; o2 = o_idx[tn]; vi2 = valid[tn]; ty2 = type32[tn]; cf2 = conf[tn]; pr2 = wt_partial ? pred[tn] : 0;
-      // pull the next row of `out` (the only DRAM-resident operand) into L2 while this one is processed
+      // pull the next row of `out` (the only DRAM-resident operand) into L2 while this one is processed (a lead of
+      // two rows measured slower: 134 vs 124 us)
       const __nv_bfloat16* nrow = out + (size_t)tn * Wd;
 #pragma unroll
       for (int u = 0; u < ASM_MAXI; ++u)
@@ -522,11 +544,11 @@ CSG_API int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const
                 "bwd_assemble_bf16: workspace too small");
     float* partial = reinterpret_cast<float*>(workspace);
     if (out_fp16) {
-      CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true, true>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream,
+      CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true, true, 0, 0>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream,
           o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, partial,
           (const int*)nullptr, 0, (float*)nullptr));
     } else {
-      CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true, false>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream,
+      CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true, false, 0, 0>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream,
           o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, partial,
           (const int*)nullptr, 0, (float*)nullptr));
     }
@@ -535,11 +557,11 @@ CSG_API int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const
     if (int rc = csg_reduce_multi(&job, 1, stream)) return rc;
   } else {
     if (out_fp16) {
-      CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<false, true>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream,
+      CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<false, true, 0, 0>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream,
           o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, (float*)nullptr,
           (const int*)nullptr, 0, (float*)nullptr));
     } else {
-      CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<false, false>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream,
+      CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<false, false, 0, 0>, dim3(blocks), dim3(ASM_WARPS * 32), 0, stream,
           o16, dS, p16, ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, g16, dconf, (float*)nullptr,
           (const int*)nullptr, 0, (float*)nullptr));
     }
@@ -575,7 +597,9 @@ int csg_triple_bwd_assemble_bf16_deferred(const void* out, const float* dS, cons
   float* cs_partial = reinterpret_cast<float*>(workspace);
   float* wt_partial = cs_partial + (size_t)blocks * Wd;
   CSG_REQUIRE(!out_fp16, "bwd_assemble_bf16 (deferred): fp16 forward tensors are inference-only");
-  CSG_CUDA(csg_launch_pdl(triple_bwd_assemble_bf16_kernel<true, false>, dim3(blocks), dim3(ASM_WARPS * 32), (size_t)ASM_WARPS * P * sizeof(float),
+  auto kernel = (H == 512 && Dp == 128) ? triple_bwd_assemble_bf16_kernel<true, false, 512, 128>
+                                        : triple_bwd_assemble_bf16_kernel<true, false, 0, 0>;
+  CSG_CUDA(csg_launch_pdl(kernel, dim3(blocks), dim3(ASM_WARPS * 32), (size_t)ASM_WARPS * P * sizeof(float),
                           stream, reinterpret_cast<const __nv_bfloat16*>(out), dS, reinterpret_cast<const __nv_bfloat16*>(d_newp),
                           ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, reinterpret_cast<__nv_bfloat16*>(g),
                           (float*)nullptr, cs_partial, pred, P, wt_partial));
