@@ -273,14 +273,23 @@ class L2Flusher:
 
 
 def time_each(fn, steps, warmup, flush=None):
-    """Per-iteration CUDA-event timing on the current stream with an (untimed) L2 flush between iterations."""
+    """CUDA-event timing on the current stream.  Without `flush` (working set larger than L2) the `steps` iterations
+    are timed back to back in one bracket; with it, every iteration is bracketed on its own and an (untimed) L2 flush
+    runs between iterations."""
     for _ in range(max(warmup, 3)):
         fn()
-    evs = []
     torch.cuda.synchronize()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / steps
+    evs = []
     for _ in range(steps):
-        if flush is not None:
-            flush()
+        flush()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
