@@ -947,7 +947,7 @@ int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K,
     return 0;
   }
   CSG_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_bf16: bad sizes M=%d N=%d K=%d", M, N, K);
-  CsgProfScope prof(CSG_PROF_GEMM_BF16, 2.0 * M * N * K, stream);
+  CsgProfScope prof(CSG_PROF_GEMM_BF16, 2.0 * M * N * K, stream);   // the GEMM kernel itself (a deferred split-K pass is not in it)
   CSG_REQUIRE(N % 32 == 0, "gemm_bf16: N=%d must be a multiple of 32", N);
   CSG_REQUIRE((ldc % 8) == 0 || out_f32, "gemm_bf16: bf16 ldc must be a multiple of 8");
   CSG_REQUIRE(!out_f32 || (ldc % 4) == 0, "gemm_bf16: fp32 ldc must be a multiple of 4");
