@@ -12,12 +12,23 @@
 // Dataflow (identical to canonicalsg2im_b200/graph_tc.py, which remains as the staged form used by the tests):
 //   forward   cast weights -> conf (graph.py:69-74) -> F1 (gather fused, graph.py:63-67) -> F2 (+bias, ReLU, x conf)
 //             -> CSR pooling (graph.py:83-107) -> net2 (graph.py:110)
-//   backward  net2 dW/db/dX -> pooling backward -> assemble d(net1 pre-activation) (+ db2, dconf) -> dW2, dhidden,
-//             dW1 (re-gathers its operand), db1, dX -> segmented sums of dX onto objects -> d w_trans
+//   backward  net2 dW/db/dX -> pooling backward -> assemble d(net1 pre-activation) (+ db2, dconf) -> dW2, dhidden ->
+//             net1's first Linear from PER-OBJECT SUMS of dhidden (below) -> d w_trans
+//
+// Backward of the gathered first Linear (graph.py:60-67).  With x_t = [obj[s_t] | pred_t | obj[o_t]] and W1 = [Ws | Wp | Wo]:
+//   dW1 = sum_t dh_t^T x_t  =  [ (S dh)^T obj | dh^T pred | (O dh)^T obj ],    db1 = colsum(S dh),
+//   d obj = (S dh) Ws + (O dh) Wo,                                              d pred = dh Wp,
+// where S dh [NO, H] / O dh [NO, H] are the sums of dhidden over the triples whose subject / object is a given object
+// (csg_segsum2_bf16, one pass each over dhidden).  The two T-sized GEMMs left have N = Dp instead of N = 2 Din + Dp and the
+// gathered weight-gradient GEMM, the column-sum pass over dhidden and the segmented sums of dX disappear; everything
+// per object is a GEMM over NO rows.  Measured on the cfg2 layer (scratch/bwd_alt.py): 144 us against 168 us.  The
+// layer that reads the embedding tables directly (n_gather / n_pred > 0) keeps the gathered dataflow (CSG_BWD_SEGSUM=0
+// selects it everywhere).
 #include "common.cuh"
 #include "internal.h"
 #include "csg2im.h"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -35,9 +46,16 @@ inline Dims read_dims(const int* d) { return Dims{d[0], d[1], d[2], d[3], d[4], 
 
 inline size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// net1's first-layer backward from per-object sums of dhidden (see the file comment)
+inline bool use_segsum(const Dims& d) {
+  if (d.n_gather || d.n_pred) return false;
+  const char* e = getenv("CSG_BWD_SEGSUM");
+  return !(e && e[0] == '0');
+}
+
 // ---- layout of `saved`
 struct Saved {
-  size_t w1b, w2b, w3b, w4b, w1t, w2t, w3t, w4t, conf, hidden, out, pooled32, pooled16, cnt, h2, total;
+  size_t w1b, w2b, w3b, w4b, w1t, w2t, w3t, w4t, w1so, conf, hidden, out, pooled32, pooled16, cnt, h2, total;
 };
 Saved plan_saved(const Dims& d, bool need_bwd) {
   Saved s;
@@ -48,6 +66,7 @@ Saved plan_saved(const Dims& d, bool need_bwd) {
   s.w1b = take(e1); s.w2b = take(e2); s.w3b = take(e3); s.w4b = take(e4);
   s.w1t = take(need_bwd ? e1 : 0); s.w2t = take(need_bwd ? e2 : 0); s.w3t = take(need_bwd ? e3 : 0);
   s.w4t = take(need_bwd ? e4 : 0);
+  s.w1so = take(need_bwd ? (size_t)d.Din * 2 * d.H * 2 : 0);     // [Din, 2H] = [Ws^T | Wo^T]: B operand of d obj = [S dh | O dh] [Ws ; Wo]
   s.conf = take((size_t)(d.NT > 0 ? d.NT : 1) * 4);
   s.hidden = take((size_t)d.NT * d.H * 2);
   s.out = take((size_t)d.NT * d.Wd() * 2);
@@ -63,8 +82,8 @@ Saved plan_saved(const Dims& d, bool need_bwd) {
 // Every producer of partial sums owns its region: the final passes of a layer run together in ONE launch at the end
 // of the layer's backward (csg_reduce_multi), so no partial buffer may be reused before that.
 struct Work {
-  size_t g4, dh2, dpooled, dS, dcnt, g, dhid, total;
-  size_t sk[4], sk_bytes[4];     // split-K partials of dw4, dw3, dw2, dw1
+  size_t g4, dh2, dpooled, dS, dcnt, g, dhid, dHso, tmp_p, tmp_so, total;
+  size_t sk[6], sk_bytes[6];     // split-K partials of dw4, dw3, dw2, dw1 (gathered), dw1 predicate block, dw1 object blocks
   size_t cs[3], cs_bytes[3];     // column-sum partials of db4, db3, db1
   size_t asm_ws, asm_bytes;      // assemble: column sums of g (db2) + per-predicate confidence-gradient bins (d w_trans)
 };
@@ -80,15 +99,19 @@ Work plan_work(const Dims& d) {
   w.dcnt = take((size_t)d.NO * 4);
   w.g = take((size_t)d.NT * d.Wd() * 2);
   w.dhid = take((size_t)d.NT * d.H * 2);
-  (void)mx;
+  w.dHso = take((size_t)d.NO * 2 * d.H * 2);          // [S dh | O dh] bf16
+  w.tmp_p = take((size_t)d.H * d.Dp * 4);             // dW1 predicate block, contiguous (scattered into dw1 by the final pass)
+  w.tmp_so = take((size_t)2 * d.H * d.Din * 4);       // dW1 subject / object blocks
   w.sk_bytes[0] = csg_gemm_bf16_workspace(d.Dout, d.H, d.NO, 1);
   w.sk_bytes[1] = csg_gemm_bf16_workspace(d.H, d.H, d.NO, 1);
   w.sk_bytes[2] = csg_gemm_bf16_workspace(d.Wd(), d.H, d.NT, 1);
   w.sk_bytes[3] = csg_gemm_bf16_workspace(d.H, d.K1(), d.NT, 1);
-  for (int i = 0; i < 4; ++i) w.sk[i] = take(w.sk_bytes[i]);
+  w.sk_bytes[4] = csg_gemm_bf16_workspace(d.H, d.Dp, d.NT, 1);
+  w.sk_bytes[5] = csg_gemm_bf16_workspace(2 * d.H, d.Din, d.NO, 1);
+  for (int i = 0; i < 6; ++i) w.sk[i] = take(w.sk_bytes[i]);
   w.cs_bytes[0] = csg_colsum_bf16_workspace(d.NO, d.Dout);
   w.cs_bytes[1] = csg_colsum_bf16_workspace(d.NO, d.H);
-  w.cs_bytes[2] = csg_colsum_bf16_workspace(d.NT, d.H);
+  w.cs_bytes[2] = mx(csg_colsum_bf16_workspace(d.NT, d.H), csg_colsum_bf16_workspace(d.NO, d.H));
   for (int i = 0; i < 3; ++i) w.cs[i] = take(w.cs_bytes[i]);
   w.asm_bytes = csg_triple_bwd_assemble_bf16_deferred_workspace(d.NT, d.H, d.Dpo, d.P);
   w.asm_ws = take(w.asm_bytes);
@@ -135,6 +158,12 @@ CSG_API size_t csg_gconv_bf16_out_offset(const int* dims, int need_bwd) {
   return plan_saved(read_dims(dims), need_bwd != 0).out;
 }
 CSG_API size_t csg_gconv_bf16_workspace(const int* dims) { return plan_work(read_dims(dims)).total; }
+// columns of the dX matrix csg_gconv_bf16_bwd writes: Dp (d pred only) when net1's first Linear is differentiated through the
+// per-object sums of dhidden, 2 Din + Dp (the whole gathered row, d pred in columns Din .. Din+Dp) on the gathered dataflow
+CSG_API int csg_gconv_bf16_dx_cols(const int* dims) {
+  const Dims d = read_dims(dims);
+  return use_segsum(d) ? d.Dp : d.K1();
+}
 
 // dims (HOST int[11]): {NT, NO, Din, Dp, H, Dout, Dpo, P, fwd_fp16, n_gather, n_pred}; index (HOST void*[12]).  params (HOST array of 9 device pointers, fp32): w1 [H, 2Din+Dp],
 // b1, w2 [2H+Dpo, H], b2, w3 [H, H], b3, w4 [Dout, H], b4, w_trans [P].  index (HOST array of 9 device pointers,
@@ -165,12 +194,16 @@ CSG_API int csg_gconv_bf16_fwd(const int* dims, const void* obj, const void* pre
   const int fmt = d.f16 ? 7 : 0;      // csg_gemm_bf16 formats: A, B and C of every forward GEMM are forward tensors
   // ---- 16-bit copies of the weights (+ transposes for the dX-type GEMMs of backward), one launch
   {
-    const void* src[8] = {w[0], w[1], w[2], w[3], w[0], w[1], w[2], w[3]};
-    void* dst[8] = {sv + s.w1b, sv + s.w2b, sv + s.w3b, sv + s.w4b, sv + s.w1t, sv + s.w2t, sv + s.w3t, sv + s.w4t};
-    const int rows[8] = {d.H, Wd, d.H, d.Dout, d.H, Wd, d.H, d.Dout};
-    const int cols[8] = {K1, d.H, d.H, d.H, K1, d.H, d.H, d.H};
-    const int tr[8] = {0, 0, 0, 0, 1, 1, 1, 1};
-    CSG_TRY(csg_cast_bf16_multi(need_bwd ? 8 : 4, src, dst, rows, cols, tr, d.f16, stream));
+    // jobs 8, 9: [Ws^T | Wo^T] = the transposes of the subject / object column blocks of w1, side by side
+    __nv_bfloat16* w1so = reinterpret_cast<__nv_bfloat16*>(sv + s.w1so);
+    const void* src[10] = {w[0], w[1], w[2], w[3], w[0], w[1], w[2], w[3], w[0], w[0] + d.Din + d.Dp};
+    void* dst[10] = {sv + s.w1b, sv + s.w2b, sv + s.w3b, sv + s.w4b, sv + s.w1t, sv + s.w2t, sv + s.w3t, sv + s.w4t, w1so, w1so + d.H};
+    const int rows[10] = {d.H, Wd, d.H, d.Dout, d.H, Wd, d.H, d.Dout, d.H, d.H};
+    const int cols[10] = {K1, d.H, d.H, d.H, K1, d.H, d.H, d.H, d.Din, d.Din};
+    const int tr[10] = {0, 0, 0, 0, 1, 1, 1, 1, 1, 1};
+    const int lds[10] = {0, 0, 0, 0, 0, 0, 0, 0, K1, K1};
+    const int ldd[10] = {0, 0, 0, 0, 0, 0, 0, 0, 2 * d.H, 2 * d.H};
+    CSG_TRY(csg_cast_bf16_multi_ld(need_bwd ? (use_segsum(d) ? 10 : 8) : 4, src, dst, rows, cols, tr, lds, ldd, d.f16, reinterpret_cast<cudaStream_t>(stream)));
   }
   float* conf = reinterpret_cast<float*>(sv + s.conf);
   CSG_TRY(csg_triple_conf(type32, pred_id, w_trans, d.NT, conf, stream));
@@ -195,7 +228,8 @@ CSG_API int csg_gconv_bf16_fwd(const int* dims, const void* obj, const void* pre
 
 // Backward of the call above.  d_new_obj [NO, Dout] (fp32, or bf16 when d_new_obj_bf16; NULL = zero),
 // d_new_p [NT, Dpo] bf16 with row pitch ld_dnewp (NULL = zero).  Written: dobj [NO, Din] (fp32, or bf16 when
-// dobj_bf16), dX [NT, 2Din+Dp] bf16 (its columns Din..Din+Dp are d pred), dparams (fp32, contiguous, in this order:
+// dobj_bf16), dX [NT, csg_gconv_bf16_dx_cols] bf16 (d pred, or the whole gathered row with d pred in its columns
+// Din..Din+Dp), dparams (fp32, contiguous, in this order:
 // dw1 [H, 2Din+Dp], db1 [H], dw2 [2H+Dpo, H], db2, dw3 [H, H], db3, dw4 [Dout, H], db4, dw_trans [P]).
 CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pred, int ldp,
                                const void* const* params, const void* const* index,
@@ -301,15 +335,62 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
   // ---- net1 backward (graph.py:63-67)
   GEMM(1, 0, Wd, H, NT, g, Wd, hidden, H, dw2, H, 1, nullptr, 0, 2);
   GEMM(0, 0, NT, H, Wd, g, Wd, sv + s.w2t, Wd, dhid, H, 0, hidden, H, -1);
-  GEMM(1, 2, H, K1, NT, dhid, H, nullptr, 0, dw1, K1, 1, nullptr, 0, 3);
-  CSG_TRY(csg_colsum_bf16_deferred(dhid, NT, H, H, db1, ws + w.cs[2], w.cs_bytes[2], st, &jobs[njobs]));
-  if (jobs[njobs].parts > 0) ++njobs;
-  GEMM(0, 0, NT, K1, H, dhid, H, sv + s.w1t, H, dX, K1, 0, nullptr, 0, -1);
+  if (!use_segsum(d)) {
+    GEMM(1, 2, H, K1, NT, dhid, H, nullptr, 0, dw1, K1, 1, nullptr, 0, 3);
+    CSG_TRY(csg_colsum_bf16_deferred(dhid, NT, H, H, db1, ws + w.cs[2], w.cs_bytes[2], st, &jobs[njobs]));
+    if (jobs[njobs].parts > 0) ++njobs;
+    GEMM(0, 0, NT, K1, H, dhid, H, sv + s.w1t, H, dX, K1, 0, nullptr, 0, -1);
+    // ---- gather backward: segmented sums of dX over ALL triples onto their subject / object rows
+    CSG_TRY(csg_segpool_bf16(dX, K1, 0, d.Din + d.Dp, d.Din, rowptr_s, perm_s, rowptr_o, perm_o, nullptr, nullptr, NO,
+                             dobj_bf16 ? nullptr : reinterpret_cast<float*>(dobj), dobj_bf16 ? dobj : nullptr, d.Din, nullptr,
+                             0, 0, stream));
+  } else {
+    // ---- per-object sums of dhidden: [S dh | O dh] (bf16, [NO, 2H])
+    void* dHso = ws + w.dHso;
+    float* tmp_p = reinterpret_cast<float*>(ws + w.tmp_p);
+    float* tmp_so = reinterpret_cast<float*>(ws + w.tmp_so);
+    const int Din = d.Din, Dp = d.Dp;
+    CSG_TRY(csg_segsum2_bf16(dhid, H, H, rowptr_s, perm_s, rowptr_o, perm_o, NO, nullptr, dHso, 2 * H, stream));
+    // db1 = colsum(dhidden) = colsum(S dh): every triple has exactly one subject
+    CSG_TRY(csg_colsum_bf16_deferred(dHso, NO, H, 2 * H, db1, ws + w.cs[2], w.cs_bytes[2], st, &jobs[njobs]));
+    if (jobs[njobs].parts > 0) ++njobs;
+    // a weight-gradient block computed into a contiguous scratch matrix and placed into dw1 (row pitch K1) by the final pass
+    auto place = [&](CsgReduceJob& j, const float* scratch, int rows, int cols, float* dst) {
+      if (j.parts == 0) {                         // written directly (no split-K): the final pass is then a copy
+        j.partial = scratch; j.parts = 1; j.stride = (long long)rows * cols; j.lanes = 1; j.op = CSG_RED_SUM; j.aux = nullptr;
+      }
+      j.n = rows * cols; j.out = dst; j.ncols = cols; j.ldo = K1;
+    };
+    // dW1[:, Din : Din+Dp] = dh^T pred
+    CSG_TRY(csg_gemm_bf16_deferred(1, 0, H, Dp, NT, dhid, H, pred, ldp, tmp_p, Dp, 1, nullptr, 0, nullptr, nullptr, 0, nullptr,
+                                   nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, bfmt, ws + w.sk[4], w.sk_bytes[4], st,
+                                   &jobs[njobs]));
+    place(jobs[njobs], tmp_p, H, Dp, dw1 + Din);
+    ++njobs;
+    // dW1[:, 0 : Din] = (S dh)^T obj and dW1[:, Din+Dp :] = (O dh)^T obj: one GEMM with M = 2H, two placements
+    CSG_TRY(csg_gemm_bf16_deferred(1, 0, 2 * H, Din, NO, dHso, 2 * H, obj, Din, tmp_so, Din, 1, nullptr, 0, nullptr, nullptr, 0,
+                                   nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, bfmt, ws + w.sk[5], w.sk_bytes[5], st,
+                                   &jobs[njobs]));
+    {
+      CsgReduceJob lo = jobs[njobs], hi = jobs[njobs];
+      const float* base_partial = lo.parts > 0 ? lo.partial : tmp_so;
+      place(lo, tmp_so, H, Din, dw1);
+      place(hi, tmp_so, H, Din, dw1 + Din + Dp);
+      lo.partial = base_partial;
+      hi.partial = base_partial + (size_t)H * Din;
+      jobs[njobs] = lo; jobs[njobs + 1] = hi;
+      njobs += 2;
+    }
+    // d pred = dh Wp  (rows Din .. Din+Dp of the transposed copy of w1)
+    CSG_TRY(csg_gemm_bf16_deferred(0, 0, NT, Dp, H, dhid, H, sv + s.w1t + (size_t)Din * H * 2, H, dX, Dp, 0, nullptr, 0, nullptr,
+                                   nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, bfmt, nullptr, 0, st,
+                                   &jobs[njobs]));
+    // d obj = [S dh | O dh] [Ws ; Wo]
+    CSG_TRY(csg_gemm_bf16_deferred(0, 0, NO, Din, 2 * H, dHso, 2 * H, sv + s.w1so, 2 * H, dobj, Din, dobj_bf16 ? 0 : 1, nullptr, 0,
+                                   nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, bfmt, nullptr, 0,
+                                   st, &jobs[njobs]));
+  }
 #undef GEMM
-  // ---- gather backward: segmented sums of dX over ALL triples onto their subject / object rows
-  CSG_TRY(csg_segpool_bf16(dX, K1, 0, d.Din + d.Dp, d.Din, rowptr_s, perm_s, rowptr_o, perm_o, nullptr, nullptr, NO,
-                           dobj_bf16 ? nullptr : reinterpret_cast<float*>(dobj), dobj_bf16 ? dobj : nullptr, d.Din, nullptr,
-                           0, 0, stream));
   // ---- all deferred final passes of the layer: dw1..dw4 (split-K), db1..db4 (column sums), d w_trans
   CSG_TRY(csg_reduce_multi(jobs, njobs, st));
   return 0;

@@ -9,13 +9,14 @@
 //   dX-type  dy W   (weights pre-transposed once per step so both operands stay K-major)
 //   dW-type  dy^T x (both operands MN-major, K = triples, split-K over persistent CTAs)
 //
-// Kernel anatomy (persistent, warp specialised, 192 threads):
+// Kernel anatomy (persistent, warp specialised, 320 threads; 448 in the gather variants):
 //   warp 0      producer: TMA tile loads (lane 0) and, in the gather variants, one TMA tile::gather4 per lane
 //               (4 gathered rows of 128 bytes each, written in the same 128-byte swizzle) into the smem ring
 //   warp 1      MMA issuer (one lane)              tcgen05.mma + tcgen05.commit -> empty / tmem_full
-//   warps 2-5   epilogue: tcgen05.ld 32x32b.x32 -> bias / ReLU / row scale / ReLU mask -> bf16 -> swizzled smem
-//               staging -> TMA store (each warp owns its 32 rows: no cross-warp barrier); the ReLU-mask operand
-//               is prefetched by TMA into smem as well, so the epilogue issues no strided global accesses
+//   warps 2-9   epilogue: tcgen05.ld 32x32b.x32 -> bias / ReLU / row scale -> bf16 -> swizzled smem staging ->
+//               coalesced 16-byte global stores, with the ReLU mask applied in that coalesced layout (each warp owns
+//               its 32 rows and its private bias row: no barrier spans more than one warp)
+//   warps 10-13 (gather variants) TMA tile::gather4 issue, 8 lanes each
 // TMEM: 512 columns = 2 accumulator stages x 256, so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "internal.h"
@@ -31,12 +32,14 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int MAX_STAGES = 8;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 320;              // producer, MMA, 8 epilogue warps
-constexpr int GATHER_WARPS = 4;               // extra warps 10-13 of the gather variants (8 issuing lanes each)
-constexpr int FIRST_GATHER_WARP = 10;
+constexpr int GATHER_WARPS = 4;               // extra warps of the gather variants, behind the epilogue warps (8 issuing lanes each)
 constexpr int ACC_STRIDE = 256;                   // TMEM columns per accumulator stage
-constexpr int EPI_WARPS = 8;                      // two per TMEM lane quarter: one warp per scheduler cannot hide its own latencies
-constexpr int CHUNK_N = 64;                       // epilogue chunk: 64 bf16 columns = one 128-byte swizzle row
+// Epilogue warps (template parameter EPW, 8 in every shipped instantiation): EPW / 4 per TMEM lane quarter.  The staged
+// bf16 epilogue comes in two geometries (template flag SUB32): 64-column chunks (stores of full 128-byte lines) and
+// 32-column sub-blocks (half the registers per warp, one tcgen05.ld per step); csg_gemm_bf16_deferred picks per shape.
+constexpr int SUB_N = 32;                         // epilogue sub-block (SUB32): 32 columns = one tcgen05.ld.32x32b.x32 per lane
+constexpr int SUB_BYTES = 32 * SUB_N * 2;         // per-warp staging buffer: 32 rows x 64 bytes
+constexpr int CHUNK_N = 64;                       // epilogue chunk (!SUB32): 64 bf16 columns = one 128-byte swizzle row
 constexpr int CHUNK_BYTES = 32 * CHUNK_N * 2;     // per-warp staging buffer: 32 rows x 128 bytes
 constexpr size_t SMEM_LIMIT = 232448;             // 227 KB opt-in maximum per CTA
 
@@ -240,12 +243,13 @@ struct __align__(8) Barriers {
 struct SmemPlan {
   uint32_t b, c, bias, bars, total;
 };
-__host__ __device__ inline SmemPlan smem_plan(int BN, int b_rows, int stages, bool smem_epi, int mt = 1) {
+__host__ __device__ inline SmemPlan smem_plan(int BN, int b_rows, int stages, bool smem_epi, int mt, int epw, bool sub32) {
   SmemPlan s;
+  (void)BN;
   s.b = (uint32_t)stages * mt * A_STAGE_BYTES;
   s.c = s.b + (uint32_t)stages * b_rows * 128;
-  s.bias = s.c + (smem_epi ? EPI_WARPS * CHUNK_BYTES : 0);
-  s.bars = s.bias + (smem_epi ? 2 * BN * 4 : 0);             // bias of the current n-tile, double-buffered by tile parity
+  s.bias = s.c + (smem_epi ? epw * (sub32 ? SUB_BYTES : CHUNK_BYTES) : 0);
+  s.bars = s.bias + (smem_epi ? epw * (sub32 ? SUB_N : CHUNK_N) * 4 : 0);        // bias of the sub-block a warp is working on (one private row per warp)
   s.total = s.bars + (uint32_t)sizeof(Barriers);
   return s;
 }
@@ -277,8 +281,8 @@ __device__ __forceinline__ bool bf16_pos(uint32_t h) { return h != 0 && h < 0x80
 // MT > 1 (gathered-B weight gradient dW1 only): one CTA owns MT 128-row m sub-tiles of the output for one 128-column
 // n-tile, i.e. MT accumulators side by side in TMEM.  The gathered operand (the TMA gather4 issue rate is what bounds
 // this GEMM) is then staged once per k-block for MT * 128 rows of M instead of once per 128-row m-tile.
-template <int BN, bool MN, int GATHER, int CG, int MT>
-__global__ void __launch_bounds__(NUM_THREADS + (GATHER != G_NONE ? GATHER_WARPS * 32 : 0), 1)
+template <int BN, bool MN, int GATHER, int CG, int MT, int EPW, bool SUB32>
+__global__ void __launch_bounds__(64 + EPW * 32 + (GATHER != G_NONE ? GATHER_WARPS * 32 : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmP, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];             // SWIZZLE_128B needs 1024-byte alignment
@@ -290,6 +294,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   static_assert(CG == 1 || !MN, "CTA pairs are implemented for the K-major kernels");
   static_assert(MT == 1 || (MN && GATHER == G_B && CG == 1 && MT * BN <= 512), "MT > 1: gathered-B MN-major kernels only");
+  static_assert(EPW == 8 || EPW == 16, "epilogue warps: 2 or 4 per TMEM lane quarter");
+  constexpr int EPI_WARPS = EPW;
+  constexpr int FIRST_GATHER_WARP = 2 + EPW;
+  constexpr int NSUB = EPW / 4;                      // epilogue warps per TMEM lane quarter
   constexpr int A_STAGE = MT * A_STAGE_BYTES;        // bytes of the A tile(s) of one stage
   constexpr int B_ROWS = BN / CG;                   // rows of the B tile staged by this CTA
   constexpr int B_STAGE = B_ROWS * BLOCK_K * 2;
@@ -298,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int worker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int nworkers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const bool has_aux = GATHER == G_NONE && p.mask_aux != nullptr;   // the gathered GEMMs never take a ReLU mask
-  const SmemPlan plan = smem_plan(BN, B_ROWS, p.stages, p.smem_epi != 0, MT);
+  const SmemPlan plan = smem_plan(BN, B_ROWS, p.stages, p.smem_epi != 0, MT, EPW, SUB32);
   const uint32_t sA = base, sB = base + plan.b;
   Barriers* bars = reinterpret_cast<Barriers*>(base_ptr + plan.bars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -358,7 +366,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1);
           const uint32_t fb = leader(&bars->full[stage]);
-          // the whole stage (of both CTAs of a pair) is accounted here by the leader; bytes gathered by warps 6-9 or
+          // the whole stage (of both CTAs of a pair) is accounted here by the leader; bytes gathered by the gather warps or
           // loaded by the peer CTA may land before or after this arrive
           if (p.debug & 1) {
             if (CG == 1 || cta_rank == 0) mbar_arrive(smem_u32(&bars->full[stage]));
@@ -396,7 +404,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= FIRST_GATHER_WARP) {
-    // ================================================================== gather producers (warps 6-9, lanes 0-7)
+    // ================================================================== gather producers (warps 10-13, lanes 0-7)
     // Object rows of the virtual operand arrive by TMA tile::gather4 (4 rows x 128 bytes per instruction, written
     // in the same 128-byte swizzle as a tile load).  A TMA instruction takes warp-uniform operands, so a warp
     // issues them one lane at a time: the work is spread over 4 warps x 8 lanes.
@@ -544,19 +552,132 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp < FIRST_GATHER_WARP) {
-    // ================================================================== epilogue (warps 2-9)
+    // ================================================================== epilogue (warps 2 .. 2+EPW-1)
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int ew = warp - 2;                      // 0..7
-    const int half = ew >> 2;                     // the two warps of a quarter take alternate 64-column chunks
+    const int ew = warp - 2;                      // 0..EPW-1
+    const int sub = ew >> 2;                      // the NSUB warps of a quarter take every NSUB-th 32-column sub-block
     int it = 0;
     if (!MN && p.smem_epi) {
+      if constexpr (SUB32) {
+      // bf16 output, 32 columns at a time: registers (one row per lane) -> bias / ReLU / row scale -> this warp's
+      // swizzled 32 x 64 B staging tile -> registers in the coalesced layout (one instruction = 8 rows x 64 B) ->
+      // ReLU mask (the mask operand is read with the same coalesced addressing, before the TMEM wait) -> 16-byte global
+      // stores.  Stores are fire-and-forget: no epilogue warp ever waits for a write to drain, and no barrier spans
+      // more than one warp (the bias of a sub-block sits in a private 128-byte row of the warp).
+      const uint32_t sC = base + plan.c + ew * SUB_BYTES;
+      float* sbias = reinterpret_cast<float*>(base_ptr + plan.bias) + ew * SUB_N;
+      // staging rows are 64 bytes (4 pieces of 16); piece j of row r sits at j ^ ((r >> 1) & 3): the 8 lanes of a
+      // shared-memory wavefront then touch 8 distinct 16-byte bank groups, for the row-per-lane writes and the
+      // coalesced reads alike
+      const uint32_t sw = ((uint32_t)lane >> 1) & 3u;
+      const uint32_t row_off = (uint32_t)lane * (SUB_N * 2);
+      const int crow = lane >> 2, cpiece = lane & 3;           // coalesced layout: rows i*8 + crow, 16-byte piece cpiece
+      __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
+      const bool cf16 = p.c_f16 != 0;
+      for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
+        int mt, nt, sp;
+        decode(tile, mt, nt, sp);
+        const int as = it & 1, aphase = (it >> 1) & 1;
+        const int row0 = mt * TILE_M + (int)cta_rank * BLOCK_M + q * 32;
+        const int row = row0 + lane;
+        const int ncols = min(BN, p.N - nt * BN);
+        const int nsb = (ncols + SUB_N - 1) / SUB_N;
+        const bool warp_rows = row0 < p.M;
+        const float rs = (p.rowscale && row < p.M) ? __ldg(p.rowscale + row) : 1.f;
+        mbar_wait(smem_u32(&bars->tmem_full[as]), aphase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
+        const int my_last = nsb > sub ? ((nsb - 1 - sub) / NSUB) * NSUB + sub : -1;   // last sub-block of this warp
+        if ((p.debug & 4) || my_last < 0) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (CG == 2) mbar_arrive_cluster(leader(&bars->tmem_empty[as])); else mbar_arrive(smem_u32(&bars->tmem_empty[as])); }
+          continue;
+        }
+#pragma unroll 1
+        for (int c = sub; c < nsb; c += NSUB) {
+          const int col0 = nt * BN + c * SUB_N;                // N % 32 == 0: a sub-block is never partial
+          const float bv = p.bias ? __ldg(p.bias + col0 + lane) : 0.f;
+          uint32_t r[32];
+          tmem_ld32(t_row + c * SUB_N, r);
+          // ReLU-mask operand of this sub-block, in the coalesced layout of the final stores: needed only after the math
+          // and the staging round trip below, which cover its latency
+          const int col = col0 + cpiece * 8;                   // first column of this lane's 16-byte piece
+          uint4 ax[4];
+          if (has_aux && warp_rows) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = row0 + i * 8 + crow;
+              ax[i] = rr < p.M ? __ldg(reinterpret_cast<const uint4*>(p.mask_aux + (size_t)rr * p.ld_aux + col))
+                               : make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+          tmem_ld_wait();
+          if (c == my_last) {
+            // accumulator fully read: hand the TMEM stage back before the math / stores of the last sub-block
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(leader(&bars->tmem_empty[as])); else mbar_arrive(smem_u32(&bars->tmem_empty[as])); }
+          }
+          if (warp_rows) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.bias) {
+              sbias[lane] = bv;
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(sbias + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.rowscale) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= rs;
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint32_t off = row_off + ((((uint32_t)j4) ^ sw) << 4);
+              const uint32_t u0 = pack16(v[j4 * 8], v[j4 * 8 + 1], cf16), u1 = pack16(v[j4 * 8 + 2], v[j4 * 8 + 3], cf16);
+              const uint32_t u2 = pack16(v[j4 * 8 + 4], v[j4 * 8 + 5], cf16), u3 = pack16(v[j4 * 8 + 6], v[j4 * 8 + 7], cf16);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sC + off), "r"(u0), "r"(u1), "r"(u2), "r"(u3) : "memory");
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rl = i * 8 + crow;
+              uint4 o;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                           : "r"(sC + (uint32_t)rl * (SUB_N * 2) + ((uint32_t)(cpiece ^ ((rl >> 1) & 3)) << 4)));
+              if (has_aux) {
+                const uint32_t a[4] = {ax[i].x, ax[i].y, ax[i].z, ax[i].w};
+                uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (!bf16_pos(a[e] & 0xFFFFu)) w[e] &= 0xFFFF0000u;
+                  if (!bf16_pos(a[e] >> 16)) w[e] &= 0x0000FFFFu;
+                }
+                o = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+              if (row0 + rl < p.M)
+                *reinterpret_cast<uint4*>(Cb + (size_t)(row0 + rl) * p.ldc + col) = o;
+            }
+            __syncwarp();                        // the staging tile and the bias row are rewritten by the next sub-block
+          }
+        }
+      }
+      } else {
       // bf16 output, 64 columns at a time: registers (one row per lane) -> bias / ReLU / row scale -> this warp's
       // swizzled 32 x 128 B staging tile -> registers in the coalesced layout (one instruction = 4 rows x 128 B) ->
       // ReLU mask (the mask operand is read with the same coalesced addressing, one chunk ahead) -> 16-byte global
       // stores.  Stores are fire-and-forget: no epilogue warp ever waits for a write to drain.
       const uint32_t sC = base + plan.c + ew * CHUNK_BYTES;
-      float* sbias_all = reinterpret_cast<float*>(base_ptr + plan.bias);
-      const int etid = threadIdx.x - 64;                      // 0..255 among the epilogue threads
+      float* sbias = reinterpret_cast<float*>(base_ptr + plan.bias) + ew * CHUNK_N;   // private bias row of this warp
       const uint32_t sw = (uint32_t)(lane & 7) << 4;           // 128B swizzle: 16-byte piece j of row r sits at j ^ (r & 7)
       const uint32_t row_off = (uint32_t)lane * 128;
       const int crow = lane >> 3, cpiece = lane & 7;           // coalesced layout: rows i*4 + crow, 16-byte piece cpiece
@@ -579,27 +700,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ncols = min(BN, p.N - nt * BN);
         const int nchunks = (ncols + CHUNK_N - 1) / CHUNK_N;
         const bool warp_rows = row0 < p.M;
-        const float* sbias = sbias_all + (it & 1) * BN;
-        if (p.bias) {
-          // one copy per CTA, filled by the 256 epilogue threads; the buffer of tile it-1 may still be in use by a
-          // slower warp, the one of tile it-2 cannot (every warp has passed the barrier of tile it-1 since)
-          for (int j = etid; j < BN; j += EPI_WARPS * 32)
-            sbias_all[(it & 1) * BN + j] = (nt * BN + j < p.N) ? __ldg(p.bias + nt * BN + j) : 0.f;
-          asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-        }
         const float rs = (p.rowscale && row < p.M) ? __ldg(p.rowscale + row) : 1.f;
         mbar_wait(smem_u32(&bars->tmem_full[as]), aphase);
         tc_fence_after();
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * ACC_STRIDE;
-        const int my_last = ((nchunks - 1 - half) & ~1) + half;      // last chunk of this warp (< half: it has none)
-        if ((p.debug & 4) || my_last < half) {
+        const int my_last = nchunks > sub ? ((nchunks - 1 - sub) / NSUB) * NSUB + sub : -1;   // last chunk of this warp
+        if ((p.debug & 4) || my_last < 0) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) { if (CG == 2) mbar_arrive_cluster(leader(&bars->tmem_empty[as])); else mbar_arrive(smem_u32(&bars->tmem_empty[as])); }
           continue;
         }
 #pragma unroll 1
-        for (int c = half; c < nchunks; c += 2) {
+        for (int c = sub; c < nchunks; c += NSUB) {
+          const int bc = nt * BN + c * CHUNK_N + lane;
+          const float bv0 = (p.bias && bc < p.N) ? __ldg(p.bias + bc) : 0.f;
+          const float bv1 = (p.bias && bc + 32 < p.N) ? __ldg(p.bias + bc + 32) : 0.f;
           uint32_t r0[32], r1[32];
           tmem_ld32(t_row + c * CHUNK_N, r0);
           tmem_ld32(t_row + c * CHUNK_N + 32, r1);
@@ -616,6 +732,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) { if (CG == 2) mbar_arrive_cluster(leader(&bars->tmem_empty[as])); else mbar_arrive(smem_u32(&bars->tmem_empty[as])); }
           }
           if (warp_rows) {
+            if (p.bias) {
+              sbias[lane] = bv0; sbias[lane + 32] = bv1;
+              __syncwarp();
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               float v[32];
@@ -624,7 +744,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (p.bias) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                  float4 b = *reinterpret_cast<const float4*>(sbias + c * CHUNK_N + h * 32 + j);
+                  float4 b = *reinterpret_cast<const float4*>(sbias + h * 32 + j);
                   v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
                 }
               }
@@ -664,9 +784,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (row0 + rl < p.M && col < p.N)
                 *reinterpret_cast<uint4*>(Cb + (size_t)(row0 + rl) * p.ldc + col) = o;
             }
-            __syncwarp();                        // the staging tile is rewritten by the next chunk
+            __syncwarp();                        // the staging tile and the bias row are rewritten by the next chunk
           }
         }
+      }
       }
     } else {
       // fp32 output (split-K partials, small fp32 results): direct 16-byte stores, 32 columns at a time
@@ -677,7 +798,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(smem_u32(&bars->tmem_full[as]), aphase);
         tc_fence_after();
 #pragma unroll 1
-        for (int ci = half; ci < MT * (BN / 32); ci += 2) {
+        for (int ci = sub; ci < MT * (BN / 32); ci += NSUB) {
           const int mi = ci / (BN / 32), c = ci % (BN / 32);          // m sub-tile (MT > 1), 32-column group
           const int row = mt * TILE_M + (int)cta_rank * BLOCK_M + mi * BLOCK_M + q * 32 + lane;
           const bool rowok = row < p.M;
@@ -788,17 +909,17 @@ struct Maps {
   CUtensorMap a, b, p;
 };
 
-template <int BN, bool MN, int GATHER, int CG, int MT = 1>
+template <int BN, bool MN, int GATHER, int CG, int MT = 1, int EPW = 8, bool SUB32 = false>
 int launch(const Maps& m, const TcParams& p, cudaStream_t stream) {
-  const size_t smem = smem_plan(BN, BN / CG, p.stages, p.smem_epi != 0, MT).total;
+  const size_t smem = smem_plan(BN, BN / CG, p.stages, p.smem_epi != 0, MT, EPW, SUB32).total;
   CSG_REQUIRE(smem <= SMEM_LIMIT, "gemm_tc: shared-memory plan of %zu bytes exceeds the limit", smem);
   static bool configured = false;
   if (!configured) {
-    CSG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN, GATHER, CG, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    CSG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, MN, GATHER, CG, MT, EPW, SUB32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     configured = true;
   }
   const int tiles = p.m_tiles * p.n_tiles * p.splits;
-  const int nthreads = NUM_THREADS + (GATHER != G_NONE ? GATHER_WARPS * 32 : 0);
+  const int nthreads = 64 + EPW * 32 + (GATHER != G_NONE ? GATHER_WARPS * 32 : 0);
   if (CG == 1) {
     const int grid = tiles < csg_num_sms() ? tiles : csg_num_sms();
     cudaLaunchConfig_t cfg;
@@ -811,7 +932,7 @@ int launch(const Maps& m, const TcParams& p, cudaStream_t stream) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see griddepcontrol.wait in the kernel
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CSG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MN, GATHER, CG, MT>, m.a, m.b, m.p, p));
+    CSG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MN, GATHER, CG, MT, EPW, SUB32>, m.a, m.b, m.p, p));
   } else {
     // one CTA pair (cluster of 2 on one TPC) per work item, persistent over the pair tiles
     const int pairs = csg_num_sms() / 2;
@@ -827,19 +948,19 @@ int launch(const Maps& m, const TcParams& p, cudaStream_t stream) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 2;
-    CSG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MN, GATHER, CG, MT>, m.a, m.b, m.p, p));
+    CSG_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MN, GATHER, CG, MT, EPW, SUB32>, m.a, m.b, m.p, p));
   }
   CSG_CHECK_LAUNCH("csg_gemm_bf16");
   return 0;
 }
 
-template <bool MN, int GATHER, int CG>
+template <bool MN, int GATHER, int CG, int EPW = 8, bool SUB32 = false>
 int launch_bn(int BN, const Maps& m, const TcParams& p, cudaStream_t stream) {
   switch (BN) {
-    case 64: return launch<64, MN, GATHER, CG>(m, p, stream);
-    case 128: return launch<128, MN, GATHER, CG>(m, p, stream);
-    case 192: return launch<192, MN, GATHER, CG>(m, p, stream);
-    case 256: return launch<256, MN, GATHER, CG>(m, p, stream);
+    case 64: return launch<64, MN, GATHER, CG, 1, EPW, SUB32>(m, p, stream);
+    case 128: return launch<128, MN, GATHER, CG, 1, EPW, SUB32>(m, p, stream);
+    case 192: return launch<192, MN, GATHER, CG, 1, EPW, SUB32>(m, p, stream);
+    case 256: return launch<256, MN, GATHER, CG, 1, EPW, SUB32>(m, p, stream);
   }
   csg_set_error("gemm_tc: unsupported BLOCK_N %d", BN);
   return 1;
@@ -940,7 +1061,7 @@ int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K,
                            int g_din, int g_dp, int g_ldp, int g_nobj, const int* g_pidx, int g_npred, int formats,
                            void* workspace, size_t workspace_bytes, cudaStream_t stream, CsgReduceJob* job) {
   job->parts = 0; job->n = 0; job->partial = nullptr; job->out = nullptr; job->stride = 0; job->lanes = 1;
-  job->op = CSG_RED_SUM; job->aux = nullptr;
+  job->op = CSG_RED_SUM; job->aux = nullptr; job->ncols = 0; job->ldo = 0;
   if (M == 0 || N == 0) return 0;
   if (K == 0 && mn_major && out_f32 && M > 0 && N > 0) {      // empty reduction (no triples): the gradient is zero
     CSG_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, M, stream));
@@ -977,6 +1098,16 @@ int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K,
   const bool pair = !mn_major && (BN % 32 == 0) && csg_num_sms() >= 2 &&
                     (g_pair_mode == 1 || (g_pair_mode < 0 && M >= 2 * BLOCK_M * csg_num_sms() && K >= 1024));
   const int CG = pair ? 2 : 1;
+  // epilogue warps: 16 for the K-major kernels that stream their operands (F2, dhid, dX: their epilogue is a latency
+  // chain that 8 warps do not hide), 8 for the gathered and the weight-gradient kernels (CSG_GEMM_EPW=8: everywhere)
+  // epilogue geometry of the K-major kernels (measured A/B in one run, scratch/bench_gemm.py): 32-column sub-blocks are
+  // 5 % faster on the gathered F1 (59.9 vs 62.8 us), 64-column chunks (full 128-byte lines per store) 2 % faster on F2;
+  // 16 epilogue warps on sub-blocks cut the epilogue ALONE from 108 to 82 us but left the whole F2 slower (153 vs 144 us):
+  // what bounds these kernels is the interference of loads, MMAs and epilogue on one SM, not the epilogue's own latency
+  const int epw = 8;
+  bool sub32 = !mn_major && gather == 1;
+  { const char* e = getenv("CSG_GEMM_EPI");      // scratch/bench_gemm.py: "8x32" / "8x64" for every K-major kernel
+    if (e && !mn_major) sub32 = !strcmp(e, "8x32"); }
   p.m_tiles = csg_div_up(M, BLOCK_M * CG * MT);
   p.n_tiles = csg_div_up(N, BN);
   p.kb_total = csg_div_up(K, BLOCK_K);
@@ -1003,7 +1134,8 @@ int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K,
     // deepest ring that fits
     int best_s = 0;
     for (int st = (pair ? 6 : 5); st >= 2 && !best_s; --st)
-      if (smem_plan(BN, BN / CG, st, p.smem_epi != 0).total <= SMEM_LIMIT) best_s = st;
+      if (smem_plan(BN, BN / CG, st, p.smem_epi != 0, 1, epw, sub32).total <= SMEM_LIMIT) best_s = st;
+    { const char* e = getenv("CSG_GEMM_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < best_s) best_s = atoi(e); }
     CSG_REQUIRE(best_s > 0, "gemm_bf16: no shared-memory plan fits BN=%d", BN);
     p.stages = best_s;
   } else {
@@ -1024,13 +1156,17 @@ int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K,
       if (int rc = make_map(&maps.b, B, N, K, (uint64_t)ldb * 2, 64)) return rc;
     }
     p.stages = 5;
-    while (p.stages > 2 && smem_plan(BN, BN, p.stages, false, MT).total > SMEM_LIMIT) --p.stages;
+    while (p.stages > 2 && smem_plan(BN, BN, p.stages, false, MT, 8, false).total > SMEM_LIMIT) --p.stages;
     CSG_REQUIRE(MT == 1 || p.m_tiles * p.n_tiles * p.splits <= csg_num_sms(),
                 "gemm_bf16: the multi-accumulator weight-gradient kernel needs one work item per CTA");
   }
   int rc;
-  if (!mn_major && pair) rc = gather == 1 ? launch_bn<false, G_A, 2>(BN, maps, p, stream) : launch_bn<false, G_NONE, 2>(BN, maps, p, stream);
-  else if (!mn_major) rc = gather == 1 ? launch_bn<false, G_A, 1>(BN, maps, p, stream) : launch_bn<false, G_NONE, 1>(BN, maps, p, stream);
+  if (!mn_major && pair)
+    rc = gather == 1 ? (sub32 ? launch_bn<false, G_A, 2, 8, true>(BN, maps, p, stream) : launch_bn<false, G_A, 2>(BN, maps, p, stream))
+                     : (sub32 ? launch_bn<false, G_NONE, 2, 8, true>(BN, maps, p, stream) : launch_bn<false, G_NONE, 2>(BN, maps, p, stream));
+  else if (!mn_major)
+    rc = gather == 1 ? (sub32 ? launch_bn<false, G_A, 1, 8, true>(BN, maps, p, stream) : launch_bn<false, G_A, 1>(BN, maps, p, stream))
+                     : (sub32 ? launch_bn<false, G_NONE, 1, 8, true>(BN, maps, p, stream) : launch_bn<false, G_NONE, 1>(BN, maps, p, stream));
   else if (MT == GB_MT) rc = launch<128, true, G_B, 1, GB_MT>(maps, p, stream);
   else rc = gather == 2 ? launch_bn<true, G_B, 1>(BN, maps, p, stream) : launch_bn<true, G_NONE, 1>(BN, maps, p, stream);
   if (rc) return rc;

@@ -53,6 +53,7 @@ struct CastJobs {
   const float* src[CAST_MAX];
   __nv_bfloat16* dst[CAST_MAX];
   int rows[CAST_MAX], cols[CAST_MAX], transpose[CAST_MAX];
+  int lds[CAST_MAX], ldd[CAST_MAX];   // row pitch of src / dst in elements
   int tile_end[CAST_MAX];      // exclusive prefix of 32x32 tiles
   int n;
 };
@@ -67,18 +68,19 @@ __global__ void cast_bf16_multi_kernel(const CastJobs jobs, bool fp16) {
   const int c0 = (local % tcols) * 32, r0 = (local / tcols) * 32;
   const float* src = jobs.src[j];
   __nv_bfloat16* dst = jobs.dst[j];
+  const int lds = jobs.lds[j], ldd = jobs.ldd[j];
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * cols + c] : 0.f;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(size_t)r * lds + c] : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     if (!jobs.transpose[j]) {
       int r = r0 + i, c = c0 + threadIdx.x;
-      if (r < rows && c < cols) reinterpret_cast<unsigned short*>(dst)[(size_t)r * cols + c] = cvt16(tile[i][threadIdx.x], fp16);
+      if (r < rows && c < cols) reinterpret_cast<unsigned short*>(dst)[(size_t)r * ldd + c] = cvt16(tile[i][threadIdx.x], fp16);
     } else {
       int c = c0 + i, r = r0 + threadIdx.x;
-      if (r < rows && c < cols) reinterpret_cast<unsigned short*>(dst)[(size_t)c * rows + r] = cvt16(tile[threadIdx.x][i], fp16);
+      if (r < rows && c < cols) reinterpret_cast<unsigned short*>(dst)[(size_t)c * ldd + r] = cvt16(tile[threadIdx.x][i], fp16);
     }
   }
 }
@@ -97,7 +99,7 @@ segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int
                     const int* __restrict__ rp_o, const int* __restrict__ perm_o,
                     const int* __restrict__ valid, const float* __restrict__ conf,
                     float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, int ldo,
-                    float* __restrict__ cnt_out, bool fp16) {
+                    float* __restrict__ cnt_out, bool fp16, int split_n) {
   CSG_PDL_WAIT();
   __shared__ float red[SP_MAX_THREADS * 8];
   __shared__ float red_cnt[SP_MAX_THREADS];
@@ -109,12 +111,17 @@ segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int
   __shared__ float s_w[SP_CHUNK];
   // objects are visited last-to-first: X was just written front-to-back by the producing GEMM and is larger than L2, so
   // its tail is what is still cached; walking forwards would evict that tail before reaching it
-  const int o = gridDim.x - 1 - blockIdx.x;
+  int o = gridDim.x - 1 - blockIdx.x;
+  // split_n > 0 (csg_segsum2_bf16): the grid holds 2 * split_n blocks; block (part, o) sums only the subject (part 0) or
+  // only the object (part 1) incidences of object o and writes columns part * W .. of the output row
+  int part = -1;
+  if (split_n > 0) { part = o >= split_n ? 1 : 0; o -= part * split_n; }
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int c = tx * 8;
   const bool colok = c < W;
-  const int bs = rp_s[o], ns = rp_s[o + 1] - bs;
-  const int bo = rp_o[o], total = ns + rp_o[o + 1] - bo;
+  const int bs = rp_s[o], ns = part == 1 ? 0 : rp_s[o + 1] - bs;
+  const int bo = rp_o[o], total = ns + (part == 0 ? 0 : rp_o[o + 1] - bo);
+  const int oc = (part == 1 ? W : 0) + c;      // output column of this thread
   const uint4* X16 = reinterpret_cast<const uint4*>(X) + tx;
   float acc[8];
 #pragma unroll
@@ -177,10 +184,10 @@ segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int
   }
   if (colok) {
     if (out_f32) {
-      st_f4(out_f32 + (size_t)o * ldo + c, make_float4(acc[0], acc[1], acc[2], acc[3]));
-      st_f4(out_f32 + (size_t)o * ldo + c + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+      st_f4(out_f32 + (size_t)o * ldo + oc, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      st_f4(out_f32 + (size_t)o * ldo + oc + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
     }
-    if (out_bf16) *reinterpret_cast<uint4*>(out_bf16 + (size_t)o * ldo + c) = pack8_16(acc, fp16);
+    if (out_bf16) *reinterpret_cast<uint4*>(out_bf16 + (size_t)o * ldo + oc) = pack8_16(acc, fp16);
   }
   if (AVG && tx == 0) cnt_out[o] = cnt;
 }
@@ -433,6 +440,12 @@ CSG_API int csg_cast_bf16(const float* src, int rows, int cols, int ld_src, void
 // The pointer / size arrays are HOST arrays of length n <= 16.
 CSG_API int csg_cast_bf16_multi(int n, const void* const* src, void* const* dst, const int* rows, const int* cols,
                                 const int* transpose, int fp16, cudaStream_t stream) {
+  return csg_cast_bf16_multi_ld(n, src, dst, rows, cols, transpose, nullptr, nullptr, fp16, stream);
+}
+
+// the same with row pitches (elements; NULL or 0 = contiguous): sub-matrices of the weights, column slices of a wider copy
+int csg_cast_bf16_multi_ld(int n, const void* const* src, void* const* dst, const int* rows, const int* cols,
+                           const int* transpose, const int* ld_src, const int* ld_dst, int fp16, cudaStream_t stream) {
   if (n == 0) return 0;
   CSG_REQUIRE(n > 0 && n <= CAST_MAX, "cast_bf16_multi: n=%d out of range", n);
   CastJobs jobs;
@@ -442,6 +455,8 @@ CSG_API int csg_cast_bf16_multi(int n, const void* const* src, void* const* dst,
     jobs.src[i] = reinterpret_cast<const float*>(src[i]);
     jobs.dst[i] = reinterpret_cast<__nv_bfloat16*>(dst[i]);
     jobs.rows[i] = rows[i]; jobs.cols[i] = cols[i]; jobs.transpose[i] = transpose[i];
+    jobs.lds[i] = (ld_src && ld_src[i]) ? ld_src[i] : cols[i];
+    jobs.ldd[i] = (ld_dst && ld_dst[i]) ? ld_dst[i] : (transpose[i] ? rows[i] : cols[i]);
     total += csg_div_up(rows[i], 32) * csg_div_up(cols[i], 32);
     jobs.tile_end[i] = total;
   }
@@ -469,12 +484,31 @@ CSG_API int csg_segpool_bf16(const void* X, int ldx, int col_s, int col_o, int W
   if (avg) {
     CSG_REQUIRE(valid && conf && cnt_out, "segpool_bf16(avg): valid/conf/cnt required");
     CSG_CUDA(csg_launch_pdl(segpool_bf16_kernel<true>, dim3(NO), dim3(threads), 0, stream, x, ldx, col_s, col_o, W, TX, TY, rowptr_s, perm_s, rowptr_o,
-                                                          perm_o, valid, conf, out_f32, ob, ldo, cnt_out, fp16 != 0));
+                                                          perm_o, valid, conf, out_f32, ob, ldo, cnt_out, fp16 != 0, 0));
   } else {
     CSG_CUDA(csg_launch_pdl(segpool_bf16_kernel<false>, dim3(NO), dim3(threads), 0, stream, x, ldx, col_s, col_o, W, TX, TY, rowptr_s, perm_s, rowptr_o,
-                                                           perm_o, nullptr, nullptr, out_f32, ob, ldo, nullptr, fp16 != 0));
+                                                           perm_o, nullptr, nullptr, out_f32, ob, ldo, nullptr, fp16 != 0, 0));
   }
   CSG_CHECK_LAUNCH("csg_segpool_bf16");
+  return 0;
+}
+
+// out[o, 0:W] = sum over the triples whose SUBJECT is o of X[t, 0:W]; out[o, W:2W] = the same over the triples whose
+// OBJECT is o (ascending triple id inside a row: fixed summation order).  One launch, 2 * NO blocks.
+CSG_API int csg_segsum2_bf16(const void* X, int ldx, int W, const int* rowptr_s, const int* perm_s, const int* rowptr_o,
+                             const int* perm_o, int NO, float* out_f32, void* out_bf16, int ldo, cudaStream_t stream) {
+  if (NO == 0) return 0;
+  CSG_REQUIRE((W & 7) == 0 && (ldx & 7) == 0 && (ldo & 7) == 0 && ldo >= 2 * W, "segsum2_bf16: W, ldx, ldo must be multiples of 8 and ldo >= 2 W");
+  CSG_REQUIRE(W <= 8 * SP_MAX_THREADS, "segsum2_bf16: W=%d too wide", W);
+  CSG_REQUIRE(out_f32 || out_bf16, "segsum2_bf16: no output");
+  const int TX = W / 8;
+  int TY = SP_MAX_THREADS / TX;
+  if (TY > 16) TY = 16;
+  if (TY < 1) TY = 1;
+  CSG_CUDA(csg_launch_pdl(segpool_bf16_kernel<false>, dim3(2 * NO), dim3(TX * TY), 0, stream, reinterpret_cast<const __nv_bfloat16*>(X), ldx, 0, 0, W,
+                          TX, TY, rowptr_s, perm_s, rowptr_o, perm_o, nullptr, nullptr, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                          ldo, nullptr, false, NO));
+  CSG_CHECK_LAUNCH("csg_segsum2_bf16");
   return 0;
 }
 
@@ -500,7 +534,7 @@ CSG_API int csg_colsum_bf16(const void* X, int M, int N, int ld, float* out, voi
 int csg_colsum_bf16_deferred(const void* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
                              cudaStream_t stream, CsgReduceJob* job) {
   job->parts = 0; job->n = 0; job->partial = nullptr; job->out = out; job->stride = N; job->lanes = 8;
-  job->op = CSG_RED_SUM; job->aux = nullptr;
+  job->op = CSG_RED_SUM; job->aux = nullptr; job->ncols = 0; job->ldo = 0;
   if (N == 0) return 0;
   CSG_REQUIRE((N & 7) == 0 && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
               "colsum_bf16: N and ld must be multiples of 8 and X 16-byte aligned");

@@ -18,6 +18,8 @@ struct CsgReduceJob {
                           // 8: eight threads per output take parts y, y + 8, ... in order and are combined in lane order
   int op;                 // CSG_RED_SUM, or CSG_RED_SIGMOID_GRAD: out = sum * s (1 - s), s = sigmoid(aux[i])
   const float* aux;
+  int ncols, ldo;         // ncols > 0: the n results form rows of ncols that are written with row pitch ldo
+                          // (out[(i / ncols) * ldo + i % ncols]): a column block of a wider matrix; 0: out[i]
 };
 enum { CSG_RED_SUM = 0, CSG_RED_SIGMOID_GRAD = 1 };
 constexpr int CSG_REDUCE_MAX_JOBS = 16;
@@ -31,6 +33,9 @@ int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K, const 
                            const void* mask_aux, int ld_aux, const void* g_obj, const void* g_pred, const int* g_sidx,
                            const int* g_oidx, int g_din, int g_dp, int g_ldp, int g_nobj, const int* g_pidx, int g_npred,
                            int formats, void* workspace, size_t workspace_bytes, cudaStream_t stream, CsgReduceJob* job);
+// csg_cast_bf16_multi with row pitches (elements; NULL / 0 = contiguous)
+int csg_cast_bf16_multi_ld(int n, const void* const* src, void* const* dst, const int* rows, const int* cols,
+                           const int* transpose, const int* ld_src, const int* ld_dst, int fp16, cudaStream_t stream);
 // csg_colsum_bf16 without its final pass
 int csg_colsum_bf16_deferred(const void* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
                              cudaStream_t stream, CsgReduceJob* job);

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceJobs jobs
       const float sg = 1.f / (1.f + expf(-q.aux[i]));
       s = s * sg * (1.f - sg);
     }
-    q.out[i] = s;
+    q.out[q.ncols > 0 ? (size_t)(i / q.ncols) * q.ldo + (i % q.ncols) : (size_t)i] = s;
   }
 }
 

@@ -204,7 +204,8 @@ class _TripleConvEngine(torch.autograd.Function):
             d_newp = d_newp.to(BF).contiguous()
         obj_bf16 = ctx.in_dtypes[0] == BF and fused is None
         dobj = torch.empty((NO, Din), dtype=BF if obj_bf16 else torch.float32, device=dev)
-        dX = torch.empty((NT, K1), dtype=BF, device=dev)
+        dxc = L.csg_gconv_bf16_dx_cols(dims)          # Dp (d pred only), or K1 on the gathered dataflow
+        dX = torch.empty((NT, dxc), dtype=BF, device=dev)
         sizes = (H * K1, H, Wd * H, Wd, H * H, H, Dout * H, Dout, P)
         dparams = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
         nws = L.csg_gconv_bf16_workspace(dims)
@@ -216,7 +217,7 @@ class _TripleConvEngine(torch.autograd.Function):
                                   ptr(ws), ws.numel(), _stream())
         _lib.check(rc, "csg_gconv_bf16_bwd")
         dw1, db1, dw2, db2, dw3, db3, dw4, db4, dwt = torch.split(dparams, sizes)
-        dpred = dX[:, Din:Din + Dp]
+        dpred = dX[:, Din:Din + Dp] if dxc == K1 else dX
         if fused is not None:
             # the gradients of the gathered rows folded back onto the embedding tables (attribute_embed.py:38-48,
             # model.py:109): per-object rows by class id, per-triple predicate rows by predicate id (one-hot GEMM)

@@ -188,6 +188,11 @@ int csg_segpool_bf16(const void* X, int ldx, int col_s, int col_o, int W,
                      const int* rowptr_s, const int* perm_s, const int* rowptr_o, const int* perm_o,
                      const int* valid, const float* conf, int NO, float* out_f32, void* out_bf16, int ldo,
                      float* cnt_out, int avg, int fp16, csg_stream_t stream);   /* fp16: X and out_bf16 hold fp16 */
+/* out[o, 0:W] = sum over the triples whose subject is o of X[t, 0:W]; out[o, W:2W] = the same over the triples whose
+ * object is o (fixed order: ascending triple id).  The per-object sums of d hidden that give net1's first-layer weight /
+ * bias / object-row gradients without a gathered GEMM over the triples (sg2im/graph.py:60-67 backward). */
+int csg_segsum2_bf16(const void* X, int ldx, int W, const int* rowptr_s, const int* perm_s, const int* rowptr_o,
+                     const int* perm_o, int NO, float* out_f32, void* out_bf16, int ldo, csg_stream_t stream);
 int csg_relu_mask_bf16(const float* dy, const void* y, void* out, long long n, csg_stream_t stream);
 size_t csg_colsum_bf16_workspace(int M, int N);
 int csg_colsum_bf16(const void* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
@@ -217,13 +222,15 @@ int csg_triple_bwd_assemble_bf16(const void* out, const float* dS, const void* d
 size_t csg_gconv_bf16_saved_bytes(const int* dims, int need_bwd);
 size_t csg_gconv_bf16_out_offset(const int* dims, int need_bwd);   /* byte offset in `saved` of net1's output [NT, 2H+Dpo] bf16 */
 size_t csg_gconv_bf16_workspace(const int* dims);
+int csg_gconv_bf16_dx_cols(const int* dims);   /* columns of the dX matrix csg_gconv_bf16_bwd writes: Dp, or 2Din+Dp (layer on the embedding tables, CSG_BWD_SEGSUM=0) */
 /* obj [NO, Din] bf16 contiguous, pred [NT, Dp] bf16 rows of pitch ldp -> new_obj [NO, Dout] bf16; new_p_vecs are
  * columns H..H+Dpo of the [NT, 2H+Dpo] matrix at saved + csg_gconv_bf16_out_offset.  `saved` 256-byte aligned. */
 int csg_gconv_bf16_fwd(const int* dims, const void* obj, const void* pred, int ldp,
                        const void* const* params, const void* const* index, int need_bwd, void* saved,
                        size_t saved_bytes, void* new_obj, csg_stream_t stream);
 /* d_new_obj [NO, Dout] fp32 or (d_new_obj_bf16) bf16, NULL = 0; d_new_p [NT, Dpo] bf16 rows of pitch ld_dnewp,
- * NULL = 0.  Writes dobj [NO, Din] fp32 or (dobj_bf16) bf16, dX [NT, 2Din+Dp] bf16 (columns Din..Din+Dp = d pred)
+ * NULL = 0.  Writes dobj [NO, Din] fp32 or (dobj_bf16) bf16, dX [NT, csg_gconv_bf16_dx_cols] bf16 (d pred; on the gathered
+ * dataflow the whole row [d obj[s] | d pred | d obj[o]])
  * and dparams: fp32, contiguous, 16-byte aligned, in the order of `params` (dw1, db1, dw2, db2, dw3, db3, dw4,
  * db4, dw_trans). */
 int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pred, int ldp,

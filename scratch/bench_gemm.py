@@ -44,9 +44,9 @@ if __name__ == "__main__":
         ("dhid 512x1152 mask", 2.0 * NT * 512 * 1152, lambda: ops.gemm_bf16(NT, 512, 1152, g, w2t, mask_aux=hid, out=outh)),
         ("dX  384x512", 2.0 * NT * 384 * 512, lambda: ops.gemm_bf16(NT, 384, 512, hid, w1t, out=outx)),
     ]
-    for dbg in (0, 1, 2, 4, 3, 5, 6):     # 1 = no loads, 2 = no MMAs, 4 = no epilogue (kernel-side switches, wrong results)
+    for dbg in [int(x) for x in os.environ.get("CSG_BENCH_DBG", "0,1,2,4,3,5,6").split(",")]:     # 1 = no loads, 2 = no MMAs, 4 = no epilogue (kernel-side switches, wrong results)
         os.environ["CSG_GEMM_DEBUG"] = str(dbg)
-        for mode in (0, 1):
+        for mode in [int(x) for x in os.environ.get("CSG_BENCH_PAIR", "0,1").split(",")]:
             lib().csg_gemm_bf16_set_pair_mode(mode)
             for name, fl, fn in cases:
                 if dbg and name.startswith("F1"):

@@ -376,12 +376,15 @@ def test_cuda_graph_replay_equals_eager_steps():
     assert torch.equal(results[0][1], results[1][1]) and torch.equal(results[0][2], results[1][2])
 
 
-def test_layer0_fused_with_embedding_tables_equals_materialised_rows(golden):
+def test_layer0_fused_with_embedding_tables_equals_materialised_rows(golden, monkeypatch):
     """with single-attribute objects layer 0 gathers its subject / object rows from the object
     embedding table by class id and its predicate rows from the predicate table by predicate id inside the net1
     producer (TMA tile::gather4 over the tables), instead of reading materialised [NO, D] / [NT, D] lookups
     (model.py:108-109).  Same bf16 values in, so outputs and all GCN gradients are bit-identical; the object table's
-    gradient is folded from fp32 per-object rows (bf16 rows in the materialised path): equal to 1e-2."""
+    gradient is folded from fp32 per-object rows (bf16 rows in the materialised path): equal to 1e-2.  The layer on the
+    tables differentiates net1's first Linear through the gathered GEMMs, so the materialised model is run on that
+    dataflow as well (CSG_BWD_SEGSUM=0; the per-object-sum dataflow has its own test below)."""
+    monkeypatch.setenv("CSG_BWD_SEGSUM", "0")
     g = golden("sg2layout_model")
     res = []
     for fuse in (True, False):
@@ -409,3 +412,27 @@ def test_layer0_fused_with_embedding_tables_equals_materialised_rows(golden):
                                            t(np.concatenate([[0], np.cumsum(n_obj)]).astype(np.int32)))
     sel = torch.cat([res[0][0][b, :n_obj[b]] for b in range(B)])
     assert_close(vecs_r.float(), sel.float(), 1e-2, "ragged fused vs padded fused")
+
+
+@pytest.mark.gpu
+def test_segsum_backward_equals_gathered_backward(golden, monkeypatch):
+    """net1's first Linear differentiated through per-object sums of dhidden (csg_segsum2_bf16 + GEMMs over the objects,
+    csrc/gconv_engine.cu) against the gathered dataflow (gathered-B weight gradient, full dX, segmented sums of dX,
+    column sums of dhidden): the same real-number sums in a different association, so every gradient agrees to the bf16
+    rounding of the intermediates (dX rows on one side, the per-object sums on the other): 1e-2 relative L2 per tensor and
+    2e-2 max-norm (measured: 1.04e-2 max-norm on the object embedding table, whose rows see one or two objects); the
+    forward is untouched (bit-identical)."""
+    g = golden("sg2layout_model")
+    res = []
+    for seg in ("1", "0"):
+        monkeypatch.setenv("CSG_BWD_SEGSUM", seg)
+        model = _model("bf16")
+        model.fuse_embeddings = False
+        obj_vecs, boxes, _ = model(t(g["objs"]), t(g["triplets"]), t(g["types"]))
+        (boxes.float().pow(2).sum() + (obj_vecs.float() * t(gi.model_obj_grad(obj_vecs.shape))).sum()).backward()
+        res.append((obj_vecs.detach(), boxes.detach(), {n: p.grad for n, p in model.named_parameters() if p.grad is not None}))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert set(res[0][2]) == set(res[1][2])
+    for n, gr in res[0][2].items():
+        assert rel_l2(gr, res[1][2][n]) <= 1e-2, (n, rel_l2(gr, res[1][2][n]))
+        assert_close(gr, res[1][2][n], 2e-2, "segsum vs gathered backward: " + n)
