@@ -803,6 +803,12 @@ def run_ours(args):
                      "frac": ach_tf / peak_tf, "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
                      "launches_timed": gemm_n, "share_of_step": gemm_sec / sec if sec > 0 else None,
                      "whole_step_tflops": mlp_flops(n_tri, n_obj) / (sec / max(args.steps, 1)) / 1e12,
+                     "algorithmic_tflops": (mlp_flops(n_tri, n_obj) * args.steps / gemm_sec / 1e12) if gemm_sec > 0 else None,
+                     "flops_note": "achieved = flops the GEMM launches EXECUTE / their summed durations.  SURVEY 8(d) counts "
+                                   "1 572 864 FLOP per triple and layer forward (x3 with backward); the bf16 engine executes "
+                                   "less: net1's first-layer backward runs on per-object sums of dhidden (N = Dp instead of "
+                                   "2 Din + Dp for the two T-sized GEMMs).  algorithmic_tflops = the 8(d) count / the same "
+                                   "GEMM time",
                      "note": "CUDA events around every GEMM entry point on the launching stream, in a separate eagerly launched "
                              "pass of the same %d steps (%.3f ms/step with the events); share_of_step = summed GEMM "
                              "time / the headline timed region" % (args.steps, 1e3 * prof_sec / max(args.steps, 1))},

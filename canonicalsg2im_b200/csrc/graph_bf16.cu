@@ -112,10 +112,12 @@ segpool_bf16_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int col_s, int
   // objects are visited last-to-first: X was just written front-to-back by the producing GEMM and is larger than L2, so
   // its tail is what is still cached; walking forwards would evict that tail before reaching it
   int o = gridDim.x - 1 - blockIdx.x;
-  // split_n > 0 (csg_segsum2_bf16): the grid holds 2 * split_n blocks; block (part, o) sums only the subject (part 0) or
+  // split_n > 0 (csg_segsum2_bf16): the grid holds 2 * split_n blocks; block 2 o + part sums only the subject (part 0) or
   // only the object (part 1) incidences of object o and writes columns part * W .. of the output row
+  // The two blocks of an object are neighbours in launch order: the triples an object takes part in belong to one graph
+  // (~1 MB of contiguous rows), so whichever of the 2 x ~18 blocks of a graph comes second finds the rows in L2
   int part = -1;
-  if (split_n > 0) { part = o >= split_n ? 1 : 0; o -= part * split_n; }
+  if (split_n > 0) { part = o & 1; o >>= 1; }
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int c = tx * 8;
   const bool colok = c < W;

@@ -6,8 +6,28 @@ namespace {
 struct ReduceJobs {
   CsgReduceJob job[CSG_REDUCE_MAX_JOBS];
   int block_end[CSG_REDUCE_MAX_JOBS];   // exclusive prefix of the blocks of each job
+  int vec[CSG_REDUCE_MAX_JOBS];         // lanes == 1 jobs: four consecutive outputs per thread through 16-byte loads
   int n;
 };
+
+// four independent ordered sums side by side (same order per output as ordered_sum): 16-byte loads, U in flight
+template <int U>
+__device__ __forceinline__ float4 ordered_sum4(const float* __restrict__ p, size_t stride, int n) {
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  int b = 0;
+  for (; b + U <= n; b += U) {
+    float4 x[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) x[i] = ld_f4(p + (size_t)(b + i) * stride);
+#pragma unroll
+    for (int i = 0; i < U; ++i) { s.x += x[i].x; s.y += x[i].y; s.z += x[i].z; s.w += x[i].w; }
+  }
+  for (; b < n; ++b) {
+    const float4 x = ld_f4(p + (size_t)b * stride);
+    s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+  }
+  return s;
+}
 
 __global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceJobs jobs) {
   CSG_PDL_WAIT();
@@ -19,7 +39,14 @@ __global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceJobs jobs
   float s = 0.f;
   int i;
   bool write;
-  if (q.lanes == 1) {
+  if (q.lanes == 1 && jobs.vec[j]) {
+    i = (blk * 256 + threadIdx.x) * 4;
+    if (i < q.n) {
+      const float4 v = ordered_sum4<8>(q.partial + i, (size_t)q.stride, q.parts);
+      st_f4(q.out + (q.ncols > 0 ? (size_t)(i / q.ncols) * q.ldo + (i % q.ncols) : (size_t)i), v);
+    }
+    return;
+  } else if (q.lanes == 1) {
     i = blk * 256 + threadIdx.x;
     write = i < q.n;
     if (write) s = ordered_sum<8>(q.partial + i, (size_t)q.stride, q.parts);
@@ -56,13 +83,18 @@ int csg_reduce_multi(const CsgReduceJob* jobs, int njobs, cudaStream_t stream) {
     const CsgReduceJob& q = jobs[k];
     if (q.parts <= 0 || q.n <= 0) continue;
     CSG_REQUIRE(q.partial && q.out && (q.lanes == 1 || q.lanes == 8), "reduce_multi: bad job %d", k);
-    blocks += csg_div_up(q.n, q.lanes == 1 ? 256 : 32);
+    // plain sums whose rows, pitches and pointers keep 16-byte alignment take four outputs per thread
+    const bool vec = q.lanes == 1 && q.op == CSG_RED_SUM && (q.n & 3) == 0 && (q.stride & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(q.partial) | reinterpret_cast<uintptr_t>(q.out)) & 15) == 0 &&
+                     (q.ncols == 0 || ((q.ncols & 3) == 0 && (q.ldo & 3) == 0));
+    blocks += csg_div_up(q.n, q.lanes == 1 ? (vec ? 1024 : 256) : 32);
+    r.vec[r.n] = vec ? 1 : 0;
     r.job[r.n] = q;
     r.block_end[r.n] = blocks;
     ++r.n;
   }
   if (r.n == 0) return 0;
-  for (int k = r.n; k < CSG_REDUCE_MAX_JOBS; ++k) { r.job[k] = r.job[0]; r.block_end[k] = blocks; }
+  for (int k = r.n; k < CSG_REDUCE_MAX_JOBS; ++k) { r.job[k] = r.job[0]; r.block_end[k] = blocks; r.vec[k] = 0; }
   CSG_CUDA(csg_launch_pdl(reduce_multi_kernel, dim3(blocks), dim3(256), 0, stream, r));
   CSG_CHECK_LAUNCH("csg_reduce_multi");
   return 0;
