@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "internal.h"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -420,6 +421,219 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
   }
 }
 
+// ---- pipelined variant (the one the layer executor runs): the rows of `out` -- the only DRAM-resident operand --
+// are streamed into a shared-memory ring by one elected producer lane, ASM_WARPS rows (one per consumer warp, contiguous
+// in memory because the rows of net1's output are packed) per cp.async.bulk, ASMP_STAGES copies in flight per CTA, and
+// the consumer warps read them from shared memory.  The per-row arithmetic, the row -> warp assignment inside a block
+// and the reduction orders are those of triple_bwd_assemble_bf16_kernel; what changes is who waits for DRAM: the
+// register-staged kernel exposes a DRAM round trip per 16-byte column step of every row (ncu r02b: 36 % warps active,
+// 49 % issue-active at 3.7 TB/s).
+constexpr int ASMP_STAGES = 4;
+constexpr int ASMP_CTAS_PER_SM = 2;
+__device__ __forceinline__ uint32_t asmp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void asmp_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void asmp_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void asmp_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void asmp_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins > (1u << 26)) {                  // a protocol bug traps instead of hanging the GPU box
+      printf("csg assemble: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void asmp_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int HT, int DPT>
+__global__ void __launch_bounds__((ASM_WARPS + 1) * 32, ASMP_CTAS_PER_SM)
+triple_bwd_assemble_pipe_kernel(const __nv_bfloat16* __restrict__ out, const float* __restrict__ dS,
+                                const __nv_bfloat16* __restrict__ d_newp, int ld_newp,
+                                const float* __restrict__ dcnt, const int* __restrict__ s_idx,
+                                const int* __restrict__ o_idx, const int* __restrict__ valid,
+                                const int* __restrict__ type32, const float* __restrict__ conf,
+                                int NT, int H_rt, int Dp_rt, __nv_bfloat16* __restrict__ g,
+                                float* __restrict__ cs_partial, const int* __restrict__ pred, int P,
+                                float* __restrict__ wt_partial) {
+  CSG_PDL_WAIT();
+  const int H = HT ? HT : H_rt, Dp = DPT ? DPT : Dp_rt;
+  const int Wd = 2 * H + Dp;
+  // dynamic shared memory: [ring: ASMP_STAGES x ASM_WARPS rows of Wd bf16][cs_red][wt_bins][barriers]
+  extern __shared__ __align__(128) unsigned char asmp_smem[];
+  const uint32_t stage_bytes = (uint32_t)ASM_WARPS * Wd * 2;
+  __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(asmp_smem);
+  float* cs_red = reinterpret_cast<float*>(asmp_smem + (size_t)ASMP_STAGES * stage_bytes);
+  float* wt_bins = cs_red + (ASM_WARPS / 2) * ASM_MAXI * 256;            // [ASM_WARPS][P]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+      (reinterpret_cast<uintptr_t>(wt_bins + ASM_WARPS * P) + 7) & ~(uintptr_t)7);
+  const uint32_t full0 = asmp_smem_u32(bars), empty0 = asmp_smem_u32(bars + ASMP_STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ASMP_STAGES; ++i) {
+      asmp_mbar_init(full0 + 8 * i, 1);
+      asmp_mbar_init(empty0 + 8 * i, ASM_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < ASM_WARPS * P; i += blockDim.x) wt_bins[i] = 0.f;
+  __syncthreads();
+
+  const int chunk = (NT + gridDim.x - 1) / gridDim.x;
+  const int t_beg = min(NT, (int)blockIdx.x * chunk), t_end = min(NT, (int)(blockIdx.x + 1) * chunk);
+  const int niter = (t_end - t_beg + ASM_WARPS - 1) / ASM_WARPS;
+  float cs[ASM_MAXI][8];
+#pragma unroll
+  for (int u = 0; u < ASM_MAXI; ++u)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cs[u][i] = 0.f;
+
+  if (warp == ASM_WARPS) {
+    // ---------------- producer: one bulk copy of up to ASM_WARPS consecutive rows per stage
+    if (lane == 0) {
+      for (int k = 0; k < niter; ++k) {
+        const int st = k % ASMP_STAGES;
+        if (k >= ASMP_STAGES) asmp_mbar_wait(empty0 + 8 * st, ((k / ASMP_STAGES) - 1) & 1);
+        const int r0 = t_beg + k * ASM_WARPS;
+        const uint32_t bytes = (uint32_t)min(ASM_WARPS, t_end - r0) * Wd * 2;
+        asmp_mbar_expect_tx(full0 + 8 * st, bytes);
+        asmp_bulk_load(asmp_smem_u32(ring) + st * stage_bytes, out + (size_t)r0 * Wd, bytes, full0 + 8 * st);
+      }
+    }
+  } else {
+    // ---------------- consumers: warp w takes row w of every stage
+    int t = t_beg + warp;
+    int s = 0, o = 0, vi = 0, ty = 0, pr = 0;
+    float cf = 0.f;
+    if (t < t_end) { s = s_idx[t]; o = o_idx[t]; vi = valid[t]; ty = type32[t]; cf = conf[t]; pr = pred[t]; }
+    for (int k = 0; k < niter; ++k, t += ASM_WARPS) {
+      const int st = k % ASMP_STAGES;
+      const int tn = t + ASM_WARPS;
+      int s2 = 0, o2 = 0, vi2 = 0, ty2 = 0, pr2 = 0;
+      float cf2 = 0.f;
+      if (tn < t_end) { s2 = s_idx[tn]; o2 = o_idx[tn]; vi2 = valid[tn]; ty2 = type32[tn]; cf2 = conf[tn]; pr2 = pred[tn]; }
+      asmp_mbar_wait(full0 + 8 * st, (k / ASMP_STAGES) & 1);
+      if (t < t_end) {
+        const bool v = vi != 0;
+        const __nv_bfloat16* orow = ring + (size_t)st * (stage_bytes / 2) + (size_t)warp * Wd;
+        __nv_bfloat16* grow = g + (size_t)t * Wd;
+        float dot = 0.f;
+#pragma unroll
+        for (int u = 0; u < ASM_MAXI; ++u) {
+          const int j = lane * 8 + u * 256;
+          if (j < Wd) {
+            float raw[8];
+            if (j < H || j >= H + Dp) {
+              const float* src = dS + (size_t)(j < H ? s : o) * H + (j < H ? j : j - H - Dp);
+              if (v) {
+                float4 a = ld_f4(src), b = ld_f4(src + 4);
+                raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) raw[i] = 0.f;
+              }
+            } else if (d_newp) {
+              unpack8(*reinterpret_cast<const uint4*>(d_newp + (size_t)t * ld_newp + (j - H)), raw);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) raw[i] = 0.f;
+            }
+            float y[8], r[8];
+            const uint4 yw = *reinterpret_cast<const uint4*>(orow + j);
+            unpack8(yw, y);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              dot += raw[i] * y[i];
+              r[i] = raw[i] * cf;
+            }
+            uint4 packed = pack8(r);
+            packed.x &= __vcmpgts2(yw.x, 0u); packed.y &= __vcmpgts2(yw.y, 0u);
+            packed.z &= __vcmpgts2(yw.z, 0u); packed.w &= __vcmpgts2(yw.w, 0u);
+            *reinterpret_cast<uint4*>(grow + j) = packed;
+            float rb[8];
+            unpack8(packed, rb);             // sum what the GEMMs will read: the bf16-rounded values
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cs[u][i] += rb[i];
+          }
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) {
+          float dc = 0.f;
+          if (ty == 1 && cf > 0.f) dc = dot / cf;
+          if (v) dc += dcnt[s] + dcnt[o];
+          if (ty == 1) wt_bins[warp * P + pr] += dc;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asmp_mbar_arrive(empty0 + 8 * st);      // the row has been read: the stage may be refilled
+      s = s2; o = o2; vi = vi2; ty = ty2; cf = cf2; pr = pr2;
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < ASM_WARPS; ++w) a += wt_bins[w * P + p];
+    wt_partial[(size_t)blockIdx.x * P + p] = a;
+  }
+  // ordered tree over the 8 consumer warps: (w, w+4), then (w, w+2), then (w, w+1); lane owns columns lane*8 + u*256 + i
+  for (int half = ASM_WARPS / 2; half >= 1; half >>= 1) {
+    if (warp >= half && warp < 2 * half) {
+      float* dst = cs_red + (warp - half) * ASM_MAXI * 256;
+#pragma unroll
+      for (int u = 0; u < ASM_MAXI; ++u) {
+        st_f4(dst + u * 256 + lane * 8, make_float4(cs[u][0], cs[u][1], cs[u][2], cs[u][3]));
+        st_f4(dst + u * 256 + lane * 8 + 4, make_float4(cs[u][4], cs[u][5], cs[u][6], cs[u][7]));
+      }
+    }
+    __syncthreads();
+    if (warp < half) {
+      const float* src = cs_red + warp * ASM_MAXI * 256;
+#pragma unroll
+      for (int u = 0; u < ASM_MAXI; ++u) {
+        float4 a = ld_f4(src + u * 256 + lane * 8), b = ld_f4(src + u * 256 + lane * 8 + 4);
+        cs[u][0] += a.x; cs[u][1] += a.y; cs[u][2] += a.z; cs[u][3] += a.w;
+        cs[u][4] += b.x; cs[u][5] += b.y; cs[u][6] += b.z; cs[u][7] += b.w;
+      }
+    }
+    __syncthreads();
+  }
+  if (warp == 0) {
+#pragma unroll
+    for (int u = 0; u < ASM_MAXI; ++u) {
+      const int j = lane * 8 + u * 256;
+      if (j < Wd) {
+        float* dst = cs_partial + (size_t)blockIdx.x * Wd + j;
+        st_f4(dst, make_float4(cs[u][0], cs[u][1], cs[u][2], cs[u][3]));
+        st_f4(dst + 4, make_float4(cs[u][4], cs[u][5], cs[u][6], cs[u][7]));
+      }
+    }
+  }
+}
+size_t asmp_smem_bytes(int Wd, int P) {
+  return (size_t)ASMP_STAGES * ASM_WARPS * Wd * 2 + (size_t)(ASM_WARPS / 2) * ASM_MAXI * 256 * 4 + (size_t)ASM_WARPS * P * 4 + 8 +
+         2 * ASMP_STAGES * 8;
+}
+int asmp_blocks(int NT) {
+  int want = csg_div_up(NT > 0 ? NT : 1, ASM_WARPS);
+  int cap = csg_num_sms() * ASMP_CTAS_PER_SM;
+  return want < cap ? want : cap;
+}
+
 int asm_blocks(int NT) {
   int want = csg_div_up(NT > 0 ? NT : 1, ASM_WARPS);
   int cap = csg_num_sms() * ASM_CTAS_PER_SM;
@@ -629,10 +843,35 @@ int csg_triple_bwd_assemble_bf16_deferred(const void* out, const float* dS, cons
   CSG_REQUIRE(P > 0 && (size_t)ASM_WARPS * P * sizeof(float) <= 24 * 1024, "bwd_assemble_bf16: P=%d predicates do not fit the per-warp bins", P);
   CSG_REQUIRE(workspace && workspace_bytes >= csg_triple_bwd_assemble_bf16_deferred_workspace(NT, H, Dp, P),
               "bwd_assemble_bf16: workspace too small");
+  CSG_REQUIRE(!out_fp16, "bwd_assemble_bf16 (deferred): fp16 forward tensors are inference-only");
+  {
+    // pipelined kernel (rows of `out` through a shared-memory ring); CSG_ASM_PIPE=0 selects the register-staged one
+    const char* e = getenv("CSG_ASM_PIPE");
+    const size_t smem = asmp_smem_bytes(Wd, P);
+    if (!(e && e[0] == '0') && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && smem <= 100 * 1024) {
+      const int blocks = asmp_blocks(NT);
+      float* cs_partial = reinterpret_cast<float*>(workspace);
+      float* wt_partial = cs_partial + (size_t)blocks * Wd;
+      auto kernel = (H == 512 && Dp == 128) ? triple_bwd_assemble_pipe_kernel<512, 128> : triple_bwd_assemble_pipe_kernel<0, 0>;
+      static bool configured[2] = {false, false};
+      const int which = (H == 512 && Dp == 128) ? 0 : 1;
+      if (!configured[which]) {
+        CSG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        configured[which] = true;
+      }
+      CSG_CUDA(csg_launch_pdl(kernel, dim3(blocks), dim3((ASM_WARPS + 1) * 32), smem, stream,
+                              reinterpret_cast<const __nv_bfloat16*>(out), dS, reinterpret_cast<const __nv_bfloat16*>(d_newp),
+                              ld_newp, dcnt, s_idx, o_idx, valid, type32, conf, NT, H, Dp, reinterpret_cast<__nv_bfloat16*>(g),
+                              cs_partial, pred, P, wt_partial));
+      CSG_CHECK_LAUNCH("csg_triple_bwd_assemble_bf16 (pipelined)");
+      job_db2->partial = cs_partial; job_db2->n = Wd; job_db2->parts = blocks;
+      job_dwt->partial = wt_partial; job_dwt->n = P; job_dwt->parts = blocks;
+      return 0;
+    }
+  }
   const int blocks = asm_blocks(NT);
   float* cs_partial = reinterpret_cast<float*>(workspace);
   float* wt_partial = cs_partial + (size_t)blocks * Wd;
-  CSG_REQUIRE(!out_fp16, "bwd_assemble_bf16 (deferred): fp16 forward tensors are inference-only");
   auto kernel = (H == 512 && Dp == 128) ? triple_bwd_assemble_bf16_kernel<true, false, 512, 128>
                                         : triple_bwd_assemble_bf16_kernel<true, false, 0, 0>;
   CSG_CUDA(csg_launch_pdl(kernel, dim3(blocks), dim3(ASM_WARPS * 32), (size_t)ASM_WARPS * P * sizeof(float),

@@ -436,3 +436,24 @@ def test_segsum_backward_equals_gathered_backward(golden, monkeypatch):
     for n, gr in res[0][2].items():
         assert rel_l2(gr, res[1][2][n]) <= 1e-2, (n, rel_l2(gr, res[1][2][n]))
         assert_close(gr, res[1][2][n], 2e-2, "segsum vs gathered backward: " + n)
+
+
+@pytest.mark.gpu
+def test_pipelined_assemble_equals_register_staged(golden, monkeypatch):
+    """The assemble kernel that streams net1's output through a shared-memory ring (cp.async.bulk, csrc/graph_bf16.cu)
+    against the register-staged one (CSG_ASM_PIPE=0): the gradient wrt net1's pre-activation is bit-identical, so every
+    gradient that depends only on it is too; the column sums (net1.2.bias) and the per-predicate confidence sums are
+    taken over a different number of blocks (fixed per kernel), i.e. in a different but fixed order: 1e-5."""
+    g = golden("sg2layout_model")
+    res = []
+    for pipe in ("1", "0"):
+        monkeypatch.setenv("CSG_ASM_PIPE", pipe)
+        model = _model("bf16")
+        obj_vecs, boxes, _ = model(t(g["objs"]), t(g["triplets"]), t(g["types"]))
+        (boxes.float().pow(2).sum() + (obj_vecs.float() * t(gi.model_obj_grad(obj_vecs.shape))).sum()).backward()
+        res.append({n: p.grad for n, p in model.named_parameters() if p.grad is not None})
+    for n, gr in res[0].items():
+        if n.endswith("net1.2.bias") or "candidates_weights" in n:
+            assert_close(gr, res[1][n], 1e-5, "pipelined vs staged assemble: " + n)
+        else:
+            assert torch.equal(gr, res[1][n]), n
