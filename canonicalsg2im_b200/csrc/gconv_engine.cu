@@ -151,6 +151,29 @@ __global__ void relu_mask_out_kernel(const void* __restrict__ dy, const __nv_bfl
 
 }  // namespace
 
+// 16-bit copies of a layer's weights (+ the transposes / column blocks backward consumes) laid out as the head of `saved`:
+// appends the jobs of one layer to the arrays of a csg_cast_bf16_multi_ld call
+static int add_cast_jobs(const Dims& d, const void* const* params, uint8_t* wv, bool need_bwd, int n, const void** src, void** dst,
+                  int* rows, int* cols, int* tr, int* lds, int* ldd) {
+  const Saved s = plan_saved(d, true);
+  const float* w[4] = {(const float*)params[0], (const float*)params[2], (const float*)params[4], (const float*)params[6]};
+  const int K1 = d.K1(), Wd = d.Wd();
+  __nv_bfloat16* w1so = reinterpret_cast<__nv_bfloat16*>(wv + s.w1so);
+  // jobs 8, 9: [Ws^T | Wo^T] = the transposes of the subject / object column blocks of w1, side by side
+  const void* jsrc[10] = {w[0], w[1], w[2], w[3], w[0], w[1], w[2], w[3], w[0], w[0] + d.Din + d.Dp};
+  void* jdst[10] = {wv + s.w1b, wv + s.w2b, wv + s.w3b, wv + s.w4b, wv + s.w1t, wv + s.w2t, wv + s.w3t, wv + s.w4t, w1so, w1so + d.H};
+  const int jrows[10] = {d.H, Wd, d.H, d.Dout, d.H, Wd, d.H, d.Dout, d.H, d.H};
+  const int jcols[10] = {K1, d.H, d.H, d.H, K1, d.H, d.H, d.H, d.Din, d.Din};
+  const int jtr[10] = {0, 0, 0, 0, 1, 1, 1, 1, 1, 1};
+  const int jlds[10] = {0, 0, 0, 0, 0, 0, 0, 0, K1, K1};
+  const int jldd[10] = {0, 0, 0, 0, 0, 0, 0, 0, 2 * d.H, 2 * d.H};
+  const int count = need_bwd ? (use_segsum(d) ? 10 : 8) : 4;
+  for (int i = 0; i < count; ++i, ++n) {
+    src[n] = jsrc[i]; dst[n] = jdst[i]; rows[n] = jrows[i]; cols[n] = jcols[i]; tr[n] = jtr[i]; lds[n] = jlds[i]; ldd[n] = jldd[i];
+  }
+  return n;
+}
+
 CSG_API size_t csg_gconv_bf16_saved_bytes(const int* dims, int need_bwd) {
   return plan_saved(read_dims(dims), need_bwd != 0).total;
 }
@@ -158,6 +181,26 @@ CSG_API size_t csg_gconv_bf16_out_offset(const int* dims, int need_bwd) {
   return plan_saved(read_dims(dims), need_bwd != 0).out;
 }
 CSG_API size_t csg_gconv_bf16_workspace(const int* dims) { return plan_work(read_dims(dims)).total; }
+// bytes of a caller-kept buffer of weight copies (the head of the `saved` layout)
+CSG_API size_t csg_gconv_bf16_wbuf_bytes(const int* dims) { return plan_saved(read_dims(dims), true).conf + 256; }
+// The 16-bit weight copies of n layers (dims: n x 11 ints, params: n x 9 device pointers as in csg_gconv_bf16_fwd, wbufs: n
+// buffers of csg_gconv_bf16_wbuf_bytes, 256-byte aligned) in ONE launch: once per optimizer step instead of once per
+// layer and forward.
+CSG_API int csg_gconv_bf16_cast_weights(int n, const int* dims, const void* const* params, void* const* wbufs, int need_bwd,
+                                        csg_stream_t stream) {
+  CSG_REQUIRE(n >= 0 && n <= 6, "gconv_bf16_cast_weights: %d layers (at most 6 per call)", n);
+  const void* src[60]; void* dst[60]; int rows[60], cols[60], tr[60], lds[60], ldd[60];
+  int jobs = 0, f16 = 0;
+  for (int l = 0; l < n; ++l) {
+    const Dims d = read_dims(dims + 11 * l);
+    CSG_TRY(check_dims(d));
+    CSG_REQUIRE(wbufs[l] && (reinterpret_cast<uintptr_t>(wbufs[l]) & 255) == 0, "gconv_bf16_cast_weights: wbuf %d must be 256-byte aligned", l);
+    CSG_REQUIRE(l == 0 || d.f16 == f16, "gconv_bf16_cast_weights: mixed formats");
+    f16 = d.f16;
+    jobs = add_cast_jobs(d, params + 9 * l, reinterpret_cast<uint8_t*>(wbufs[l]), need_bwd != 0, jobs, src, dst, rows, cols, tr, lds, ldd);
+  }
+  return csg_cast_bf16_multi_ld(jobs, src, dst, rows, cols, tr, lds, ldd, f16, reinterpret_cast<cudaStream_t>(stream));
+}
 // columns of the dX matrix csg_gconv_bf16_bwd writes: Dp (d pred only) when net1's first Linear is differentiated through the
 // per-object sums of dhidden, 2 Din + Dp (the whole gathered row, d pred in columns Din .. Din+Dp) on the gathered dataflow
 CSG_API int csg_gconv_bf16_dx_cols(const int* dims) {
@@ -172,7 +215,8 @@ CSG_API int csg_gconv_bf16_dx_cols(const int* dims) {
 // `saved` must be 256-byte aligned; new_p = saved + csg_gconv_bf16_out_offset, rows of pitch 2H+Dpo, columns H..H+Dpo.
 CSG_API int csg_gconv_bf16_fwd(const int* dims, const void* obj, const void* pred, int ldp,
                                const void* const* params, const void* const* index, int need_bwd, void* saved,
-                               size_t saved_bytes, void* new_obj, csg_stream_t stream) {
+                               size_t saved_bytes, void* new_obj, const void* wbuf, const float* conf_ext,
+                               csg_stream_t stream) {
   const Dims d = read_dims(dims);
   CSG_TRY(check_dims(d));
   CSG_REQUIRE(!(d.f16 && need_bwd), "gconv_bf16_fwd: fp16 forward tensors (dims[8] = 1) are inference-only");
@@ -193,35 +237,35 @@ CSG_API int csg_gconv_bf16_fwd(const int* dims, const void* obj, const void* pre
   const int K1 = d.K1(), Wd = d.Wd();
   const int fmt = d.f16 ? 7 : 0;      // csg_gemm_bf16 formats: A, B and C of every forward GEMM are forward tensors
   // ---- 16-bit copies of the weights (+ transposes for the dX-type GEMMs of backward), one launch
-  {
-    // jobs 8, 9: [Ws^T | Wo^T] = the transposes of the subject / object column blocks of w1, side by side
-    __nv_bfloat16* w1so = reinterpret_cast<__nv_bfloat16*>(sv + s.w1so);
-    const void* src[10] = {w[0], w[1], w[2], w[3], w[0], w[1], w[2], w[3], w[0], w[0] + d.Din + d.Dp};
-    void* dst[10] = {sv + s.w1b, sv + s.w2b, sv + s.w3b, sv + s.w4b, sv + s.w1t, sv + s.w2t, sv + s.w3t, sv + s.w4t, w1so, w1so + d.H};
-    const int rows[10] = {d.H, Wd, d.H, d.Dout, d.H, Wd, d.H, d.Dout, d.H, d.H};
-    const int cols[10] = {K1, d.H, d.H, d.H, K1, d.H, d.H, d.H, d.Din, d.Din};
-    const int tr[10] = {0, 0, 0, 0, 1, 1, 1, 1, 1, 1};
-    const int lds[10] = {0, 0, 0, 0, 0, 0, 0, 0, K1, K1};
-    const int ldd[10] = {0, 0, 0, 0, 0, 0, 0, 0, 2 * d.H, 2 * d.H};
-    CSG_TRY(csg_cast_bf16_multi_ld(need_bwd ? (use_segsum(d) ? 10 : 8) : 4, src, dst, rows, cols, tr, lds, ldd, d.f16, reinterpret_cast<cudaStream_t>(stream)));
+  // wbuf != NULL: the caller keeps the weight copies (csg_gconv_bf16_cast_weights, once per optimizer step for all
+  // layers); conf_ext != NULL: the triple confidences were computed once for all the layers that share w_trans
+  const uint8_t* wv = wbuf ? reinterpret_cast<const uint8_t*>(wbuf) : sv;
+  if (!wbuf) {
+    const void* src[10]; void* dst[10]; int rows[10], cols[10], tr[10], lds[10], ldd[10];
+    const int n = add_cast_jobs(d, params, sv, need_bwd != 0, 0, src, dst, rows, cols, tr, lds, ldd);
+    CSG_TRY(csg_cast_bf16_multi_ld(n, src, dst, rows, cols, tr, lds, ldd, d.f16, reinterpret_cast<cudaStream_t>(stream)));
   }
-  float* conf = reinterpret_cast<float*>(sv + s.conf);
-  CSG_TRY(csg_triple_conf(type32, pred_id, w_trans, d.NT, conf, stream));
+  const float* conf = conf_ext;
+  if (!conf) {
+    float* own = reinterpret_cast<float*>(sv + s.conf);
+    CSG_TRY(csg_triple_conf(type32, pred_id, w_trans, d.NT, own, stream));
+    conf = own;
+  }
   // ---- net1 on the gathered triple rows
-  CSG_TRY(csg_gemm_bf16(0, 1, d.NT, d.H, K1, nullptr, 0, sv + s.w1b, K1, sv + s.hidden, d.H, 0, b[0], 1, nullptr, nullptr, 0,
+  CSG_TRY(csg_gemm_bf16(0, 1, d.NT, d.H, K1, nullptr, 0, wv + s.w1b, K1, sv + s.hidden, d.H, 0, b[0], 1, nullptr, nullptr, 0,
                         obj, pred, d.n_gather ? (const int*)index[9] : s_idx, d.n_gather ? (const int*)index[10] : o_idx,
                         d.Din, d.Dp, ldp, d.n_gather ? d.n_gather : d.NO, d.n_pred ? (const int*)index[11] : nullptr,
                         d.n_pred, fmt, nullptr, 0, stream));
-  CSG_TRY(csg_gemm_bf16(0, 0, d.NT, Wd, d.H, sv + s.hidden, d.H, sv + s.w2b, d.H, sv + s.out, Wd, 0, b[1], 1, conf, nullptr, 0,
+  CSG_TRY(csg_gemm_bf16(0, 0, d.NT, Wd, d.H, sv + s.hidden, d.H, wv + s.w2b, d.H, sv + s.out, Wd, 0, b[1], 1, conf, nullptr, 0,
                         nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, fmt, nullptr, 0, stream));
   // ---- confidence-weighted average onto objects
   CSG_TRY(csg_segpool_bf16(sv + s.out, Wd, 0, d.H + d.Dpo, d.H, rowptr_s, perm_s, rowptr_o, perm_o, valid, conf, d.NO,
                            reinterpret_cast<float*>(sv + s.pooled32), sv + s.pooled16, d.H,
                            reinterpret_cast<float*>(sv + s.cnt), 1, d.f16, stream));
   // ---- net2
-  CSG_TRY(csg_gemm_bf16(0, 0, d.NO, d.H, d.H, sv + s.pooled16, d.H, sv + s.w3b, d.H, sv + s.h2, d.H, 0, b[2], 1, nullptr,
+  CSG_TRY(csg_gemm_bf16(0, 0, d.NO, d.H, d.H, sv + s.pooled16, d.H, wv + s.w3b, d.H, sv + s.h2, d.H, 0, b[2], 1, nullptr,
                         nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, fmt, nullptr, 0, stream));
-  CSG_TRY(csg_gemm_bf16(0, 0, d.NO, d.Dout, d.H, sv + s.h2, d.H, sv + s.w4b, d.H, new_obj, d.Dout, 0, b[3], 1, nullptr,
+  CSG_TRY(csg_gemm_bf16(0, 0, d.NO, d.Dout, d.H, sv + s.h2, d.H, wv + s.w4b, d.H, new_obj, d.Dout, 0, b[3], 1, nullptr,
                         nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, fmt, nullptr, 0, stream));
   return 0;
 }
@@ -235,7 +279,8 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
                                const void* const* params, const void* const* index,
                                const void* d_new_obj, int d_new_obj_bf16, const void* d_new_p, int ld_dnewp,
                                const void* saved, const void* new_obj, void* dobj, int dobj_bf16, void* dX,
-                               float* dparams, void* workspace, size_t workspace_bytes, csg_stream_t stream) {
+                               float* dparams, void* workspace, size_t workspace_bytes, const void* wbuf,
+                               const float* conf_ext, csg_stream_t stream) {
   const Dims d = read_dims(dims);
   CSG_TRY(check_dims(d));
   // tcgen05.mma kind::f16 takes ONE 16-bit format for both operands (a mixed fp16 x bf16 instruction descriptor raises
@@ -281,7 +326,8 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
   const void* out = sv + s.out;
   const void* h2 = sv + s.h2;
   const void* pooled16 = sv + s.pooled16;
-  const float* conf = reinterpret_cast<const float*>(sv + s.conf);
+  const float* conf = conf_ext ? conf_ext : reinterpret_cast<const float*>(sv + s.conf);
+  const uint8_t* wv = wbuf ? reinterpret_cast<const uint8_t*>(wbuf) : sv;     // weight copies: the caller's, or the head of `saved`
   CsgReduceJob jobs[CSG_REDUCE_MAX_JOBS];
   int njobs = 0;
   // gather indices of the triple input (the embedding tables' class / predicate ids when layer 0 reads them directly)
@@ -316,14 +362,11 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
       CSG_CHECK_LAUNCH("csg_gconv_bf16_bwd relu mask");
     }
   }
+  // (the bias gradients db4 = colsum(g4), db3 = colsum(dh2), db1 are taken in ONE launch further down)
   GEMM(1, 0, Dout, H, NO, g4, Dout, h2, H, dw4, H, 1, nullptr, 0, 0);
-  CSG_TRY(csg_colsum_bf16_deferred(g4, NO, Dout, Dout, db4, ws + w.cs[0], w.cs_bytes[0], st, &jobs[njobs]));
-  if (jobs[njobs].parts > 0) ++njobs;
-  GEMM(0, 0, NO, H, Dout, g4, Dout, sv + s.w4t, Dout, dh2, H, 0, h2, H, -1);
+  GEMM(0, 0, NO, H, Dout, g4, Dout, wv + s.w4t, Dout, dh2, H, 0, h2, H, -1);
   GEMM(1, 0, H, H, NO, dh2, H, pooled16, H, dw3, H, 1, nullptr, 0, 1);
-  CSG_TRY(csg_colsum_bf16_deferred(dh2, NO, H, H, db3, ws + w.cs[1], w.cs_bytes[1], st, &jobs[njobs]));
-  if (jobs[njobs].parts > 0) ++njobs;
-  GEMM(0, 0, NO, H, H, dh2, H, sv + s.w3t, H, dpooled, H, 1, nullptr, 0, -1);
+  GEMM(0, 0, NO, H, H, dh2, H, wv + s.w3t, H, dpooled, H, 1, nullptr, 0, -1);
   // ---- pooling backward (graph.py:83-107)
   CSG_TRY(csg_pool_bwd_obj(dpooled, reinterpret_cast<const float*>(sv + s.pooled32),
                            reinterpret_cast<const float*>(sv + s.cnt), NO, H, dS, dcnt, stream));
@@ -334,12 +377,24 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
   if (jobs[njobs].parts > 0) { if (jobs[njobs + 1].parts > 0) { njobs += 2; } else { ++njobs; } }
   // ---- net1 backward (graph.py:63-67)
   GEMM(1, 0, Wd, H, NT, g, Wd, hidden, H, dw2, H, 1, nullptr, 0, 2);
-  GEMM(0, 0, NT, H, Wd, g, Wd, sv + s.w2t, Wd, dhid, H, 0, hidden, H, -1);
+  GEMM(0, 0, NT, H, Wd, g, Wd, wv + s.w2t, Wd, dhid, H, 0, hidden, H, -1);
+  // db4, db3 and db1 (column sums of g4, dh2 and of dhidden or its per-subject sums) in one launch
+  auto colsums = [&](const void* X1, int M1, int ld1) -> int {
+    const void* X[3] = {g4, dh2, X1};
+    const int Ms[3] = {NO, NO, M1}, Ns[3] = {Dout, H, H}, lds[3] = {Dout, H, ld1};
+    float* outs[3] = {db4, db3, db1};
+    void* wsp[3] = {ws + w.cs[0], ws + w.cs[1], ws + w.cs[2]};
+    const size_t wsb[3] = {w.cs_bytes[0], w.cs_bytes[1], w.cs_bytes[2]};
+    CsgReduceJob cj[3];
+    if (int rc = csg_colsum_bf16_multi_deferred(3, X, Ms, Ns, lds, outs, wsp, wsb, st, cj)) return rc;
+    for (int i = 0; i < 3; ++i)
+      if (cj[i].parts > 0) jobs[njobs++] = cj[i];
+    return 0;
+  };
   if (!use_segsum(d)) {
     GEMM(1, 2, H, K1, NT, dhid, H, nullptr, 0, dw1, K1, 1, nullptr, 0, 3);
-    CSG_TRY(csg_colsum_bf16_deferred(dhid, NT, H, H, db1, ws + w.cs[2], w.cs_bytes[2], st, &jobs[njobs]));
-    if (jobs[njobs].parts > 0) ++njobs;
-    GEMM(0, 0, NT, K1, H, dhid, H, sv + s.w1t, H, dX, K1, 0, nullptr, 0, -1);
+    CSG_TRY(colsums(dhid, NT, H));
+    GEMM(0, 0, NT, K1, H, dhid, H, wv + s.w1t, H, dX, K1, 0, nullptr, 0, -1);
     // ---- gather backward: segmented sums of dX over ALL triples onto their subject / object rows
     CSG_TRY(csg_segpool_bf16(dX, K1, 0, d.Din + d.Dp, d.Din, rowptr_s, perm_s, rowptr_o, perm_o, nullptr, nullptr, NO,
                              dobj_bf16 ? nullptr : reinterpret_cast<float*>(dobj), dobj_bf16 ? dobj : nullptr, d.Din, nullptr,
@@ -352,8 +407,7 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
     const int Din = d.Din, Dp = d.Dp;
     CSG_TRY(csg_segsum2_bf16(dhid, H, H, rowptr_s, perm_s, rowptr_o, perm_o, NO, nullptr, dHso, 2 * H, stream));
     // db1 = colsum(dhidden) = colsum(S dh): every triple has exactly one subject
-    CSG_TRY(csg_colsum_bf16_deferred(dHso, NO, H, 2 * H, db1, ws + w.cs[2], w.cs_bytes[2], st, &jobs[njobs]));
-    if (jobs[njobs].parts > 0) ++njobs;
+    CSG_TRY(colsums(dHso, NO, 2 * H));
     // a weight-gradient block computed into a contiguous scratch matrix and placed into dw1 (row pitch K1) by the final pass
     auto place = [&](CsgReduceJob& j, const float* scratch, int rows, int cols, float* dst) {
       if (j.parts == 0) {                         // written directly (no split-K): the final pass is then a copy
@@ -382,11 +436,11 @@ CSG_API int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pre
       njobs += 2;
     }
     // d pred = dh Wp  (rows Din .. Din+Dp of the transposed copy of w1)
-    CSG_TRY(csg_gemm_bf16_deferred(0, 0, NT, Dp, H, dhid, H, sv + s.w1t + (size_t)Din * H * 2, H, dX, Dp, 0, nullptr, 0, nullptr,
+    CSG_TRY(csg_gemm_bf16_deferred(0, 0, NT, Dp, H, dhid, H, wv + s.w1t + (size_t)Din * H * 2, H, dX, Dp, 0, nullptr, 0, nullptr,
                                    nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, bfmt, nullptr, 0, st,
                                    &jobs[njobs]));
     // d obj = [S dh | O dh] [Ws ; Wo]
-    CSG_TRY(csg_gemm_bf16_deferred(0, 0, NO, Din, 2 * H, dHso, 2 * H, sv + s.w1so, 2 * H, dobj, Din, dobj_bf16 ? 0 : 1, nullptr, 0,
+    CSG_TRY(csg_gemm_bf16_deferred(0, 0, NO, Din, 2 * H, dHso, 2 * H, wv + s.w1so, 2 * H, dobj, Din, dobj_bf16 ? 0 : 1, nullptr, 0,
                                    nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, 0, bfmt, nullptr, 0,
                                    st, &jobs[njobs]));
   }

@@ -49,7 +49,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int co
 
 // Several fp32 -> bf16 casts (optionally transposed) in one launch: the 4 weight matrices of a layer and their
 // transposes are needed once per step each.
-constexpr int CAST_MAX = 16;
+constexpr int CAST_MAX = 64;      // 10 copies per GraphTripleConv layer x 6 layers (csg_gconv_bf16_cast_weights)
 struct CastJobs {
   const float* src[CAST_MAX];
   __nv_bfloat16* dst[CAST_MAX];
@@ -246,6 +246,65 @@ __global__ void __launch_bounds__(CS_TX * CS_TY) colsum_bf16_partial_kernel(cons
 #pragma unroll
       for (int r = 0; r < CS_TY; ++r) s += red[r][threadIdx.x];
       partial[(size_t)blockIdx.y * N + n] = s;
+    }
+  }
+}
+// The same for up to CSM_MAX matrices in one launch (1-D grid, a block finds its job by prefix): the three per-object
+// bias gradients of a layer's backward (db4, db3, db1) are ~4 us launches each otherwise.  Same per-block arithmetic and
+// the same chunking as the single-matrix kernel, hence bit-identical partials.
+constexpr int CSM_MAX = 4;
+struct ColsumJobs {
+  const __nv_bfloat16* X[CSM_MAX];
+  float* partial[CSM_MAX];
+  int M[CSM_MAX], N[CSM_MAX], ld[CSM_MAX], rpc[CSM_MAX], xblocks[CSM_MAX], block_end[CSM_MAX];
+  int n;
+};
+__global__ void __launch_bounds__(CS_TX * CS_TY) colsum_bf16_multi_partial_kernel(const ColsumJobs jobs) {
+  CSG_PDL_WAIT();
+  __shared__ float red[CS_TY][CS_TX * CS_VEC + 4];
+  int j = 0;
+  while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.block_end[j]) ++j;
+  const int local = (int)blockIdx.x - (j ? jobs.block_end[j - 1] : 0);
+  const int bx = local % jobs.xblocks[j], by = local / jobs.xblocks[j];
+  const __nv_bfloat16* X = jobs.X[j];
+  const int M = jobs.M[j], N = jobs.N[j], ld = jobs.ld[j], rows_per_chunk = jobs.rpc[j];
+  const int tx = threadIdx.x % CS_TX, ty = threadIdx.x / CS_TX;
+  const int col = (bx * CS_TX + tx) * CS_VEC;
+  const int mbeg = by * rows_per_chunk, mend = min(M, mbeg + rows_per_chunk);
+  float acc[CS_VEC];
+#pragma unroll
+  for (int q = 0; q < CS_VEC; ++q) acc[q] = 0.f;
+  if (col < N) {
+    int m = mbeg + ty;
+    for (; m + 3 * CS_TY < mend; m += 4 * CS_TY) {
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const uint4*>(X + (size_t)(m + u * CS_TY) * ld + col);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        unpack8(q[u], v);
+#pragma unroll
+        for (int i = 0; i < CS_VEC; ++i) acc[i] += v[i];
+      }
+    }
+    for (; m < mend; m += CS_TY) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(X + (size_t)m * ld + col), v);
+#pragma unroll
+      for (int i = 0; i < CS_VEC; ++i) acc[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CS_VEC; ++i) red[ty][tx * CS_VEC + i] = acc[i];
+  __syncthreads();
+  {
+    const int n = bx * CS_TX * CS_VEC + threadIdx.x;
+    if (n < N) {
+      float sum = 0.f;
+#pragma unroll
+      for (int r = 0; r < CS_TY; ++r) sum += red[r][threadIdx.x];
+      jobs.partial[j][(size_t)by * N + n] = sum;
     }
   }
 }
@@ -653,7 +712,7 @@ CSG_API int csg_cast_bf16(const float* src, int rows, int cols, int ld_src, void
 }
 
 // n contiguous fp32 matrices src[i] [rows[i], cols[i]] -> contiguous bf16 dst[i] ([cols, rows] when transpose[i]).
-// The pointer / size arrays are HOST arrays of length n <= 16.
+// The pointer / size arrays are HOST arrays of length n <= 64.
 CSG_API int csg_cast_bf16_multi(int n, const void* const* src, void* const* dst, const int* rows, const int* cols,
                                 const int* transpose, int fp16, cudaStream_t stream) {
   return csg_cast_bf16_multi_ld(n, src, dst, rows, cols, transpose, nullptr, nullptr, fp16, stream);
@@ -762,6 +821,42 @@ int csg_colsum_bf16_deferred(const void* X, int M, int N, int ld, float* out, vo
       reinterpret_cast<const __nv_bfloat16*>(X), M, N, ld, rows_per_chunk, partial));
   CSG_CHECK_LAUNCH("csg_colsum_bf16 partial");
   job->partial = partial; job->n = N; job->parts = chunks;
+  return 0;
+}
+
+// n <= 4 column sums in one launch; job[i] describes the final pass of matrix i (as csg_colsum_bf16_deferred)
+int csg_colsum_bf16_multi_deferred(int n, const void* const* X, const int* M, const int* N, const int* ld, float* const* out,
+                                   void* const* workspace, const size_t* workspace_bytes, cudaStream_t stream,
+                                   CsgReduceJob* job) {
+  CSG_REQUIRE(n >= 0 && n <= CSM_MAX, "colsum_bf16_multi: n=%d out of range", n);
+  ColsumJobs jobs;
+  jobs.n = 0;
+  int blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    job[i].parts = 0; job[i].n = 0; job[i].partial = nullptr; job[i].out = out[i]; job[i].stride = N[i]; job[i].lanes = 8;
+    job[i].op = CSG_RED_SUM; job[i].aux = nullptr; job[i].ncols = 0; job[i].ldo = 0;
+    if (N[i] == 0) continue;
+    CSG_REQUIRE((N[i] & 7) == 0 && (ld[i] & 7) == 0 && (reinterpret_cast<uintptr_t>(X[i]) & 15) == 0,
+                "colsum_bf16: N and ld must be multiples of 8 and X 16-byte aligned");
+    CSG_REQUIRE(workspace_bytes[i] >= csg_colsum_bf16_workspace(M[i], N[i]), "colsum_bf16: workspace too small");
+    const int chunks = colsum_bf16_chunks(M[i], N[i]);
+    const int k = jobs.n++;
+    jobs.X[k] = reinterpret_cast<const __nv_bfloat16*>(X[i]);
+    jobs.partial[k] = reinterpret_cast<float*>(workspace[i]);
+    jobs.M[k] = M[i]; jobs.N[k] = N[i]; jobs.ld[k] = ld[i];
+    jobs.rpc[k] = csg_div_up(M[i] > 0 ? M[i] : 1, chunks);
+    jobs.xblocks[k] = csg_div_up(N[i], CS_TX * CS_VEC);
+    blocks += jobs.xblocks[k] * chunks;
+    jobs.block_end[k] = blocks;
+    job[i].partial = jobs.partial[k]; job[i].n = N[i]; job[i].parts = chunks;
+  }
+  if (jobs.n == 0) return 0;
+  for (int k = jobs.n; k < CSM_MAX; ++k) {
+    jobs.X[k] = jobs.X[0]; jobs.partial[k] = jobs.partial[0]; jobs.M[k] = 0; jobs.N[k] = 0; jobs.ld[k] = 0; jobs.rpc[k] = 1;
+    jobs.xblocks[k] = 1; jobs.block_end[k] = blocks;
+  }
+  CSG_CUDA(csg_launch_pdl(colsum_bf16_multi_partial_kernel, dim3(blocks), dim3(CS_TX * CS_TY), 0, stream, jobs));
+  CSG_CHECK_LAUNCH("csg_colsum_bf16 multi partial");
   return 0;
 }
 

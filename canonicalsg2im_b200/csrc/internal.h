@@ -39,6 +39,10 @@ int csg_cast_bf16_multi_ld(int n, const void* const* src, void* const* dst, cons
 // csg_colsum_bf16 without its final pass
 int csg_colsum_bf16_deferred(const void* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
                              cudaStream_t stream, CsgReduceJob* job);
+// up to 4 column sums in one partial launch (job[i]: the final pass of matrix i)
+int csg_colsum_bf16_multi_deferred(int n, const void* const* X, const int* M, const int* N, const int* ld, float* const* out,
+                                   void* const* workspace, const size_t* workspace_bytes, cudaStream_t stream,
+                                   CsgReduceJob* job);
 // csg_triple_bwd_assemble_bf16 with the column sums of g (db2) and the per-predicate sums of the confidence gradient
 // (d w_trans, graph.py:69-74) left as two jobs; dconf itself is not materialised.  workspace:
 // csg_triple_bwd_assemble_bf16_deferred_workspace bytes.

@@ -388,6 +388,7 @@ class GraphTripleConv(nn.Module):
             raise ValueError("only mlp_normalization='none' (the reference default, args.py:53) is supported")
         self.return_new_p_vecs = return_new_p_vecs
         self.hidden_dim = hidden_dim
+        self.obj_input_dim, self.predicate_input_dim = obj_input_dim, predicate_input_dim
         self.num_attributes = num_attributes
         self.predicate_output_dim = predicate_output_dim
         self.pooling = pooling            # accepted and ignored, as in the reference

@@ -115,6 +115,71 @@ def _ptr_array(tensors):
     return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
+# --------------------------------------------------------------------------------------------
+# caller-kept 16-bit weight copies: one cast launch for all layers per optimizer step instead of one per layer and
+# forward (csg_gconv_bf16_cast_weights).  An entry is valid while the fp32 weights it was cast from are unchanged:
+# autograd's version counters catch every in-place torch update (torch.optim, load_state_dict, init), and FusedAdam,
+# which writes the parameters through raw pointers, invalidates the entries of its parameters itself (optim.py).
+# --------------------------------------------------------------------------------------------
+_WCOPIES = {}      # data_ptr of net1.0.weight -> dict(wbuf, versions, key, params)
+
+
+def _wkey(params, act, dims):
+    return (tuple(int(x) for x in list(dims)[2:9]), act, tuple(p.data_ptr() for p in params[:8]))
+
+
+def invalidate_weight_copies(params=None):
+    """Mark the cached weight copies stale (of the layers that own any of ``params``; all when None).  The buffers stay
+    where they are -- a captured CUDA graph may hold their addresses -- and are refilled by refresh_weight_copies."""
+    ptrs = None if params is None else {p.data_ptr() for p in params}
+    for e in _WCOPIES.values():
+        if ptrs is None or ptrs & {q.data_ptr() for q in e["params"]}:
+            e["versions"] = None
+
+
+def refresh_weight_copies(layers, act=BF):
+    """Cast the weights of ``layers`` (``GraphTripleConv`` modules on the tensor-core engine) into their cached 16-bit
+    copies, six layers per launch.  Call after every optimizer step; a layer without a valid copy casts its weights
+    itself inside its forward call, so forgetting to call this costs time, never correctness."""
+    L = lib()
+    todo = []
+    for layer in layers:
+        params = tuple(layer.layer_params()) + (layer.predicates_transitive_weights,)
+        if any(p.dtype != torch.float32 or not p.is_contiguous() or not p.is_cuda for p in params):
+            continue
+        din, dp = layer.obj_input_dim, layer.predicate_input_dim
+        H, Dout, Dpo = layer.hidden_dim, params[6].shape[0], layer.predicate_output_dim
+        if din % 64 or dp % 64 or H % 64 or Dout % 64 or Dpo % 64:
+            continue                    # zero-padded on the fly (triple_conv): those layers cast per call
+        dims = (ctypes.c_int * 11)(0, 0, din, dp, H, Dout, Dpo, max(params[8].numel(), 1), int(act == F16), 0, 0)
+        todo.append((params, dims))
+    for i in range(0, len(todo), 6):
+        grp = todo[i:i + 6]
+        ents = []
+        for params, dims in grp:
+            key, k = params[0].data_ptr(), _wkey(params, act, dims)
+            e = _WCOPIES.get(key)
+            if e is None or e["key"] != k:
+                nb = L.csg_gconv_bf16_wbuf_bytes(dims)
+                e = _WCOPIES[key] = {"wbuf": torch.empty(nb, dtype=torch.uint8, device=params[0].device), "key": k,
+                                     "params": params[:8]}
+            ents.append(e)
+        n = len(grp)
+        dims_flat = (ctypes.c_int * (11 * n))(*[x for _, d in grp for x in list(d)])
+        pp = (ctypes.c_void_p * (9 * n))(*[p.data_ptr() for params, _ in grp for p in params])
+        wb = (ctypes.c_void_p * n)(*[e["wbuf"].data_ptr() for e in ents])
+        _lib.check(L.csg_gconv_bf16_cast_weights(n, dims_flat, pp, wb, 1, _stream()), "csg_gconv_bf16_cast_weights")
+        for e, (params, _) in zip(ents, grp):
+            e["versions"] = tuple(p._version for p in params[:8])
+
+
+def _cached_wbuf(params, act, dims):
+    e = _WCOPIES.get(params[0].data_ptr())
+    if e is None or e["key"] != _wkey(params, act, dims) or e.get("versions") != tuple(p._version for p in params[:8]):
+        return None
+    return e["wbuf"]
+
+
 class FusedTables:
     """Layer 0 reading straight from the embedding tables (sg2im/model.py:108-109 fused into the net1 producer): the
     layer's `obj` / `pred` arguments are then the fp32 TABLES, gathered per triple by class id / predicate id."""
@@ -168,6 +233,11 @@ class _TripleConvEngine(torch.autograd.Function):
                                    n_gather, n_pred)
         nsaved = L.csg_gconv_bf16_saved_bytes(dims, need_bwd)
         saved = torch.empty(nsaved, dtype=torch.uint8, device=dev)
+        # hoisted preparation (both optional): weight copies kept across calls, confidences shared by the layers of a model
+        wbuf = _cached_wbuf(params, act, dims) if os.environ.get("CSG_WCOPIES", "1") != "0" else None
+        shared = getattr(batch, "_conf_shared", None)
+        conf_ext = shared[1] if shared is not None and shared[0] == (w_trans.data_ptr(), w_trans._version) else None
+        ctx.wbuf, ctx.conf_ext = wbuf, conf_ext
         new_obj = torch.empty((batch.NO, Dout), dtype=act, device=dev)
         index = batch.index_array()
         if fused is not None:
@@ -175,7 +245,7 @@ class _TripleConvEngine(torch.autograd.Function):
             ctx.gather_idx = (gs, go)
         ctx.index = index
         rc = L.csg_gconv_bf16_fwd(dims, ptr(obj_b), ptr(pred_b), pred_b.stride(0), _ptr_array(params), index, need_bwd,
-                                  ptr(saved), nsaved, ptr(new_obj), _stream())
+                                  ptr(saved), nsaved, ptr(new_obj), ptr(wbuf), ptr(conf_ext), _stream())
         _lib.check(rc, "csg_gconv_bf16_fwd")
         Wd = 2 * H + Dpo
         off = L.csg_gconv_bf16_out_offset(dims, need_bwd)
@@ -214,7 +284,7 @@ class _TripleConvEngine(torch.autograd.Function):
                                   ptr(d_obj_out), int(d_obj_out is not None and d_obj_out.dtype == BF),
                                   ptr(d_newp), d_newp.stride(0) if d_newp is not None else 0,
                                   ptr(saved), ptr(new_obj), ptr(dobj), int(obj_bf16), ptr(dX), ptr(dparams),
-                                  ptr(ws), ws.numel(), _stream())
+                                  ptr(ws), ws.numel(), ptr(ctx.wbuf), ptr(ctx.conf_ext), _stream())
         _lib.check(rc, "csg_gconv_bf16_bwd")
         dw1, db1, dw2, db2, dw3, db3, dw4, db4, dwt = torch.split(dparams, sizes)
         dpred = dX[:, Din:Din + Dp] if dxc == K1 else dX

@@ -253,9 +253,25 @@ class Sg2LayoutModel(nn.Module):
         pred_vecs = embedding_lookup(self.pred_embeddings.weight, pred_ids, self._act_dtype())
         return self._run(batch, obj_vecs, pred_vecs)
 
+    def refresh_weight_copies(self):
+        """Tensor-core engine: refresh the cached 16-bit copies of all layers' weights in one launch (call after every
+        optimizer step; ``pipeline.SgToLayoutStep`` does).  Without it every layer casts its weights inside its call."""
+        if self.precision in ("bf16", "fp16"):
+            from . import graph_tc
+            graph_tc.refresh_weight_copies(list(self.gconvs), self._act_dtype())
+
     def _run(self, batch, obj_vecs, pred_vecs, first=0):
-        for layer in list(self.gconvs)[first:]:
-            obj_vecs, pred_vecs = layer.forward_flat(batch, obj_vecs, pred_vecs)
+        layers = list(self.gconvs)[first:]
+        w = self.trans_candidates_weights
+        if self.precision in ("bf16", "fp16") and batch.NT > 0 and all(l.predicates_transitive_weights is w for l in layers):
+            # the triple confidences (graph.py:69-74) depend on the batch and on w_trans only: once for all layers
+            from .graph import triple_confidence
+            batch._conf_shared = ((w.data_ptr(), w._version), triple_confidence(batch, w))
+        try:
+            for layer in layers:
+                obj_vecs, pred_vecs = layer.forward_flat(batch, obj_vecs, pred_vecs)
+        finally:
+            batch._conf_shared = None
         boxes = dense_mlp2(obj_vecs, self.box_net[0].weight, self.box_net[0].bias,
                            self.box_net[2].weight, self.box_net[2].bias, False, self.precision)
         return obj_vecs, boxes

@@ -23,6 +23,7 @@ class FusedAdam:
                 raise _lib.CsgError("FusedAdam needs contiguous fp32 CUDA parameters (there is no CPU path)")
         self.lr, self.betas, self.eps, self.weight_decay = lr, tuple(betas), eps, weight_decay
         self.state = {}
+        self.post_step = []       # callables run after every step (e.g. Sg2LayoutModel.refresh_weight_copies)
 
     def _state(self, p):
         st = self.state.get(p)
@@ -54,6 +55,12 @@ class FusedAdam:
                                   float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
                                   float(self.weight_decay), IA(*[s["step"] for s in sts]), _stream())
         _lib.check(rc, "csg_adam_multi")
+        # the kernel wrote the parameters through raw pointers: autograd's version counters did not move, so the cached
+        # 16-bit weight copies of the tensor-core engine (graph_tc._WCOPIES) must be dropped here ...
+        from . import graph_tc
+        graph_tc.invalidate_weight_copies(live)
+        for cb in self.post_step:       # ... and are rebuilt in one launch by whoever registered for it
+            cb()
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:

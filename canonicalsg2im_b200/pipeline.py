@@ -121,6 +121,9 @@ class SgToLayoutStep:
         params = [p for p in self.model.parameters() if p is not self.model.converse_candidates_weights]
         params += list(self.layout_embedding.parameters())
         self.opt = FusedAdam(params, lr=lr)                      # torch.optim.Adam arithmetic, one multi-tensor launch
+        # 16-bit copies of all layers' weights: one cast launch behind every optimizer step instead of one per layer and forward
+        self.opt.post_step.append(self.model.refresh_weight_copies)
+        self.model.refresh_weight_copies()
 
     def refresh_tables(self):
         """The reference pushes the symmetrised converse weights into the dataset every step

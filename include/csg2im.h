@@ -180,7 +180,7 @@ void csg_gemm_bf16_set_pair_mode(int mode);
 /* bf16-activation twins of the pooling / assembly kernels (fp32 accumulation) + weight cast */
 int csg_cast_bf16(const float* src, int rows, int cols, int ld_src, void* dst, int ld_dst, int transpose, int fp16,
                   csg_stream_t stream);
-/* n <= 16 contiguous fp32 matrices -> contiguous 16-bit copies (transposed when transpose[i]; fp16 when fp16, else
+/* n <= 64 contiguous fp32 matrices -> contiguous 16-bit copies (transposed when transpose[i]; fp16 when fp16, else
  * bf16); HOST arrays */
 int csg_cast_bf16_multi(int n, const void* const* src, void* const* dst, const int* rows, const int* cols,
                         const int* transpose, int fp16, csg_stream_t stream);
@@ -227,7 +227,7 @@ int csg_gconv_bf16_dx_cols(const int* dims);   /* columns of the dX matrix csg_g
  * columns H..H+Dpo of the [NT, 2H+Dpo] matrix at saved + csg_gconv_bf16_out_offset.  `saved` 256-byte aligned. */
 int csg_gconv_bf16_fwd(const int* dims, const void* obj, const void* pred, int ldp,
                        const void* const* params, const void* const* index, int need_bwd, void* saved,
-                       size_t saved_bytes, void* new_obj, csg_stream_t stream);
+                       size_t saved_bytes, void* new_obj, const void* wbuf, const float* conf_ext, csg_stream_t stream);
 /* d_new_obj [NO, Dout] fp32 or (d_new_obj_bf16) bf16, NULL = 0; d_new_p [NT, Dpo] bf16 rows of pitch ld_dnewp,
  * NULL = 0.  Writes dobj [NO, Din] fp32 or (dobj_bf16) bf16, dX [NT, csg_gconv_bf16_dx_cols] bf16 (d pred; on the gathered
  * dataflow the whole row [d obj[s] | d pred | d obj[o]])
@@ -237,7 +237,16 @@ int csg_gconv_bf16_bwd(const int* dims, const void* obj, const void* pred, int l
                        const void* const* params, const void* const* index,
                        const void* d_new_obj, int d_new_obj_bf16, const void* d_new_p, int ld_dnewp,
                        const void* saved, const void* new_obj, void* dobj, int dobj_bf16, void* dX,
-                       float* dparams, void* workspace, size_t workspace_bytes, csg_stream_t stream);
+                       float* dparams, void* workspace, size_t workspace_bytes, const void* wbuf, const float* conf_ext,
+                       csg_stream_t stream);
+/* Optional hoisting of per-layer preparation out of the layer calls.  wbuf (may be NULL): the 16-bit weight copies of the
+ * layer kept by the caller (csg_gconv_bf16_wbuf_bytes bytes, 256-byte aligned, filled by csg_gconv_bf16_cast_weights for up
+ * to 6 layers in one launch -- once per optimizer step); NULL = the layer casts its weights itself into `saved`.  conf_ext
+ * (may be NULL): the triple confidences [NT] (csg_triple_conf), computed once when all layers share w_trans as in
+ * sg2im/model.py:47-55; NULL = computed by the layer.  The same pointers must be given to the backward call. */
+size_t csg_gconv_bf16_wbuf_bytes(const int* dims);
+int csg_gconv_bf16_cast_weights(int n, const int* dims, const void* const* params, void* const* wbufs, int need_bwd,
+                                csg_stream_t stream);
 
 /* out[i] = map[idx[i]] (int32): composes the per-triple class ids of the fused layer 0 from the triples' object indices
  * and the objects' class ids.  idx values outside [0, n_map) and (n_values > 0) map values outside [0, n_values) --

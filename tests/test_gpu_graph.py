@@ -457,3 +457,50 @@ def test_pipelined_assemble_equals_register_staged(golden, monkeypatch):
             assert_close(gr, res[1][n], 1e-5, "pipelined vs staged assemble: " + n)
         else:
             assert torch.equal(gr, res[1][n]), n
+
+
+@pytest.mark.gpu
+def test_cached_weight_copies_follow_the_optimizer(golden, monkeypatch):
+    """The 16-bit weight copies kept across calls (graph_tc.refresh_weight_copies: one cast launch per optimizer step for
+    all layers) and the confidences shared by the layers of a model give bit-identical results to every layer casting
+    its weights / computing its confidences itself (CSG_WCOPIES=0), before and after FusedAdam has rewritten the
+    parameters through raw pointers (which autograd's version counters do not see: FusedAdam marks the copies stale)."""
+    from canonicalsg2im_b200 import graph_tc
+    from canonicalsg2im_b200.optim import FusedAdam
+    g = golden("sg2layout_model")
+    model = _model("bf16")
+    args = (t(g["objs"]), t(g["triplets"]), t(g["types"]))
+
+    def run():
+        for p in model.parameters():
+            p.grad = None
+        obj_vecs, boxes, _ = model(*args)
+        (boxes.float().pow(2).sum() + (obj_vecs.float() * t(gi.model_obj_grad(obj_vecs.shape))).sum()).backward()
+        return obj_vecs.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    def both():
+        monkeypatch.setenv("CSG_WCOPIES", "1")
+        a = run()
+        monkeypatch.setenv("CSG_WCOPIES", "0")
+        b = run()
+        assert torch.equal(a[0], b[0])
+        for n in a[1]:
+            assert torch.equal(a[1][n], b[1][n]), n
+        return a
+
+    graph_tc.invalidate_weight_copies()
+    first = both()                                   # no copies yet: both runs cast per layer
+    model.refresh_weight_copies()
+    l0 = model.gconvs[0]
+    assert graph_tc._WCOPIES[l0.net1[0].weight.data_ptr()]["versions"] is not None
+    cached = both()                                  # copies valid
+    assert torch.equal(first[0], cached[0])
+    opt = FusedAdam([p for p in model.parameters() if p.grad is not None], lr=1e-2)
+    opt.step()                                       # no refresh hook registered: the copies must be stale now
+    assert graph_tc._WCOPIES[l0.net1[0].weight.data_ptr()]["versions"] is None
+    after = both()
+    assert not torch.equal(after[0], cached[0])      # the step moved the weights, and the forward saw it
+    opt.post_step.append(model.refresh_weight_copies)
+    opt.step()
+    assert graph_tc._WCOPIES[l0.net1[0].weight.data_ptr()]["versions"] is not None
+    both()
