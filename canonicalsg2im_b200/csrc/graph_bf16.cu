@@ -487,7 +487,8 @@ triple_bwd_assemble_bf16_kernel(const __nv_bfloat16* __restrict__ out, const flo
 // and the reduction orders are those of triple_bwd_assemble_bf16_kernel; what changes is who waits for DRAM: the
 // register-staged kernel exposes a DRAM round trip per 16-byte column step of every row (ncu r02b: 36 % warps active,
 // 49 % issue-active at 3.7 TB/s).
-constexpr int ASMP_STAGES = 4;
+constexpr int ASMP_STAGES_DEFAULT = 3;      // 3 x 18 KB per CTA: what the ring does not take stays L1 for the gathered dS rows (ncu r02g:
+                                    // long-scoreboard stalls on those gathers lead; L1 hit rate 61 % with a 4-stage ring + separate scratch)
 constexpr int ASMP_CTAS_PER_SM = 2;
 __device__ __forceinline__ uint32_t asmp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void asmp_mbar_init(uint32_t bar, uint32_t count) {
@@ -519,7 +520,11 @@ __device__ __forceinline__ void asmp_bulk_load(uint32_t dst, const void* src, ui
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int HT, int DPT>
+__host__ __device__ inline size_t asmp_ring_bytes(int Wd, int ASMP_STAGES) {
+  const size_t ring = (size_t)ASMP_STAGES * ASM_WARPS * Wd * 2, red = (size_t)(ASM_WARPS / 2) * ASM_MAXI * 256 * 4;
+  return ((ring > red ? ring : red) + 127) & ~(size_t)127;
+}
+template <int HT, int DPT, int ASMP_STAGES>
 __global__ void __launch_bounds__((ASM_WARPS + 1) * 32, ASMP_CTAS_PER_SM)
 triple_bwd_assemble_pipe_kernel(const __nv_bfloat16* __restrict__ out, const float* __restrict__ dS,
                                 const __nv_bfloat16* __restrict__ d_newp, int ld_newp,
@@ -532,12 +537,13 @@ triple_bwd_assemble_pipe_kernel(const __nv_bfloat16* __restrict__ out, const flo
   CSG_PDL_WAIT();
   const int H = HT ? HT : H_rt, Dp = DPT ? DPT : Dp_rt;
   const int Wd = 2 * H + Dp;
-  // dynamic shared memory: [ring: ASMP_STAGES x ASM_WARPS rows of Wd bf16][cs_red][wt_bins][barriers]
+  // dynamic shared memory: [ring: ASMP_STAGES x ASM_WARPS rows of Wd bf16][wt_bins][barriers]; the scratch of the final
+  // column-sum tree (cs_red, 20 KB) reuses the ring, which is idle by then
   extern __shared__ __align__(128) unsigned char asmp_smem[];
   const uint32_t stage_bytes = (uint32_t)ASM_WARPS * Wd * 2;
   __nv_bfloat16* ring = reinterpret_cast<__nv_bfloat16*>(asmp_smem);
-  float* cs_red = reinterpret_cast<float*>(asmp_smem + (size_t)ASMP_STAGES * stage_bytes);
-  float* wt_bins = cs_red + (ASM_WARPS / 2) * ASM_MAXI * 256;            // [ASM_WARPS][P]
+  float* cs_red = reinterpret_cast<float*>(asmp_smem);
+  float* wt_bins = reinterpret_cast<float*>(asmp_smem + asmp_ring_bytes(Wd, ASMP_STAGES));   // [ASM_WARPS][P]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(
       (reinterpret_cast<uintptr_t>(wt_bins + ASM_WARPS * P) + 7) & ~(uintptr_t)7);
   const uint32_t full0 = asmp_smem_u32(bars), empty0 = asmp_smem_u32(bars + ASMP_STAGES);
@@ -683,9 +689,8 @@ triple_bwd_assemble_pipe_kernel(const __nv_bfloat16* __restrict__ out, const flo
     }
   }
 }
-size_t asmp_smem_bytes(int Wd, int P) {
-  return (size_t)ASMP_STAGES * ASM_WARPS * Wd * 2 + (size_t)(ASM_WARPS / 2) * ASM_MAXI * 256 * 4 + (size_t)ASM_WARPS * P * 4 + 8 +
-         2 * ASMP_STAGES * 8;
+size_t asmp_smem_bytes(int Wd, int P, int stages) {
+  return asmp_ring_bytes(Wd, stages) + (size_t)ASM_WARPS * P * 4 + 8 + 2 * stages * 8;
 }
 int asmp_blocks(int NT) {
   int want = csg_div_up(NT > 0 ? NT : 1, ASM_WARPS);
@@ -942,14 +947,19 @@ int csg_triple_bwd_assemble_bf16_deferred(const void* out, const float* dS, cons
   {
     // pipelined kernel (rows of `out` through a shared-memory ring); CSG_ASM_PIPE=0 selects the register-staged one
     const char* e = getenv("CSG_ASM_PIPE");
-    const size_t smem = asmp_smem_bytes(Wd, P);
+    const char* es = getenv("CSG_ASM_STAGES");
+    const int stages = (es && (atoi(es) == 4 || atoi(es) == 2)) ? atoi(es) : ASMP_STAGES_DEFAULT;
+    const size_t smem = asmp_smem_bytes(Wd, P, stages);
     if (!(e && e[0] == '0') && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && smem <= 100 * 1024) {
       const int blocks = asmp_blocks(NT);
       float* cs_partial = reinterpret_cast<float*>(workspace);
       float* wt_partial = cs_partial + (size_t)blocks * Wd;
-      auto kernel = (H == 512 && Dp == 128) ? triple_bwd_assemble_pipe_kernel<512, 128> : triple_bwd_assemble_pipe_kernel<0, 0>;
-      static bool configured[2] = {false, false};
-      const int which = (H == 512 && Dp == 128) ? 0 : 1;
+      const bool ref_geom = H == 512 && Dp == 128;
+      auto kernel = stages == 4 ? (ref_geom ? triple_bwd_assemble_pipe_kernel<512, 128, 4> : triple_bwd_assemble_pipe_kernel<0, 0, 4>)
+                  : stages == 2 ? (ref_geom ? triple_bwd_assemble_pipe_kernel<512, 128, 2> : triple_bwd_assemble_pipe_kernel<0, 0, 2>)
+                                : (ref_geom ? triple_bwd_assemble_pipe_kernel<512, 128, 3> : triple_bwd_assemble_pipe_kernel<0, 0, 3>);
+      static bool configured[6] = {false, false, false, false, false, false};
+      const int which = (ref_geom ? 0 : 1) + (stages == 4 ? 2 : (stages == 2 ? 4 : 0));
       if (!configured[which]) {
         CSG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         configured[which] = true;
