@@ -783,6 +783,7 @@ def run_ours(args):
 
     peak_tf = pk["tf_sustained"]
     ach_tf = gemm_flops / gemm_sec / 1e12 if gemm_sec > 0 else 0.0
+    alg_tf = (mlp_flops(n_tri, n_obj) * args.steps / gemm_sec / 1e12) if gemm_sec > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tpath):
@@ -799,16 +800,18 @@ def run_ours(args):
         "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {"kernel": "net1/net2 GEMMs (%s)" % ("gemm_f32_kernel" if args.precision == "fp32" else "gemm_tc_kernel"),
-                     "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": ach_tf / peak_tf, "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
+                     "bound": "tensor", "achieved": alg_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": alg_tf / peak_tf, "executed_tflops": ach_tf, "executed_frac": ach_tf / peak_tf,
+                     "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
                      "launches_timed": gemm_n, "share_of_step": gemm_sec / sec if sec > 0 else None,
                      "whole_step_tflops": mlp_flops(n_tri, n_obj) / (sec / max(args.steps, 1)) / 1e12,
-                     "algorithmic_tflops": (mlp_flops(n_tri, n_obj) * args.steps / gemm_sec / 1e12) if gemm_sec > 0 else None,
-                     "flops_note": "achieved = flops the GEMM launches EXECUTE / their summed durations.  SURVEY 8(d) counts "
-                                   "1 572 864 FLOP per triple and layer forward (x3 with backward); the bf16 engine executes "
-                                   "less: net1's first-layer backward runs on per-object sums of dhidden (N = Dp instead of "
-                                   "2 Din + Dp for the two T-sized GEMMs).  algorithmic_tflops = the 8(d) count / the same "
-                                   "GEMM time",
+                     "flops_note": "achieved = ALGORITHMIC MLP flops of the step (SURVEY 8(d): 1 572 864 FLOP per triple and layer "
+                                   "+ 655 360 per object and layer forward, x3 with backward) / the summed durations of the "
+                                   "step's GEMM launches.  executed_tflops = the flops those launches really execute / the "
+                                   "same time: fewer since net1's first-layer backward runs on per-object sums of dhidden (the "
+                                   "two T-sized GEMMs have N = Dp instead of 2 Din + Dp; the segment-sum kernel that makes "
+                                   "this possible is NOT in the GEMM time: 45 us per layer, DESIGN.md section 9).  With the "
+                                   "fp32 engine both counts coincide",
                      "note": "CUDA events around every GEMM entry point on the launching stream, in a separate eagerly launched "
                              "pass of the same %d steps (%.3f ms/step with the events); share_of_step = summed GEMM "
                              "time / the headline timed region" % (args.steps, 1e3 * prof_sec / max(args.steps, 1))},
