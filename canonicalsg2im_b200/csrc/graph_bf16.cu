@@ -792,6 +792,69 @@ CSG_API int csg_segsum2_bf16(const void* X, int ldx, int W, const int* rowptr_s,
   return 0;
 }
 
+// ---- fp32 accuracy on the tensor cores: x = hi + mid + lo with three bf16 terms (8 + 8 + 8 = the 24 significant bits of
+// fp32, so the split is exact outside the subnormal range) and
+//     a b  ~=  a_hi b_hi + a_hi b_mid + a_mid b_hi + a_hi b_lo + a_lo b_hi + a_mid b_mid
+// (the three dropped products are below 2^-24 |a b|; every kept product of two bf16 numbers is exact in fp32 and the sums
+// run in the fp32 accumulators of tcgen05.mma).  Laid out along the reduction dimension this is ONE bf16 GEMM with a 6x
+// longer K: the A operand carries its parts in the order (hi, hi, mid, hi, lo, mid), the B operand (hi, mid, hi, lo, hi, mid).
+// csg_split3_bf16 writes that K-concatenated operand: reduction dimension = columns (K-major operand, out [rows, 6 cols])
+// or = rows (MN-major operand, out [6 rows, cols]); `transpose` first transposes the fp32 input (weights given as [K, N]).
+namespace {
+__global__ void split3_bf16_kernel(const float* __restrict__ X, int rows, int cols, int ld, int transpose, int k_is_cols,
+                                   int role, __nv_bfloat16* __restrict__ out, int ld_out) {
+  CSG_PDL_WAIT();
+  __shared__ float tile[32][33];
+  // logical matrix L [R, C] = X (or X^T); tiles of 32 x 32 through shared memory so that reads and writes stay coalesced
+  const int R = transpose ? cols : rows, C = transpose ? rows : cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    float v = 0.f;
+    if (!transpose) {
+      const int r = r0 + i, c = c0 + threadIdx.x;
+      if (r < R && c < C) v = X[(size_t)r * ld + c];
+      tile[i][threadIdx.x] = v;
+    } else {
+      // L[r, c] = X[c, r]: read X rows c0+i (= L columns), contiguous along r
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < R && c < C) v = X[(size_t)c * ld + r];
+      tile[threadIdx.x][i] = v;
+    }
+  }
+  __syncthreads();
+  const int pa[6] = {0, 0, 1, 0, 2, 1}, pb[6] = {0, 1, 0, 2, 0, 1};
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r >= R || c >= C) continue;
+    const float x = tile[i][threadIdx.x];
+    __nv_bfloat16 part[3];
+    part[0] = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(part[0]);
+    part[1] = __float2bfloat16_rn(r1);
+    part[2] = __float2bfloat16_rn(r1 - __bfloat162float(part[1]));
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const __nv_bfloat16 v = part[role ? pb[k] : pa[k]];
+      if (k_is_cols) out[(size_t)r * ld_out + (size_t)k * C + c] = v;
+      else out[((size_t)k * R + r) * ld_out + c] = v;
+    }
+  }
+}
+}  // namespace
+
+CSG_API int csg_split3_bf16(const float* X, int rows, int cols, int ld, int transpose, int k_is_cols, int role, void* out,
+                            int ld_out, cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return 0;
+  CSG_REQUIRE(role == 0 || role == 1, "split3_bf16: role must be 0 (A operand) or 1 (B operand)");
+  const int R = transpose ? cols : rows, C = transpose ? rows : cols;
+  CSG_REQUIRE(ld_out >= (k_is_cols ? 6 * C : C), "split3_bf16: ld_out too small");
+  dim3 grid(csg_div_up(C, 32), csg_div_up(R, 32));
+  CSG_CUDA(csg_launch_pdl(split3_bf16_kernel, grid, dim3(32, 8), 0, stream, X, rows, cols, ld, transpose, k_is_cols, role,
+                          reinterpret_cast<__nv_bfloat16*>(out), ld_out));
+  CSG_CHECK_LAUNCH("csg_split3_bf16");
+  return 0;
+}
+
 CSG_API int csg_relu_mask_bf16(const float* dy, const void* y, void* out, long long n, cudaStream_t stream) {
   if (n == 0) return 0;
   relu_mask_bf16_kernel<<<csg_div_up(n, 256), 256, 0, stream>>>(dy, reinterpret_cast<const __nv_bfloat16*>(y),

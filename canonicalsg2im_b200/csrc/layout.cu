@@ -604,6 +604,7 @@ int pick_splits(int N, int D, int H, int W) {
   const long long want = 6LL * 2 * csg_num_sms();
   int s = 1;
   while (s * 2 <= nbands && nbands % (s * 2) == 0 && base * s < want) s *= 2;
+  { const char* e = getenv("CSG_LAYOUT_SPLITS"); if (e && atoi(e) > 0 && nbands % atoi(e) == 0) s = atoi(e); }   // scratch/bench_layout.py
   return s;
 }
 

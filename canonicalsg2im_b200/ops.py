@@ -87,8 +87,78 @@ class Gather:
         return 2 * self.din + self.dp
 
 
+# fp32 engine: "simt" = csg_gemm_f32 (fp32 FMA pipes, the 1e-5 parity engine), "tc" = the same GEMMs on tcgen05 through an
+# exact three-term bf16 split of both operands, K-concatenated (csg_split3_bf16 + csg_gemm_bf16 with fp32 accumulation
+# and output).  Products are exact and the dropped cross terms are < 2^-24 relative, but tcgen05.mma adds into its fp32
+# accumulator with truncation, so the error grows linearly with the number of accumulating MMAs (measured against
+# float64: 1.1e-8 x K relative rms; 9e-5 on the 5-layer model where the SIMT engine is at 1e-6): a 1e-4 engine.
+# Process-wide switch, default "simt".
+F32_ENGINE = __import__("os").environ.get("CSG_F32_ENGINE", "simt")
+
+
+def set_f32_engine(name):
+    global F32_ENGINE
+    if name not in ("simt", "tc"):
+        raise ValueError("fp32 engine must be 'simt' or 'tc'")
+    F32_ENGINE = name
+
+
+def _split3(X, rows, cols, transpose, k_is_cols, role):
+    """K-concatenated three-term bf16 split of the fp32 matrix X [rows, cols] (or of its transpose)."""
+    R, C = (cols, rows) if transpose else (rows, cols)
+    out = torch.empty((R, 6 * C) if k_is_cols else (6 * R, C), dtype=torch.bfloat16, device=X.device)
+    _lib.check(lib().csg_split3_bf16(ptr(X), rows, cols, X.stride(0), int(transpose), int(k_is_cols), role, ptr(out),
+                                     out.stride(0), _stream()), "csg_split3_bf16")
+    return out
+
+
+def _gemm_f32_tc(amode, bmode, M, N, K, A, B, out, bias, relu, rowscale, mask_aux, gather):
+    """The fp32 GEMM modes of the parity engine on the tensor cores; returns None for shapes the tcgen05 kernels do not
+    take (the caller then runs the SIMT kernel)."""
+    if (N % 32 or (amode != A_COL and K % 8) or (amode == A_COL and M % 8) or M == 0 or N == 0 or K == 0
+            or (out is not None and (out.stride(0) % 4 or not out.is_contiguous()))):
+        return None
+    dev = (A if A is not None else B).device
+    if amode == A_GATHER or bmode == B_GATHER:
+        g = gather
+        X = torch.cat([g.obj[g.s_idx.long()], g.pred, g.obj[g.o_idx.long()]], dim=1)      # the reference's own concat
+        if amode == A_GATHER:
+            A, amode = X, A_ROW
+        else:
+            B, bmode = X, B_KN
+    A, B = f32c(A), f32c(B)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    L = lib()
+    if amode == A_ROW:
+        # C[M, N] = A[M, K] B^T with B as [N, K] (B_NK) or [K, N] (B_KN, transposed while it is split): K-major GEMM
+        a6 = _split3(A, M, K, False, True, 0)
+        b6 = _split3(B, N, K, False, True, 1) if bmode == B_NK else _split3(B, K, N, True, True, 1)
+        rc = L.csg_gemm_bf16(0, 0, M, N, 6 * K, ptr(a6), a6.stride(0), ptr(b6), b6.stride(0), ptr(out), out.stride(0), 1,
+                             ptr(bias), int(relu), ptr(rowscale), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, _stream())
+    else:
+        # C[M, N] = A[K, M]^T B[K, N]: MN-major GEMM, parts stacked along the rows (= K)
+        if bmode != B_KN or bias is not None or relu or rowscale is not None or mask_aux is not None:
+            return None
+        a6 = _split3(A, K, M, False, False, 0)
+        b6 = _split3(B, K, N, False, False, 1)
+        ws = workspace(L.csg_gemm_bf16_workspace(M, N, 6 * K, 1), dev)
+        rc = L.csg_gemm_bf16(1, 0, M, N, 6 * K, ptr(a6), a6.stride(0), ptr(b6), b6.stride(0), ptr(out), out.stride(0), 1,
+                             0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "csg_gemm_bf16 (fp32 through three-term split)")
+    if mask_aux is not None:
+        # ReLU mask of the epilogue as its own exact pass (the tensor-core epilogue takes a 16-bit mask operand)
+        m = f32c(mask_aux)
+        _lib.check(L.csg_relu_mask_f32(ptr(out), ptr(m), ptr(out), out.numel(), _stream()), "csg_relu_mask_f32")
+    return out
+
+
 def gemm_f32(amode, bmode, M, N, K, A, B, out=None, bias=None, relu=False, rowscale=None, mask_aux=None,
              gather=None, lda=None, ldb=None):
+    if F32_ENGINE == "tc" and lda in (None, 0) and ldb in (None, 0):
+        r = _gemm_f32_tc(amode, bmode, M, N, K, A, B, out, bias, relu, rowscale, mask_aux, gather)
+        if r is not None:
+            return r
     dev = (A if A is not None else B).device
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=dev)

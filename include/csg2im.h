@@ -193,6 +193,13 @@ int csg_segpool_bf16(const void* X, int ldx, int col_s, int col_o, int W,
  * bias / object-row gradients without a gathered GEMM over the triples (sg2im/graph.py:60-67 backward). */
 int csg_segsum2_bf16(const void* X, int ldx, int W, const int* rowptr_s, const int* perm_s, const int* rowptr_o,
                      const int* perm_o, int NO, float* out_f32, void* out_bf16, int ldo, csg_stream_t stream);
+/* fp32 accuracy on tcgen05: x = hi + mid + lo (three bf16 terms = the 24 significant bits of fp32) and a b ~= the six
+ * products of parts down to 2^-24 |a b|, accumulated in fp32 -- as ONE bf16 GEMM with a 6x longer reduction: this writes an
+ * operand with its parts concatenated along the reduction dimension (k_is_cols: out [R, 6 C], else out [6 R, C]; [R, C] = X or,
+ * with `transpose`, X^T) in the order (hi, hi, mid, hi, lo, mid) for role 0 (A) / (hi, mid, hi, lo, hi, mid) for role 1 (B).
+ * The 1e-5 parity engine of sg2im/graph.py:33-41,67,110 on tensor cores instead of fp32 FMA pipes (ops.gemm_f32). */
+int csg_split3_bf16(const float* X, int rows, int cols, int ld, int transpose, int k_is_cols, int role, void* out,
+                    int ld_out, csg_stream_t stream);
 int csg_relu_mask_bf16(const float* dy, const void* y, void* out, long long n, csg_stream_t stream);
 size_t csg_colsum_bf16_workspace(int M, int N);
 int csg_colsum_bf16(const void* X, int M, int N, int ld, float* out, void* workspace, size_t workspace_bytes,
