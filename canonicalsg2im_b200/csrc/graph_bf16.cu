@@ -797,7 +797,7 @@ CSG_API int csg_segsum2_bf16(const void* X, int ldx, int W, const int* rowptr_s,
 //     a b  ~=  a_hi b_hi + a_hi b_mid + a_mid b_hi + a_hi b_lo + a_lo b_hi + a_mid b_mid
 // (the three dropped products are below 2^-24 |a b|; every kept product of two bf16 numbers is exact in fp32 and the sums
 // run in the fp32 accumulators of tcgen05.mma).  Laid out along the reduction dimension this is ONE bf16 GEMM with a 6x
-// longer K: the A operand carries its parts in the order (hi, hi, mid, hi, lo, mid), the B operand (hi, mid, hi, lo, hi, mid).
+// longer K: the A operand carries its parts in the order (mid, lo, hi, mid, hi, hi), the B operand (mid, hi, lo, hi, mid, hi).
 // csg_split3_bf16 writes that K-concatenated operand: reduction dimension = columns (K-major operand, out [rows, 6 cols])
 // or = rows (MN-major operand, out [6 rows, cols]); `transpose` first transposes the fp32 input (weights given as [K, N]).
 namespace {
@@ -822,7 +822,15 @@ __global__ void split3_bf16_kernel(const float* __restrict__ X, int rows, int co
     }
   }
   __syncthreads();
-  const int pa[6] = {0, 0, 1, 0, 2, 1}, pb[6] = {0, 1, 0, 2, 0, 1};
+  // order of the six products along K: smallest first (mid*mid, lo*hi, hi*lo ~ 2^-16; mid*hi, hi*mid ~ 2^-8), hi*hi LAST.
+  // tcgen05.mma truncates its fp32 accumulator at every instruction, by up to an ulp of the RUNNING sum: while the
+  // corrections accumulate the running sum is 2^-8 .. 2^-16 of the result, so only the K/16 instructions of the hi*hi
+  // block truncate at full scale (measured: 6x less error than with hi*hi first)
+  const int pa[6] = {1, 2, 0, 1, 0, 0}, pb[6] = {1, 0, 2, 0, 1, 0};
+  // role: 0 / 1 = all six blocks of the A / B operand; 2 / 3 = the hi block alone; 4 / 5 = the five correction blocks
+  // (weight gradients reduce over ~1e5 rows: their hi*hi products are run as short chains of their own, ops.py)
+  const bool is_b = role & 1;
+  const int kbeg = (role >> 1) == 1 ? 5 : 0, kend = (role >> 1) == 2 ? 5 : 6;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = r0 + i, c = c0 + threadIdx.x;
     if (r >= R || c >= C) continue;
@@ -834,9 +842,11 @@ __global__ void split3_bf16_kernel(const float* __restrict__ X, int rows, int co
     part[2] = __float2bfloat16_rn(r1 - __bfloat162float(part[1]));
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      const __nv_bfloat16 v = part[role ? pb[k] : pa[k]];
-      if (k_is_cols) out[(size_t)r * ld_out + (size_t)k * C + c] = v;
-      else out[((size_t)k * R + r) * ld_out + c] = v;
+      if (k < kbeg || k >= kend) continue;
+      const __nv_bfloat16 v = part[is_b ? pb[k] : pa[k]];
+      const int kk = k - kbeg;
+      if (k_is_cols) out[(size_t)r * ld_out + (size_t)kk * C + c] = v;
+      else out[((size_t)kk * R + r) * ld_out + c] = v;
     }
   }
 }
@@ -845,9 +855,10 @@ __global__ void split3_bf16_kernel(const float* __restrict__ X, int rows, int co
 CSG_API int csg_split3_bf16(const float* X, int rows, int cols, int ld, int transpose, int k_is_cols, int role, void* out,
                             int ld_out, cudaStream_t stream) {
   if (rows == 0 || cols == 0) return 0;
-  CSG_REQUIRE(role == 0 || role == 1, "split3_bf16: role must be 0 (A operand) or 1 (B operand)");
+  CSG_REQUIRE(role >= 0 && role <= 5, "split3_bf16: role must be 0..5");
   const int R = transpose ? cols : rows, C = transpose ? rows : cols;
-  CSG_REQUIRE(ld_out >= (k_is_cols ? 6 * C : C), "split3_bf16: ld_out too small");
+  const int nblk = (role >> 1) == 0 ? 6 : ((role >> 1) == 1 ? 1 : 5);
+  CSG_REQUIRE(ld_out >= (k_is_cols ? nblk * C : C), "split3_bf16: ld_out too small");
   dim3 grid(csg_div_up(C, 32), csg_div_up(R, 32));
   CSG_CUDA(csg_launch_pdl(split3_bf16_kernel, grid, dim3(32, 8), 0, stream, X, rows, cols, ld, transpose, k_is_cols, role,
                           reinterpret_cast<__nv_bfloat16*>(out), ld_out));

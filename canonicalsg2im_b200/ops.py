@@ -87,12 +87,11 @@ class Gather:
         return 2 * self.din + self.dp
 
 
-# fp32 engine: "simt" = csg_gemm_f32 (fp32 FMA pipes, the 1e-5 parity engine), "tc" = the same GEMMs on tcgen05 through an
-# exact three-term bf16 split of both operands, K-concatenated (csg_split3_bf16 + csg_gemm_bf16 with fp32 accumulation
-# and output).  Products are exact and the dropped cross terms are < 2^-24 relative, but tcgen05.mma adds into its fp32
-# accumulator with truncation, so the error grows linearly with the number of accumulating MMAs (measured against
-# float64: 1.1e-8 x K relative rms; 9e-5 on the 5-layer model where the SIMT engine is at 1e-6): a 1e-4 engine.
-# Process-wide switch, default "simt".
+# fp32 engine: "simt" = csg_gemm_f32 (fp32 FMA pipes, the default parity engine), "tc" = the same GEMMs on tcgen05 through
+# an exact three-term bf16 split of both operands, K-concatenated (csg_split3_bf16 + csg_gemm_bf16 with fp32 accumulation
+# and output).  tcgen05.mma truncates its accumulator at every instruction, so the six products are ordered smallest
+# first and the hi*hi products of long reductions run as short chains: as accurate against float64
+# as the FMA kernel (relative rms 1e-7 .. 1e-6), 1.8x faster on the cfg2 step.  Process-wide switch.
 F32_ENGINE = __import__("os").environ.get("CSG_F32_ENGINE", "simt")
 
 
@@ -104,9 +103,11 @@ def set_f32_engine(name):
 
 
 def _split3(X, rows, cols, transpose, k_is_cols, role):
-    """K-concatenated three-term bf16 split of the fp32 matrix X [rows, cols] (or of its transpose)."""
+    """K-concatenated three-term bf16 split of the fp32 matrix X [rows, cols] (or of its transpose); role 0 / 1: all six
+    blocks of an A / B operand, 2 / 3: the hi block alone, 4 / 5: the five correction blocks."""
     R, C = (cols, rows) if transpose else (rows, cols)
-    out = torch.empty((R, 6 * C) if k_is_cols else (6 * R, C), dtype=torch.bfloat16, device=X.device)
+    nb = (6, 1, 5)[role >> 1]
+    out = torch.empty((R, nb * C) if k_is_cols else (nb * R, C), dtype=torch.bfloat16, device=X.device)
     _lib.check(lib().csg_split3_bf16(ptr(X), rows, cols, X.stride(0), int(transpose), int(k_is_cols), role, ptr(out),
                                      out.stride(0), _stream()), "csg_split3_bf16")
     return out
@@ -140,11 +141,31 @@ def _gemm_f32_tc(amode, bmode, M, N, K, A, B, out, bias, relu, rowscale, mask_au
         # C[M, N] = A[K, M]^T B[K, N]: MN-major GEMM, parts stacked along the rows (= K)
         if bmode != B_KN or bias is not None or relu or rowscale is not None or mask_aux is not None:
             return None
-        a6 = _split3(A, K, M, False, False, 0)
-        b6 = _split3(B, K, N, False, False, 1)
-        ws = workspace(L.csg_gemm_bf16_workspace(M, N, 6 * K, 1), dev)
-        rc = L.csg_gemm_bf16(1, 0, M, N, 6 * K, ptr(a6), a6.stride(0), ptr(b6), b6.stride(0), ptr(out), out.stride(0), 1,
-                             0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, ptr(ws), ws.numel(), _stream())
+        # The reduction is long here (K = triples): the hi*hi products must not sit in one accumulator for thousands of
+        # truncating MMAs.  K is cut into chunks of KC rows; per chunk the hi*hi block is a GEMM of its own, whose split-K
+        # leaves chains of <= ~64 MMAs, and the five correction blocks (2^-8 .. 2^-16 of the result) another; the chunk
+        # results are added in fp32 (round to nearest).
+        KC = 8192
+        rc = 0
+        first = True
+        for k0 in range(0, K, KC):
+            k1 = min(K, k0 + KC)
+            kc = k1 - k0
+            Ak, Bk = A[k0:k1], B[k0:k1]
+            for ra, rb, nb in ((4, 5, 5), (2, 3, 1)):
+                a6 = _split3(Ak, kc, M, False, False, ra)
+                b6 = _split3(Bk, kc, N, False, False, rb)
+                dst = out if first else torch.empty_like(out)
+                ws = workspace(L.csg_gemm_bf16_workspace(M, N, nb * kc, 1), dev)
+                rc = L.csg_gemm_bf16(1, 0, M, N, nb * kc, ptr(a6), a6.stride(0), ptr(b6), b6.stride(0), ptr(dst), dst.stride(0), 1,
+                                     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, ptr(ws), ws.numel(), _stream())
+                if rc:
+                    break
+                if not first:
+                    out += dst
+                first = False
+            if rc:
+                break
     _lib.check(rc, "csg_gemm_bf16 (fp32 through three-term split)")
     if mask_aux is not None:
         # ReLU mask of the epilogue as its own exact pass (the tensor-core epilogue takes a 16-bit mask operand)

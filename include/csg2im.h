@@ -196,7 +196,9 @@ int csg_segsum2_bf16(const void* X, int ldx, int W, const int* rowptr_s, const i
 /* fp32 accuracy on tcgen05: x = hi + mid + lo (three bf16 terms = the 24 significant bits of fp32) and a b ~= the six
  * products of parts down to 2^-24 |a b|, accumulated in fp32 -- as ONE bf16 GEMM with a 6x longer reduction: this writes an
  * operand with its parts concatenated along the reduction dimension (k_is_cols: out [R, 6 C], else out [6 R, C]; [R, C] = X or,
- * with `transpose`, X^T) in the order (hi, hi, mid, hi, lo, mid) for role 0 (A) / (hi, mid, hi, lo, hi, mid) for role 1 (B).
+ * with `transpose`, X^T) in the order (mid, lo, hi, mid, hi, hi) for role 0 (A) / (mid, hi, lo, hi, mid, hi) for role 1 (B):
+ * smallest products first, hi*hi last.  role 2 / 3: the hi block alone; role 4 / 5: the five correction blocks (out is then
+ * [R, C] / [R, 5 C] resp. [R, C] / [5 R, C]).
  * The 1e-5 parity engine of sg2im/graph.py:33-41,67,110 on tensor cores instead of fp32 FMA pipes (ops.gemm_f32). */
 int csg_split3_bf16(const float* X, int rows, int cols, int ld, int transpose, int k_is_cols, int role, void* out,
                     int ld_out, csg_stream_t stream);
