@@ -504,3 +504,49 @@ def test_cached_weight_copies_follow_the_optimizer(golden, monkeypatch):
     opt.step()
     assert graph_tc._WCOPIES[l0.net1[0].weight.data_ptr()]["versions"] is not None
     both()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Din,Dp,H,Dout,Dpo", [(64, 64, 256, 64, 64), (128, 64, 384, 192, 128), (192, 128, 512, 128, 64)])
+def test_layer_other_geometries_bf16(Din, Dp, H, Dout, Dpo):
+    """The tensor-core layer on feature widths other than the reference's 128 / 512 (the generic, not compile-time
+    specialised, instantiations of the assemble kernels, the per-object-sum backward with Din != Dp != Dout, odd tile
+    counts in every GEMM) against a plain-PyTorch model of the same bf16 arithmetic (tests/bf16_ref.py) on a ragged
+    batch: outputs and every gradient to 1e-2 max-norm, as in test_layer_bf16_vs_golden."""
+    from canonicalsg2im_b200.graph import GraphTripleConv, TripleBatch, get_predicates_weights
+    from tests.bf16_ref import layer_bf16_ref
+    torch.manual_seed(Din + H)
+    P = 12
+    n_obj = [5, 9, 3, 12, 7, 8]
+    n_tri = [40, 90, 7, 150, 66, 71]
+    NO, NT = sum(n_obj), sum(n_tri)
+    trip, types = [], []
+    for no, nt in zip(n_obj, n_tri):
+        trip.append(torch.stack([torch.randint(0, no, (nt,)), torch.randint(1, P, (nt,)), torch.randint(0, no, (nt,))], 1))
+        types.append(torch.randint(0, 2, (nt,)))
+    trip, types = torch.cat(trip).cuda(), torch.cat(types).cuda()
+    tri_off = torch.tensor([0] + list(np.cumsum(n_tri)), dtype=torch.int32).cuda()
+    obj_off = torch.tensor([0] + list(np.cumsum(n_obj)), dtype=torch.int32).cuda()
+    batch = TripleBatch.from_ragged(trip, types, tri_off, obj_off, NO, 0, P)
+    w = torch.nn.Parameter(get_predicates_weights(P, "uniform").detach().cuda())
+    layer = GraphTripleConv(Din, Dout, Dp, Dpo, H, 1, predicates_transitive_weights=w, precision="bf16").cuda()
+    obj0, pred0 = torch.randn(NO, Din, device="cuda"), torch.randn(NT, Dp, device="cuda")
+    go, gp = torch.randn(NO, Dout, device="cuda"), torch.randn(NT, Dpo, device="cuda")
+    o, p = obj0.clone().requires_grad_(True), pred0.clone().requires_grad_(True)
+    new_obj, new_p = layer.forward_flat(batch, o, p)
+    ((new_obj.float() * go).sum() + (new_p.float() * gp).sum()).backward()
+    # the same arithmetic in PyTorch
+    st = {k: v.detach().clone().requires_grad_(True) for k, v in layer.state_dict().items()}
+    ro, rp = obj0.clone().requires_grad_(True), pred0.clone().requires_grad_(True)
+    sg = (trip[:, 0] + obj_off.long()[torch.bucketize(torch.arange(NT, device="cuda"), tri_off.long()[1:], right=True)])
+    og = (trip[:, 2] + obj_off.long()[torch.bucketize(torch.arange(NT, device="cuda"), tri_off.long()[1:], right=True)])
+    pf = trip[:, 1]
+    conf_fn = lambda: (types == 0).float() + (types == 1).float() * torch.sigmoid(st["predicates_transitive_weights"])[pf]
+    r_obj, r_p = layer_bf16_ref(st, ro, rp, sg, og, pf != 0, conf_fn, H, Dpo)
+    assert_close(new_obj.float(), r_obj, TOL_BF16, "new_obj vs bf16 model")      # one or two bf16 ulps (summation order)
+    assert_close(new_p.float(), r_p, TOL_BF16, "new_p vs bf16 model")
+    ((r_obj * go).sum() + (r_p * gp).sum()).backward()
+    assert_close(o.grad, ro.grad, TOL_BF16, "d_obj")
+    assert_close(p.grad, rp.grad, TOL_BF16, "d_pred")
+    for name, prm in layer.named_parameters():
+        assert_close(prm.grad, st[name].grad, TOL_BF16, "d " + name)
