@@ -512,7 +512,7 @@ def test_layer_other_geometries_bf16(Din, Dp, H, Dout, Dpo):
     """The tensor-core layer on feature widths other than the reference's 128 / 512 (the generic, not compile-time
     specialised, instantiations of the assemble kernels, the per-object-sum backward with Din != Dp != Dout, odd tile
     counts in every GEMM) against a plain-PyTorch model of the same bf16 arithmetic (tests/bf16_ref.py) on a ragged
-    batch: outputs and every gradient to 1e-2 max-norm, as in test_layer_bf16_vs_golden."""
+    batch: outputs to 1e-2 max-norm, every gradient to 5e-2 relative L2."""
     from canonicalsg2im_b200.graph import GraphTripleConv, TripleBatch, get_predicates_weights
     from tests.bf16_ref import layer_bf16_ref
     torch.manual_seed(Din + H)
@@ -546,7 +546,8 @@ def test_layer_other_geometries_bf16(Din, Dp, H, Dout, Dpo):
     assert_close(new_obj.float(), r_obj, TOL_BF16, "new_obj vs bf16 model")      # one or two bf16 ulps (summation order)
     assert_close(new_p.float(), r_p, TOL_BF16, "new_p vs bf16 model")
     ((r_obj * go).sum() + (r_p * gp).sum()).backward()
-    assert_close(o.grad, ro.grad, TOL_BF16, "d_obj")
-    assert_close(p.grad, rp.grad, TOL_BF16, "d_pred")
+    # gradients: relative L2 (a wrong index or stride shows up as O(1)); on 44 objects a single ReLU whose pre-activation
+    # sits within one bf16 ulp of zero and flips between the two summation orders moves a max-norm by 3e-2
+    assert rel_l2(o.grad, ro.grad) <= 5e-2 and rel_l2(p.grad, rp.grad) <= 5e-2
     for name, prm in layer.named_parameters():
-        assert_close(prm.grad, st[name].grad, TOL_BF16, "d " + name)
+        assert rel_l2(prm.grad, st[name].grad) <= 5e-2, (name, rel_l2(prm.grad, st[name].grad))
