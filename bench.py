@@ -720,12 +720,13 @@ def run_ours(args):
 
     # ---- timed region 2: end to end through the public API with HOST buffers (H2D + D2H every step)
     # the data pipeline cycles through two device batch buffers (host -> device copies land in the buffer that is not
-    # being trained on), so the step's CUDA graph is captured once per buffer
+    # being trained on, on the step's look-ahead stream, behind the last step that used that buffer and beside the step
+    # in flight), so the step's CUDA graph is captured once per buffer
     d.pop("_canon_plan", None)
     bufs = [hb.to_device(dev), hb.to_device(dev)]
     dd = bufs[0]
     for i in range(0 if args.profile else 4):
-        nxt = hb.to_device(dev, out=bufs[(i + 1) & 1])
+        nxt = hb.to_device(dev, out=bufs[(i + 1) & 1], stream=step.side)
         l, _ = step.step(dd, G, prefetch=nxt)
         dd = nxt
         float(l.item())
@@ -739,7 +740,7 @@ def run_ours(args):
         # step runs (one upload + one count + one emit per step inside the timed region).  Every step's loss is copied
         # to pinned host memory; the host reads it one step later (as a logging loop would), so that the read never
         # drains the launch queue.  The last loss is read before the clock stops.
-        nxt = hb.to_device(dev, out=bufs[(i + 1) & 1])
+        nxt = hb.to_device(dev, out=bufs[(i + 1) & 1], stream=step.side)
         l, _ = step.step(dd, G, prefetch=nxt)
         dd = nxt
         loss_host[i & 1].copy_(l, non_blocking=True)

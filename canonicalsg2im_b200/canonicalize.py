@@ -128,6 +128,12 @@ def canon_emit(plan, out=None):
     launches ``csg_canon_emit``.  Returns a :class:`CanonResult`."""
     total = canon_total(plan)
     dev = plan.out_off.device
+    # the counting pass may have run on another stream (a data pipeline's look-ahead stream): its buffers were allocated
+    # there, so tell the caching allocator that this stream reads them now (canon_total has already waited for the pass)
+    cur = torch.cuda.current_stream()
+    for x in plan.keep + (plan.out_off, plan.conv_counts):
+        if torch.is_tensor(x) and x.is_cuda:
+            x.record_stream(cur)
     if out is not None:
         out_t, out_ty = out
         if out_t.shape[0] < total or out_ty.shape[0] < total or out_t.dtype != torch.int64 or not out_t.is_contiguous():

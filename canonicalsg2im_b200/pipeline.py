@@ -60,16 +60,27 @@ class HostBatch:
             self.t[k] = x
         self.nbytes = sum(x.numel() * x.element_size() for x in self.t.values())
 
-    def to_device(self, device, out=None):
+    def to_device(self, device, out=None, stream=None):
         """Upload (asynchronously, from pinned memory).  ``out``: a dict returned by an earlier ``to_device`` of a batch
         with the same shapes: its tensors are overwritten in place, so the device addresses stay the same (a data
-        pipeline cycling through a fixed set of batch buffers; what the CUDA-graph replay of the step keys on)."""
+        pipeline cycling through a fixed set of batch buffers; what the CUDA-graph replay of the step keys on).
+        ``stream``: a look-ahead stream (``SgToLayoutStep.side``): the copies are issued there, behind everything the
+        current stream has been given so far (the previous user of ``out``), and overlap the step that is launched next;
+        ``d["_ready"]`` is the event consumers on other streams wait for."""
+        if stream is not None:
+            stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(stream):
+                d = self.to_device(device, out=out)
+                d["_ready"] = torch.cuda.Event()
+                d["_ready"].record(stream)
+            return d
         if out is not None:
             if any(out[k].shape != v.shape for k, v in self.t.items()):
                 raise ValueError("to_device(out=...): shapes differ from the buffers' batch")
             for k, v in self.t.items():
                 out[k].copy_(v, non_blocking=True)
             out.pop("_canon_plan", None)
+            out.pop("_ready", None)
             d = out
         else:
             d = {k: v.to(device, non_blocking=True) for k, v in self.t.items()}
@@ -114,6 +125,7 @@ class SgToLayoutStep:
         self.tail_events = None      # set to [] to time the part of the all-reduce that trails the backward pass
         # CUDA-graph replay of forward + backward (see _step_graphed): one captured graph per (batch buffers, sizes)
         self.use_graph = use_graph
+        self.side = torch.cuda.Stream(device=device)     # look-ahead stream: uploads and counting passes of the next batch
         self._graphs = {}
         self.graph_replays = 0
         self.graph_launches = 0
@@ -135,10 +147,19 @@ class SgToLayoutStep:
     def prefetch(self, d):
         """Launch the counting pass of the canonicalization of batch ``d`` now (no host wait); ``step(d, ...)``
         later finds the output sizes on the host.  The reference canonicalizes in DataLoader workers ahead of the
-        training step (base_dataset.py:89-139 inside ``__getitem__``); this is the same look-ahead on the device."""
-        d["_canon_plan"] = canon_count_async(d["triplets"], d["tri_off"], d["obj_off"], self.vocab.num_preds,
-                                             self.vocab.meta_ids, None, self.flags[0], self.flags[1], d["uniforms"],
-                                             max_objs_per_graph=d["max_objs"], tables=self.tables)
+        training step (base_dataset.py:89-139 inside ``__getitem__``); this is the same look-ahead on the device, on
+        its own stream (``self.side``): the pass (one CTA per graph, ~40 us) then runs beside the kernels of the step in
+        flight instead of in front of them."""
+        side = self.side
+        ready = d.get("_ready")
+        if ready is not None:
+            side.wait_event(ready)                 # upload of `d` (HostBatch.to_device(stream=...))
+        else:
+            side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            d["_canon_plan"] = canon_count_async(d["triplets"], d["tri_off"], d["obj_off"], self.vocab.num_preds,
+                                                 self.vocab.meta_ids, None, self.flags[0], self.flags[1], d["uniforms"],
+                                                 max_objs_per_graph=d["max_objs"], tables=self.tables)
 
     def canonicalize(self, d):
         if d.get("_canon_plan") is None:
@@ -256,6 +277,8 @@ class SgToLayoutStep:
     def step(self, d, canvas_grad, prefetch=None):
         """One training step on batch ``d``.  ``prefetch``: the batch of the NEXT step (may be ``d`` itself); its
         canonicalization counting pass is enqueued right behind this step's emit pass."""
+        if d.get("_ready") is not None:            # `d` was uploaded on the look-ahead stream
+            torch.cuda.current_stream().wait_event(d["_ready"])
         if self.use_graph:
             out = self._step_graphed(d, canvas_grad, prefetch)
             if out is not None:
