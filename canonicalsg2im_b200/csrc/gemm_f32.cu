@@ -279,6 +279,10 @@ CSG_API int csg_gemm_f32(int amode, int bmode, int M, int N, int K,
                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (M == 0 || N == 0) return 0;
   CSG_REQUIRE(M > 0 && N > 0 && K >= 0, "gemm_f32: bad sizes M=%d N=%d K=%d", M, N, K);
+  if (K == 0 && !bias && !relu) {      // empty reduction (a batch without triples): the product is zero, no operand is read
+    CSG_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, stream));
+    return 0;
+  }
   CsgProfScope prof(CSG_PROF_GEMM_F32, 2.0 * M * N * K, stream);
   GemmParams p;
   p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldb = ldb; p.ldc = ldc;

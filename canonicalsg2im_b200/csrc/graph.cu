@@ -454,7 +454,8 @@ CSG_API int csg_segpool_f32(const float* X, int ldx, int col_s, int col_o, int W
   CSG_REQUIRE(W <= 4096, "segpool: W=%d too wide", W);
   int threads = ((W / 4 + 31) / 32) * 32;
   if (avg) {
-    CSG_REQUIRE(valid && conf && cnt_out, "segpool(avg): valid/conf/cnt required");
+    // valid / conf are read per incidence only: a batch without triples may pass NULL for them
+    CSG_REQUIRE(cnt_out, "segpool(avg): cnt_out required");
     segpool_kernel<true><<<NO, threads, 0, stream>>>(X, ldx, col_s, col_o, W, rowptr_s, perm_s, rowptr_o, perm_o,
                                                      valid, conf, out, ldo, cnt_out);
   } else {

@@ -762,7 +762,8 @@ CSG_API int csg_segpool_bf16(const void* X, int ldx, int col_s, int col_o, int W
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(X);
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   if (avg) {
-    CSG_REQUIRE(valid && conf && cnt_out, "segpool_bf16(avg): valid/conf/cnt required");
+    // valid / conf are read per incidence only: a batch without triples may pass NULL for them
+    CSG_REQUIRE(cnt_out, "segpool_bf16(avg): cnt_out required");
     CSG_CUDA(csg_launch_pdl(segpool_bf16_kernel<true>, dim3(NO), dim3(threads), 0, stream, x, ldx, col_s, col_o, W, TX, TY, rowptr_s, perm_s, rowptr_o,
                                                           perm_o, valid, conf, out_f32, ob, ldo, cnt_out, fp16 != 0, 0));
   } else {

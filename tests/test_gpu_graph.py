@@ -551,3 +551,42 @@ def test_layer_other_geometries_bf16(Din, Dp, H, Dout, Dpo):
     assert rel_l2(o.grad, ro.grad) <= 5e-2 and rel_l2(p.grad, rp.grad) <= 5e-2
     for name, prm in layer.named_parameters():
         assert rel_l2(prm.grad, st[name].grad) <= 5e-2, (name, rel_l2(prm.grad, st[name].grad))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_layer_degenerate_batches(prec):
+    """Edge cases of the ragged batch (empty and ragged inputs): a graph without triples in the middle of the
+    batch, objects that no triple touches (their pooled row is zero, graph.py:104-107, and so is the gradient that
+    reaches them through the gathers), and a batch without any triple at all: both engines run them, the outputs
+    of untouched objects equal net2(0) and every gradient is finite."""
+    from canonicalsg2im_b200.graph import GraphTripleConv, TripleBatch, get_predicates_weights
+    torch.manual_seed(3)
+    P = 9
+    w = torch.nn.Parameter(get_predicates_weights(P, "uniform").detach().cuda())
+    layer = GraphTripleConv(128, 128, 128, 128, 512, 1, predicates_transitive_weights=w, precision=prec).cuda()
+    for n_obj, n_tri in (([4, 3, 5], [6, 0, 9]), ([3, 2], [0, 0])):
+        NO, NT = sum(n_obj), sum(n_tri)
+        trip = [torch.stack([torch.randint(0, max(no - 1, 1), (nt,)), torch.randint(1, P, (nt,)),
+                             torch.randint(0, max(no - 1, 1), (nt,))], 1) for no, nt in zip(n_obj, n_tri)]
+        trip = torch.cat(trip).cuda().reshape(-1, 3)
+        types = torch.randint(0, 2, (NT,)).cuda()
+        tri_off = torch.tensor([0] + list(np.cumsum(n_tri)), dtype=torch.int32).cuda()
+        obj_off = torch.tensor([0] + list(np.cumsum(n_obj)), dtype=torch.int32).cuda()
+        batch = TripleBatch.from_ragged(trip, types, tri_off, obj_off, NO, 0, P)
+        o = torch.randn(NO, 128, device="cuda").requires_grad_(True)
+        p = torch.randn(NT, 128, device="cuda").requires_grad_(True)
+        for q in layer.parameters():
+            q.grad = None
+        new_obj, new_p = layer.forward_flat(batch, o, p)
+        assert new_obj.shape == (NO, 128) and new_p.shape == (NT, 128)
+        (new_obj.float().sum() + new_p.float().sum()).backward()
+        # the last object of every graph is touched by no triple (ids are drawn below n_obj - 1): its row is net2(0)
+        last = [int(obj_off[b + 1]) - 1 for b in range(len(n_obj))]
+        zero_row = layer.net2(torch.zeros(1, 512, device="cuda")).float()
+        for i in last:
+            assert_close(new_obj[i:i + 1].float(), zero_row, 1e-2 if prec == "bf16" else 1e-5, "untouched object")
+            assert float(o.grad[i].abs().max()) == 0.0
+        assert torch.isfinite(o.grad).all() and (NT == 0 or torch.isfinite(p.grad).all())
+        for n, q in layer.named_parameters():
+            assert q.grad is not None and torch.isfinite(q.grad).all(), n
