@@ -126,6 +126,7 @@ class SgToLayoutStep:
         # CUDA-graph replay of forward + backward (see _step_graphed): one captured graph per (batch buffers, sizes)
         self.use_graph = use_graph
         self.side = torch.cuda.Stream(device=device)     # look-ahead stream: uploads and counting passes of the next batch
+        self._opt_done = None          # event of an optimizer step that was issued on the look-ahead stream
         self._graphs = {}
         self.graph_replays = 0
         self.graph_launches = 0
@@ -264,12 +265,22 @@ class SgToLayoutStep:
             ent["tri_off"].copy_(res.tri_off)
         if prefetch is not None:
             self.prefetch(prefetch)
+        main = torch.cuda.current_stream()
+        if self._opt_done is not None:     # the optimizer step of the previous iteration (look-ahead stream, below)
+            main.wait_event(self._opt_done)
+            self._opt_done = None
         ent["graph"].replay()
         self.graph_replays += 1
         self.graph_launches += ent["launches"]      # kernel-launch sites executed by the replay (counted at capture)
         for p, g in zip(self.opt.params, ent["grads"]):
             p.grad = g
-        self.opt.step()
+        # Adam and the refresh of the 16-bit weight copies go to the look-ahead stream: the next step's emit pass (main
+        # stream, ~50 us, independent of the weights) then runs beside them instead of behind them
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self.opt.step()
+            self._opt_done = torch.cuda.Event()
+            self._opt_done.record(self.side)
         for p in self.opt.params:          # the entry keeps its gradient buffers; an eager step must not accumulate into them
             p.grad = None
         return ent["loss"], total
@@ -283,6 +294,9 @@ class SgToLayoutStep:
             out = self._step_graphed(d, canvas_grad, prefetch)
             if out is not None:
                 return out
+        if self._opt_done is not None:
+            torch.cuda.current_stream().wait_event(self._opt_done)
+            self._opt_done = None
         loss, n_tri = self.backward(d, canvas_grad, prefetch)
         self._eager_steps += 1
         self.opt.step()
@@ -291,6 +305,14 @@ class SgToLayoutStep:
         else:
             self.opt.zero_grad(set_to_none=True)
         return loss.detach(), n_tri
+
+    def finish(self):
+        """Make the current stream wait for the optimizer step of the last ``step()`` call.  With CUDA-graph replay Adam
+        and the refresh of the 16-bit weight copies are issued on the look-ahead stream (so that the next step's emit
+        pass overlaps them); the next ``step()`` waits for them by itself, anything ELSE that reads the parameters
+        (evaluation, checkpoints, tests) calls this first."""
+        if self._opt_done is not None:
+            torch.cuda.current_stream().wait_event(self._opt_done)
 
     def named_grads(self):
         out = {"model." + n: p.grad for n, p in self.model.named_parameters() if p.grad is not None}
