@@ -11,6 +11,8 @@ table (generator.py:16,80), not from the GCN output, so the canvas gradient reac
 trained by the box loss.  All stages are csg2im kernels; torch provides memory and autograd bookkeeping.
 """
 import numpy as np
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -127,6 +129,8 @@ class SgToLayoutStep:
         self.use_graph = use_graph
         self.side = torch.cuda.Stream(device=device)     # look-ahead stream: uploads and counting passes of the next batch
         self._opt_done = None          # event of an optimizer step that was issued on the look-ahead stream
+        self.branch = torch.cuda.Stream(device=device)   # the canvas branch of forward / backward (see forward())
+        self.overlap_canvas = os.environ.get("CSG_OVERLAP_CANVAS", "1") != "0"
         self._graphs = {}
         self.graph_replays = 0
         self.graph_launches = 0
@@ -168,14 +172,25 @@ class SgToLayoutStep:
         return canon_emit(d.pop("_canon_plan"))
 
     def forward(self, d, res):
-        obj_vecs, boxes_pred = self.model.forward_ragged(d["objs"], res.triplets, res.triplet_type, res.tri_off,
-                                                         d["obj_off"])
         # canvas: the generator's own embedding of the objects on the GT boxes (train.py:358, generator.py:80-96).
         # remove_dummy_objects (utils.py:56-63) needs no filtering pass: the __image__ dummy has box -1 and
-        # contributes exact zeros to the canvas and receives an exactly zero gradient
-        layout_vecs = self.layout_embedding(d["objs"])
-        canvas = layout_batched(layout_vecs, d["boxes"], d["obj_off"], self.H, self.W,
-                                max_objs_per_image=d["max_objs"])
+        # contributes exact zeros to the canvas and receives an exactly zero gradient.
+        # The canvas branch shares nothing with the GCN but the batch, so it is issued on its own stream: autograd runs
+        # a node's backward on the stream of its forward, so both the compositor (bandwidth-bound, every SM) and its
+        # backward run beside the GCN's latency-bound first / last kernels (triple index + CSR build, box head) -- as a
+        # parallel branch of the captured graph under CUDA-graph replay.
+        main = torch.cuda.current_stream()
+        branch = self.branch if self.overlap_canvas else main
+        if branch is not main:
+            branch.wait_stream(main)
+        with torch.cuda.stream(branch):
+            layout_vecs = self.layout_embedding(d["objs"])
+            canvas = layout_batched(layout_vecs, d["boxes"], d["obj_off"], self.H, self.W,
+                                    max_objs_per_image=d["max_objs"])
+        obj_vecs, boxes_pred = self.model.forward_ragged(d["objs"], res.triplets, res.triplet_type, res.tri_off,
+                                                         d["obj_off"])
+        if branch is not main:
+            main.wait_stream(branch)
         weight = self.bbox_pred_loss_weight
         if self.global_batch is not None:
             weight = weight * d["B"] / float(self.global_batch)
