@@ -580,6 +580,24 @@ def run_cfg5(dev, pk, args, world, rank, want_check):
                              "gradients)" % world}
             del solo, ref
         del mine
+        # the same sharded batch through the graph-replayed step (look-ahead streams, canvas branch, Adam beside the next
+        # emit pass) and through eagerly launched single-stream steps: identical weights after 4 optimizer steps
+        sums = []
+        for use_graph, overlap in ((False, False), (True, True)):
+            st2 = SgToLayoutStep(vocab, dev, precision=args.precision, distributed=True, seed=0, global_batch=NG,
+                                 use_graph=use_graph)
+            st2.overlap_canvas = overlap
+            for _ in range(4):
+                st2.step(d, G, prefetch=d)
+            st2.finish()
+            torch.cuda.synchronize()
+            sums.append(torch.stack([p.detach().double().sum() for p in st2.opt.params]))
+            del st2
+        same = bool(torch.equal(sums[0], sums[1]))
+        flag = torch.tensor([1.0 if same else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if check is not None:
+            check["graph_replay_with_streams_equals_eager_single_stream"] = bool(flag.item() == 1.0)
     del probe, d_all
     if not (want_check and world > 1):
         pass

@@ -51,6 +51,11 @@ class BucketedGradAllReduce:
         self.params, self.pending = [], []
         self._bucket_of = {}
         self._inflight = []          # (handle, region, unpack list or None)
+        # Stream a bucket's all-reduce is launched from.  Autograd runs a node's backward on the stream of its forward,
+        # so a gradient of a bucket may become final on another stream than its neighbours (the canvas branch of
+        # pipeline.SgToLayoutStep): the hook then leaves an event there and the launch makes `home` wait for it.
+        self.home = None
+        self._events = [[] for _ in buckets]
         self.in_place_buckets = 0    # statistics of the last step (tests / bench)
         seen = set()
         for bi, params in enumerate(buckets):
@@ -90,6 +95,17 @@ class BucketedGradAllReduce:
         grads = [p.grad for p in self.params[bi] if p.grad is not None]
         if not grads:
             return
+        if self.home is not None and grads[0].is_cuda:
+            # everything below (packing included) is issued on `home`, behind the gradients that became final elsewhere
+            for ev in self._events[bi]:
+                self.home.wait_event(ev)
+            with torch.cuda.stream(self.home):
+                self._launch_on_current(bi, grads)
+        else:
+            self._launch_on_current(bi, grads)
+        self._events[bi] = []
+
+    def _launch_on_current(self, bi, grads):
         op = dist.ReduceOp.AVG if self.native_avg else dist.ReduceOp.SUM
         region = self._contiguous_region(grads)
         unpack = None
@@ -103,6 +119,12 @@ class BucketedGradAllReduce:
 
     def _hook(self, p):
         bi = self._bucket_of[id(p)]
+        if self.home is not None and p.is_cuda:
+            cur = torch.cuda.current_stream()
+            if cur != self.home:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self._events[bi].append(ev)
         self._count[bi] -= 1
         if self._count[bi] == 0:
             self._launch(bi)

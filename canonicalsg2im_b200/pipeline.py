@@ -130,6 +130,7 @@ class SgToLayoutStep:
         self.side = torch.cuda.Stream(device=device)     # look-ahead stream: uploads and counting passes of the next batch
         self._opt_done = None          # event of an optimizer step that was issued on the look-ahead stream
         self.branch = torch.cuda.Stream(device=device)   # the canvas branch of forward / backward (see forward())
+        # (the bucketed gradient all-reduce copes with gradients that become final on the branch stream: reducer.home)
         self.overlap_canvas = os.environ.get("CSG_OVERLAP_CANVAS", "1") != "0"
         self._graphs = {}
         self.graph_replays = 0
@@ -202,6 +203,8 @@ class SgToLayoutStep:
         res = self.canonicalize(d)
         if prefetch is not None:
             self.prefetch(prefetch)
+        if self.reducer is not None:
+            self.reducer.home = torch.cuda.current_stream()
         canvas, loss = self.forward(d, res)
         torch.autograd.backward([canvas, loss], [canvas_grad, None])
         if self.reducer is not None:
@@ -253,6 +256,8 @@ class SgToLayoutStep:
         except AttributeError:
             pass
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            if self.reducer is not None:
+                self.reducer.home = torch.cuda.current_stream()       # the capture stream
             canvas, loss = self.forward(d, static)
             torch.autograd.backward([canvas, loss], [G, None])
             if self.reducer is not None:

@@ -591,3 +591,31 @@ def test_layer_degenerate_batches(prec):
         assert torch.isfinite(o.grad).all() and (NT == 0 or torch.isfinite(p.grad).all())
         for n, q in layer.named_parameters():
             assert q.grad is not None and torch.isfinite(q.grad).all(), n
+
+
+@pytest.mark.gpu
+def test_canvas_branch_and_lookahead_streams_change_nothing():
+    """SgToLayoutStep runs the canvas branch (generator embedding -> compositor -> its backward) on its own stream and,
+    under graph replay, Adam + the weight-copy refresh on the look-ahead stream.  Neither may change a bit: after
+    several steps every parameter (GCN, box head, both embedding tables) equals the single-stream run."""
+    from canonicalsg2im_b200.pipeline import SgToLayoutStep, HostBatch
+    vocab = synth.Vocab(42)
+    hb = HostBatch(synth.make_graphs(12, 700, 3, 20, vocab, include_dummies=True), seed=1)
+    results = []
+    for overlap, use_graph in ((False, False), (True, False), (True, True)):
+        step = SgToLayoutStep(vocab, torch.device("cuda"), precision="bf16", seed=0, use_graph=use_graph)
+        step.overlap_canvas = overlap
+        d = hb.to_device("cuda")
+        G = torch.randn((12, 128, 64, 64), device="cuda", generator=torch.Generator("cuda").manual_seed(3)) * 1e-3
+        for it in range(5):
+            step.step(d, G, prefetch=d)
+        step.finish()
+        torch.cuda.synchronize()
+        results.append({n: p.detach().clone() for n, p in list(step.model.named_parameters()) +
+                        [("layout." + k, v) for k, v in step.layout_embedding.named_parameters()]})
+    for other in results[1:]:
+        for n, v in results[0].items():
+            assert torch.equal(v, other[n]), n
+    # the canvas gradient really moved the generator's table (so the comparison above is not vacuous)
+    fresh = SgToLayoutStep(vocab, torch.device("cuda"), precision="bf16", seed=0)
+    assert not torch.equal(fresh.layout_embedding.att_emb_0.weight, results[0]["layout.att_emb_0.weight"])
