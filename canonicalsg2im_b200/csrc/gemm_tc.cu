@@ -1135,7 +1135,7 @@ int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K,
     int best_s = 0;
     for (int st = (pair ? 6 : 5); st >= 2 && !best_s; --st)
       if (smem_plan(BN, BN / CG, st, p.smem_epi != 0, 1, epw, sub32).total <= SMEM_LIMIT) best_s = st;
-    { const char* e = getenv("CSG_GEMM_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < best_s) best_s = atoi(e); }
+    { const char* e = getenv("CSG_GEMM_STAGES"); if (e && atoi(e) >= 3 && atoi(e) < best_s) best_s = atoi(e); }   // scratch/bench_gemm.py (3 stages: -4 %)
     CSG_REQUIRE(best_s > 0, "gemm_bf16: no shared-memory plan fits BN=%d", BN);
     p.stages = best_s;
   } else {
