@@ -18,7 +18,7 @@ torch.cuda.set_device(0)
 vocab = synth.Vocab(42)
 graphs = synth.make_graphs(128, 1000, 3, 30, vocab, include_dummies=True)
 hb = HostBatch(graphs, seed=0)
-step = SgToLayoutStep(vocab, dev, precision=prec, seed=0)
+step = SgToLayoutStep(vocab, dev, precision=prec, seed=0, use_graph="--graph" in sys.argv)     # --graph: CUDA-graph replay
 G = torch.randn((128, 128, 64, 64), device=dev) * 1e-3
 d = hb.to_device(dev)
 for _ in range(5):
