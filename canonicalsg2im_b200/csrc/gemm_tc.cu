@@ -65,6 +65,10 @@ struct TcParams {
   int g_din, g_dp, g_rows;
   int debug;                   // scratch/bench_gemm.py only: 1 = no operand loads, 2 = no MMAs, 4 = no epilogue work
   int a_f16, b_f16, c_f16;     // operand / 16-bit output element formats: 0 = bf16, 1 = fp16 (kind::f16 takes both, per operand)
+  // Tail split (K-major kernels with the staged epilogue): when the last round of the static tile schedule would leave
+  // more than half of the workers idle, its tiles (indices >= tail_from) are cut into two half-width tiles each, so the
+  // round costs half a tile time (dhid: 918 pair tiles on 74 pairs = 12.4 rounds -> 12.5 instead of 13).  -1: off.
+  int tail_from, num_items;
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -310,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sA = base, sB = base + plan.b;
   Barriers* bars = reinterpret_cast<Barriers*>(base_ptr + plan.bars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int num_tiles = p.num_items;
   const int STAGES = p.stages;
 
   if (warp == 1 && lane == 0) {
@@ -343,11 +347,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // shared::cluster address of a barrier of the pair's leader (identity for the 1-CTA kernel)
   auto leader = [&](const uint64_t* bar) -> uint32_t { return CG == 2 ? mapa(smem_u32(bar), 0u) : smem_u32(bar); };
 
-  auto decode = [&](int tile, int& mt, int& nt, int& sp) {
+  // work item -> (m-tile, n-tile, split) and the columns [n0, n0 + nw) of C it covers (a half tile of the split tail
+  // covers BN / 2 of them)
+  auto decode = [&](int tile, int& mt, int& nt, int& sp, int& n0, int& nw) {
+    int half = -1;
+    if (p.tail_from >= 0 && tile >= p.tail_from) {
+      const int h = tile - p.tail_from;
+      half = h & 1;
+      tile = p.tail_from + (h >> 1);
+    }
     nt = tile % p.n_tiles;
     int r = tile / p.n_tiles;
     mt = r % p.m_tiles;
     sp = r / p.m_tiles;
+    n0 = nt * BN;
+    nw = BN;
+    if (half >= 0) { nw = BN / 2; n0 += half * nw; }
   };
   auto kb_range = [&](int sp, int& kb0, int& kb1) {
     kb0 = sp * p.kb_per_split;
@@ -359,8 +374,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0, phase = 0;
       for (int tile = worker; tile < num_tiles; tile += nworkers) {
-        int mt, nt, sp, kb0, kb1;
-        decode(tile, mt, nt, sp);
+        int mt, nt, sp, kb0, kb1, n0, nw;
+        decode(tile, mt, nt, sp, n0, nw);
         kb_range(sp, kb0, kb1);
         const int m0 = mt * TILE_M + (int)cta_rank * BLOCK_M;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -381,7 +396,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int c0 = kb * BLOCK_K;
               if (!p.g_pidx && c0 >= p.g_din && c0 < p.g_din + p.g_dp) tma_load_2d_pair(a_dst, &tmP, fb, c0 - p.g_din, m0);
             }
-            tma_load_2d_pair(b_dst, &tmB, fb, kb * BLOCK_K, nt * BN + (int)cta_rank * B_ROWS);
+            // (a half tile loads the whole box as well: the MMA reads only its first nw / 2 rows of each CTA)
+            tma_load_2d_pair(b_dst, &tmB, fb, kb * BLOCK_K, n0 + (int)cta_rank * (nw / 2));
           } else if (!MN) {
             // K-major: rows = M (or N), 64 contiguous k elements per 128-byte row
             if (GATHER == G_NONE) tma_load_2d(a_dst, &tmA, fb, kb * BLOCK_K, mt * BLOCK_M);
@@ -389,7 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int c0 = kb * BLOCK_K;     // predicate block of the virtual row [obj[s] | pred | obj[o]]
               if (!p.g_pidx && c0 >= p.g_din && c0 < p.g_din + p.g_dp) tma_load_2d(a_dst, &tmP, fb, c0 - p.g_din, mt * BLOCK_M);
             }
-            tma_load_2d(b_dst, &tmB, fb, kb * BLOCK_K, nt * BN);
+            tma_load_2d(b_dst, &tmB, fb, kb * BLOCK_K, n0);
           } else {
             // MN-major: rows = k (64 per block), one [64 k x 64 mn] box per 64-wide chunk
             for (int c = 0; c < MT * BLOCK_M / 64; ++c) tma_load_2d(a_dst + c * 8192, &tmA, fb, mt * TILE_M + c * 64, kb * BLOCK_K);
@@ -412,8 +428,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int gl = (warp - FIRST_GATHER_WARP) * 8 + lane;          // 0..31
       int stage = 0, phase = 0;
       for (int tile = worker; tile < num_tiles; tile += nworkers) {
-        int mt, nt, sp, kb0, kb1;
-        decode(tile, mt, nt, sp);
+        int mt, nt, sp, kb0, kb1, n0, nw;
+        decode(tile, mt, nt, sp, n0, nw);
         kb_range(sp, kb0, kb1);
         if (GATHER == G_A) {
           // A tile [128 triples x 64 k]: this lane owns rows 4*gl .. 4*gl+3 (tmA = object table)
@@ -505,13 +521,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0 && cta_rank == 0) {
       int stage = 0, phase = 0, it = 0;
       for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
-        int mt, nt, sp, kb0, kb1;
-        decode(tile, mt, nt, sp);
+        int mt, nt, sp, kb0, kb1, n0, nw;
+        decode(tile, mt, nt, sp, n0, nw);
         kb_range(sp, kb0, kb1);
         const int as = it & 1, aphase = (it >> 1) & 1;
         // the last n-tile may be narrower than BN: issue MMAs of its real width (N % 32 == 0 is required by the host
         // side; an MMA of N = 192 costs as much as N = 256, which is why BN is 256 with a narrow tail and not 192)
-        const int mma_n = (!MN && CG == 1) ? min(BN, p.N - nt * BN) : BN;
+        const int mma_n = !MN ? (CG == 1 ? min(nw, p.N - n0) : nw) : BN;
         const uint32_t idesc = make_idesc(BLOCK_M * CG, mma_n, MN, MN, p.a_f16 != 0, p.b_f16 != 0);
         mbar_wait(smem_u32(&bars->tmem_empty[as]), aphase ^ 1);
         tc_fence_after();
@@ -575,12 +591,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __nv_bfloat16* Cb = reinterpret_cast<__nv_bfloat16*>(p.C);
       const bool cf16 = p.c_f16 != 0;
       for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
-        int mt, nt, sp;
-        decode(tile, mt, nt, sp);
+        int mt, nt, sp, n0, nw;
+        decode(tile, mt, nt, sp, n0, nw);
         const int as = it & 1, aphase = (it >> 1) & 1;
         const int row0 = mt * TILE_M + (int)cta_rank * BLOCK_M + q * 32;
         const int row = row0 + lane;
-        const int ncols = min(BN, p.N - nt * BN);
+        const int ncols = min(nw, p.N - n0);
         const int nsb = (ncols + SUB_N - 1) / SUB_N;
         const bool warp_rows = row0 < p.M;
         const float rs = (p.rowscale && row < p.M) ? __ldg(p.rowscale + row) : 1.f;
@@ -596,7 +612,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 #pragma unroll 1
         for (int c = sub; c < nsb; c += NSUB) {
-          const int col0 = nt * BN + c * SUB_N;                // N % 32 == 0: a sub-block is never partial
+          const int col0 = n0 + c * SUB_N;                     // N % 32 == 0: a sub-block is never partial
           const float bv = p.bias ? __ldg(p.bias + col0 + lane) : 0.f;
           uint32_t r[32];
           tmem_ld32(t_row + c * SUB_N, r);
@@ -692,12 +708,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
       for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
-        int mt, nt, sp;
-        decode(tile, mt, nt, sp);
+        int mt, nt, sp, n0, nw;
+        decode(tile, mt, nt, sp, n0, nw);
         const int as = it & 1, aphase = (it >> 1) & 1;
         const int row0 = mt * TILE_M + (int)cta_rank * BLOCK_M + q * 32;
         const int row = row0 + lane;
-        const int ncols = min(BN, p.N - nt * BN);
+        const int ncols = min(nw, p.N - n0);
         const int nchunks = (ncols + CHUNK_N - 1) / CHUNK_N;
         const bool warp_rows = row0 < p.M;
         const float rs = (p.rowscale && row < p.M) ? __ldg(p.rowscale + row) : 1.f;
@@ -713,13 +729,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 #pragma unroll 1
         for (int c = sub; c < nchunks; c += NSUB) {
-          const int bc = nt * BN + c * CHUNK_N + lane;
+          const int bc = n0 + c * CHUNK_N + lane;
           const float bv0 = (p.bias && bc < p.N) ? __ldg(p.bias + bc) : 0.f;
           const float bv1 = (p.bias && bc + 32 < p.N) ? __ldg(p.bias + bc + 32) : 0.f;
           uint32_t r0[32], r1[32];
           tmem_ld32(t_row + c * CHUNK_N, r0);
           tmem_ld32(t_row + c * CHUNK_N + 32, r1);
-          const int col = nt * BN + c * CHUNK_N + cpiece * 8;  // first column of this lane's 16-byte piece
+          const int col = n0 + c * CHUNK_N + cpiece * 8;       // first column of this lane's 16-byte piece
           // ReLU-mask operand of this chunk, in the coalesced layout of the final stores: needed only after the math
           // and the staging round trip below, which cover its latency
           uint4 ax[8];
@@ -792,8 +808,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
       // fp32 output (split-K partials, small fp32 results): direct 16-byte stores, 32 columns at a time
       for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
-        int mt, nt, sp;
-        decode(tile, mt, nt, sp);
+        int mt, nt, sp, n0, nw;
+        decode(tile, mt, nt, sp, n0, nw);
         const int as = it & 1, aphase = (it >> 1) & 1;
         mbar_wait(smem_u32(&bars->tmem_full[as]), aphase);
         tc_fence_after();
@@ -1159,6 +1175,16 @@ int csg_gemm_bf16_deferred(int mn_major, int gather, int M, int N, int K,
     while (p.stages > 2 && smem_plan(BN, BN, p.stages, false, MT, 8, false).total > SMEM_LIMIT) --p.stages;
     CSG_REQUIRE(MT == 1 || p.m_tiles * p.n_tiles * p.splits <= csg_num_sms(),
                 "gemm_bf16: the multi-accumulator weight-gradient kernel needs one work item per CTA");
+  }
+  p.tail_from = -1;
+  p.num_items = p.m_tiles * p.n_tiles * p.splits;
+  {
+    const char* e = getenv("CSG_GEMM_TAIL_SPLIT");
+    const int T = p.m_tiles * p.n_tiles, W = pair ? csg_num_sms() / 2 : csg_num_sms();
+    if (!(e && e[0] == '0') && !mn_major && p.smem_epi && p.splits == 1 && N % BN == 0 && BN >= 128 && T > W) {
+      const int rem = T % W;
+      if (rem > 0 && 2 * rem <= W) { p.tail_from = T - rem; p.num_items = T + rem; }
+    }
   }
   int rc;
   if (!mn_major && pair)

@@ -160,3 +160,23 @@ def test_pair_auto_large(pair_mode):
     W = _rand((512, 384), 45, 0.05)
     out3 = ops.gemm_bf16(M, 512, 384, None, W, bias=bias[:512].contiguous(), relu=True, gather=g, gather_mode=1)
     assert_close(out3.float(), torch.relu(X.float() @ W.float().T + bias[:512]), 1e-2, "F1 shape, pairs")
+
+
+@pytest.mark.parametrize("M,N,K", [(128 * 326, 512, 128), (256 * 90, 512, 192), (128 * 190, 128, 256), (117321, 512, 64)])
+def test_tail_split_of_the_tile_schedule(M, N, K, monkeypatch):
+    """When the last round of the static tile schedule would leave more than half of the workers idle, its tiles are
+    cut into two half-width tiles (csrc/gemm_tc.cu, TcParams::tail_from).  Shapes chosen so that the split triggers on
+    the 1-CTA and / or the CTA-pair kernels: the result must be bit-identical to the unsplit schedule
+    (CSG_GEMM_TAIL_SPLIT=0) -- same products, same K order per output element -- with every epilogue."""
+    from canonicalsg2im_b200 import ops
+    A, B = _rand((M, K), 11), _rand((N, K), 12, 0.05)
+    bias = torch.randn(N, device="cuda")
+    rs = torch.rand(M, device="cuda")
+    aux = _rand((M, N), 13)
+    outs = []
+    for split in ("1", "0"):
+        monkeypatch.setenv("CSG_GEMM_TAIL_SPLIT", split)
+        outs.append((ops.gemm_bf16(M, N, K, A, B, bias=bias, relu=True, rowscale=rs), ops.gemm_bf16(M, N, K, A, B, mask_aux=aux)))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    ref = torch.relu(A[-300:].float() @ B.float().T + bias) * rs[-300:, None]
+    assert_close(outs[0][0][-300:].float(), ref, 1e-2, "tail rows")
