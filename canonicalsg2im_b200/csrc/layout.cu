@@ -536,6 +536,8 @@ __global__ void __launch_bounds__(NTHREADS) layout_bwd_ring_kernel(Params q) {
       // Weights outside an object's column interval are exact zeros, so the dot product over the whole 32-pixel
       // sub-band needs no per-quarter test (adding 0 * g changes nothing), and two objects are walked per iteration:
       // their weight loads, FMA chains and accumulator updates are independent and overlap.
+      // (the same dot product on the packed fp32 pipe -- fma.rn.f32x2, 16 FFMA2 per object in two 8-deep or four 4-deep
+      // chains -- measured 89 us against 81 us for this scalar form on the cfg2 canvas: dropped)
       auto dot = [&](const float* wrow) {
         float sum = 0.f;
 #pragma unroll
