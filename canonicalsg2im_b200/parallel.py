@@ -42,7 +42,13 @@ class BucketedGradAllReduce:
 
     ``finish()`` waits for the collectives; ``zero()`` drops the gradients (``set_to_none``)."""
 
-    def __init__(self, buckets, group=None, average=True):
+    def __init__(self, buckets, group=None, average=True, launch_groups=None):
+        """``launch_groups``: lists of bucket indices whose all-reduces are issued TOGETHER, as one coalesced NCCL
+        launch (``ncclGroupStart`` ... ``ncclGroupEnd``: one kernel for all regions), once the last of them is final.
+        ``None``: every bucket on its own.  The kernels of the backward pass are persistent and fill every SM, so an
+        all-reduce kernel does not run beside them but between two of them: each launch costs its latency floor
+        (~20-30 us) on the critical path however small the bucket, and fewer, larger launches are cheaper than one per
+        layer (measured: DESIGN.md section 5)."""
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.average = average
@@ -57,6 +63,7 @@ class BucketedGradAllReduce:
         self.home = None
         self._events = [[] for _ in buckets]
         self.in_place_buckets = 0    # statistics of the last step (tests / bench)
+        self.launches = 0            # collective launches of the last step
         seen = set()
         for bi, params in enumerate(buckets):
             params = [p for p in params if p.requires_grad and id(p) not in seen]
@@ -68,6 +75,16 @@ class BucketedGradAllReduce:
             self.params.append(params)
             self.pending.append(len(params))
         self._count = list(self.pending)
+        if launch_groups is None:
+            launch_groups = [[bi] for bi in range(len(buckets))]
+        covered = sorted(bi for g in launch_groups for bi in g)
+        if covered != list(range(len(buckets))):
+            raise ValueError("launch_groups must cover every bucket exactly once")
+        self.launch_groups = [list(g) for g in launch_groups]
+        self._group_of = {bi: gi for gi, g in enumerate(self.launch_groups) for bi in g}
+        self._group_left = [sum(1 for bi in g if self.params[bi]) for g in self.launch_groups]
+        self._group_pending = list(self._group_left)
+        self._launched = [False] * len(self.launch_groups)
 
     @staticmethod
     def _contiguous_region(grads):
@@ -91,31 +108,53 @@ class BucketedGradAllReduce:
         n = (spans[-1][1] - spans[0][0]) // esz
         return torch.empty(0, dtype=g0.dtype, device=g0.device).set_(st, off, (n,), (1,))
 
-    def _launch(self, bi):
-        grads = [p.grad for p in self.params[bi] if p.grad is not None]
-        if not grads:
+    def _launch(self, gi):
+        """Issue the all-reduces of launch group ``gi`` (all of its buckets that have gradients) as one launch."""
+        self._launched[gi] = True
+        items = []
+        for bi in self.launch_groups[gi]:
+            grads = [p.grad for p in self.params[bi] if p.grad is not None]
+            if grads:
+                items.append((bi, grads))
+        if not items:
             return
-        if self.home is not None and grads[0].is_cuda:
+        if self.home is not None and items[0][1][0].is_cuda:
             # everything below (packing included) is issued on `home`, behind the gradients that became final elsewhere
-            for ev in self._events[bi]:
-                self.home.wait_event(ev)
+            for bi, _ in items:
+                for ev in self._events[bi]:
+                    self.home.wait_event(ev)
             with torch.cuda.stream(self.home):
-                self._launch_on_current(bi, grads)
+                self._launch_on_current(items)
         else:
-            self._launch_on_current(bi, grads)
-        self._events[bi] = []
+            self._launch_on_current(items)
+        for bi, _ in items:
+            self._events[bi] = []
 
-    def _launch_on_current(self, bi, grads):
+    def _launch_on_current(self, items):
         op = dist.ReduceOp.AVG if self.native_avg else dist.ReduceOp.SUM
-        region = self._contiguous_region(grads)
-        unpack = None
-        if region is None:
-            region = torch.cat([g.reshape(-1) for g in grads])
-            unpack = grads
+        regions, unpacks = [], []
+        for _, grads in items:
+            region = self._contiguous_region(grads)
+            unpack = None
+            if region is None:
+                region = torch.cat([g.reshape(-1) for g in grads])
+                unpack = grads
+            else:
+                self.in_place_buckets += 1
+            regions.append(region)
+            unpacks.append(unpack)
+        if len(regions) == 1:
+            h = dist.all_reduce(regions[0], op=op, group=self.group, async_op=True)
         else:
-            self.in_place_buckets += 1
-        h = dist.all_reduce(region, op=op, group=self.group, async_op=True)
-        self._inflight.append((h, region, unpack))
+            pg = self.group if self.group is not None else dist.distributed_c10d._get_default_group()
+            opts = dist.AllreduceCoalescedOptions()
+            opts.reduceOp = op
+            opts.asyncOp = True
+            h = pg.allreduce_coalesced(regions, opts)
+        self.launches += 1
+        for region, unpack in zip(regions, unpacks):
+            self._inflight.append((h, region, unpack))
+            h = None          # one handle per launch: waited once
 
     def _hook(self, p):
         bi = self._bucket_of[id(p)]
@@ -127,16 +166,20 @@ class BucketedGradAllReduce:
                 self._events[bi].append(ev)
         self._count[bi] -= 1
         if self._count[bi] == 0:
-            self._launch(bi)
+            gi = self._group_of[bi]
+            self._group_pending[gi] -= 1
+            if self._group_pending[gi] == 0:
+                self._launch(gi)
 
     def finish(self):
         """Wait for outstanding all-reduces; launch the ones whose hooks did not all fire (unused params)."""
         if self.world > 1:
-            for bi, c in enumerate(self._count):
-                if c != 0 and self.params[bi]:
-                    self._launch(bi)
+            for gi, done in enumerate(self._launched):
+                if not done and self._group_left[gi]:
+                    self._launch(gi)
             for h, region, unpack in self._inflight:
-                h.wait()
+                if h is not None:
+                    h.wait()
                 if self.average and not self.native_avg:
                     region.div_(self.world)
                 if unpack is not None:
@@ -146,9 +189,12 @@ class BucketedGradAllReduce:
                         off += g.numel()
         self._inflight = []
         self._count = list(self.pending)
+        self._group_pending = list(self._group_left)
+        self._launched = [False] * len(self.launch_groups)
 
     def zero(self):
         self.in_place_buckets = 0
+        self.launches = 0
         for params in self.params:
             for p in params:
                 p.grad = None

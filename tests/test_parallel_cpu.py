@@ -105,3 +105,41 @@ def test_bucket_reduced_in_place_on_the_producers_flat_buffer():
         ga, gb, n_in_place = out[rank]
         assert n_in_place == 1                      # no pack / unpack copies for this bucket
         assert torch.allclose(gb, db, rtol=1e-6) and torch.allclose(ga, db[:, None].expand(6, 4), rtol=1e-6)
+
+
+def _worker_groups(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = torch.arange(24, dtype=torch.float32).view(4, 6) / 10 + rank
+    res = {}
+    for name, groups in (("each", None), ("two", [[0, 1], [2]]), ("end", [[0, 1, 2]])):
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 4), torch.nn.ReLU(),
+                                  torch.nn.Linear(4, 3))
+        red = BucketedGradAllReduce([list(net[4].parameters()), list(net[2].parameters()), list(net[0].parameters())],
+                                    launch_groups=groups)
+        for _ in range(2):          # second step: the group bookkeeping is reset by finish()
+            red.zero()
+            net(x).pow(2).sum().backward()
+            red.finish()
+            res[name] = ([p.grad.clone() for p in net.parameters()], red.launches)
+    out[rank] = res
+    with pytest.raises(ValueError):
+        BucketedGradAllReduce([[torch.nn.Parameter(torch.ones(2))], [torch.nn.Parameter(torch.ones(2))]],
+                              launch_groups=[[0]])
+    dist.destroy_process_group()
+
+
+def test_coalesced_launch_groups_give_the_same_gradients_with_fewer_launches():
+    world, port = 2, 29615
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_groups, args=(world, port, out), nprocs=world, join=True)
+    for rank in range(world):
+        res = out[rank]
+        assert res["each"][1] == 3 and res["two"][1] == 2 and res["end"][1] == 1
+        for name in ("two", "end"):
+            for a, b in zip(res[name][0], res["each"][0]):
+                assert torch.equal(a, b)
+        for a, b in zip(out[0]["each"][0], res["each"][0]):
+            assert torch.equal(a, b)
