@@ -330,7 +330,8 @@ def layout_roofline(boxes, off, max_objs, N, D, H, W, pk, masks=None, iters=20, 
         sec = time_each(fn, iters, 3, flush)
         res[name] = {"us": sec * 1e6, "achieved": nbytes / sec / 1e9, "frac": nbytes / sec / 1e9 / pk["hbm"]}
     kind = "masks_to_layout" if masks is not None else "boxes_to_layout"
-    return {"kernel": "layout_fwd_kernel / layout_bwd_ring_kernel (%s %dx%dx%dx%d)" % (kind, N, D, H, W),
+    bwd_kernel = "layout_bwd_ring_kernel" if masks is not None else "layout_bwd_colsum_kernel"
+    return {"kernel": "layout_fwd_kernel / %s (%s %dx%dx%dx%d)" % (bwd_kernel, kind, N, D, H, W),
             "bound": "hbm", "unit": "GB/s", "peak": pk["hbm"], "peak_source": pk["src"] + " copy bandwidth",
             "bytes_per_launch": nbytes, "fwd": res["fwd"], "bwd": res["bwd"],
             "l2": "canvas of %.0f MB %s the 126 MB L2%s" % (nbytes / 1e6, "exceeds" if nbytes > 126e6 else "fits in",

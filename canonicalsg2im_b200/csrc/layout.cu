@@ -798,10 +798,13 @@ __global__ void layout_bwd_sum_splits_kernel(const float* __restrict__ partial, 
   dvecs[i] = acc;
 }
 
-int pick_splits(int N, int D, int H, int W) {
+int pick_splits(int N, int D, int H, int W, bool colsum = false) {
   const int nbands = (H * W) / BAND;
   const long long base = (long long)N * (D / DC);
-  const long long want = 6LL * 2 * csg_num_sms();
+  // CTAs wanted: ~7 waves of two CTAs per SM for the ring kernel; the column-sum kernel has little to do per band and
+  // pays ~2.9 us of set-up per CTA against 1.6 us per band, so it takes half as many CTAs of twice the length
+  // (cfg2 canvas: 61.5 us with 1024 CTAs of 8 bands, 64 us with 2048 of 4, 75 us with 512 of 16)
+  const long long want = (colsum ? 3LL : 6LL) * 2 * csg_num_sms();
   int s = 1;
   while (s * 2 <= nbands && nbands % (s * 2) == 0 && base * s < want) s *= 2;
   while (H / s > cs::RR_MAX && s * 2 <= nbands && nbands % (s * 2) == 0) s *= 2;   // column-sum kernel: short running sums
@@ -1152,7 +1155,8 @@ CSG_API int csg_layout_bwd_vecs(const float* dout, const float* boxes, const flo
     q.p.TW = W; q.p.TH = H; q.p.tiles_x = q.p.tiles_y = 1;
     q.p.lcap = bw::pick_lcap(max_objs_per_image, H, W, masks != nullptr);
     q.dout = dout; q.partial = partial; q.NO = NO;
-    q.splits = bw::pick_splits(N, D, H, W);
+    const bool want_cs = !masks && !(force && force[0] == 'r') && bw::cs::shape_ok(H, W);
+    q.splits = bw::pick_splits(N, D, H, W, want_cs);
     q.bands_per_item = (H * W) / bw::BAND / q.splits;
     q.cblocks = D / bw::DC;
     float* axg = partial + (size_t)q.splits * NO * D;
@@ -1164,7 +1168,7 @@ CSG_API int csg_layout_bwd_vecs(const float* dout, const float* boxes, const flo
     CSG_CHECK_LAUNCH("csg_layout_bwd_vecs tables");
     const int grid = N * q.cblocks * q.splits;
     const int RR = q.bands_per_item * bw::BAND / W;       // rows per CTA
-    if (!masks && !(force && force[0] == 'r') && bw::cs::shape_ok(H, W) && RR <= bw::cs::RR_MAX) {
+    if (want_cs && RR <= bw::cs::RR_MAX) {
       // boxes: running column sums + summation by parts along y (layout_bwd_colsum_kernel)
       q.p.lcap = bw::cs::pick_lcap(max_objs_per_image, W, RR);
       const size_t smem = bw::cs::smem_bytes(q.p.lcap, W, RR);
