@@ -14,6 +14,10 @@
 //             -- walk the objects that touch their sub-band, so the pixel weights are warp-uniform broadcasts and
 //             zero weights are skipped without divergence; per-(object, channel) sums live in shared memory and
 //             the per-range partials are combined in a fixed order by a second kernel.
+//   backward, boxes_to_layout (W = 64 / 128 / 256): the same gradient ring, but the contraction is summed by parts
+//             along y (layout_bwd_colsum_kernel below): thread = (channel, strip of W / 8 columns) keeps running
+//             column sums in registers and an object costs a short dot product only on the rows where its row
+//             factor changes.
 //   generic   the previous tile/butterfly backward is kept for shapes the ring cannot serve (W % 64, H*W % 256,
 //             D % 32 or unaligned gradients).
 //

@@ -74,9 +74,11 @@ if __name__ == "__main__":
     _lib.load()
     torch.cuda.set_device(0)
     only = os.environ.get("CSG_BL_ONLY", "")          # "boxes": the boxes_to_layout rows only
-    run("cfg2 boxes 128x128x64x64", 128, 3, 31, 128, 64, 64, 16, False)
+    if only != "masks":
+        run("cfg2 boxes 128x128x64x64", 128, 3, 31, 128, 64, 64, 16, False)
     if only != "boxes":
         run("cfg3 masks 16x128x256x256", 16, 3, 8, 128, 256, 256, 16, True)
         run("cfg3b masks O=16-24", 16, 16, 24, 128, 256, 256, 16, True)
-    run("boxes 32x128x128x128", 32, 3, 31, 128, 128, 128, 16, False)
-    run("boxes 8x128x256x256", 8, 3, 31, 128, 256, 256, 16, False)
+    if only != "masks":
+        run("boxes 32x128x128x128", 32, 3, 31, 128, 128, 128, 16, False)
+        run("boxes 8x128x256x256", 8, 3, 31, 128, 256, 256, 16, False)
