@@ -86,6 +86,37 @@ def test_batched_equals_per_image_oracle(L, H, W, D, M, use_masks):
     assert_close(v.grad, vc.grad, TOL, "batched dvecs")
 
 
+@pytest.mark.parametrize("H,W,D,n_img,n_min,n_max,splits", [
+    (128, 128, 32, 3, 1, 9, 0),      # 16-column strips
+    (64, 256, 32, 2, 1, 9, 0),       # 32-column strips, one row per band
+    (256, 256, 32, 2, 3, 20, 0),     # row ranges of a single row
+    (64, 64, 64, 3, 40, 70, 0),      # more than 32 objects per image: several chunks
+    (36, 64, 32, 2, 1, 9, 0),        # odd band count: one row range per image
+    (64, 64, 32, 3, 3, 20, 1),       # the longest running sums: 64 rows per CTA (large batches select this)
+    (64, 64, 32, 3, 3, 20, 2)])      # 32 rows per CTA (the cfg2 launch)
+def test_column_sum_backward_shapes(L, monkeypatch, H, W, D, n_img, n_min, n_max, splits):
+    """d/dvecs of boxes_to_layout on the shapes that select layout_bwd_colsum_kernel<8 / 16 / 32> (running column
+    sums + summation by parts along y), against the per-image oracle: every strip width, several object chunks
+    per image, an image without objects, row ranges from one row to the whole image (CSG_LAYOUT_SPLITS is read
+    on every call)."""
+    from oracle import layout as olayout
+    if splits:
+        monkeypatch.setenv("CSG_LAYOUT_SPLITS", str(splits))
+    vecs, boxes, _, off = _rand_objs(11, n_img, n_min, n_max, D, 4)
+    off = np.insert(off, 1, off[1]).astype(np.int32)                    # an empty image after the first one
+    N = len(off) - 1
+    v = t(vecs).requires_grad_(True)
+    y = L.layout_batched(v, t(boxes), t(off), H, W, max_objs_per_image=int(np.diff(off).max()))
+    gy = synth.det_tensor(tuple(y.shape), 92, 1.0)
+    (y * t(gy)).sum().backward()
+    vc = torch.from_numpy(vecs).requires_grad_(True)
+    outs = olayout.batched_layout([vc[off[i]:off[i + 1]] for i in range(N)],
+                                  [torch.from_numpy(boxes[off[i]:off[i + 1]]) for i in range(N)], None, H, W)
+    (outs * torch.from_numpy(gy)).sum().backward()
+    assert_close(y, outs, TOL, "fwd")
+    assert_close(v.grad, vc.grad, TOL, "dvecs (column sums)")
+
+
 def test_many_objects_chunking(L):
     """More objects per tile than the shared-memory list holds -> multi-pass accumulation."""
     from oracle import layout as olayout
