@@ -45,10 +45,10 @@ class BucketedGradAllReduce:
     def __init__(self, buckets, group=None, average=True, launch_groups=None):
         """``launch_groups``: lists of bucket indices whose all-reduces are issued TOGETHER, as one coalesced NCCL
         launch (``ncclGroupStart`` ... ``ncclGroupEnd``: one kernel for all regions), once the last of them is final.
-        ``None``: every bucket on its own.  The kernels of the backward pass are persistent and fill every SM, so an
-        all-reduce kernel does not run beside them but between two of them: each launch costs its latency floor
-        (~20-30 us) on the critical path however small the bucket, and fewer, larger launches are cheaper than one per
-        layer (measured: DESIGN.md section 5)."""
+        ``None``: every bucket on its own.  Why one might group: the kernels of the backward pass are persistent and
+        fill every SM, so an all-reduce kernel runs between two of them rather than beside them and each launch puts
+        its latency floor on the critical path.  Measured: worth 2 % of a cfg2 step at N = 2 and
+        nothing at N = 8, so ``SgToLayoutStep`` keeps one launch per bucket unless ``CSG_GRAD_GROUPS`` says otherwise."""
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.average = average
